@@ -1,0 +1,138 @@
+"""Value-iteration / Whittle-index restatement (oracle, test-only).
+
+Follows the vendored, locally modified pymdptoolbox in the reference:
+  MDP._bellmanOperator        mdptoolbox/mdp.py:217-246   Q[a,s] = R[a][s] + g * P[a][s,:].V ; max / first argmax
+  MDP._computeMatrixReward    mdptoolbox/mdp.py:292-302   R[a][s] = sum_s' P[a][s,s'] R[a,s,s']
+  ValueIteration.__init__     mdptoolbox/mdp.py:1293-1318 thresh = eps(1-g)/g
+  ValueIteration._boundIter   mdptoolbox/mdp.py:1320-1364 max_iter = ceil(log(thresh/span)/log(g k))
+  ValueIteration.run          mdptoolbox/mdp.py:1366-1410 stop 'full': max(V-Vprev) < thresh, or iter == max_iter
+and the call site robust_rmab/simulator.py:504-521 (R_i[a,s,s'] = R[i][s], i.e. reward on the
+CURRENT state; indexes[i,a,s] = R[i,s] + g V_i . T[i,s,a]).
+
+lambda-probes: the per-(arm, lambda) MDP has reward R[i,s] - lambda*C[a]  (lp_methods.py:63,181).
+The Whittle index of (arm, state) is the lambda at which Q(s,1;lambda) = Q(s,0;lambda)
+(lp_methods.py:181).  The reference solves that with a Gurobi LP, which cannot run here
+(gurobipy absent, unpinned): the index / Hawkins parts below are PARITY UNPINNED against the
+reference's LP; they are pinned only against mdptoolbox.ValueIteration per probe.
+"""
+import math
+
+import numpy as np
+
+
+def bound_iter(P, R, gamma, eps):
+    """_boundIter for one MDP.  P `[A,S,S]`, R `[A,S]` (already collapsed).  Returns max_iter (int).
+
+    Raises ZeroDivisionError / ValueError exactly where the reference's math.log / division does.
+    """
+    A, S, _ = P.shape
+    h = P.min(axis=(0, 1))            # h[ss] = min over (a, s) of P[a][s, ss]   (:1344-1352)
+    k = 1 - h.sum()
+    V0 = np.zeros(S)
+    Q = R + gamma * (P @ V0)          # _bellmanOperator on V = 0
+    value = Q.max(axis=0)
+    diff = value - V0
+    span = diff.max() - diff.min()    # util.getSpan
+    max_iter = math.log((eps * (1 - gamma) / gamma) / span) / math.log(gamma * k)
+    return int(math.ceil(max_iter))
+
+
+def value_iteration(P, R, gamma, eps=0.01, stop="full", max_iter=None):
+    """ValueIteration(...).run() for one MDP; float64.  Returns (V[S], policy[S], iters, max_iter)."""
+    P = np.asarray(P, dtype=np.float64)
+    R = np.asarray(R, dtype=np.float64)
+    A, S, _ = P.shape
+    if max_iter is None:
+        max_iter = bound_iter(P, R, gamma, eps)
+    thresh = eps * (1 - gamma) / gamma
+    V = np.zeros(S)
+    it = 0
+    while True:
+        it += 1
+        Vprev = V
+        Q = R + gamma * (P @ V)
+        policy = Q.argmax(axis=0)
+        V = Q.max(axis=0)
+        d = V - Vprev
+        variation = (d.max() - d.min()) if stop == "fast" else d.max()
+        if variation < thresh:
+            break
+        if it == max_iter:
+            break
+    return V, policy, it, max_iter
+
+
+def probe_mdp(T_arm, R_arm, C, lam):
+    """(P[A,S,S], R[A,S]) of one arm at one lambda: simulator.py:506-510 with R - lambda*C[a]."""
+    P = np.swapaxes(np.asarray(T_arm, np.float64), 0, 1)
+    R = np.asarray(R_arm, np.float64)[None, :] - lam * np.asarray(C, np.float64)[:, None]
+    return P, R
+
+
+def batched_vi(T, R, C, lambdas, gamma, eps, stop="full"):
+    """All arms x lambda-probes.  T `[N,S,A,S]`, R `[N,S]`, C `[A]`, lambdas `[L]` or `[N,L]`.
+
+    Returns V `[N,L,S]` f64, policy `[N,L,S]` u8, iters `[N,L]` i32, max_iter `[N,L]` i32.  Probes whose
+    `_boundIter` raises in the reference (span == 0 or gamma*k in {0,1}) get iters = -1 and V = NaN.
+    """
+    T = np.asarray(T, np.float64)
+    N, S, A, _ = T.shape
+    lambdas = np.asarray(lambdas, np.float64)
+    if lambdas.ndim == 1:
+        lambdas = np.broadcast_to(lambdas[None], (N, lambdas.shape[0]))
+    L = lambdas.shape[1]
+    V = np.full((N, L, S), np.nan)
+    pol = np.zeros((N, L, S), np.uint8)
+    iters = np.full((N, L), -1, np.int32)
+    mi = np.full((N, L), -1, np.int32)
+    for n in range(N):
+        for l in range(L):
+            P, Rl = probe_mdp(T[n], R[n], C, lambdas[n, l])
+            try:
+                v, p, it, m = value_iteration(P, Rl, gamma, eps, stop)
+            except (ZeroDivisionError, ValueError, OverflowError):
+                continue
+            V[n, l], pol[n, l], iters[n, l], mi[n, l] = v, p, it, m
+    return V, pol, iters, mi
+
+
+def q_values(T, R, C, V, lambdas, gamma):
+    """Q[n,l,s,a] = R[n,s] - lambda*C[a] + gamma * T[n,s,a,:].V[n,l,:]  (simulator.py:518-521)."""
+    T = np.asarray(T, np.float64)
+    lambdas = np.asarray(lambdas, np.float64)
+    if lambdas.ndim == 1:
+        lambdas = np.broadcast_to(lambdas[None], (T.shape[0], lambdas.shape[0]))
+    ev = np.einsum('nsat,nlt->nlsa', T, V)
+    return (np.asarray(R, np.float64)[:, None, :, None]
+            - lambdas[:, :, None, None] * np.asarray(C, np.float64)[None, None, None, :] + gamma * ev)
+
+
+def whittle_bisect(T, R, C, gamma, eps, lam_lo, lam_hi, n_rounds, stop="full"):
+    """Binary search over lambda for the indifference point Q(s,1;l) = Q(s,0;l) per (arm, state).
+
+    PARITY UNPINNED vs lp_methods.py:111-212 (Gurobi).  Deterministic schedule shared with the CUDA
+    path: per (arm, state) interval [lo, hi]; each round probes mid = (lo+hi)/2 with value_iteration,
+    and moves lo = mid where Q(s,1) - Q(s,0) > 0 (acting still preferred), else hi = mid.
+    Returns index `[N,S]` = (lo+hi)/2 after n_rounds.
+    """
+    T = np.asarray(T, np.float64)
+    N, S, A, _ = T.shape
+    lo = np.full((N, S), float(lam_lo))
+    hi = np.full((N, S), float(lam_hi))
+    for _ in range(n_rounds):
+        mid = 0.5 * (lo + hi)
+        V, _, _, _ = batched_vi(T, R, C, mid, gamma, eps, stop)   # probes = one per state
+        Q = q_values(T, R, C, V, mid, gamma)                      # [N,S(probe),S,A]
+        idx = np.arange(S)
+        gap = Q[:, idx, idx, 1] - Q[:, idx, idx, 0]
+        act = gap > 0
+        lo = np.where(act, mid, lo)
+        hi = np.where(act, hi, mid)
+    return 0.5 * (lo + hi)
+
+
+def hawkins_objective(V, start_state, lambdas, B, gamma):
+    """lp_methods.py:63 objective (without the 1e-6 tie term): sum_i V_i(s_i; l) + l*B/(1-gamma); `[L]`."""
+    N = V.shape[0]
+    vs = V[np.arange(N), :, np.asarray(start_state, np.int64)]     # [N,L]
+    return vs.sum(axis=0) + np.asarray(lambdas, np.float64) * B / (1 - gamma)

@@ -1,0 +1,191 @@
+"""Pin the CPU oracle against golden vectors generated from the reference's own classes
+(oracle/gen_golden.py) and against the mdptoolbox docstring known answers.  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import buffer as obuf
+from oracle import envs as oenv
+from oracle import nets as onets
+from oracle import philox
+from oracle import select as osel
+from oracle import vi as ovi
+
+F32 = np.float32
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors for philox4x32-10
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for c, k, want in kat:
+        got = philox.philox4x32_10(*c, *k)
+        assert tuple(int(x) for x in got) == want
+
+
+def test_categorical_rule():
+    p = np.array([[0.2, 0.3, 0.5], [0.0, 1.0, 0.0], [0.5, 0.5, 0.0]], F32)
+    assert philox.categorical(p, np.array([0.1, 0.999, 0.75], F32)).tolist() == [0, 1, 1]
+    assert philox.categorical(p[0], F32(0.2)) == 1          # cdf <= u moves on
+    assert philox.categorical(p[0], F32(0.99999994)) == 2
+
+
+def test_env_ce(golden):
+    g = golden("env")
+    K, N = g["ce_s"].shape
+    for t in range(K):
+        sn, r = oenv.ce_step(g["ce_s"][t][:, None], g["ce_a"][t][:, None], g["ce_nature"][t],
+                             g["ce_ranges"], g["ce_R"], g["ce_u"][t][:, None])
+        assert np.array_equal(sn[:, 0], g["ce_s_next"][t])
+        assert np.array_equal(r[:, 0], g["ce_r"][t].astype(F32))
+    assert np.allclose(oenv.ce_param_ranges(N), g["ce_PARAMETER_RANGES"])
+    s0 = oenv.reset_states(11, 0, 2, 1, N)[:, 0]
+    assert np.array_equal(s0, g["ce_s0"])
+
+
+def test_env_armman(golden):
+    g = golden("env")
+    K, N = g["armman_s"].shape
+    for t in range(K):
+        nat = np.moveaxis(g["armman_nature"][t][None], 0, 2)        # [N,A,E=1]
+        sn, r = oenv.armman_step(g["armman_s"][t][:, None], g["armman_a"][t][:, None], nat,
+                                 g["armman_ranges"], g["armman_R"], g["armman_u"][t][:, None],
+                                 nature_is_table=False)
+        assert np.array_equal(sn[:, 0], g["armman_s_next"][t])
+        assert np.array_equal(r[:, 0], g["armman_r"][t].astype(F32))
+    assert np.allclose(oenv.armman_param_ranges(N), g["armman_PARAMETER_RANGES"])
+    assert np.array_equal(oenv.reset_states(12, 0, 3, 1, N)[:, 0], g["armman_s0"])
+
+
+def test_env_sis(golden):
+    g = golden("env")
+    K, N = g["sis_s"].shape
+    pop = int(g["sis_pop"])
+    for t in range(K):
+        sn, r = oenv.sis_step(pop, g["sis_s"][t][:, None], g["sis_a"][t][:, None], g["sis_nature"][t],
+                              g["sis_R"], g["sis_u"][t][:, None])
+        assert np.array_equal(sn[:, 0], g["sis_s_next"][t])
+        assert np.allclose(r[:, 0], g["sis_r"][t], rtol=1e-7)
+    T = g["sis_T"]
+    for n in range(N):
+        for s in range(pop + 1):
+            for a in range(3):
+                assert np.array_equal(oenv.sis_distro(pop, s, a, g["sis_nature"][-1][n]), T[n, s, a])
+    T50 = g["sis50_T"]
+    for s in (0, 1, 17, 49, 50):
+        for a in range(3):
+            assert np.array_equal(oenv.sis_distro(50, s, a, g["sis50_params"][0]), T50[0, s, a])
+    assert np.array_equal(oenv.reset_states(13, 0, pop + 1, 1, N)[:, 0], g["sis_s0"])
+
+
+def test_bound_nature(golden):
+    g = golden("env")
+    r = g["ce_ranges"]
+    assert np.array_equal(oenv.bound_nature(g["ce_bound_raw"], r[:, 0], r[:, 1]), g["ce_bound_out"])
+    r = g["armman_ranges"]
+    N = r.shape[0]
+    s = g["armman_bound_state"].astype(int)
+    lo, hi = r[np.arange(N), s, :, 0], r[np.arange(N), s, :, 1]
+    got = oenv.bound_nature(g["armman_bound_raw"].reshape(N, 2), lo, hi)
+    assert np.array_equal(got, g["armman_bound_out"])
+    r = g["sis_ranges"]
+    got = oenv.bound_nature(g["sis_bound_raw"].reshape(-1, 4), r[..., 0], r[..., 1])
+    assert np.array_equal(got, g["sis_bound_out"])
+
+
+@pytest.mark.parametrize("name", ["oh3", "oh2", "sis", "oh3h64"])
+def test_ac_step(golden, name):
+    g = golden("ac")
+    N, S, A, h, one_hot, norm = [int(x) for x in g[name + "_meta"]]
+    K = g[name + "_obs"].shape[0]
+    for k in range(K):
+        a, v, logp, p1, probs = onets.ac_step(g[name + "_Wpi"], g[name + "_Wv"], g[name + "_obs"][k][:, None],
+                                             g[name + "_lamb"][k:k + 1], g[name + "_u"][k][:, None],
+                                             S, A, h, bool(one_hot), norm)
+        np.testing.assert_allclose(p1[:, 0], g[name + "_p1"][k], rtol=2e-6, atol=1e-7)
+        np.testing.assert_allclose(v[:, 0], g[name + "_v"][k], rtol=2e-6, atol=1e-6)
+        np.testing.assert_allclose(logp[:, 0], g[name + "_logp"][k], rtol=2e-6, atol=1e-6)
+        assert np.array_equal(a[:, 0], g[name + "_a"][k])
+    lam = [g[f"{name}_lam{i}"] for i in range(6)]
+    obs = g[name + "_obs"].astype(F32) / (1.0 if one_hot else norm)
+    np.testing.assert_allclose(onets.lambda_net_forward(lam, obs), g[name + "_lam_out"], rtol=2e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_buffer(golden, name):
+    g = golden("buffer")
+    gamma, lam = g[name + "_hyper"]
+    tr = lambda z: np.ascontiguousarray(np.asarray(z, F32).T[:, :, None])     # [T,N] -> [N,T,1]
+    adv, ret, q, cdcost = obuf.finish_path(tr(g[name + "_rew"]), tr(g[name + "_cost"]), tr(g[name + "_val"]),
+                                           np.asarray(g[name + "_last"])[:, None],
+                                           np.asarray(g[name + "_lamb"], F32)[:, None], gamma, lam)
+    assert np.array_equal(adv[:, :, 0].T, g[name + "_adv_raw"])
+    assert np.array_equal(ret[:, :, 0].T, g[name + "_get_ret"])
+    assert np.array_equal(q[:, :, 0].T, g[name + "_get_qs"])
+    assert np.array_equal(cdcost[:, 0], g[name + "_get_costs"])
+    np.testing.assert_allclose(obuf.normalize_adv(adv)[:, :, 0].T, g[name + "_get_adv"], rtol=1e-6, atol=1e-7)
+
+
+def test_select(golden):
+    g = golden("select")
+    for ci in range(int(g["n_cases"])):
+        p, C, B = g[f"c{ci}_probs"], g[f"c{ci}_C"], float(g[f"c{ci}_B"])
+        want = g[f"c{ci}_multi"]
+        assert np.array_equal(osel.greedy_multiaction(p, C, B), want), ci
+        assert np.array_equal(osel.greedy_multiaction_stepwise(p, C, B), want), ci
+        assert (C[want].sum() <= B) or not want.any()
+        if p.shape[1] == 2:
+            assert np.array_equal(osel.topk_binary(p[:, 1], C, B), g[f"c{ci}_binary"]), ci
+            assert np.array_equal(want, g[f"c{ci}_binary"]), ci     # binary multi == top-B
+
+
+def test_select_known_answers():
+    p = np.array([[.05, .05, .9], [.2, .7, .1], [.6, .3, .1], [.3, .4, .3]])
+    C = np.array([0, 1, 2])
+    assert osel.greedy_multiaction(p, C, 1).tolist() == [0, 0, 0, 0]
+    assert osel.greedy_multiaction(p, C, 3).tolist() == [2, 1, 0, 0]
+    assert osel.greedy_multiaction(p, C, 4).tolist() == [2, 1, 0, 1]
+
+
+def test_select_stepwise_property():
+    rs = np.random.RandomState(3)
+    for trial in range(150):
+        N = rs.randint(1, 25)
+        A = rs.randint(2, 5)
+        C = np.arange(A)
+        p = rs.dirichlet(np.ones(A) * rs.choice([0.2, 1, 5]), size=N).astype(F32)
+        if trial % 5 == 0:                       # exact ties
+            p = np.round(p * 4) / 4
+        B = rs.randint(0, 2 * N + 2)
+        a1 = osel.greedy_multiaction(p, C, B)
+        a2 = osel.greedy_multiaction_stepwise(p, C, B)
+        assert np.array_equal(a1, a2), (trial, p, B)
+        assert C[a1].sum() <= B or not a1.any()
+
+
+def test_vi_docstring_known_answers(golden):
+    g = golden("vi")
+    P, R = g["forest_P"], g["forest_R"]
+    Rm = np.stack([R[:, a] for a in range(2)])
+    V, pol, it, _ = ovi.value_iteration(P, Rm, 0.96, 0.01, stop="fast")
+    assert np.allclose(V, (5.93215488, 9.38815488, 13.38815488), atol=1e-8) and it == 4 and pol.tolist() == [0, 0, 0]
+    P2 = np.array([[[0.5, 0.5], [0.8, 0.2]], [[0, 1], [0.1, 0.9]]])
+    R2 = np.array([[5, 10], [-1, 2]], float)
+    V, pol, it, _ = ovi.value_iteration(P2, R2.T.copy(), 0.9, 0.01, stop="fast")
+    assert np.allclose(V, (40.048625392716815, 33.65371175967546), atol=1e-12) and it == 26 and pol.tolist() == [1, 0]
+    V, pol, it, _ = ovi.value_iteration(P, Rm, 0.96, 0.01, stop="full")
+    assert np.allclose(V, g["forest_V_full"], atol=1e-10) and it == int(g["forest_iter_full"])
+
+
+@pytest.mark.parametrize("dom,eps", [("ce", 1e-1), ("ce", 1e-8), ("armman", 1e-4), ("armman", 1e-8), ("sis", None)])
+def test_vi_probes(golden, dom, eps):
+    g = golden("vi")
+    lambdas = g["lambdas"] if dom != "sis" else g["lambdas"][:5]
+    sfx = f"_{eps}" if eps is not None else ""
+    V, pol, it, mi = ovi.batched_vi(g[dom + "_T"], g[dom + "_R"], g[dom + "_C"], lambdas, 0.9, eps or 1e-4)
+    assert np.array_equal(it, g[f"{dom}_it{sfx}"])
+    assert np.array_equal(mi, g[f"{dom}_mi{sfx}"])
+    ok = it >= 0
+    np.testing.assert_allclose(V[ok], g[f"{dom}_V{sfx}"][ok], rtol=1e-12, atol=1e-12)
+    assert np.array_equal(pol[ok], g[f"{dom}_pol{sfx}"][ok])
