@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- RMABPPO arm-steps/sec (rollout + update) on B200, with the CPU path timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--hidden 16|64]
+
+A "step" is one RMABPPO epoch (agent_oracle.py:492-593) over one batch of synthetic arms: lambda-net
+forward, T rollout steps (actor sample + env transition), bootstrap, GAE + advantage normalisation,
+train_pi_iters + train_v_iters full-batch Adam steps per arm, lambda SGD step when due, env reset.
+Workload at N=1: BASELINE.json configs[1] -- counterexample domain, N=4098 arms (4096 rounded to a
+multiple of 3, bandit_env_robust.py:755) x 256 envs, T=100, hidden [16,16], 20+20 iterations.
+Under torchrun every rank holds that many arms (weak scaling by arm).
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "RMABPPO arm-steps/sec (rollout+update)"
+UNIT = "arm-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--arms", type=int, default=4098)
+    ap.add_argument("--envs", type=int, default=256)
+    ap.add_argument("--horizon", type=int, default=100)
+    ap.add_argument("--hidden", type=int, default=16)
+    ap.add_argument("--domain", default="counterexample", choices=["counterexample", "armman"])
+    ap.add_argument("--pi-iters", type=int, default=20)
+    ap.add_argument("--v-iters", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-arms", type=int, default=48)
+    ap.add_argument("--cpu-envs", type=int, default=4)
+    return ap.parse_args()
+
+
+def workload_name(a, n_ranks):
+    return (f"RMABPPO {a.domain} domain, N={a.arms} arms/GPU x {a.envs} envs, T={a.horizon}, hidden [{a.hidden},{a.hidden}], "
+            f"{a.pi_iters}+{a.v_iters} iters, binary action" + (f", {n_ranks} ranks sharded by arm" if n_ranks > 1 else ""))
+
+
+# ------------------------------------------------------------------------------------------ CPU legs
+def _cpu_problem(a, n_arms, n_envs, seed=0):
+    """Synthetic problem of the bench's shape at a CPU-sized arm / env count (oracle objects)."""
+    import numpy as np
+    from oracle import envs as oenv, nets as onets
+    rs = np.random.RandomState(seed)
+    dom = oenv.DOMAIN_CE if a.domain == "counterexample" else oenv.DOMAIN_ARMMAN
+    S = 2 if dom == oenv.DOMAIN_CE else 3
+    base = oenv.ce_param_ranges(n_arms) if dom == oenv.DOMAIN_CE else oenv.armman_param_ranges(n_arms)
+    ranges = oenv.sample_sub_ranges(base, rs).astype(np.float32)
+    nature = (ranges[..., 0] + rs.rand(*ranges.shape[:-1]) * (ranges[..., 1] - ranges[..., 0])).astype(np.float32)
+    Wpi = onets.init_linear_default(rs, n_arms, S + 1, a.hidden, 2)
+    Wv = onets.init_linear_default(rs, n_arms, S + 1, a.hidden, 1)
+    b = 1 / np.sqrt(n_arms)
+    lam = [rs.uniform(-b, b, (8, n_arms)), rs.uniform(-b, b, 8), rs.uniform(-.35, .35, (8, 8)), rs.uniform(-.35, .35, 8),
+           rs.uniform(-.35, .35, (1, 8)), rs.uniform(-.35, .35, 1)]
+    return dom, S, Wpi, Wv, lam, nature, ranges, oenv.rewards_table(dom, n_arms, S), np.array([0, 1], np.float32)
+
+
+def _cpu_worker(args):
+    a, n_arms, n_envs, epochs, seed = args
+    import torch
+    torch.set_num_threads(1)
+    from oracle.train import CpuRMABPPO
+    dom, S, Wpi, Wv, lam, nature, ranges, R, C = _cpu_problem(a, n_arms, n_envs, seed)
+    tr = CpuRMABPPO(dom, Wpi, Wv, lam, nature, ranges, R, C, n_envs, a.horizon, a.hidden, n_arms // 3,
+                    train_pi_iters=a.pi_iters, train_v_iters=a.v_iters, seed=seed)
+    tr.epoch()                                            # warm-up (imports, torch autograd setup)
+    t0 = time.perf_counter()
+    for _ in range(epochs):
+        tr.epoch()
+    return time.perf_counter() - t0
+
+
+def cpu_port_rate(a, cores, epochs=1):
+    """arm-steps/s of the oracle port on `cores` host processes (one env shard each, like mpirun -np)."""
+    import multiprocessing as mp
+    jobs = [(a, a.cpu_arms, a.cpu_envs, epochs, 100 + i) for i in range(cores)]
+    t0 = time.perf_counter()
+    if cores == 1:
+        times = [_cpu_worker(jobs[0])]
+    else:
+        with mp.get_context("spawn").Pool(cores) as pool:
+            times = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    per_job = a.cpu_arms * a.cpu_envs * a.horizon * epochs
+    rate = sum(per_job / t for t in times)
+    return rate, max(times), wall
+
+
+def run_reference(a):
+    """--impl reference: the reference algorithm on the host cores.  The reference is pure Python and cannot
+    travel to the GPU box (nor be compiled), so this times its CPU restatement (oracle/, pinned to the
+    reference by tests/golden) with one process per host core, as `--cpu k` / mpirun would."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = max(1, min(os.cpu_count() or 1, 32))
+    rates, t0 = [], time.perf_counter()
+    for _ in range(a.warmup):
+        cpu_port_rate(a, cores, 1)
+        if time.perf_counter() - t0 > 60:
+            break
+    step_times = []
+    for _ in range(a.steps):
+        s0 = time.perf_counter()
+        rate, tmax, wall = cpu_port_rate(a, cores, 1)
+        rates.append(rate)
+        step_times.append(tmax)
+        if time.perf_counter() - t0 > 240:
+            break
+    value = sum(rates) / len(rates)
+    sample = (f"{cores} processes x (N={a.cpu_arms} arms x {a.cpu_envs} envs x T={a.horizon}) per step, oracle port, "
+              f"1 torch thread each")
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": len(rates), "warmup": a.warmup,
+           "ms_per_step": 1e3 * sum(step_times) / len(step_times), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+           "config": {"workload": workload_name(a, 1), "sample": sample},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ ours
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from robustrmab_b200 import _lib
+    from robustrmab_b200.trainer import RMABPPOTrainer
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+
+    tr = RMABPPOTrainer(a.domain, a.arms * world, a.envs, a.horizon, hidden=a.hidden, train_pi_iters=a.pi_iters,
+                        train_v_iters=a.v_iters, epochs=max(20, a.warmup + a.steps), seed=0, device=dev, rank=rank,
+                        world_size=world)
+    N, E, T = tr.N, tr.E, tr.T
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        tr.epoch()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    tr.timers = {}
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(a.steps):
+        tr.epoch()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count() - launches0
+    stage_ms = tr.stage_times()
+    tr.timers = None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clk = clocks.stop() if rank == 0 else None
+    total_arm_steps = float(a.arms * world) * E * T * a.steps
+    value = total_arm_steps / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer API: H2D of the step's inputs, D2H of its results ----
+    s0_host = torch.empty((N, E), dtype=torch.uint8).pin_memory()
+    s0_host.copy_(tr.s_traj[:, 0])
+    nat_host = tr.nature.cpu().pin_memory()
+    for _ in range(2):
+        tr.epoch_host(s0_host, nat_host)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        res = tr.epoch_host(s0_host, nat_host)
+    e1.record()
+    barrier()
+    ems = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    e2e_value = total_arm_steps / (float(ems.item()) * 1e-3)
+    h2d = s0_host.numel() + nat_host.numel() * 4
+    d2h = sum(v.numel() * v.element_size() for v in res.values())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    dom_name, dom_ms, dom_bytes = tr.dominant_kernel(stage_ms)
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms else 0.0
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+           "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": workload_name(a, world), "l2": "per-step working set (trajectory + advantage "
+                      f"buffers, {tr.buffer_bytes() / 2**20:.0f} MiB/GPU) exceeds the 126 MB L2; no explicit flush",
+                      "parallelism": f"arm-sharded x{world}"},
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+           "gpu_launches": int(launches),
+           "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms},
+           "stage_ms_per_step": stage_ms, "clocks": clk}
+    if not a.no_cpu_baseline:
+        t0 = time.perf_counter()
+        rate, tmax, _ = cpu_port_rate(a, 1, 1)
+        out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": f"1 epoch of N={a.cpu_arms} arms x {a.cpu_envs} envs x T={a.horizon} "
+                                         f"(oracle port, 1 thread, {tmax:.1f} s)"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

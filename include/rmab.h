@@ -1,0 +1,222 @@
+/*
+ * rmab.h -- C ABI of librmab_b200.so: the B200 (sm_100a) kernels behind the RobustRMAB hot path.
+ *
+ * The reference (killian-34/RobustRMAB) is pure Python and has no FFI layer; each entry point
+ * below replaces the BODY of one reference function and is what a ctypes binding inside that
+ * function would call (see INTEGRATION.md for the stubs).  Reference file:line per entry point.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer owned by the caller (torch tensors); nothing is allocated
+ *     or freed inside.  Workspaces are caller-provided and sized by the *_ws_bytes helpers.
+ *   - Every call only enqueues work on `stream` (a cudaStream_t passed as void*) and returns.
+ *   - Return 0 on success, <0 on error (RMAB_E_*); never throws.  rmab_last_error() gives the
+ *     thread-local message of the last failing call.
+ *   - Layout is arm-major, env fastest: states [N,E], trajectories [N,T,E], packed per-arm weights
+ *     [N,P] with P = (in+1)h + (h+1)h + (h+1)out in torch.nn.Linear order W1 b1 W2 b2 W3 b3.
+ *   - N is the number of arms held by THIS rank; `arm0` is the global index of its first arm so the
+ *     Philox counters (stream, t, env, global_arm) give the same draws under any arm sharding.
+ *   - RNG: Philox4x32-10, key = seed, u = (x0 >> 8) * 2^-24; categorical draw k = #{j: cdf_j <= u}
+ *     with the cdf accumulated left to right in fp32, clamped to the last category with p > 0.
+ *     If `u_inject` is non-NULL it supplies the uniforms ([N,E]) instead (parity tests).
+ */
+#ifndef RMAB_H_
+#define RMAB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RMAB_ABI_VERSION 1
+
+typedef void* rmab_stream_t; /* cudaStream_t */
+
+enum { RMAB_OK = 0, RMAB_E_BADARG = -1, RMAB_E_SHAPE = -2, RMAB_E_ARCH = -3, RMAB_E_LAUNCH = -4 };
+enum { RMAB_DOMAIN_CE = 0, RMAB_DOMAIN_ARMMAN = 1, RMAB_DOMAIN_SIS = 2 };
+enum { RMAB_STREAM_ENV = 0, RMAB_STREAM_ACT = 1, RMAB_STREAM_NATURE = 2, RMAB_STREAM_RESET = 3,
+       RMAB_STREAM_CF = 4, RMAB_STREAM_INIT = 7 };
+enum { RMAB_STOP_FULL = 0, RMAB_STOP_FAST = 1 }; /* mdptoolbox stop_criterion 'full' / 'fast' */
+
+/* Philox counter block shared by the sampling kernels. */
+typedef struct RmabRng {
+  uint64_t seed;   /* Philox key */
+  uint32_t stream; /* RMAB_STREAM_* */
+  uint32_t t;      /* time counter */
+  uint32_t env0;   /* global index of the first env in the call */
+  uint32_t arm0;   /* global index of the first arm in the call */
+} RmabRng;
+
+/* Shape of the N per-arm actor / critic nets (rmabppo_core.py:131-174). Two hidden layers of equal
+ * width `hidden` (8, 16, 32 or 64), tanh.  in_dim = (one_hot ? n_states : 1) + 1 (+ n_extra). */
+typedef struct RmabNetDesc {
+  int32_t n_arms;    /* N on this rank */
+  int32_t n_envs;    /* E */
+  int32_t n_states;  /* S */
+  int32_t n_actions; /* A (actor outputs) */
+  int32_t hidden;    /* h */
+  int32_t one_hot;   /* 1: x = onehot(s) ++ [lambda]; 0: x = [s/state_norm, lambda] */
+  float state_norm;  /* used when one_hot == 0 */
+  int32_t n_extra;   /* extra critic inputs (MA-RMABPPO bounded nature vector); 0 for RMABPPO */
+} RmabNetDesc;
+
+/* PPO / Adam hyper-parameters of one update() call (agent_oracle.py:233-242, :383-388). */
+typedef struct RmabHyper {
+  double clip_ratio;
+  double entropy_coeff;
+  double pi_lr, vf_lr;
+  double beta1, beta2, adam_eps; /* torch.optim.Adam defaults: 0.9, 0.999, 1e-8 */
+  int32_t pi_iters, v_iters;
+  int32_t adam_step0_pi, adam_step0_v; /* Adam steps already taken (optimisers persist across epochs) */
+} RmabHyper;
+
+int rmab_abi_version(void);
+const char* rmab_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t rmab_launch_count(void);
+
+/* ---- environment ------------------------------------------------------------------------- */
+
+/* env.reset(): uniform random start states (bandit_env_robust.py:941-944, :715-718, :1285-1290).
+ * s[N,E] = min(floor(u*S), S-1). */
+int rmab_reset_states(int E, int N, int S, const RmabRng* rng, const float* u_inject, uint8_t* s,
+                      rmab_stream_t stream);
+
+/* CounterExampleRobustEnv.step (bandit_env_robust.py:860-893) / ARMMANRobustEnv.step (:575-634).
+ *   nature_per_env == 0: per-arm table  CE [N]      ARMMAN [N,S,A] (looked up at the current state,
+ *                        nature_baselines_armman.py:224-232)
+ *   nature_per_env == 1: per-env action CE [N,E]    ARMMAN [N,A,E]
+ *   ranges: CE [N,2], ARMMAN [N,S,A,2] (sampled_parameter_ranges; the clamp of :867-874 / :583-592)
+ *   R [N,S]; r may be NULL.  Reward is R[arm, s_next]. */
+int rmab_env_step_table(int domain, int E, int N, const uint8_t* s, const uint8_t* a,
+                        const float* nature, int nature_per_env, const float* ranges, const float* R,
+                        const RmabRng* rng, const float* u_inject, uint8_t* s_next, float* r,
+                        rmab_stream_t stream);
+
+/* SISRobustEnv.step (bandit_env_robust.py:1224-1243) with compute_distro (:1025-1084) evaluated on
+ * the fly in fp64.  params [N,4] (nature_per_env == 0) or [N,4,E]; pop <= 255. */
+int rmab_env_step_sis(int E, int N, int pop, const uint8_t* s, const uint8_t* a, const float* params,
+                      int nature_per_env, const float* R, const RmabRng* rng, const float* u_inject,
+                      uint8_t* s_next, float* r, rmab_stream_t stream);
+
+/* SISRobustEnv.get_T_for_a_nature (:1247-1256): full table T[N,S,A,S] (fp32) for params [N,4]. */
+int rmab_sis_table(int N, int pop, const float* params, float* T, rmab_stream_t stream);
+
+/* env.bound_nature_actions (:703, :930, :1274): out = ((tanh(x)+1)/2)*(hi-lo)+lo, elementwise fp32.
+ * lo/hi already gathered to the shape of x (n elements). */
+int rmab_bound_nature(int64_t n, const float* x, const float* lo, const float* hi, float* out,
+                      rmab_stream_t stream);
+
+/* ---- actor-critic ------------------------------------------------------------------------ */
+
+/* MLPActorCriticRMAB.step (rmabppo_core.py:198-244) for all arms x envs.
+ * Wpi [N,Ppi], Wv [N,Pv]; s [N,E]; lamb [E]; extra [E,n_extra] or NULL (critic only).
+ * Outputs a [N,E] u8, v/logp/p1 [N,E] fp32, probs [N,A,E] fp32 (may be NULL). */
+int rmab_ac_step(const RmabNetDesc* net, const float* Wpi, const float* Wv, const uint8_t* s,
+                 const float* lamb, const float* extra, const RmabRng* rng, const float* u_inject,
+                 uint8_t* a, float* v, float* logp, float* p1, float* probs, rmab_stream_t stream);
+
+/* MLPLambdaNet forward (rmabppo_core.py:108-115; N -> 8 -> 8 -> 1): lamb[E] from states s[N,E]
+ * (obs = s * obs_scale).  params packed W1[8,N] b1[8] W2[8,8] b2[8] W3[1,8] b3[1].
+ * h1_partial (may be NULL) receives the first-layer pre-activation partial sums [E,8] WITHOUT bias so
+ * that arm-sharded ranks can all-reduce them; when sharded, pass h1_in = the reduced sums instead of s. */
+int rmab_lambda_forward(int E, int N, const float* params, int n_total, int arm0, const uint8_t* s,
+                        float obs_scale, const float* h1_in, float* h1_partial, float* lamb,
+                        rmab_stream_t stream);
+
+/* SGD step on the lambda net for loss = mean_e lamb_e * coef_e  (compute_loss_lambda,
+ * agent_oracle.py:360-376, :440-454; coef_e = B/(1-gamma) - cdcost_e[0]; the mean over envs is what
+ * mpi_avg_grads does over ranks).  In place on params.  h1 [E,8] = the (all-reduced) first-layer sums
+ * that rmab_lambda_forward wrote to h1_partial for the same states s; delta1_ws [E,8] scratch;
+ * grad_out [P] (may be NULL) receives the gradient (W1 columns of this rank's arms only). */
+int rmab_lambda_sgd(int E, int N, float* params, int n_total, int arm0, const uint8_t* s, float obs_scale,
+                    const float* h1, const float* coef, float lr, float* delta1_ws, float* grad_out,
+                    rmab_stream_t stream);
+
+/* Fused rollout of T steps for the table domains with a per-arm nature table (the baseline nature
+ * policies): actor tables are evaluated once per (arm, env, state), then each (arm, env) chain runs
+ * T steps of  a ~ pi(.|s, lamb_e) ; s' ~ T(s, a, nature)  from Philox streams ACT / ENV with time
+ * counters t_act0 + t and t_env0 + t.  s_traj [N,T+1,E] (row 0 = start state on input), a/logp/val
+ * [N,T,E], last_val [N,E] = V(s_T). */
+int rmab_rollout_table(int domain, const RmabNetDesc* net, int T, const float* Wpi, const float* Wv,
+                       const float* lamb, const float* nature, const float* ranges, uint64_t seed,
+                       uint32_t t_act0, uint32_t t_env0, uint32_t env0, uint32_t arm0, uint8_t* s_traj,
+                       uint8_t* a, float* logp, float* val, float* last_val, rmab_stream_t stream);
+
+/* ---- buffer ------------------------------------------------------------------------------ */
+
+/* RMABPPO_Buffer.finish_path + get (agent_oracle.py:90-161): GAE-lambda advantages, rewards-to-go
+ * and per-arm advantage normalisation, one CTA per arm, reverse scan over T per env.
+ *   s_traj [N,T+1,E] (reward r_t = R[arm, s_{t+1}]), a [N,T,E], val [N,T,E], last_val [N,E], lamb [E],
+ *   C [A], R [N,S].  Outputs adv (normalised when normalize != 0), ret, q (may be NULL) [N,T,E];
+ *   adv_stats [N,2] = (mean, std) (may be NULL).  Recurrences run in fp64 like scipy's lfilter. */
+int rmab_gae(int T, int E, int N, int S, int A, const uint8_t* s_traj, const uint8_t* a, const float* val,
+             const float* last_val, const float* lamb, const float* C, const float* R, double gamma,
+             double lam, int normalize, float* adv, float* ret, float* q, float* adv_stats,
+             rmab_stream_t stream);
+
+/* Same with explicit reward / cost arrays (the drop-in RMABPPO_Buffer.store path): rew, cost [N,T,E]. */
+int rmab_gae_explicit(int T, int E, int N, const float* rew, const float* cost, const float* val,
+                      const float* last_val, const float* lamb, double gamma, double lam, int normalize,
+                      float* adv, float* ret, float* q, float* adv_stats, rmab_stream_t stream);
+
+/* cdcost_buf (agent_oracle.py:117,:139): arm-summed, discounted cost-to-go [T,E] of this rank's arms.
+ * ws: T*E doubles of scratch. */
+int rmab_cost_togo(int T, int E, int N, int A, const uint8_t* a, const float* C, double gamma, double* ws,
+                   float* cdcost, rmab_stream_t stream);
+
+/* ---- PPO update -------------------------------------------------------------------------- */
+
+/* update() (agent_oracle.py:399-436) for all arms: pi_iters full-batch Adam steps on the clipped
+ * policy loss (compute_loss_pi :285-322) then v_iters on the value loss (compute_loss_v :325-339).
+ * One CTA per arm; weights, gradients and Adam moments stay in shared memory across iterations.
+ *   s, a [N,T,E] u8 (s = first T rows of s_traj); adv, logp_old, ret [N,T,E]; lamb [E];
+ *   adam_pi [N,2,Ppi], adam_v [N,2,Pv] (m then v); loss_pi [N,pi_iters], loss_v [N,v_iters] (may be NULL)
+ *   hold the loss evaluated before each step.  s_stride = row stride of s in elements of E per arm
+ *   (T+1 when s aliases s_traj, T otherwise). */
+int rmab_ppo_update(const RmabNetDesc* net, const RmabHyper* hp, int T, int s_rows, float* Wpi, float* Wv,
+                    float* adam_pi, float* adam_v, const uint8_t* s, const uint8_t* a, const float* adv,
+                    const float* logp_old, const float* ret, const float* lamb, float* loss_pi,
+                    float* loss_v, rmab_stream_t stream);
+
+/* ---- budget-constrained selection -------------------------------------------------------- */
+
+size_t rmab_select_ws_bytes(int E, int N, int A);
+
+/* act_test for binary actions (rmabppo_core.py:289-334 == :338-445 when C=[0,1]): action 1 for the
+ * top-k arms by p1 per env, k = number of C[1]-cost actions that fit in B; ties -> higher arm index.
+ * p1 [N,E] -> actions [N,E]. */
+int rmab_budget_select_binary(int E, int N, const float* p1, float cost1, float B, uint8_t* actions,
+                              void* ws, size_t ws_bytes, rmab_stream_t stream);
+
+/* act_test_deterministic_multiaction (rmabppo_core.py:338-445), one CTA per env, stepwise argmax
+ * formulation (oracle/select.py::greedy_multiaction_stepwise).  probs [N,A,E], C [A] strictly
+ * increasing. */
+int rmab_budget_select_multi(int E, int N, int A, const float* probs, const float* C, float B,
+                             uint8_t* actions, void* ws, size_t ws_bytes, rmab_stream_t stream);
+
+/* ---- value iteration / Whittle index ----------------------------------------------------- */
+
+/* mdptoolbox.mdp.ValueIteration (mdp.py:1293-1410 incl. _boundIter) for all arms x lambda-probes, on the
+ * per-probe MDP of simulator.py:504-510 with reward R[n,s] - lambda*C[a].  All fp64 like the reference.
+ *   T [N,S,A,S], R [N,S], C [A], lambdas [L] (lambdas_per_arm == 0) or [N,L].
+ *   V [N,L,S], policy [N,L,S] u8 (may be NULL), iters [N,L] i32 (-1 and V = NaN where the reference raises;
+ *   may be NULL), max_iter [N,L] i32 (may be NULL), Q [N,L,S,A] (may be NULL; Q from the final V as
+ *   simulator.py:518-521). */
+int rmab_vi_batched(int N, int S, int A, int L, const double* T, const double* R, const double* C,
+                    const double* lambdas, int lambdas_per_arm, double gamma, double eps, int stop_mode,
+                    double* V, uint8_t* policy, int32_t* iters, int32_t* max_iter, double* Q,
+                    rmab_stream_t stream);
+
+/* Whittle index by bisection on the indifference condition Q(s,1;l) = Q(s,0;l) (lp_methods.py:181),
+ * n_rounds halvings of [lam_lo, lam_hi] per (arm, state), each probe one ValueIteration as above.
+ * index [N,S] fp64. */
+int rmab_whittle_bisect(int N, int S, int A, const double* T, const double* R, const double* C, double gamma,
+                        double eps, int stop_mode, double lam_lo, double lam_hi, int n_rounds, double* index,
+                        rmab_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RMAB_H_ */

@@ -1,0 +1,99 @@
+// Shared device/host helpers for librmab_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include "../../include/rmab.h"
+
+namespace rmab {
+
+extern thread_local char g_err[256];
+extern std::atomic<uint64_t> g_launches;
+
+int fail(int code, const char* fmt, ...);
+int check_launch(const char* what);
+
+#define RMAB_REQUIRE(cond, code, ...) \
+  do {                                \
+    if (!(cond)) return ::rmab::fail(code, __VA_ARGS__); \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+// ---- Philox4x32-10 (Salmon et al. SC'11; same constants as cuRAND / Random123) -----------------
+struct Rng {
+  uint32_t k0, k1, stream, t, env0, arm0;
+};
+
+__host__ inline Rng make_rng(const RmabRng* r) {
+  Rng g;
+  g.k0 = (uint32_t)(r->seed & 0xFFFFFFFFull);
+  g.k1 = (uint32_t)(r->seed >> 32);
+  g.stream = r->stream;
+  g.t = r->t;
+  g.env0 = r->env0;
+  g.arm0 = r->arm0;
+  return g;
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                               uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// u = (x0 >> 8) * 2^-24 for counter (stream, t, env, arm)
+__device__ __forceinline__ float philox_uniform(uint32_t k0, uint32_t k1, uint32_t stream, uint32_t t, uint32_t env,
+                                                uint32_t arm) {
+  const uint4 x = philox4x32_10(stream, t, env, arm, k0, k1);
+  return (float)(x.x >> 8) * 5.9604644775390625e-08f;
+}
+
+__device__ __forceinline__ float draw_uniform(const Rng& g, const float* __restrict__ u_inject, int64_t idx, int e,
+                                              int n) {
+  if (u_inject) return u_inject[idx];
+  return philox_uniform(g.k0, g.k1, g.stream, g.t, g.env0 + (uint32_t)e, g.arm0 + (uint32_t)n);
+}
+
+// Inverse-CDF categorical draw: k = #{j : cdf_j <= u}, cdf accumulated left to right in fp32 with
+// round-to-nearest adds (no fma contraction), clamped to the last category with p > 0.
+template <int K>
+__device__ __forceinline__ int categorical(const float (&p)[K], float u) {
+  float cdf = 0.f;
+  int k = 0, last = 0;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    cdf = __fadd_rn(cdf, p[j]);
+    k += (cdf <= u) ? 1 : 0;
+    if (p[j] > 0.f) last = j;
+  }
+  return k < last ? k : last;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Deterministic block-wide sum (all threads get the result); `red` holds >= 32 floats of smem.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+
+}  // namespace rmab

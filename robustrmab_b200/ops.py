@@ -1,0 +1,245 @@
+"""Torch-tensor front end of the C ABI: validates dtype / device / contiguity, passes data_ptr() and the
+current CUDA stream.  PyTorch is only the memory and stream plumbing here; all compute is in
+librmab_b200.so.  Every function fails loudly on CPU tensors (there is no fallback path).
+
+Layouts (arm-major, env fastest): states `[N,E]` uint8, trajectories `[N,T,E]`, packed weights `[N,P]`.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import RmabHyper, RmabNetDesc, RmabRng, check, lib
+
+u8, f32, f64, i32 = torch.uint8, torch.float32, torch.float64, torch.int32
+
+
+def _p(t, dtype=None, name="tensor"):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name}: robustrmab_b200 runs on CUDA tensors only (no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def rng(seed, stream, t, env0=0, arm0=0):
+    return RmabRng(int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream), int(t) & 0xFFFFFFFF, int(env0), int(arm0))
+
+
+def net_desc(N, E, S, A, hidden, one_hot=True, state_norm=1.0, n_extra=0):
+    return RmabNetDesc(int(N), int(E), int(S), int(A), int(hidden), int(bool(one_hot)),
+                       float(state_norm if state_norm else 1.0), int(n_extra))
+
+
+def n_params(in_dim, h, out):
+    return (in_dim + 1) * h + (h + 1) * h + (h + 1) * out
+
+
+def in_dim(net):
+    return (net.n_states if net.one_hot else 1) + 1
+
+
+def _rng_ptr(r):
+    return C.byref(r) if r is not None else None
+
+
+# ---------------------------------------------------------------------------------------------- env
+def reset_states(N, E, S, r=None, u=None, out=None, device="cuda"):
+    out = torch.empty((N, E), dtype=u8, device=device) if out is None else out
+    check(lib().rmab_reset_states(E, N, S, _rng_ptr(r), _p(u, f32, "u"), _p(out, u8, "s"), _stream()))
+    return out
+
+
+def env_step_table(domain, s, a, nature, ranges, R, r=None, u=None, nature_per_env=False, s_next=None,
+                   rew=None, want_reward=True):
+    N, E = s.shape
+    s_next = torch.empty_like(s) if s_next is None else s_next
+    if rew is None and want_reward:
+        rew = torch.empty((N, E), dtype=f32, device=s.device)
+    check(lib().rmab_env_step_table(int(domain), E, N, _p(s, u8, "s"), _p(a, u8, "a"), _p(nature, f32, "nature"),
+                                    int(bool(nature_per_env)), _p(ranges, f32, "ranges"), _p(R, f32, "R"),
+                                    _rng_ptr(r), _p(u, f32, "u"), _p(s_next, u8, "s_next"), _p(rew, f32, "r"),
+                                    _stream()))
+    return s_next, rew
+
+
+def env_step_sis(pop, s, a, params, R, r=None, u=None, nature_per_env=False, s_next=None, rew=None,
+                 want_reward=True):
+    N, E = s.shape
+    s_next = torch.empty_like(s) if s_next is None else s_next
+    if rew is None and want_reward:
+        rew = torch.empty((N, E), dtype=f32, device=s.device)
+    check(lib().rmab_env_step_sis(E, N, int(pop), _p(s, u8, "s"), _p(a, u8, "a"), _p(params, f32, "params"),
+                                  int(bool(nature_per_env)), _p(R, f32, "R"), _rng_ptr(r), _p(u, f32, "u"),
+                                  _p(s_next, u8, "s_next"), _p(rew, f32, "r"), _stream()))
+    return s_next, rew
+
+
+def sis_table(pop, params):
+    N = params.shape[0]
+    T = torch.empty((N, pop + 1, 3, pop + 1), dtype=f32, device=params.device)
+    check(lib().rmab_sis_table(N, int(pop), _p(params, f32, "params"), _p(T, f32, "T"), _stream()))
+    return T
+
+
+def bound_nature(x, lo, hi):
+    out = torch.empty_like(x)
+    check(lib().rmab_bound_nature(x.numel(), _p(x, f32, "x"), _p(lo, f32, "lo"), _p(hi, f32, "hi"), _p(out, f32, "out"),
+                                  _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------- actor-critic
+def ac_step(net, Wpi, Wv, s, lamb, r=None, u=None, want_probs=False):
+    N, E = s.shape
+    dev = s.device
+    a = torch.empty((N, E), dtype=u8, device=dev)
+    v = torch.empty((N, E), dtype=f32, device=dev)
+    logp = torch.empty((N, E), dtype=f32, device=dev)
+    p1 = torch.empty((N, E), dtype=f32, device=dev)
+    probs = torch.empty((N, net.n_actions, E), dtype=f32, device=dev) if want_probs else None
+    check(lib().rmab_ac_step(C.byref(net), _p(Wpi, f32, "Wpi"), _p(Wv, f32, "Wv"), _p(s, u8, "s"),
+                             _p(lamb, f32, "lamb"), None, _rng_ptr(r), _p(u, f32, "u"), _p(a, u8), _p(v, f32),
+                             _p(logp, f32), _p(p1, f32), _p(probs, f32), _stream()))
+    return a, v, logp, p1, probs
+
+
+def lambda_forward(params, s, n_total, arm0=0, obs_scale=1.0, h1_in=None, want_h1=False, want_lamb=True):
+    N, E = s.shape
+    dev = s.device
+    h1 = torch.empty((E, 8), dtype=f32, device=dev) if want_h1 else None
+    lamb = torch.empty((E,), dtype=f32, device=dev) if want_lamb else None
+    check(lib().rmab_lambda_forward(E, N, _p(params, f32, "params"), int(n_total), int(arm0), _p(s, u8, "s"),
+                                    float(obs_scale), _p(h1_in, f32, "h1_in"), _p(h1, f32), _p(lamb, f32), _stream()))
+    return lamb, h1
+
+
+def lambda_sgd(params, s, n_total, arm0, obs_scale, h1, coef, lr, want_grad=False):
+    N, E = s.shape
+    ws = torch.empty((E, 8), dtype=f32, device=s.device)
+    grad = torch.zeros_like(params) if want_grad else None
+    check(lib().rmab_lambda_sgd(E, N, _p(params, f32, "params"), int(n_total), int(arm0), _p(s, u8, "s"),
+                                float(obs_scale), _p(h1, f32, "h1"), _p(coef, f32, "coef"), float(lr), _p(ws, f32),
+                                _p(grad, f32), _stream()))
+    return grad
+
+
+def rollout_table(domain, net, T, Wpi, Wv, lamb, nature, ranges, seed, t_act0, t_env0, s_traj, a, logp, val,
+                  last_val, env0=0, arm0=0):
+    check(lib().rmab_rollout_table(int(domain), C.byref(net), int(T), _p(Wpi, f32, "Wpi"), _p(Wv, f32, "Wv"),
+                                   _p(lamb, f32, "lamb"), _p(nature, f32, "nature"), _p(ranges, f32, "ranges"),
+                                   int(seed) & 0xFFFFFFFFFFFFFFFF, int(t_act0), int(t_env0), int(env0), int(arm0),
+                                   _p(s_traj, u8, "s_traj"), _p(a, u8, "a"), _p(logp, f32, "logp"), _p(val, f32, "val"),
+                                   _p(last_val, f32, "last_val"), _stream()))
+
+
+# -------------------------------------------------------------------------------------------- buffer
+def gae(s_traj, a, val, last_val, lamb, Cc, R, gamma, lam, normalize=True, want_q=False, want_stats=False):
+    N, T, E = a.shape
+    S, A = R.shape[1], Cc.shape[0]
+    dev = a.device
+    adv = torch.empty((N, T, E), dtype=f32, device=dev)
+    ret = torch.empty((N, T, E), dtype=f32, device=dev)
+    q = torch.empty((N, T, E), dtype=f32, device=dev) if want_q else None
+    stats = torch.empty((N, 2), dtype=f32, device=dev) if want_stats else None
+    check(lib().rmab_gae(T, E, N, S, A, _p(s_traj, u8, "s_traj"), _p(a, u8, "a"), _p(val, f32, "val"),
+                         _p(last_val, f32, "last_val"), _p(lamb, f32, "lamb"), _p(Cc, f32, "C"), _p(R, f32, "R"),
+                         float(gamma), float(lam), int(bool(normalize)), _p(adv, f32), _p(ret, f32), _p(q, f32),
+                         _p(stats, f32), _stream()))
+    return adv, ret, q, stats
+
+
+def gae_explicit(rew, cost, val, last_val, lamb, gamma, lam, normalize=True, want_q=False, want_stats=False):
+    N, T, E = rew.shape
+    dev = rew.device
+    adv = torch.empty((N, T, E), dtype=f32, device=dev)
+    ret = torch.empty((N, T, E), dtype=f32, device=dev)
+    q = torch.empty((N, T, E), dtype=f32, device=dev) if want_q else None
+    stats = torch.empty((N, 2), dtype=f32, device=dev) if want_stats else None
+    check(lib().rmab_gae_explicit(T, E, N, _p(rew, f32, "rew"), _p(cost, f32, "cost"), _p(val, f32, "val"),
+                                  _p(last_val, f32, "last_val"), _p(lamb, f32, "lamb"), float(gamma), float(lam),
+                                  int(bool(normalize)), _p(adv, f32), _p(ret, f32), _p(q, f32), _p(stats, f32),
+                                  _stream()))
+    return adv, ret, q, stats
+
+
+def cost_togo(a, Cc, gamma):
+    N, T, E = a.shape
+    ws = torch.empty((T, E), dtype=f64, device=a.device)
+    out = torch.empty((T, E), dtype=f32, device=a.device)
+    check(lib().rmab_cost_togo(T, E, N, Cc.shape[0], _p(a, u8, "a"), _p(Cc, f32, "C"), float(gamma), _p(ws, f64),
+                               _p(out, f32), _stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------- PPO update
+def hyper(clip_ratio, entropy_coeff, pi_lr, vf_lr, pi_iters, v_iters, step0_pi=0, step0_v=0, beta1=0.9,
+          beta2=0.999, eps=1e-8):
+    return RmabHyper(float(clip_ratio), float(entropy_coeff), float(pi_lr), float(vf_lr), beta1, beta2, eps,
+                     int(pi_iters), int(v_iters), int(step0_pi), int(step0_v))
+
+
+def ppo_update(net, hp, Wpi, Wv, adam_pi, adam_v, s, a, adv, logp_old, ret, lamb, want_loss=False):
+    """s may be the `[N,T+1,E]` trajectory (its first T rows are used) or `[N,T,E]`."""
+    N, T, E = a.shape
+    s_rows = s.shape[1]
+    dev = a.device
+    lp = torch.zeros((N, max(hp.pi_iters, 1)), dtype=f32, device=dev) if want_loss else None
+    lv = torch.zeros((N, max(hp.v_iters, 1)), dtype=f32, device=dev) if want_loss else None
+    check(lib().rmab_ppo_update(C.byref(net), C.byref(hp), T, s_rows, _p(Wpi, f32, "Wpi"), _p(Wv, f32, "Wv"),
+                                _p(adam_pi, f32, "adam_pi"), _p(adam_v, f32, "adam_v"), _p(s, u8, "s"), _p(a, u8, "a"),
+                                _p(adv, f32, "adv"), _p(logp_old, f32, "logp_old"), _p(ret, f32, "ret"),
+                                _p(lamb, f32, "lamb"), _p(lp, f32), _p(lv, f32), _stream()))
+    return lp, lv
+
+
+# ------------------------------------------------------------------------------------------ selection
+def budget_select_binary(p1, cost1, B):
+    N, E = p1.shape
+    out = torch.empty((N, E), dtype=u8, device=p1.device)
+    check(lib().rmab_budget_select_binary(E, N, _p(p1, f32, "p1"), float(cost1), float(B), _p(out, u8), None, 0,
+                                          _stream()))
+    return out
+
+
+def budget_select_multi(probs, Cc, B):
+    N, A, E = probs.shape
+    out = torch.empty((N, E), dtype=u8, device=probs.device)
+    check(lib().rmab_budget_select_multi(E, N, A, _p(probs, f32, "probs"), _p(Cc, f32, "C"), float(B), _p(out, u8),
+                                         None, 0, _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------ value iteration
+def vi_batched(T, R, Cc, lambdas, gamma, eps, stop="full", want_q=False):
+    N, S, A, _ = T.shape
+    per_arm = lambdas.dim() == 2
+    L = lambdas.shape[-1]
+    dev = T.device
+    V = torch.empty((N, L, S), dtype=f64, device=dev)
+    pol = torch.empty((N, L, S), dtype=u8, device=dev)
+    iters = torch.empty((N, L), dtype=i32, device=dev)
+    mi = torch.empty((N, L), dtype=i32, device=dev)
+    Q = torch.empty((N, L, S, A), dtype=f64, device=dev) if want_q else None
+    check(lib().rmab_vi_batched(N, S, A, L, _p(T, f64, "T"), _p(R, f64, "R"), _p(Cc, f64, "C"),
+                                _p(lambdas, f64, "lambdas"), int(per_arm), float(gamma), float(eps),
+                                _lib.STOP_FAST if stop == "fast" else _lib.STOP_FULL, _p(V, f64), _p(pol, u8),
+                                _p(iters, i32), _p(mi, i32), _p(Q, f64), _stream()))
+    return V, pol, iters, mi, Q
+
+
+def whittle_bisect(T, R, Cc, gamma, eps, lam_lo, lam_hi, n_rounds, stop="full"):
+    N, S, A, _ = T.shape
+    idx = torch.empty((N, S), dtype=f64, device=T.device)
+    check(lib().rmab_whittle_bisect(N, S, A, _p(T, f64, "T"), _p(R, f64, "R"), _p(Cc, f64, "C"), float(gamma),
+                                    float(eps), _lib.STOP_FAST if stop == "fast" else _lib.STOP_FULL, float(lam_lo),
+                                    float(lam_hi), int(n_rounds), _p(idx, f64), _stream()))
+    return idx

@@ -1,0 +1,278 @@
+"""Batched RMABPPO epoch on device: the rollout-and-update loop of AgentOracle.best_response_per_cpu
+(robust_rmab/algos/rmabppo/agent_oracle.py:456-593) for N arms x E env replicas, all state resident in HBM.
+
+One `epoch()` =  lambda-net forward (:497)  ->  T steps of ac.step / nature / env.step / buf.store (:506-537)
+              ->  bootstrap value + finish_path (:553-563)  ->  env.reset (:568)  ->  update() (:399-454).
+Arms shard across ranks: every rank holds all E envs of its contiguous arm range;
+the only exchanges are the lambda-net first-layer partial sums [E,8], the arm-summed discounted cost
+[T,E] and the logging scalars, each one NCCL all-reduce on the compute stream.
+
+Layout: states [N,E] u8, trajectories [N,T,E], packed per-arm weights [N,P] (see include/rmab.h).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+
+DOMAINS = {"counterexample": _lib.DOMAIN_CE, "armman": _lib.DOMAIN_ARMMAN, "sis": _lib.DOMAIN_SIS}
+_DOMAIN_S = {_lib.DOMAIN_CE: 2, _lib.DOMAIN_ARMMAN: 3}
+
+
+def linear_default_init_(W, in_dim, h, out, generator):
+    """torch.nn.Linear default init (uniform(+-1/sqrt(fan_in)) for weight and bias, rmabppo_core.py:24-29)
+    written straight into a packed [N,P] tensor."""
+    o = 0
+    for fan_out, fan_in in ((h, in_dim), (h, h), (out, h)):
+        b = 1.0 / math.sqrt(fan_in)
+        n = fan_out * fan_in + fan_out
+        W[:, o:o + n].uniform_(-b, b, generator=generator)
+        o += n
+    assert o == W.shape[1]
+    return W
+
+
+class _Stage:
+    def __init__(self, timers, name):
+        self.t, self.name = timers, name
+
+    def __enter__(self):
+        self.a = torch.cuda.Event(enable_timing=True)
+        self.b = torch.cuda.Event(enable_timing=True)
+        self.a.record()
+
+    def __exit__(self, *exc):
+        self.b.record()
+        self.t.setdefault(self.name, []).append((self.a, self.b))
+        return False
+
+
+class _Null:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL = _Null()
+
+
+class RMABPPOTrainer:
+    """Device-resident RMABPPO for the table domains (counterexample, ARMMAN) under a per-arm nature table
+    (the baseline nature policies: nature_baselines_counterexample.py:255-256, nature_baselines_armman.py:224-232).
+    """
+
+    def __init__(self, domain, n_arms, n_envs, steps_per_epoch, hidden=16, B=None, gamma=0.9, lam_other=0.97,
+                 clip_ratio=2.0, pi_lr=2e-3, vf_lr=2e-3, lm_lr=2e-3, train_pi_iters=20, train_v_iters=20,
+                 epochs=20, lamb_update_freq=4, final_train_lambdas=2, start_entropy_coeff=0.5,
+                 end_entropy_coeff=0.0, seed=0, ranges=None, nature=None, device="cuda", rank=0, world_size=1,
+                 process_group=None):
+        self.domain = DOMAINS[domain] if isinstance(domain, str) else int(domain)
+        if self.domain not in _DOMAIN_S:
+            raise ValueError("RMABPPOTrainer covers the table domains; SIS goes through ops.env_step_sis")
+        self.S, self.A = _DOMAIN_S[self.domain], 2
+        self.N_total, self.E, self.T, self.h = int(n_arms), int(n_envs), int(steps_per_epoch), int(hidden)
+        self.rank, self.world, self.pg = int(rank), int(world_size), process_group
+        per = (self.N_total + self.world - 1) // self.world
+        self.arm0 = min(self.rank * per, self.N_total)
+        self.N = min(per, self.N_total - self.arm0)
+        self.B = float(B if B is not None else self.N_total // 3)
+        self.gamma, self.lam_other, self.clip_ratio = float(gamma), float(lam_other), float(clip_ratio)
+        self.pi_lr, self.vf_lr, self.lm_lr = float(pi_lr), float(vf_lr), float(lm_lr)
+        self.pi_iters, self.v_iters, self.epochs = int(train_pi_iters), int(train_v_iters), int(epochs)
+        self.lamb_update_freq, self.final_train_lambdas = int(lamb_update_freq), int(final_train_lambdas)
+        self.ent0, self.ent1 = float(start_entropy_coeff), float(end_entropy_coeff)
+        self.seed = int(seed)
+        self.dev = torch.device(device)
+        if self.dev.type != "cuda":
+            raise RuntimeError("RMABPPOTrainer runs on CUDA only (no CPU fallback)")
+        N, E, T, S, A, h = self.N, self.E, self.T, self.S, self.A, self.h
+        dev = self.dev
+        f32, u8 = torch.float32, torch.uint8
+        self.net = ops.net_desc(N, E, S, A, h, True, 1.0)
+        self.Ppi, self.Pv = ops.n_params(S + 1, h, A), ops.n_params(S + 1, h, 1)
+        # every rank draws the full-size init stream and keeps its slice, so sharding does not change the nets
+        g = torch.Generator(device="cpu").manual_seed(self.seed)
+        Wpi = linear_default_init_(torch.empty((self.N_total, self.Ppi)), S + 1, h, A, g)
+        Wv = linear_default_init_(torch.empty((self.N_total, self.Pv)), S + 1, h, 1, g)
+        self.Wpi = Wpi[self.arm0:self.arm0 + N].contiguous().to(dev)
+        self.Wv = Wv[self.arm0:self.arm0 + N].contiguous().to(dev)
+        self.lam_params = self._init_lambda_net(g).to(dev)
+        self.adam_pi = torch.zeros((N, 2, self.Ppi), dtype=f32, device=dev)
+        self.adam_v = torch.zeros((N, 2, self.Pv), dtype=f32, device=dev)
+        self.steps_pi = self.steps_v = 0
+        rs = np.random.RandomState(self.seed)
+        if ranges is None:
+            ranges = self.default_ranges(self.domain, self.N_total, rs)
+        if nature is None:
+            lo, hi = ranges[..., 0], ranges[..., 1]
+            nature = lo + rs.rand(*lo.shape) * (hi - lo)
+        sl = slice(self.arm0, self.arm0 + N)
+        self.ranges = torch.as_tensor(np.ascontiguousarray(ranges[sl]), dtype=f32).to(dev)
+        self.nature = torch.as_tensor(np.ascontiguousarray(nature[sl]), dtype=f32).to(dev)
+        Rrow = [0.0, 1.0] if self.domain == _lib.DOMAIN_CE else [1.0, 0.5, 0.0]
+        self.R = torch.tensor(Rrow, dtype=f32).repeat(N, 1).contiguous().to(dev)
+        self.C = torch.tensor([0.0, 1.0], dtype=f32, device=dev)
+        self.s_traj = torch.empty((N, T + 1, E), dtype=u8, device=dev)
+        self.a = torch.empty((N, T, E), dtype=u8, device=dev)
+        self.logp = torch.empty((N, T, E), dtype=f32, device=dev)
+        self.val = torch.empty((N, T, E), dtype=f32, device=dev)
+        self.last_val = torch.empty((N, E), dtype=f32, device=dev)
+        self.epoch_idx = 0
+        self.t_global = 0
+        self.s_traj[:, 0] = ops.reset_states(N, E, S, ops.rng(self.seed, _lib.STREAM_RESET, 0, arm0=self.arm0))
+        self.last_stats = None
+        self._timers = None
+        self._timer_epoch0 = 0
+
+    @property
+    def timers(self):
+        return self._timers
+
+    @timers.setter
+    def timers(self, v):
+        self._timers = v
+        self._timer_epoch0 = self.epoch_idx
+
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def default_ranges(domain, N, rs):
+        """sampled_parameter_ranges: sorted U(0,1) pair scaled into PARAMETER_RANGES
+        (bandit_env_robust.py:468-481, :790-818)."""
+        if domain == _lib.DOMAIN_CE:
+            base = np.array([[0.0, 1.0], [0.05, 0.9], [0.1, 0.95]])[np.arange(N) % 3]
+        else:
+            rA = [[[0.0, 1.0], [0.0, 1.0]], [[0.5, 1.0], [0.5, 1.0]], [[0.35, 0.85], [0.35, 0.85]]]
+            rB = [[[0.0, 1.0], [0.0, 1.0]], [[0.35, 0.85], [0.15, 0.65]], [[0.35, 0.85], [0.35, 0.85]]]
+            rC = [[[0.0, 1.0], [0.0, 1.0]], [[0.35, 0.85], [0.0, 0.5]], [[0.35, 0.85], [0.35, 0.85]]]
+            nA, nB = int(N * 0.2), int(N * 0.2)
+            base = np.empty((N, 3, 2, 2))
+            base[:nA], base[nA:nA + nB], base[nA + nB:] = rA, rB, rC
+        draw = np.sort(rs.rand(*base.shape), axis=-1)
+        lo = base.min(-1)[..., None]
+        return draw * (base.max(-1)[..., None] - lo) + lo
+
+    def _init_lambda_net(self, g):
+        """MLPLambdaNet N -> 8 -> 8 -> 1 (rmabppo_core.py:108-115, :170-171), packed W1 b1 W2 b2 W3 b3."""
+        Nt = self.N_total
+        P = 8 * Nt + 8 + 64 + 8 + 8 + 1
+        p = torch.empty((1, P))
+        o = 0
+        for fan_out, fan_in in ((8, Nt), (8, 8), (1, 8)):
+            b = 1.0 / math.sqrt(fan_in)
+            n = fan_out * fan_in + fan_out
+            p[:, o:o + n].uniform_(-b, b, generator=g)
+            o += n
+        return p[0].contiguous()
+
+    def _allreduce(self, t):
+        if self.world > 1:
+            torch.distributed.all_reduce(t, group=self.pg)
+        return t
+
+    def entropy_coeff(self, epoch):
+        """agent_oracle.py:402-409 with head = linspace(start, end, epochs)[epoch] (:491, :578)."""
+        head = float(np.linspace(self.ent0, self.ent1, self.epochs)[min(epoch, self.epochs - 1)])
+        if (self.epochs - epoch) > self.final_train_lambdas:
+            return float(np.linspace(head, 0, self.lamb_update_freq)[epoch % self.lamb_update_freq])
+        return 0.0
+
+    def lambda_update_due(self, epoch):
+        return epoch % self.lamb_update_freq == 0 and epoch > 0 and (self.epochs - epoch) > self.final_train_lambdas
+
+    # ------------------------------------------------------------------------------------------
+    def compute_lambda(self):
+        s0 = self._s0()
+        if self.world == 1:
+            lamb, h1 = ops.lambda_forward(self.lam_params, s0, self.N_total, self.arm0, 1.0, want_h1=True)
+        else:
+            _, h1 = ops.lambda_forward(self.lam_params, s0, self.N_total, self.arm0, 1.0, want_h1=True,
+                                       want_lamb=False)
+            self._allreduce(h1)
+            lamb, _ = ops.lambda_forward(self.lam_params, s0, self.N_total, self.arm0, 1.0, h1_in=h1)
+        return lamb, h1, s0
+
+    def _s0(self):
+        # s_traj[:, 0] is a strided view; the lambda kernels want [N,E] contiguous
+        return self.s_traj[:, 0].contiguous()
+
+    # ------------------------------------------------------------------------------------------
+    def _stage(self, name):
+        """Context manager recording a CUDA-event pair around one stage on the launching stream
+        (only when `self.timers` is a dict, i.e. inside bench.py's timed region)."""
+        return _Stage(self.timers, name) if self.timers is not None else _NULL
+
+    def stage_times(self):
+        """Average ms per epoch of each recorded stage (synchronises)."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, pairs in (self.timers or {}).items():
+            out[name] = sum(a.elapsed_time(b) for a, b in pairs) / max(1, self.epoch_idx - self._timer_epoch0)
+        return out
+
+    def buffer_bytes(self):
+        N, T, E = self.N, self.T, self.E
+        return N * (T + 1) * E + N * T * E * (1 + 4 * 4)
+
+    def algorithmic_bytes(self):
+        """Algorithmic HBM bytes per launch of each stage (SURVEY.md section 8d per-unit figures x N*T*E)."""
+        n = self.N * self.T * self.E
+        return {"rollout": 10 * n, "gae": 14 * n, "ppo_update": 14 * n + 24 * self.N * (self.Ppi + self.Pv)}
+
+    def dominant_kernel(self, stage_ms):
+        if not stage_ms:
+            return "none", 0.0, 0
+        name = max(stage_ms, key=stage_ms.get)
+        return name, stage_ms[name], self.algorithmic_bytes().get(name, 0)
+
+    def epoch_host(self, s0_host, nature_host):
+        """End-to-end epoch through host buffers: H2D of the start states and the nature policy's parameter
+        table (pinned), the epoch, D2H of the per-env results."""
+        self.s_traj[:, 0].copy_(s0_host.to(self.dev, non_blocking=True))
+        self.nature.copy_(nature_host, non_blocking=True)
+        st = self.epoch(want_stats=True)
+        out = {k: v.to("cpu", non_blocking=True) for k, v in st.items()}
+        torch.cuda.current_stream().synchronize()
+        return out
+
+    def epoch(self, want_stats=True):
+        """One rollout + update epoch.  Returns a dict of device scalars (no host sync)."""
+        ep = self.epoch_idx
+        N, E, T = self.N, self.E, self.T
+        with self._stage("lambda"):
+            lamb, h1, s0 = self.compute_lambda()
+        with self._stage("rollout"):
+            ops.rollout_table(self.domain, self.net, T, self.Wpi, self.Wv, lamb, self.nature, self.ranges, self.seed,
+                              self.t_global, self.t_global, self.s_traj, self.a, self.logp, self.val, self.last_val,
+                              env0=0, arm0=self.arm0)
+        with self._stage("gae"):
+            adv, ret, _, _ = ops.gae(self.s_traj, self.a, self.val, self.last_val, lamb, self.C, self.R, self.gamma,
+                                     self.lam_other, normalize=True)
+        hp = ops.hyper(self.clip_ratio, self.entropy_coeff(ep), self.pi_lr, self.vf_lr, self.pi_iters, self.v_iters,
+                       self.steps_pi, self.steps_v)
+        with self._stage("ppo_update"):
+            ops.ppo_update(self.net, hp, self.Wpi, self.Wv, self.adam_pi, self.adam_v, self.s_traj, self.a, adv,
+                           self.logp, ret, lamb)
+        self.steps_pi += self.pi_iters
+        self.steps_v += self.v_iters
+        if self.lambda_update_due(ep):
+            cd = ops.cost_togo(self.a, self.C, self.gamma)          # [T,E] arm-summed over this rank's arms
+            cd0 = self._allreduce(cd[0].contiguous())
+            coef = self.B / (1.0 - self.gamma) - cd0               # compute_loss_lambda (:360-376)
+            ops.lambda_sgd(self.lam_params, s0, self.N_total, self.arm0, 1.0, h1, coef, self.lm_lr)
+        stats = None
+        if want_stats:
+            with self._stage("stats"):
+                # EpActualRet per env = sum_t sum_arms R[arm, s'] (:521-527); VVals / Lamb as logged (:536, :498)
+                rew = torch.gather(self.R, 1, self.s_traj[:, 1:].reshape(N, -1).long()).view(N, T, E)
+                ep_ret = self._allreduce(rew.sum(dim=(0, 1)))
+                stats = {"EpActualRet": ep_ret, "Lamb": lamb, "VVals": self.val.mean().reshape(1)}
+        # env.reset() at the end of the epoch (:568)
+        self.epoch_idx += 1
+        self.t_global += T
+        self.s_traj[:, 0] = ops.reset_states(N, E, self.S, ops.rng(self.seed, _lib.STREAM_RESET, self.epoch_idx,
+                                                                   arm0=self.arm0))
+        self.last_stats = stats
+        return stats
