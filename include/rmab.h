@@ -180,6 +180,36 @@ int rmab_ppo_update(const RmabNetDesc* net, const RmabHyper* hp, int T, int s_ro
                     const float* logp_old, const float* ret, const float* lamb, float* loss_pi,
                     float* loss_v, rmab_stream_t stream);
 
+/* ---- fused epoch for the one-hot table domains ------------------------------------------- */
+
+/* Number of statistics rows K = 4*S*A + 3*S of rmab_epoch_table for a table domain (-1 otherwise).
+ * Row order (c = s*A + a):  Aplus[c] | Aminus[c] | logp_old[c] | n[s] | mean_ret[s] | v_old[s] | n[c]. */
+int rmab_stat_rows(int domain);
+size_t rmab_epoch_ws_bytes(int N, int E);
+
+/* One epoch's rollout + finish_path + get() for all arms x envs in one kernel (agent_oracle.py:506-570,
+ * :90-161) and the per-(arm, env, state, action) sufficient statistics of compute_loss_pi / compute_loss_v
+ * (:285-339) that rmab_ppo_update_table consumes:
+ *   Aplus / Aminus = sums of the positive / negative normalised advantages of the samples that visited
+ *   (s, a); logp_old = log pi_old(a | s, lambda_e); n = visit counts; mean_ret = mean reward-to-go per state.
+ * Inputs as rmab_rollout_table plus R [N,S], C [A], gamma, lam (GAE lambda).  s_traj [N,T+1,E] (row 0 =
+ * start state on input) and a [N,T,E] are written; stats [N,K,E]; arm_stats [N,4] = (adv mean, adv std,
+ * sum (ret - mean_ret[s,e])^2, 0) (may be NULL); env_sums [2,E] = per-env sum over arms and steps of the
+ * reward, and of the discounted cost-to-go at t = 0 (cdcost_buf[0], :117/:139) (may be NULL; needs ws of
+ * rmab_epoch_ws_bytes); adv (normalised), ret [N,T,E] and last_val [N,E] are written when non-NULL. */
+int rmab_epoch_table(int domain, const RmabNetDesc* net, int T, const float* Wpi, const float* Wv,
+                     const float* lamb, const float* nature, const float* ranges, const float* R, const float* C,
+                     double gamma, double lam, uint64_t seed, uint32_t t_act0, uint32_t t_env0, uint32_t env0,
+                     uint32_t arm0, uint8_t* s_traj, uint8_t* a, float* stats, float* arm_stats, float* env_sums,
+                     void* ws, size_t ws_bytes, float* adv, float* ret, float* last_val, rmab_stream_t stream);
+
+/* update() (agent_oracle.py:399-436) on the statistics of rmab_epoch_table: the same pi_iters + v_iters
+ * full-batch Adam steps as rmab_ppo_update, evaluated on S*E rows per arm instead of T*E samples (exact
+ * regrouping of the loss sums; see csrc/epoch.cu).  T only enters as the 1/(T*E) mean. */
+int rmab_ppo_update_table(const RmabNetDesc* net, const RmabHyper* hp, int T, float* Wpi, float* Wv,
+                          float* adam_pi, float* adam_v, const float* stats, const float* arm_stats,
+                          const float* lamb, float* loss_pi, float* loss_v, rmab_stream_t stream);
+
 /* ---- budget-constrained selection -------------------------------------------------------- */
 
 size_t rmab_select_ws_bytes(int E, int N, int A);

@@ -108,3 +108,33 @@ def entropy_coeff_for(epoch, epochs, start, end, lamb_update_freq, final_train_l
 def lambda_update_due(epoch, epochs, lamb_update_freq, final_train_lambdas):
     """agent_oracle.py:440."""
     return epoch % lamb_update_freq == 0 and epoch > 0 and (epochs - epoch) > final_train_lambdas
+
+
+def loss_statistics(s, a, adv_n, ret, S, A):
+    """Per-(arm, env, state, action) sufficient statistics of compute_loss_pi / compute_loss_v for one-hot
+    inputs (the regrouping the CUDA table update uses; csrc/epoch.cu).  s, a `[N,T,E]` ints; adv_n (normalised),
+    ret `[N,T,E]`.  Returns dict of float64 arrays: Ap, Am, cnt `[N,S*A,E]`; cntS, mean_ret `[N,S,E]`;
+    ret_var_sum `[N]` = sum_t (ret_t - mean_ret[s_t, e])^2.
+    """
+    s = np.asarray(s).astype(np.int64)
+    a = np.asarray(a).astype(np.int64)
+    N, T, E = s.shape
+    x = np.asarray(adv_n, np.float64)
+    r = np.asarray(ret, np.float64)
+    Ap = np.zeros((N, S * A, E)); Am = np.zeros((N, S * A, E)); cnt = np.zeros((N, S * A, E))
+    cntS = np.zeros((N, S, E)); Sr = np.zeros((N, S, E))
+    for si in range(S):
+        ms = s == si
+        cntS[:, si] = ms.sum(1)
+        Sr[:, si] = (r * ms).sum(1)
+        for ai in range(A):
+            m = ms & (a == ai)
+            c = si * A + ai
+            Ap[:, c] = (np.where(x > 0, x, 0.0) * m).sum(1)
+            Am[:, c] = (np.where(x < 0, x, 0.0) * m).sum(1)
+            cnt[:, c] = m.sum(1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        mean_ret = np.where(cntS > 0, Sr / cntS, 0.0)
+    mr = np.take_along_axis(mean_ret.astype(np.float32).astype(np.float64), s, axis=1)  # [N,T,E]: mean_ret[n, s_t, e]
+    var_sum = ((r - mr) ** 2).sum(axis=(1, 2))
+    return dict(Ap=Ap, Am=Am, cnt=cnt, cntS=cntS, mean_ret=mean_ret, ret_var_sum=var_sum)

@@ -1,0 +1,357 @@
+// Fused epoch front half for the one-hot table domains (counterexample, ARMMAN) under a per-arm nature table:
+// rollout (actor sample + env transition) -> GAE / rewards-to-go -> per-arm advantage normalisation -> the
+// per-(env, state, action) sufficient statistics of the PPO losses.
+//
+// Reference behaviour: robust_rmab/algos/rmabppo/agent_oracle.py rollout loop :506-570 (ac.step, env.step,
+// buf.store, bootstrap ac.step, finish_path), RMABPPO_Buffer.finish_path :90-139, get :144-161,
+// compute_loss_pi :285-322, compute_loss_v :325-339; env laws bandit_env_robust.py:860-893 / :575-634.
+//
+// Why statistics are enough: with one-hot inputs a net only ever sees (state, lambda_env), so for a fixed
+// (arm, env) the new log-probabilities, entropies and values take S distinct values, and
+//   sum_t min(r_t A_t, clip(r_t) A_t) = sum_{s,a} [ min(r_sa, 1+c) * Aplus_sa + max(r_sa, 1-c) * Aminus_sa ]
+//   sum_t (v(s_t) - ret_t)^2          = sum_s   [ n_s (v_s - mean_ret_s)^2 ] + const
+// with Aplus/Aminus the sums of the positive / negative normalised advantages of the samples that visited
+// (s, a).  The update kernel (ppo_table.cu) then runs every Adam iteration on E*S rows instead of E*T samples.
+//
+// One CTA walks arms blockIdx.x, blockIdx.x + gridDim.x, ...; one thread per env.  HBM traffic per arm-step:
+// the trajectory write (s' 1 B + a 1 B) and its two L2-resident re-reads by the same thread; the statistics
+// are (4*S*A + 3*S) floats per (arm, env), i.e. < 1 B per arm-step at T = 100.
+#include "common.cuh"
+#include "mlp.cuh"
+
+namespace rmab {
+
+template <int S>
+__device__ __forceinline__ float pick_f(const float (&t)[S], int s) {
+  float v = t[0];
+#pragma unroll
+  for (int k = 1; k < S; ++k) v = (s == k) ? t[k] : v;
+  return v;
+}
+
+template <int DOMAIN>
+__device__ __forceinline__ int table_next(int s, int a, float p, float u) {
+  if (DOMAIN == RMAB_DOMAIN_CE) {
+    // T[s=0] = [.5,.5]; T[1,0] = [1,0]; T[1,1] = [1-p, p]   (bandit_env_robust.py:831-836, :876-877)
+    float pr[2];
+    if (s == 0) { pr[0] = 0.5f; pr[1] = 0.5f; }
+    else if (a == 0) { pr[0] = 1.f; pr[1] = 0.f; }
+    else { pr[0] = __fsub_rn(1.f, p); pr[1] = p; }
+    return categorical<2>(pr, u);
+  } else {
+    // s=0: [p,1-p,0]; s=1,a=0: [0,1-p,p]; s=1,a=1: [p,1-p,0]; s=2: [0,1-p,p]   (:595-616)
+    const bool to0 = (s == 0) || (s == 1 && a == 1);
+    float pr[3];
+    pr[0] = to0 ? p : 0.f;
+    pr[1] = __fsub_rn(1.f, p);
+    pr[2] = to0 ? 0.f : p;
+    return categorical<3>(pr, u);
+  }
+}
+
+struct EpochArgs {
+  RmabNetDesc d;
+  int T;
+  const float* Wpi; const float* Wv; const float* lamb; const float* nature; const float* ranges;
+  const float* R; const float* C;
+  double gamma, gl;  // discount, gamma * lam_OTHER
+  uint32_t k0, k1, t_act0, t_env0, env0, arm0;
+  uint8_t* s_traj; uint8_t* a;
+  float* stats; float* arm_stats; double* env_part;
+  float* adv; float* ret; float* last_val;
+};
+
+template <int H, int DOMAIN>
+__global__ void __launch_bounds__(256) epoch_table_kernel(EpochArgs g) {
+  constexpr int S = DOMAIN == RMAB_DOMAIN_CE ? 2 : 3;
+  constexpr int A = 2;
+  using SR = StatRows<S, A>;
+  extern __shared__ __align__(16) float smem[];
+  __shared__ double dred[3][8];
+  __shared__ float s_ms[2];
+  const int E = g.d.n_envs, T = g.T, N = g.d.n_arms;
+  const SmemNet Lp(S + 1, H, A), Lv(S + 1, H, 1);
+  const MlpLayout Gp(S + 1, H, A), Gv(S + 1, H, 1);
+  float* sp = smem;
+  float* sv = smem + Lp.size;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const double gamma = g.gamma, gl = g.gl;
+  const float C0 = __ldg(g.C), C1 = __ldg(g.C + 1);
+
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    __syncthreads();  // previous arm's readers of the staged nets are done
+    stage_net(sp, Lp, g.Wpi + (int64_t)n * Gp.P);
+    stage_net(sv, Lv, g.Wv + (int64_t)n * Gv.P);
+    __syncthreads();
+    // clamped nature parameter per (state, action) of this arm (:867-874 / :583-592)
+    float pn0[S], pn1[S], Rn[S];
+#pragma unroll
+    for (int si = 0; si < S; ++si) {
+      Rn[si] = __ldg(g.R + (int64_t)n * S + si);
+      if (DOMAIN == RMAB_DOMAIN_CE) {
+        const float p = fminf(fmaxf(__ldg(g.nature + n), __ldg(g.ranges + 2 * (int64_t)n)), __ldg(g.ranges + 2 * (int64_t)n + 1));
+        pn0[si] = p;
+        pn1[si] = p;
+      } else {
+        const int64_t c0 = ((int64_t)n * S + si) * A;
+        pn0[si] = fminf(fmaxf(__ldg(g.nature + c0), __ldg(g.ranges + 2 * c0)), __ldg(g.ranges + 2 * c0 + 1));
+        pn1[si] = fminf(fmaxf(__ldg(g.nature + c0 + 1), __ldg(g.ranges + 2 * c0 + 2)), __ldg(g.ranges + 2 * c0 + 3));
+      }
+    }
+    const int64_t traj0 = (int64_t)n * (T + 1) * E;
+    const int64_t step0 = (int64_t)n * T * E;
+    const uint32_t gn = g.arm0 + (uint32_t)n;
+
+    // ---- pass 0: tables + forward chain; pass 1: backward scan for the advantage moments ----
+    double asum = 0.0, asq = 0.0;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      const float lam = g.lamb[e];
+      float p0t[S], p1t[S], vt[S];
+#pragma unroll
+      for (int si = 0; si < S; ++si) {
+        float a1[H], logit[kMaxA], vout[kMaxA], p[kMaxA], lp[kMaxA];
+        mlp_layer1<H>(sp, Lp, 1, si, 1.f, lam, a1);
+        mlp_tail<H>(sp, Lp, a1, A, logit);
+        mlp_layer1<H>(sv, Lv, 1, si, 1.f, lam, a1);
+        mlp_tail<H>(sv, Lv, a1, 1, vout);
+        softmax_small(logit, A, p, lp);
+        p0t[si] = p[0]; p1t[si] = p[1]; vt[si] = vout[0];
+        float* st = g.stats + ((int64_t)n * SR::K) * E + e;
+        st[(int64_t)(SR::kLp + si * A + 0) * E] = lp[0];
+        st[(int64_t)(SR::kLp + si * A + 1) * E] = lp[1];
+        st[(int64_t)(SR::kV + si) * E] = vout[0];
+      }
+      uint8_t* tr = g.s_traj + traj0 + e;
+      uint8_t* ac = g.a + step0 + e;
+      int si = tr[0];
+      si = si < S ? si : S - 1;
+      const uint32_t ge = g.env0 + (uint32_t)e;
+      for (int t = 0; t < T; ++t) {
+        float pr[2] = {pick_f<S>(p0t, si), pick_f<S>(p1t, si)};
+        const float ua = philox_uniform(g.k0, g.k1, RMAB_STREAM_ACT, g.t_act0 + (uint32_t)t, ge, gn);
+        const int act = categorical<2>(pr, ua);
+        ac[(int64_t)t * E] = (uint8_t)act;
+        const float p = act ? pick_f<S>(pn1, si) : pick_f<S>(pn0, si);
+        const float ue = philox_uniform(g.k0, g.k1, RMAB_STREAM_ENV, g.t_env0 + (uint32_t)t, ge, gn);
+        si = table_next<DOMAIN>(si, act, p, ue);
+        tr[(int64_t)(t + 1) * E] = (uint8_t)si;
+      }
+      // backward scan 1 (finish_path :120-130 in fp64 like scipy's lfilter)
+      const double lv = (double)pick_f<S>(vt, si);
+      if (g.last_val) g.last_val[(int64_t)n * E + e] = (float)lv;
+      const double lm = (double)lam;
+      double next_v = lv, adv_acc = 0.0;
+      int sn = si;
+      for (int t = T - 1; t >= 0; --t) {
+        const int a_t = ac[(int64_t)t * E];
+        const int s_t = tr[(int64_t)t * E];
+        const double r = (double)pick_f<S>(Rn, sn), c = (double)(a_t ? C1 : C0), v = (double)pick_f<S>(vt, s_t);
+        const double rt = __dsub_rn(r, __dmul_rn(lm, c));
+        const double qv = __dadd_rn(rt, __dmul_rn(gamma, next_v));
+        const double delta = __dsub_rn(qv, v);
+        adv_acc = __dadd_rn(delta, __dmul_rn(gl, adv_acc));
+        const double af = (double)(float)adv_acc;
+        asum += af;
+        asq = fma(af, af, asq);
+        next_v = v;
+        sn = s_t;
+      }
+    }
+    // ---- per-arm mean / population std over all T*E samples (get() :152-155, mpi_tools.py:76-97) ----
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      asum += __shfl_xor_sync(0xffffffffu, asum, o);
+      asq += __shfl_xor_sync(0xffffffffu, asq, o);
+    }
+    if (lane == 0) { dred[0][warp] = asum; dred[1][warp] = asq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s1 = 0.0, s2 = 0.0;
+      for (int w = 0; w < nwarp; ++w) { s1 += dred[0][w]; s2 += dred[1][w]; }
+      const double cnt = (double)T * (double)E;
+      const double mean = s1 / cnt;
+      double var = s2 / cnt - mean * mean;
+      var = var > 0.0 ? var : 0.0;
+      s_ms[0] = (float)mean;
+      s_ms[1] = (float)sqrt(var);
+      if (g.arm_stats) { g.arm_stats[4 * (int64_t)n] = s_ms[0]; g.arm_stats[4 * (int64_t)n + 1] = s_ms[1]; }
+    }
+    __syncthreads();
+    const float mean = s_ms[0], stdv = s_ms[1];
+
+    // ---- pass 2: backward scan again, normalised advantages into the per-(s,a) statistics ----
+    double var_sum = 0.0;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      float* st = g.stats + ((int64_t)n * SR::K) * E + e;
+      float vt[S];
+#pragma unroll
+      for (int si = 0; si < S; ++si) vt[si] = st[(int64_t)(SR::kV + si) * E];
+      const uint8_t* tr = g.s_traj + traj0 + e;
+      const uint8_t* ac = g.a + step0 + e;
+      const double lm = (double)g.lamb[e];
+      int sn = tr[(int64_t)T * E];
+      const double lv = (double)pick_f<S>(vt, sn);
+      double next_v = lv, adv_acc = 0.0, ret_acc = lv, dcost = 0.0, rsum = 0.0;
+      double Ap[S * A], Am[S * A], Sr[S], Sr2[S];
+      int cnt[S * A];
+#pragma unroll
+      for (int c = 0; c < S * A; ++c) { Ap[c] = 0.0; Am[c] = 0.0; cnt[c] = 0; }
+#pragma unroll
+      for (int s = 0; s < S; ++s) { Sr[s] = 0.0; Sr2[s] = 0.0; }
+      for (int t = T - 1; t >= 0; --t) {
+        const int a_t = ac[(int64_t)t * E];
+        const int s_t = tr[(int64_t)t * E];
+        const double r = (double)pick_f<S>(Rn, sn), c = (double)(a_t ? C1 : C0), v = (double)pick_f<S>(vt, s_t);
+        const double rt = __dsub_rn(r, __dmul_rn(lm, c));
+        const double qv = __dadd_rn(rt, __dmul_rn(gamma, next_v));
+        const double delta = __dsub_rn(qv, v);
+        adv_acc = __dadd_rn(delta, __dmul_rn(gl, adv_acc));
+        ret_acc = __dadd_rn(rt, __dmul_rn(gamma, ret_acc));
+        dcost = __dadd_rn(c, __dmul_rn(gamma, dcost));
+        rsum += r;
+        const float x = __fdiv_rn(__fsub_rn((float)adv_acc, mean), stdv);  // (adv - mean) / std in fp32 (:155)
+        const float rf = (float)ret_acc;
+        if (g.adv) g.adv[step0 + (int64_t)t * E + e] = x;
+        if (g.ret) g.ret[step0 + (int64_t)t * E + e] = rf;
+        const int cell = s_t * A + a_t;
+        const double xp = x > 0.f ? (double)x : 0.0, xm = x < 0.f ? (double)x : 0.0;
+#pragma unroll
+        for (int cc = 0; cc < S * A; ++cc) {
+          const bool hit = cell == cc;
+          Ap[cc] += hit ? xp : 0.0;
+          Am[cc] += hit ? xm : 0.0;
+          cnt[cc] += hit ? 1 : 0;
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const bool hit = s_t == s;
+          Sr[s] += hit ? (double)rf : 0.0;
+          Sr2[s] = hit ? fma((double)rf, (double)rf, Sr2[s]) : Sr2[s];
+        }
+        next_v = v;
+        sn = s_t;
+      }
+#pragma unroll
+      for (int c = 0; c < S * A; ++c) {
+        st[(int64_t)(SR::kAp + c) * E] = (float)Ap[c];
+        st[(int64_t)(SR::kAm + c) * E] = (float)Am[c];
+        st[(int64_t)(SR::kCnt + c) * E] = (float)cnt[c];
+      }
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int ns = cnt[s * A] + cnt[s * A + 1];
+        const double m = ns > 0 ? Sr[s] / (double)ns : 0.0;
+        const double mf = (double)(float)m;  // the update kernel sees the fp32-rounded mean
+        // sum (ret - mf)^2 = Sr2 - 2 mf Sr + n mf^2
+        const double centred = ns > 0 ? fma((double)ns * mf, mf, fma(-2.0 * mf, Sr[s], Sr2[s])) : 0.0;
+        var_sum += centred > 0.0 ? centred : 0.0;
+        st[(int64_t)(SR::kRetMean + s) * E] = (float)m;
+        st[(int64_t)(SR::kCntS + s) * E] = (float)ns;
+      }
+      if (g.env_part) {
+        // accumulated over the arms this CTA walks; written once at the end (below)
+        double* ep = g.env_part + ((int64_t)blockIdx.x * 2) * E + e;
+        const bool first = n == (int)blockIdx.x;
+        ep[0] = (first ? 0.0 : ep[0]) + rsum;
+        ep[E] = (first ? 0.0 : ep[E]) + dcost;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) var_sum += __shfl_xor_sync(0xffffffffu, var_sum, o);
+    if (lane == 0) dred[2][warp] = var_sum;
+    __syncthreads();
+    if (threadIdx.x == 0 && g.arm_stats) {
+      double s = 0.0;
+      for (int w = 0; w < nwarp; ++w) s += dred[2][w];
+      g.arm_stats[4 * (int64_t)n + 2] = (float)s;  // sum_t (ret_t - mean_ret[s_t, e])^2 over the arm's batch
+      g.arm_stats[4 * (int64_t)n + 3] = 0.f;
+    }
+  }
+}
+
+// out[k, e] = sum_b in[b, k, e] in fp64, fixed order (deterministic).
+__global__ void part_sum_kernel(int nb, int64_t ke, const double* __restrict__ in, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ke) return;
+  double acc = 0.0;
+  for (int b = 0; b < nb; ++b) acc += in[(int64_t)b * ke + i];
+  out[i] = (float)acc;
+}
+
+template <typename K>
+static int set_smem_attr(K kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return 0;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess ? 0 : -1;
+}
+
+static int epoch_grid(int N) {
+  const int cap = kNumSMs * 4;
+  return N < cap ? N : cap;
+}
+
+}  // namespace rmab
+
+using namespace rmab;
+
+extern "C" int rmab_stat_rows(int domain) {
+  if (domain == RMAB_DOMAIN_CE) return StatRows<2, 2>::K;
+  if (domain == RMAB_DOMAIN_ARMMAN) return StatRows<3, 2>::K;
+  return -1;
+}
+
+extern "C" size_t rmab_epoch_ws_bytes(int N, int E) { return (size_t)epoch_grid(N) * 2 * (size_t)E * sizeof(double); }
+
+extern "C" int rmab_epoch_table(int domain, const RmabNetDesc* net, int T, const float* Wpi, const float* Wv,
+                                const float* lamb, const float* nature, const float* ranges, const float* R,
+                                const float* C, double gamma, double lam, uint64_t seed, uint32_t t_act0,
+                                uint32_t t_env0, uint32_t env0, uint32_t arm0, uint8_t* s_traj, uint8_t* a,
+                                float* stats, float* arm_stats, float* env_sums, void* ws, size_t ws_bytes, float* adv,
+                                float* ret, float* last_val, rmab_stream_t stream) {
+  RMAB_REQUIRE(net, RMAB_E_BADARG, "rmab_epoch_table: null net descriptor");
+  RMAB_REQUIRE(domain == RMAB_DOMAIN_CE || domain == RMAB_DOMAIN_ARMMAN, RMAB_E_BADARG,
+               "rmab_epoch_table: domain %d is not a table domain", domain);
+  const int S = domain == RMAB_DOMAIN_CE ? 2 : 3;
+  const int h = net->hidden;
+  RMAB_REQUIRE(h == 8 || h == 16 || h == 32 || h == 64, RMAB_E_SHAPE,
+               "rmab_epoch_table: hidden width %d unsupported (8, 16, 32 or 64; two hidden layers)", h);
+  RMAB_REQUIRE(net->one_hot && net->n_states == S && net->n_actions == 2 && net->n_extra == 0, RMAB_E_SHAPE,
+               "rmab_epoch_table: needs one-hot S=%d, A=2 nets", S);
+  RMAB_REQUIRE(T > 0 && net->n_envs > 0 && net->n_arms >= 0, RMAB_E_SHAPE, "rmab_epoch_table: bad T/E/N");
+  RMAB_REQUIRE(Wpi && Wv && lamb && nature && ranges && R && C && s_traj && a && stats, RMAB_E_BADARG,
+               "rmab_epoch_table: null pointer");
+  RMAB_REQUIRE(!env_sums || (ws && ws_bytes >= rmab_epoch_ws_bytes(net->n_arms, net->n_envs)), RMAB_E_BADARG,
+               "rmab_epoch_table: env_sums needs a workspace of rmab_epoch_ws_bytes()");
+  if (net->n_arms == 0) return RMAB_OK;
+  EpochArgs g;
+  g.d = *net; g.T = T; g.Wpi = Wpi; g.Wv = Wv; g.lamb = lamb; g.nature = nature; g.ranges = ranges; g.R = R; g.C = C;
+  g.gamma = gamma; g.gl = gamma * lam;
+  g.k0 = (uint32_t)(seed & 0xFFFFFFFFull); g.k1 = (uint32_t)(seed >> 32);
+  g.t_act0 = t_act0; g.t_env0 = t_env0; g.env0 = env0; g.arm0 = arm0;
+  g.s_traj = s_traj; g.a = a; g.stats = stats; g.arm_stats = arm_stats; g.env_part = env_sums ? (double*)ws : nullptr;
+  g.adv = adv; g.ret = ret; g.last_val = last_val;
+  const size_t smem = sizeof(float) * (SmemNet(S + 1, h, 2).size + SmemNet(S + 1, h, 1).size);
+  const int grid = epoch_grid(net->n_arms);
+  int threads = ((net->n_envs + 31) / 32) * 32;
+  threads = threads > 256 ? 256 : threads;
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(H, D)                                                                                           \
+  {                                                                                                            \
+    RMAB_REQUIRE(set_smem_attr(epoch_table_kernel<H, D>, smem) == 0, RMAB_E_LAUNCH, "rmab_epoch_table: smem %zu B", smem); \
+    epoch_table_kernel<H, D><<<grid, threads, smem, st>>>(g);                                                  \
+  }
+#define LAUNCH_H(D)               \
+  switch (h) {                    \
+    case 8: LAUNCH(8, D) break;   \
+    case 16: LAUNCH(16, D) break; \
+    case 32: LAUNCH(32, D) break; \
+    default: LAUNCH(64, D) break; \
+  }
+  if (domain == RMAB_DOMAIN_CE) { LAUNCH_H(RMAB_DOMAIN_CE) } else { LAUNCH_H(RMAB_DOMAIN_ARMMAN) }
+#undef LAUNCH_H
+#undef LAUNCH
+  int rc = check_launch("rmab_epoch_table");
+  if (rc || !env_sums) return rc;
+  const int64_t ke = 2 * (int64_t)net->n_envs;
+  part_sum_kernel<<<(int)((ke + 127) / 128), 128, 0, st>>>(grid, ke, (const double*)ws, env_sums);
+  return check_launch("rmab_epoch_table(sum)");
+}

@@ -120,4 +120,14 @@ __device__ __forceinline__ int categorical_rt(const float (&p)[kMaxA], int A, fl
   return categorical<kMaxA>(p, u);
 }
 
+// Rows of the statistics block of one (arm): stats[n][row][e]
+template <int S, int A>
+struct StatRows {
+  static constexpr int SA = S * A;
+  // policy update reads rows [0, 3SA+S); value update reads rows [3SA, 3SA+2S)
+  static constexpr int kAp = 0, kAm = SA, kLp = 2 * SA, kCntS = 3 * SA, kRetMean = 3 * SA + S, kV = 3 * SA + 2 * S,
+                       kCnt = 3 * SA + 3 * S, K = 4 * SA + 3 * S;
+};
+
+
 }  // namespace rmab

@@ -23,11 +23,15 @@ struct PpoCfg {
   static constexpr int SPW = 32 / LPS;         // samples per warp pass
 };
 
-template <int H, bool IS_PI>
+// TABLE = false: one row per sample (s_buf, a_buf, adv, logp_old, ret are [N,T,E] arrays).
+// TABLE = true : one row per (state, env) with the sufficient statistics written by rmab_epoch_table
+//                (stats [N,K,E], rows as StatRows; arm_stats [N,4]); see epoch.cu for the identity.
+template <int H, bool IS_PI, bool TABLE>
 __global__ void __launch_bounds__(256, (H >= 64 ? 1 : 2))
 ppo_update_kernel(RmabNetDesc d, RmabHyper hp, int T, int s_rows, float* __restrict__ Wg, float* __restrict__ adam,
                   const uint8_t* __restrict__ s_buf, const uint8_t* __restrict__ a_buf, const float* __restrict__ adv,
                   const float* __restrict__ logp_old, const float* __restrict__ ret, const float* __restrict__ lamb,
+                  const float* __restrict__ stats, const float* __restrict__ arm_stats, int stage_stats,
                   float* __restrict__ loss_out) {
   using Cfg = PpoCfg<H>;
   constexpr int LPS = Cfg::LPS, FPL = Cfg::FPL, SPW = Cfg::SPW;
@@ -64,8 +68,24 @@ ppo_update_kernel(RmabNetDesc d, RmabHyper hp, int T, int s_rows, float* __restr
   for (int i = threadIdx.x; i < H * H; i += blockDim.x) w2t[(i % H) * H + (i / H)] = w[L.oW2 + i];
   __syncthreads();
 
-  const int M = T * E;
-  const float invM = 1.f / (float)M;
+  // statistics rows this pass needs: policy [0, 3SA+S) = Ap Am Lp CntS, value [3SA, 3SA+2S) = CntS RetMean
+  const int SA = S * d.n_actions;
+  const int row0 = IS_PI ? 0 : 3 * SA, nrows = IS_PI ? 3 * SA + S : 2 * S;
+  const int K = 4 * SA + 3 * S;
+  const float* st = nullptr;  // st[(row - row0) * E + e]
+  if (TABLE) {
+    const float* gst = stats + ((int64_t)n * K + row0) * E;
+    if (stage_stats) {
+      float* sst = scr + NW * 2 * SPW * H;
+      for (int i = threadIdx.x; i < nrows * E; i += blockDim.x) sst[i] = gst[i];
+      __syncthreads();
+      st = sst;
+    } else {
+      st = gst;
+    }
+  }
+  const int M = TABLE ? S * E : T * E;
+  const float invM = 1.f / (float)((int64_t)T * E);
   const int64_t sbase = (int64_t)n * s_rows * E;
   const int64_t base = (int64_t)n * T * E;
   const int iters = IS_PI ? hp.pi_iters : hp.v_iters;
@@ -98,9 +118,13 @@ ppo_update_kernel(RmabNetDesc d, RmabHyper hp, int T, int s_rows, float* __restr
       const int m = grp * SPW + sub;
       const bool valid = m < M;
       const int mm = valid ? m : M - 1;
-      const int t = mm / E, e = mm - t * E;
-      int si = s_buf[sbase + (int64_t)t * E + e];
-      si = si < S ? si : S - 1;
+      const int t = mm / E, e = mm - t * E;  // TABLE: t is the state of the row
+      int si;
+      if (TABLE) si = t;
+      else {
+        si = s_buf[sbase + (int64_t)t * E + e];
+        si = si < S ? si : S - 1;
+      }
       const float lam = lamb[e];
       const float x0 = d.one_hot ? 0.f : __fdiv_rn((float)si, d.state_norm);
 
@@ -155,7 +179,42 @@ ppo_update_kernel(RmabNetDesc d, RmabHyper hp, int T, int s_rows, float* __restr
 #pragma unroll
       for (int a = 0; a < kMaxA; ++a) g[a] = 0.f;
       const int64_t o = base + (int64_t)t * E + e;
-      if (IS_PI) {
+      if (TABLE) {
+        const float wrow = st[(int64_t)(3 * SA - row0 + si) * E + e];  // CntS: samples of this env in state si
+        if (IS_PI) {
+          float p[kMaxA], lp[kMaxA], ga[kMaxA];
+          softmax_small(logit, A, p, lp);
+          float ent = 0.f, sumg = 0.f, lrow = 0.f;
+#pragma unroll
+          for (int a = 0; a < kMaxA; ++a)
+            if (a < A) ent = fmaf(-p[a], lp[a], ent);
+#pragma unroll
+          for (int a = 0; a < kMaxA; ++a) {
+            ga[a] = 0.f;
+            if (a < A) {
+              const int c = si * A + a;
+              const float Ap = st[(int64_t)c * E + e], Am = st[(int64_t)(SA + c) * E + e];
+              const float ratio = expf(lp[a] - st[(int64_t)(2 * SA + c) * E + e]);
+              // positive advantages: min(r, 1+c) * A ; negative: max(r, 1-c) * A   (:301-305)
+              lrow -= fminf(ratio, clip_hi) * Ap + fmaxf(ratio, clip_lo) * Am;
+              ga[a] = -((ratio <= clip_hi ? ratio * Ap : 0.f) + (ratio >= clip_lo ? ratio * Am : 0.f));
+              sumg += ga[a];
+            }
+          }
+          if (valid) {
+            loss_acc += lrow - beta_ent * wrow * ent;
+#pragma unroll
+            for (int a = 0; a < kMaxA; ++a)
+              if (a < A) g[a] = invM * (ga[a] - p[a] * sumg + beta_ent * wrow * p[a] * (lp[a] + ent));
+          }
+        } else {
+          const float diff = logit[0] - st[(int64_t)(3 * SA + S - row0 + si) * E + e];
+          if (valid) {
+            loss_acc = fmaf(wrow * diff, diff, loss_acc);
+            g[0] = invM * 2.f * wrow * diff;
+          }
+        }
+      } else if (IS_PI) {
         float p[kMaxA], lp[kMaxA];
         softmax_small(logit, A, p, lp);
         const int act = a_buf[o];
@@ -294,7 +353,11 @@ ppo_update_kernel(RmabNetDesc d, RmabHyper hp, int T, int s_rows, float* __restr
       __syncthreads();
     }
     const float loss_tot = block_sum(f0 == 0 ? loss_acc : 0.f, red);
-    if (loss_out && threadIdx.x == 0) loss_out[(int64_t)n * iters + it] = loss_tot * invM;
+    if (loss_out && threadIdx.x == 0) {
+      float extra = 0.f;
+      if (TABLE && !IS_PI && arm_stats) extra = arm_stats[4 * (int64_t)n + 2];  // sum (ret - mean_ret[s,e])^2
+      loss_out[(int64_t)n * iters + it] = (loss_tot + extra) * invM;
+    }
 
     // ---- Adam (torch.optim.Adam defaults; _single_tensor_adam form) ----
     const int step = step0 + it + 1;
@@ -328,20 +391,43 @@ ppo_update_kernel(RmabNetDesc d, RmabHyper hp, int T, int s_rows, float* __restr
   }
 }
 
-template <int H, bool IS_PI>
+template <int H, bool IS_PI, bool TABLE>
 static int launch_ppo(const RmabNetDesc& d, const RmabHyper& hp, int T, int s_rows, float* W, float* adam,
                       const uint8_t* s, const uint8_t* a, const float* adv, const float* logp_old, const float* ret,
-                      const float* lamb, float* loss, cudaStream_t st) {
+                      const float* lamb, const float* stats, const float* arm_stats, float* loss, cudaStream_t st) {
   using Cfg = PpoCfg<H>;
   const int in = (d.one_hot ? d.n_states : 1) + 1;
   const MlpLayout L(in, H, IS_PI ? d.n_actions : 1);
-  const size_t smem = sizeof(float) * (4 * (size_t)L.padded() + H * H + 8 * 2 * Cfg::SPW * H);
-  auto kern = ppo_update_kernel<H, IS_PI>;
+  size_t smem = sizeof(float) * (4 * (size_t)L.padded() + H * H + 8 * 2 * Cfg::SPW * H);
+  int stage = 0;
+  if (TABLE) {
+    const int SA = d.n_states * d.n_actions;
+    const size_t rows = IS_PI ? 3 * SA + d.n_states : 2 * d.n_states;
+    const size_t extra = rows * (size_t)d.n_envs * sizeof(float);
+    if (smem + extra <= 200 * 1024) { smem += extra; stage = 1; }
+  }
+  auto kern = ppo_update_kernel<H, IS_PI, TABLE>;
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return fail(RMAB_E_LAUNCH, "rmab_ppo_update: cannot reserve %zu B of shared memory", smem);
-  kern<<<d.n_arms, 256, smem, st>>>(d, hp, T, s_rows, W, adam, s, a, adv, logp_old, ret, lamb, loss);
+  kern<<<d.n_arms, 256, smem, st>>>(d, hp, T, s_rows, W, adam, s, a, adv, logp_old, ret, lamb, stats, arm_stats, stage,
+                                    loss);
   return check_launch(IS_PI ? "rmab_ppo_update(pi)" : "rmab_ppo_update(v)");
+}
+
+static int check_ppo_args(const RmabNetDesc* net, const RmabHyper* hp, int T, const char* who) {
+  RMAB_REQUIRE(net && hp, RMAB_E_BADARG, "%s: null descriptor", who);
+  const int h = net->hidden;
+  RMAB_REQUIRE(h == 8 || h == 16 || h == 32 || h == 64, RMAB_E_SHAPE,
+               "%s: hidden width %d unsupported (8, 16, 32 or 64; two hidden layers)", who, h);
+  RMAB_REQUIRE(net->n_actions >= 2 && net->n_actions <= kMaxA, RMAB_E_SHAPE, "%s: n_actions %d not in [2,%d]", who,
+               net->n_actions, kMaxA);
+  RMAB_REQUIRE(net->n_extra == 0, RMAB_E_SHAPE, "%s: extra critic inputs not supported here", who);
+  RMAB_REQUIRE(!net->one_hot || net->n_states + 1 <= kMaxIn, RMAB_E_SHAPE, "%s: S=%d too large for one-hot", who,
+               net->n_states);
+  RMAB_REQUIRE(T > 0 && net->n_envs > 0 && (int64_t)T * net->n_envs < (1ll << 30), RMAB_E_SHAPE, "%s: bad T/E", who);
+  RMAB_REQUIRE(hp->pi_iters >= 0 && hp->v_iters >= 0, RMAB_E_BADARG, "%s: negative iteration count", who);
+  return RMAB_OK;
 }
 
 }  // namespace rmab
@@ -352,31 +438,52 @@ extern "C" int rmab_ppo_update(const RmabNetDesc* net, const RmabHyper* hp, int 
                                float* adam_pi, float* adam_v, const uint8_t* s, const uint8_t* a, const float* adv,
                                const float* logp_old, const float* ret, const float* lamb, float* loss_pi,
                                float* loss_v, rmab_stream_t stream) {
-  RMAB_REQUIRE(net && hp, RMAB_E_BADARG, "rmab_ppo_update: null descriptor");
-  const int h = net->hidden;
-  RMAB_REQUIRE(h == 8 || h == 16 || h == 32 || h == 64, RMAB_E_SHAPE,
-               "rmab_ppo_update: hidden width %d unsupported (8, 16, 32 or 64; two hidden layers)", h);
-  RMAB_REQUIRE(net->n_actions >= 2 && net->n_actions <= kMaxA, RMAB_E_SHAPE, "rmab_ppo_update: n_actions %d not in [2,%d]",
-               net->n_actions, kMaxA);
-  RMAB_REQUIRE(net->n_extra == 0, RMAB_E_SHAPE, "rmab_ppo_update: extra critic inputs not supported here");
-  RMAB_REQUIRE(!net->one_hot || net->n_states + 1 <= kMaxIn, RMAB_E_SHAPE, "rmab_ppo_update: S=%d too large for one-hot",
-               net->n_states);
-  RMAB_REQUIRE(T > 0 && s_rows >= T && net->n_envs > 0 && (int64_t)T * net->n_envs < (1ll << 30), RMAB_E_SHAPE,
-               "rmab_ppo_update: bad T/E");
+  int rc = check_ppo_args(net, hp, T, "rmab_ppo_update");
+  if (rc) return rc;
+  RMAB_REQUIRE(s_rows >= T, RMAB_E_SHAPE, "rmab_ppo_update: s_rows < T");
   RMAB_REQUIRE(Wpi && Wv && adam_pi && adam_v && s && a && adv && logp_old && ret && lamb, RMAB_E_BADARG,
                "rmab_ppo_update: null pointer");
-  RMAB_REQUIRE(hp->pi_iters >= 0 && hp->v_iters >= 0, RMAB_E_BADARG, "rmab_ppo_update: negative iteration count");
   if (net->n_arms == 0) return RMAB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = RMAB_OK;
 #define RUN(H)                                                                                                    \
   {                                                                                                               \
     if (hp->pi_iters > 0)                                                                                         \
-      rc = launch_ppo<H, true>(*net, *hp, T, s_rows, Wpi, adam_pi, s, a, adv, logp_old, ret, lamb, loss_pi, st);   \
+      rc = launch_ppo<H, true, false>(*net, *hp, T, s_rows, Wpi, adam_pi, s, a, adv, logp_old, ret, lamb, nullptr, \
+                                      nullptr, loss_pi, st);                                                      \
     if (rc == RMAB_OK && hp->v_iters > 0)                                                                         \
-      rc = launch_ppo<H, false>(*net, *hp, T, s_rows, Wv, adam_v, s, a, adv, logp_old, ret, lamb, loss_v, st);     \
+      rc = launch_ppo<H, false, false>(*net, *hp, T, s_rows, Wv, adam_v, s, a, adv, logp_old, ret, lamb, nullptr,  \
+                                       nullptr, loss_v, st);                                                      \
   }
-  switch (h) {
+  switch (net->hidden) {
+    case 8: RUN(8) break;
+    case 16: RUN(16) break;
+    case 32: RUN(32) break;
+    default: RUN(64) break;
+  }
+#undef RUN
+  return rc;
+}
+
+extern "C" int rmab_ppo_update_table(const RmabNetDesc* net, const RmabHyper* hp, int T, float* Wpi, float* Wv,
+                                     float* adam_pi, float* adam_v, const float* stats, const float* arm_stats,
+                                     const float* lamb, float* loss_pi, float* loss_v, rmab_stream_t stream) {
+  int rc = check_ppo_args(net, hp, T, "rmab_ppo_update_table");
+  if (rc) return rc;
+  RMAB_REQUIRE(net->one_hot, RMAB_E_SHAPE, "rmab_ppo_update_table: needs one-hot state inputs");
+  RMAB_REQUIRE(Wpi && Wv && adam_pi && adam_v && stats && lamb, RMAB_E_BADARG, "rmab_ppo_update_table: null pointer");
+  RMAB_REQUIRE(arm_stats || !loss_v, RMAB_E_BADARG, "rmab_ppo_update_table: loss_v needs arm_stats");
+  if (net->n_arms == 0) return RMAB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+#define RUN(H)                                                                                                     \
+  {                                                                                                                \
+    if (hp->pi_iters > 0)                                                                                          \
+      rc = launch_ppo<H, true, true>(*net, *hp, T, T, Wpi, adam_pi, nullptr, nullptr, nullptr, nullptr, nullptr,   \
+                                     lamb, stats, arm_stats, loss_pi, st);                                         \
+    if (rc == RMAB_OK && hp->v_iters > 0)                                                                          \
+      rc = launch_ppo<H, false, true>(*net, *hp, T, T, Wv, adam_v, nullptr, nullptr, nullptr, nullptr, nullptr,    \
+                                      lamb, stats, arm_stats, loss_v, st);                                         \
+  }
+  switch (net->hidden) {
     case 8: RUN(8) break;
     case 16: RUN(16) break;
     case 32: RUN(32) break;

@@ -201,6 +201,46 @@ def ppo_update(net, hp, Wpi, Wv, adam_pi, adam_v, s, a, adv, logp_old, ret, lamb
     return lp, lv
 
 
+# --------------------------------------------------------------------------- fused table-domain epoch
+def stat_rows(domain):
+    return int(lib().rmab_stat_rows(int(domain)))
+
+
+def epoch_table(domain, net, T, Wpi, Wv, lamb, nature, ranges, R, Cc, gamma, lam, seed, t_act0, t_env0, s_traj, a,
+                stats=None, arm_stats=None, env_sums=None, ws=None, adv=None, ret=None, last_val=None, env0=0, arm0=0):
+    """Rollout + GAE + normalisation + loss statistics in one launch.  Returns (stats, arm_stats, env_sums)."""
+    N, E = net.n_arms, net.n_envs
+    dev = s_traj.device
+    K = stat_rows(domain)
+    stats = torch.empty((N, K, E), dtype=f32, device=dev) if stats is None else stats
+    arm_stats = torch.empty((N, 4), dtype=f32, device=dev) if arm_stats is None else arm_stats
+    env_sums = torch.empty((2, E), dtype=f32, device=dev) if env_sums is None else env_sums
+    need = int(lib().rmab_epoch_ws_bytes(N, E))
+    if ws is None or ws.numel() * ws.element_size() < need:
+        ws = torch.empty((max(need, 8) + 7) // 8, dtype=f64, device=dev)
+    check(lib().rmab_epoch_table(int(domain), C.byref(net), int(T), _p(Wpi, f32, "Wpi"), _p(Wv, f32, "Wv"),
+                                 _p(lamb, f32, "lamb"), _p(nature, f32, "nature"), _p(ranges, f32, "ranges"),
+                                 _p(R, f32, "R"), _p(Cc, f32, "C"), float(gamma), float(lam),
+                                 int(seed) & 0xFFFFFFFFFFFFFFFF, int(t_act0), int(t_env0), int(env0), int(arm0),
+                                 _p(s_traj, u8, "s_traj"), _p(a, u8, "a"), _p(stats, f32, "stats"),
+                                 _p(arm_stats, f32, "arm_stats"), _p(env_sums, f32, "env_sums"), _p(ws, f64, "ws"),
+                                 ws.numel() * ws.element_size(), _p(adv, f32, "adv"), _p(ret, f32, "ret"),
+                                 _p(last_val, f32, "last_val"), _stream()))
+    return stats, arm_stats, env_sums
+
+
+def ppo_update_table(net, hp, T, Wpi, Wv, adam_pi, adam_v, stats, arm_stats, lamb, want_loss=False):
+    N = net.n_arms
+    dev = stats.device
+    lp = torch.zeros((N, max(hp.pi_iters, 1)), dtype=f32, device=dev) if want_loss else None
+    lv = torch.zeros((N, max(hp.v_iters, 1)), dtype=f32, device=dev) if want_loss else None
+    check(lib().rmab_ppo_update_table(C.byref(net), C.byref(hp), int(T), _p(Wpi, f32, "Wpi"), _p(Wv, f32, "Wv"),
+                                      _p(adam_pi, f32, "adam_pi"), _p(adam_v, f32, "adam_v"), _p(stats, f32, "stats"),
+                                      _p(arm_stats, f32, "arm_stats"), _p(lamb, f32, "lamb"), _p(lp, f32), _p(lv, f32),
+                                      _stream()))
+    return lp, lv
+
+
 # ------------------------------------------------------------------------------------------ selection
 def budget_select_binary(p1, cost1, B):
     N, E = p1.shape

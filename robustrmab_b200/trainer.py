@@ -117,9 +117,13 @@ class RMABPPOTrainer:
         self.C = torch.tensor([0.0, 1.0], dtype=f32, device=dev)
         self.s_traj = torch.empty((N, T + 1, E), dtype=u8, device=dev)
         self.a = torch.empty((N, T, E), dtype=u8, device=dev)
-        self.logp = torch.empty((N, T, E), dtype=f32, device=dev)
-        self.val = torch.empty((N, T, E), dtype=f32, device=dev)
         self.last_val = torch.empty((N, E), dtype=f32, device=dev)
+        self.stats = torch.empty((N, ops.stat_rows(self.domain), E), dtype=f32, device=dev)
+        self.arm_stats = torch.empty((N, 4), dtype=f32, device=dev)
+        self.env_sums = torch.empty((2, E), dtype=f32, device=dev)
+        self.ws = torch.empty((max(int(_lib.lib().rmab_epoch_ws_bytes(N, E)), 8) + 7) // 8, dtype=torch.float64,
+                              device=dev)
+        self.adv = self.ret = None
         self.epoch_idx = 0
         self.t_global = 0
         self.s_traj[:, 0] = ops.reset_states(N, E, S, ops.rng(self.seed, _lib.STREAM_RESET, 0, arm0=self.arm0))
@@ -214,12 +218,13 @@ class RMABPPOTrainer:
 
     def buffer_bytes(self):
         N, T, E = self.N, self.T, self.E
-        return N * (T + 1) * E + N * T * E * (1 + 4 * 4)
+        return N * (T + 1) * E + N * T * E + self.stats.numel() * 4
 
     def algorithmic_bytes(self):
-        """Algorithmic HBM bytes per launch of each stage (SURVEY.md section 8d per-unit figures x N*T*E)."""
+        """Algorithmic HBM bytes per launch of each stage: SURVEY.md section 8d per-unit figures x N*T*E
+        (rollout 10 B + GAE 14 B per arm-step; update 14 B per arm-step + 24 B per parameter)."""
         n = self.N * self.T * self.E
-        return {"rollout": 10 * n, "gae": 14 * n, "ppo_update": 14 * n + 24 * self.N * (self.Ppi + self.Pv)}
+        return {"rollout_gae_stats": 24 * n, "ppo_update": 14 * n + 24 * self.N * (self.Ppi + self.Pv)}
 
     def dominant_kernel(self, stage_ms):
         if not stage_ms:
@@ -237,38 +242,41 @@ class RMABPPOTrainer:
         torch.cuda.current_stream().synchronize()
         return out
 
-    def epoch(self, want_stats=True):
-        """One rollout + update epoch.  Returns a dict of device scalars (no host sync)."""
+    def epoch(self, want_stats=True, keep_buffers=False):
+        """One rollout + update epoch.  Returns a dict of device tensors (no host sync):
+        EpActualRet [E] (sum over arms and steps of the reward, agent_oracle.py:521-527), Lamb [E], VVals [1].
+        keep_buffers: also materialise the normalised advantages / returns / last values of buf.get()."""
         ep = self.epoch_idx
-        N, E, T = self.N, self.E, self.T
+        N, E, T, S, A = self.N, self.E, self.T, self.S, self.A
         with self._stage("lambda"):
             lamb, h1, s0 = self.compute_lambda()
-        with self._stage("rollout"):
-            ops.rollout_table(self.domain, self.net, T, self.Wpi, self.Wv, lamb, self.nature, self.ranges, self.seed,
-                              self.t_global, self.t_global, self.s_traj, self.a, self.logp, self.val, self.last_val,
-                              env0=0, arm0=self.arm0)
-        with self._stage("gae"):
-            adv, ret, _, _ = ops.gae(self.s_traj, self.a, self.val, self.last_val, lamb, self.C, self.R, self.gamma,
-                                     self.lam_other, normalize=True)
+        if keep_buffers and self.adv is None:
+            self.adv = torch.empty((N, T, E), dtype=torch.float32, device=self.dev)
+            self.ret = torch.empty((N, T, E), dtype=torch.float32, device=self.dev)
+        with self._stage("rollout_gae_stats"):
+            ops.epoch_table(self.domain, self.net, T, self.Wpi, self.Wv, lamb, self.nature, self.ranges, self.R, self.C,
+                            self.gamma, self.lam_other, self.seed, self.t_global, self.t_global, self.s_traj, self.a,
+                            stats=self.stats, arm_stats=self.arm_stats, env_sums=self.env_sums, ws=self.ws,
+                            adv=self.adv if keep_buffers else None, ret=self.ret if keep_buffers else None,
+                            last_val=self.last_val, env0=0, arm0=self.arm0)
         hp = ops.hyper(self.clip_ratio, self.entropy_coeff(ep), self.pi_lr, self.vf_lr, self.pi_iters, self.v_iters,
                        self.steps_pi, self.steps_v)
         with self._stage("ppo_update"):
-            ops.ppo_update(self.net, hp, self.Wpi, self.Wv, self.adam_pi, self.adam_v, self.s_traj, self.a, adv,
-                           self.logp, ret, lamb)
+            ops.ppo_update_table(self.net, hp, T, self.Wpi, self.Wv, self.adam_pi, self.adam_v, self.stats,
+                                 self.arm_stats, lamb)
         self.steps_pi += self.pi_iters
         self.steps_v += self.v_iters
-        if self.lambda_update_due(ep):
-            cd = ops.cost_togo(self.a, self.C, self.gamma)          # [T,E] arm-summed over this rank's arms
-            cd0 = self._allreduce(cd[0].contiguous())
-            coef = self.B / (1.0 - self.gamma) - cd0               # compute_loss_lambda (:360-376)
-            ops.lambda_sgd(self.lam_params, s0, self.N_total, self.arm0, 1.0, h1, coef, self.lm_lr)
-        stats = None
-        if want_stats:
-            with self._stage("stats"):
-                # EpActualRet per env = sum_t sum_arms R[arm, s'] (:521-527); VVals / Lamb as logged (:536, :498)
-                rew = torch.gather(self.R, 1, self.s_traj[:, 1:].reshape(N, -1).long()).view(N, T, E)
-                ep_ret = self._allreduce(rew.sum(dim=(0, 1)))
-                stats = {"EpActualRet": ep_ret, "Lamb": lamb, "VVals": self.val.mean().reshape(1)}
+        with self._stage("lambda_sgd_stats"):
+            sums = self._allreduce(self.env_sums) if (want_stats or self.lambda_update_due(ep)) else self.env_sums
+            if self.lambda_update_due(ep):
+                coef = self.B / (1.0 - self.gamma) - sums[1]            # compute_loss_lambda (:360-376)
+                ops.lambda_sgd(self.lam_params, s0, self.N_total, self.arm0, 1.0, h1, coef, self.lm_lr)
+            stats = None
+            if want_stats:
+                SA = S * A
+                vv = (self.stats[:, 3 * SA:3 * SA + S] * self.stats[:, 3 * SA + 2 * S:3 * SA + 3 * S]).sum()
+                vv = self._allreduce(vv.reshape(1)) / float(self.N_total * T * E)
+                stats = {"EpActualRet": sums[0].clone(), "Lamb": lamb, "VVals": vv}
         # env.reset() at the end of the epoch (:568)
         self.epoch_idx += 1
         self.t_global += T

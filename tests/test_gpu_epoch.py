@@ -1,0 +1,185 @@
+"""Fused table-domain epoch (rmab_epoch_table) and the statistics-based PPO update (rmab_ppo_update_table)
+against the per-sample CPU oracle, and the device trainer against the CPU epoch loop.  GPU only."""
+import numpy as np
+import pytest
+
+from oracle import buffer as obuf
+from oracle import envs as oenv
+from oracle import nets as onets
+from oracle import ppo as oppo
+from oracle.train import CpuRMABPPO
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def K():
+    import torch
+    assert torch.cuda.is_available()
+    from robustrmab_b200 import _lib, ops
+
+    class NS:
+        pass
+    ns = NS()
+    ns.torch, ns.ops, ns.lib = torch, ops, _lib
+    ns.dev = torch.device("cuda:0")
+    ns.t = lambda x, dt=None: torch.as_tensor(np.ascontiguousarray(x if dt is None else np.asarray(x).astype(dt)),
+                                              device=ns.dev)
+    ns.n = lambda x: x.detach().cpu().numpy()
+    return ns
+
+
+def _problem(domain, N, E, h, seed):
+    rs = np.random.RandomState(seed)
+    S = 2 if domain == 0 else 3
+    base = oenv.ce_param_ranges(N) if domain == 0 else oenv.armman_param_ranges(N)
+    ranges = oenv.sample_sub_ranges(base, rs).astype(F32)
+    nature = (ranges[..., 0] + rs.rand(*ranges.shape[:-1]) * (ranges[..., 1] - ranges[..., 0])).astype(F32)
+    Wpi = onets.init_linear_default(rs, N, S + 1, h, 2)
+    Wv = onets.init_linear_default(rs, N, S + 1, h, 1)
+    b = 1 / np.sqrt(N)
+    lam = [rs.uniform(-b, b, (8, N)).astype(F32), rs.uniform(-b, b, 8).astype(F32),
+           rs.uniform(-.35, .35, (8, 8)).astype(F32), rs.uniform(-.35, .35, 8).astype(F32),
+           rs.uniform(-.35, .35, (1, 8)).astype(F32), rs.uniform(0.2, .5, 1).astype(F32)]
+    R = oenv.rewards_table(domain, N, S)
+    C = np.array([0, 1], F32)
+    return S, ranges, nature, Wpi, Wv, lam, R, C
+
+
+@pytest.mark.parametrize("domain,h,N,E,T", [(0, 16, 9, 40, 25), (1, 64, 5, 128, 10), (1, 8, 700, 3, 6),
+                                            (0, 32, 4, 300, 12)])
+def test_epoch_table_vs_oracle(K, domain, h, N, E, T):
+    S, ranges, nature, Wpi, Wv, lam, R, C = _problem(domain, N, E, h, 11 + h)
+    cpu = CpuRMABPPO(domain, Wpi, Wv, lam, nature, ranges, R, C, E, T, h, N // 3, train_pi_iters=0, train_v_iters=0,
+                     seed=77, arm0=3)
+    w = cpu.epoch()
+    torch = K.torch
+    net = K.ops.net_desc(N, E, S, 2, h)
+    s_traj = torch.zeros((N, T + 1, E), dtype=torch.uint8, device=K.dev)
+    s_traj[:, 0] = K.t(w["s_traj"][:, 0])
+    a = torch.empty((N, T, E), dtype=torch.uint8, device=K.dev)
+    adv = torch.empty((N, T, E), dtype=torch.float32, device=K.dev)
+    ret = torch.empty((N, T, E), dtype=torch.float32, device=K.dev)
+    last = torch.empty((N, E), dtype=torch.float32, device=K.dev)
+    stats, arm_stats, env_sums = K.ops.epoch_table(domain, net, T, K.t(Wpi), K.t(Wv), K.t(w["lamb"]), K.t(nature),
+                                                   K.t(ranges), K.t(R), K.t(C), 0.9, 0.97, 77, 0, 0, s_traj, a,
+                                                   adv=adv, ret=ret, last_val=last, arm0=3)
+    assert np.array_equal(K.n(s_traj), w["s_traj"])                # integer outputs bit-exact
+    assert np.array_equal(K.n(a), w["a"])
+    np.testing.assert_allclose(K.n(last), w["last_val"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(K.n(ret), w["ret"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(K.n(adv), w["adv"], rtol=1e-4, atol=2e-5)
+    # statistics rows against the oracle's regrouping of its own per-sample arrays
+    st = oppo.loss_statistics(w["s_traj"][:, :T], w["a"], w["adv"], w["ret"], S, 2)
+    g = K.n(stats)
+    SA = S * 2
+    np.testing.assert_allclose(g[:, 0:SA], st["Ap"], rtol=1e-4, atol=2e-4)
+    np.testing.assert_allclose(g[:, SA:2 * SA], st["Am"], rtol=1e-4, atol=2e-4)
+    assert np.array_equal(g[:, 3 * SA + 3 * S:], st["cnt"])
+    assert np.array_equal(g[:, 3 * SA:3 * SA + S], st["cntS"])
+    np.testing.assert_allclose(g[:, 3 * SA + S:3 * SA + 2 * S], st["mean_ret"], rtol=1e-5, atol=1e-5)
+    # logp_old / v_old rows reproduce the per-sample logp / val of the rollout
+    lp_rows = g[:, 2 * SA:3 * SA]
+    cell = (w["s_traj"][:, :T].astype(np.int64) * 2 + w["a"]).astype(np.int64)
+    np.testing.assert_allclose(np.take_along_axis(lp_rows, cell, axis=1), w["logp"], rtol=1e-5, atol=2e-6)
+    v_rows = g[:, 3 * SA + 2 * S:3 * SA + 3 * S]
+    np.testing.assert_allclose(np.take_along_axis(v_rows, w["s_traj"][:, :T].astype(np.int64), axis=1), w["val"],
+                               rtol=1e-5, atol=2e-6)
+    raw_adv, _, _, cd = obuf.finish_path(
+        np.stack([np.take_along_axis(R, w["s_traj"][:, t + 1].astype(np.int64), axis=1) for t in range(T)], 1),
+        C[w["a"]], w["val"], w["last_val"], w["lamb"], 0.9, 0.97)
+    am = K.n(arm_stats)
+    np.testing.assert_allclose(am[:, 0], raw_adv.reshape(N, -1).astype(np.float64).mean(1), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(am[:, 1], raw_adv.reshape(N, -1).astype(np.float64).std(1), rtol=1e-5)
+    np.testing.assert_allclose(am[:, 2], st["ret_var_sum"], rtol=1e-4, atol=1e-4)
+    es = K.n(env_sums)
+    assert np.array_equal(es[0], w["rew_sum"])                     # rewards are multiples of 0.5: exact
+    np.testing.assert_allclose(es[1], w["cdcost"][0], rtol=1e-6)
+
+
+@pytest.mark.parametrize("S,h,N,T,E", [(2, 16, 4, 30, 8), (3, 64, 3, 10, 32), (3, 8, 3, 7, 5), (3, 32, 2, 12, 70)])
+def test_ppo_update_table_equals_per_sample(K, S, h, N, T, E):
+    """The statistics-based update against the oracle's per-sample torch-autograd update on the same batch."""
+    rs = np.random.RandomState(S * 10 + h)
+    A = 2
+    Wpi = onets.init_linear_default(rs, N, S + 1, h, A)
+    Wv = onets.init_linear_default(rs, N, S + 1, h, 1)
+    s = rs.randint(0, S, size=(N, T, E)).astype(np.uint8)
+    s[0, :, 0] = 0                                                # a state that is never visited in one env
+    a = rs.randint(0, A, size=(N, T, E)).astype(np.uint8)
+    lamb = rs.uniform(0, 2, size=E).astype(F32)
+    adv = obuf.normalize_adv(rs.randn(N, T, E).astype(F32) * 3 + 1)
+    ret = (rs.randn(N, T, E) * 2 + 3).astype(F32)
+    # logp_old must be a function of (arm, env, s, a), as it is after a rollout: evaluate the old policy
+    x = onets.features(s.reshape(N, T * E), np.tile(lamb, T), S, True)
+    _, lp_all = onets.softmax_logits(onets.mlp_forward(Wpi, x, S + 1, h, A))
+    logp_old = np.take_along_axis(lp_all, a.reshape(N, T * E, 1).astype(np.int64), axis=2)[..., 0].reshape(N, T, E)
+    logp_old = (logp_old + rs.uniform(-0.3, 0.3, size=(N, 1, E)) * (s == 1)).astype(F32)   # off-policy ratio != 1
+    clip, ent, lr, iters = 0.2, 0.3, 2e-3, 6
+    opt = oppo.ArmOptim(Wpi, Wv, lr, lr)
+    wlp, wlv = oppo.update(opt, s, a, adv, logp_old, ret, lamb, S, A, h, clip, ent, iters, iters)
+    st = oppo.loss_statistics(s, a, adv, ret, S, A)
+    SA = S * A
+    rows = np.zeros((N, 4 * SA + 3 * S, E), F32)
+    rows[:, 0:SA], rows[:, SA:2 * SA] = st["Ap"], st["Am"]
+    for si in range(S):
+        for ai in range(A):
+            m = (s == si) & (a == ai)
+            with np.errstate(invalid="ignore"):
+                v = np.where(m.any(1), (logp_old * m).sum(1) / np.maximum(m.sum(1), 1), 0.0)
+            rows[:, 2 * SA + si * A + ai] = v
+    rows[:, 3 * SA:3 * SA + S] = st["cntS"]
+    rows[:, 3 * SA + S:3 * SA + 2 * S] = st["mean_ret"]
+    rows[:, 3 * SA + 3 * S:] = st["cnt"]
+    arm_stats = np.zeros((N, 4), F32)
+    arm_stats[:, 2] = st["ret_var_sum"]
+    torch = K.torch
+    net = K.ops.net_desc(N, E, S, A, h)
+    hp = K.ops.hyper(clip, ent, lr, lr, iters, iters)
+    dWpi, dWv = K.t(Wpi), K.t(Wv)
+    adam_pi = torch.zeros((N, 2, Wpi.shape[1]), device=K.dev)
+    adam_v = torch.zeros((N, 2, Wv.shape[1]), device=K.dev)
+    lp, lv = K.ops.ppo_update_table(net, hp, T, dWpi, dWv, adam_pi, adam_v, K.t(rows), K.t(arm_stats), K.t(lamb),
+                                    want_loss=True)
+    np.testing.assert_allclose(K.n(lp)[:, 0], wlp[0], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(K.n(lv)[:, 0], wlv[0], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(K.n(lp).T, wlp, rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(K.n(lv).T, wlv, rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(K.n(dWpi), opt.Wpi.detach().numpy(), rtol=0, atol=2e-4)
+    np.testing.assert_allclose(K.n(dWv), opt.Wv.detach().numpy(), rtol=0, atol=2e-4)
+
+
+@pytest.mark.parametrize("domain,h", [(0, 16), (1, 64)])
+def test_trainer_matches_cpu_epoch_loop(K, domain, h):
+    """Device trainer vs the CPU restatement of best_response_per_cpu's loop over several epochs, including a
+    lambda-net SGD step (epoch 2 with lamb_update_freq = 2)."""
+    from robustrmab_b200.trainer import RMABPPOTrainer
+    N, E, T = 12, 16, 20
+    kw = dict(gamma=0.9, lam_other=0.97, clip_ratio=2.0, pi_lr=2e-3, vf_lr=2e-3, lm_lr=2e-3, train_pi_iters=5,
+              train_v_iters=5, epochs=6, lamb_update_freq=2, final_train_lambdas=1, start_entropy_coeff=0.5,
+              end_entropy_coeff=0.0, seed=5)
+    tr = RMABPPOTrainer(domain, N, E, T, hidden=h, B=N // 3, device=K.dev, **kw)
+    S = tr.S
+    lam_flat = K.n(tr.lam_params)
+    lam = [lam_flat[:8 * N].reshape(8, N), lam_flat[8 * N:8 * N + 8], lam_flat[8 * N + 8:8 * N + 72].reshape(8, 8),
+           lam_flat[8 * N + 72:8 * N + 80], lam_flat[8 * N + 80:8 * N + 88].reshape(1, 8), lam_flat[8 * N + 88:]]
+    cpu = CpuRMABPPO(domain, K.n(tr.Wpi), K.n(tr.Wv), lam, K.n(tr.nature), K.n(tr.ranges), K.n(tr.R), K.n(tr.C), E, T, h,
+                     N // 3, **kw)
+    agree = []
+    for ep in range(4):
+        st = tr.epoch()
+        w = cpu.epoch()
+        np.testing.assert_allclose(K.n(st["Lamb"]), w["lamb"], rtol=1e-4, atol=1e-5)
+        assert np.array_equal(K.n(tr.s_traj[:, 0]), oenv.reset_states(5, ep + 1, S, E, N))
+        agree.append((K.n(tr.a) == w["a"]).mean())
+        if ep == 0:
+            assert np.array_equal(K.n(tr.a), w["a"])
+            assert np.array_equal(K.n(st["EpActualRet"]), w["rew_sum"])
+    # after an update the two fp32 paths differ in the last bits of the weights, so a vanishing fraction of the
+    # draws may land on the other side of a cdf edge; anything systematic would show up as a large mismatch
+    assert min(agree) > 0.995, agree
+    np.testing.assert_allclose(K.n(tr.Wpi), cpu.opt.Wpi.detach().numpy(), atol=5e-3)
+    np.testing.assert_allclose(K.n(tr.Wv), cpu.opt.Wv.detach().numpy(), atol=5e-3)
+    lam_cpu = np.concatenate([p.detach().numpy().reshape(-1) for p in cpu.lam_params])
+    np.testing.assert_allclose(K.n(tr.lam_params), lam_cpu, rtol=1e-3, atol=1e-5)
