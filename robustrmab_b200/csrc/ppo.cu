@@ -23,9 +23,10 @@ struct PpoCfg {
   static constexpr int SPW = 32 / LPS;         // samples per warp pass
 };
 
-// TABLE = false: one row per sample (s_buf, a_buf, adv, logp_old, ret are [N,T,E] arrays).
-// TABLE = true : one row per (state, env) with the sufficient statistics written by rmab_epoch_table
-//                (stats [N,K,E], rows as StatRows; arm_stats [N,4]); see epoch.cu for the identity.
+// TABLE = false: one row per sample (s_buf, a_buf, adv, logp_old, ret are [N,T,E] arrays) -- the general path
+//                (any input encoding, any A <= 4; SIS / MA-RMABPPO).
+// TABLE = true : one row per (state, env) with the statistics of rmab_epoch_table; kept as the simple
+//                reference formulation of the table update -- the shipped table path is ppo_table.cu.
 template <int H, bool IS_PI, bool TABLE>
 __global__ void __launch_bounds__(256, (H >= 64 ? 1 : 2))
 ppo_update_kernel(RmabNetDesc d, RmabHyper hp, int T, int s_rows, float* __restrict__ Wg, float* __restrict__ adam,
@@ -453,35 +454,6 @@ extern "C" int rmab_ppo_update(const RmabNetDesc* net, const RmabHyper* hp, int 
     if (rc == RMAB_OK && hp->v_iters > 0)                                                                         \
       rc = launch_ppo<H, false, false>(*net, *hp, T, s_rows, Wv, adam_v, s, a, adv, logp_old, ret, lamb, nullptr,  \
                                        nullptr, loss_v, st);                                                      \
-  }
-  switch (net->hidden) {
-    case 8: RUN(8) break;
-    case 16: RUN(16) break;
-    case 32: RUN(32) break;
-    default: RUN(64) break;
-  }
-#undef RUN
-  return rc;
-}
-
-extern "C" int rmab_ppo_update_table(const RmabNetDesc* net, const RmabHyper* hp, int T, float* Wpi, float* Wv,
-                                     float* adam_pi, float* adam_v, const float* stats, const float* arm_stats,
-                                     const float* lamb, float* loss_pi, float* loss_v, rmab_stream_t stream) {
-  int rc = check_ppo_args(net, hp, T, "rmab_ppo_update_table");
-  if (rc) return rc;
-  RMAB_REQUIRE(net->one_hot, RMAB_E_SHAPE, "rmab_ppo_update_table: needs one-hot state inputs");
-  RMAB_REQUIRE(Wpi && Wv && adam_pi && adam_v && stats && lamb, RMAB_E_BADARG, "rmab_ppo_update_table: null pointer");
-  RMAB_REQUIRE(arm_stats || !loss_v, RMAB_E_BADARG, "rmab_ppo_update_table: loss_v needs arm_stats");
-  if (net->n_arms == 0) return RMAB_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-#define RUN(H)                                                                                                     \
-  {                                                                                                                \
-    if (hp->pi_iters > 0)                                                                                          \
-      rc = launch_ppo<H, true, true>(*net, *hp, T, T, Wpi, adam_pi, nullptr, nullptr, nullptr, nullptr, nullptr,   \
-                                     lamb, stats, arm_stats, loss_pi, st);                                         \
-    if (rc == RMAB_OK && hp->v_iters > 0)                                                                          \
-      rc = launch_ppo<H, false, true>(*net, *hp, T, T, Wv, adam_v, nullptr, nullptr, nullptr, nullptr, nullptr,    \
-                                      lamb, stats, arm_stats, loss_v, st);                                         \
   }
   switch (net->hidden) {
     case 8: RUN(8) break;
