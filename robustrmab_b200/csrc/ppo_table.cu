@@ -9,10 +9,9 @@
 //   P1  a1 = tanh(W1 x + b1)                      thread per row (x = onehot(s) ++ lambda, so W1 x is a lookup)
 //   P2  a2 = tanh(W2 a1 + b2)                     register-tiled GEMM, TJ features x 4 rows per thread
 //   P3  logits, loss, dL/dlogit, d2 = W3^T g (1-a2^2)   thread per row
-//   P5a dW2 += d2 a1^T                            register-tiled GEMM over the rows, 4x4 tile per thread
-//       db2 += sum d2 ; dW3 += g a2^T ; db3 += sum g      warp per feature, lanes over rows
-//   P4  d1 = (W2^T d2)(1-a1^2)                    register-tiled GEMM (overwrites a2)
-//   P5b db1, dW1 from d1                          warp per feature, lanes over rows
+//   P5  dW2 += d2 a1^T                            register-tiled GEMM over the rows, 4x4 tile per thread
+//   P4  d1 = (W2^T d2)(1-a1^2)                    register-tiled GEMM (overwrites a2); the bias / W1 / W3
+//                                                 gradients are row sums of tiles this phase already holds
 // then one fixed-order reduction of the partial sums, Adam, and the refresh of the derived weight tables.
 // FFMA-bound: 6 * P flops per row per iteration; every shared-memory wavefront feeds >= 8 FMA instructions.
 #include "common.cuh"
@@ -30,7 +29,7 @@ struct TblCfg {
   static constexpr int NT = (H / WT) * (H / WT);  // dW2 tiles
   static constexpr int NSL = 256 / NT;            // row slices per tile
   static constexpr int RPS = RC / NSL;            // rows per slice
-  static constexpr int FPW = H / 8 > 0 ? H / 8 : 1;  // features per warp in the row-sum phases
+  static constexpr int NB2 = H / NJB;             // db2 features accumulated per thread (j = jb + NJB * i)
 };
 
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -52,7 +51,7 @@ template <int H, int S, bool IS_PI>
 __global__ void __launch_bounds__(256, (H >= 64 ? 1 : 2)) ppo_table_kernel(TblArgs g) {
   using C = TblCfg<H>;
   constexpr int RC = C::RC, LDA = C::LDA, TJ = C::TJ, NJB = C::NJB, WT = C::WT, NT = C::NT, NSL = C::NSL, RPS = C::RPS,
-                FPW = C::FPW;
+                NB2 = C::NB2;
   constexpr int A = 2, OUT = IS_PI ? A : 1, IN = S + 1, SA = S * A;
   constexpr int ROW0 = IS_PI ? 0 : 3 * SA, NROWS = IS_PI ? 3 * SA + S : 2 * S, KST = 4 * SA + 3 * S;
   extern __shared__ __align__(16) float smem[];
@@ -72,7 +71,9 @@ __global__ void __launch_bounds__(256, (H >= 64 ? 1 : 2)) ppo_table_kernel(TblAr
   float* B2 = B1 + H * LDA;           // a2, later d1  [H][LDA]
   float* B3 = B2 + H * LDA;           // d2  [H][LDA]
   float* g3 = B3 + H * LDA;           // dL/dlogit [OUT][RC]
-  float* slam = g3 + OUT * RC;        // lambda per env [E]
+  float* rlam = g3 + OUT * RC;        // lambda of each row of the chunk [RC]
+  float* roh = rlam + RC;             // one-hot state of each row of the chunk [S][RC]
+  float* slam = roh + S * RC;         // lambda per env [E]
   float* sst = slam + ((E + 3) & ~3); // staged statistics rows [NROWS][E]
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(256, (H >= 64 ? 1 : 2)) ppo_table_kernel(TblAr
   const int tile = tid % NT, slice = tid / NT;       // P5a: dW2 tile and row slice
   const int tj = tile / (H / WT), tk = tile % (H / WT);
 
+  double b1p = pow(g.hp.beta1, (double)step0), b2p = pow(g.hp.beta2, (double)step0);
   for (int it = 0; it < iters; ++it) {
     // ---- derived weight tables for this iteration ----
     for (int i = tid; i < H * H; i += 256) w2t[(i % H) * H + (i / H)] = w[L.oW2 + i];
@@ -127,15 +129,18 @@ __global__ void __launch_bounds__(256, (H >= 64 ? 1 : 2)) ppo_table_kernel(TblAr
     for (int i = 0; i < WT; ++i)
 #pragma unroll
       for (int j = 0; j < WT; ++j) accW2[i][j] = 0.f;
-    float s_b2[FPW], s_w3[FPW][OUT], s_b1[FPW], s_w1[FPW][S], s_wl[FPW], s_b3[OUT];
+    // row-sum gradients accumulated by the P4 tile owner (features TJ*jb + j, rows of block rb)
+    float s_w3[OUT][TJ], s_b1[TJ], s_wl[TJ], s_w1[S][TJ], s_b2[NB2], s_b3[OUT];
 #pragma unroll
-    for (int f = 0; f < FPW; ++f) {
-      s_b2[f] = 0.f; s_b1[f] = 0.f; s_wl[f] = 0.f;
+    for (int j = 0; j < TJ; ++j) {
+      s_b1[j] = 0.f; s_wl[j] = 0.f;
 #pragma unroll
-      for (int a = 0; a < OUT; ++a) s_w3[f][a] = 0.f;
+      for (int a = 0; a < OUT; ++a) s_w3[a][j] = 0.f;
 #pragma unroll
-      for (int c = 0; c < S; ++c) s_w1[f][c] = 0.f;
+      for (int c = 0; c < S; ++c) s_w1[c][j] = 0.f;
     }
+#pragma unroll
+    for (int i = 0; i < NB2; ++i) s_b2[i] = 0.f;
 #pragma unroll
     for (int a = 0; a < OUT; ++a) s_b3[a] = 0.f;
     float loss_acc = 0.f;
@@ -148,6 +153,10 @@ __global__ void __launch_bounds__(256, (H >= 64 ? 1 : 2)) ppo_table_kernel(TblAr
         const int s = m / E, e = m - s * E;
         const float lam = slam[e];
         const float* wbs = wb + s * H;
+        const bool live = m0 + tid < M;
+        rlam[tid] = live ? lam : 0.f;
+#pragma unroll
+        for (int c = 0; c < S; ++c) roh[c * RC + tid] = (live && s == c) ? 1.f : 0.f;
 #pragma unroll
         for (int k4 = 0; k4 < H / 4; ++k4) {
           const float4 b = *reinterpret_cast<const float4*>(wbs + 4 * k4);
@@ -257,7 +266,7 @@ __global__ void __launch_bounds__(256, (H >= 64 ? 1 : 2)) ppo_table_kernel(TblAr
         }
       }
       __syncthreads();
-      // ---- P5a: dW2 tile += d2 a1^T over this thread's row slice ----
+      // ---- P5: dW2 tile += d2 a1^T over this thread's row slice ----
       {
         const int r0 = slice * RPS;
 #pragma unroll 2
@@ -278,26 +287,9 @@ __global__ void __launch_bounds__(256, (H >= 64 ? 1 : 2)) ppo_table_kernel(TblAr
               accW2[i][j] = fmaf(dv[i].w, xv[j].w, accW2[i][j]);
             }
         }
-        // row sums on d2 / a2 / g: warp `warp` owns features warp, warp+8, ... ; lanes stride the rows
-#pragma unroll
-        for (int f = 0; f < FPW; ++f) {
-          const int j = warp + 8 * f;
-          if (j < H) {
-            for (int r = lane; r < RC; r += 32) {
-              s_b2[f] += B3[j * LDA + r];
-              const float a2 = B2[j * LDA + r];
-#pragma unroll
-              for (int a = 0; a < OUT; ++a) s_w3[f][a] = fmaf(g3[a * RC + r], a2, s_w3[f][a]);
-            }
-          }
-        }
-        if (warp == 0)
-          for (int r = lane; r < RC; r += 32)
-#pragma unroll
-            for (int a = 0; a < OUT; ++a) s_b3[a] += g3[a * RC + r];
       }
       __syncthreads();
-      // ---- P4: d1 = (W2^T d2) (1 - a1^2), tile TJ x 4, written over a2 ----
+      // ---- P4: d1 = (W2^T d2) (1 - a1^2), tile TJ x 4, written over a2; row-sum gradients on the way ----
       {
         float acc[TJ][4];
 #pragma unroll
@@ -324,35 +316,43 @@ __global__ void __launch_bounds__(256, (H >= 64 ? 1 : 2)) ppo_table_kernel(TblAr
             acc[j][3] = fmaf(wv[j], x.w, acc[j][3]);
           }
         }
+        // db2[j] = sum_rows d2[j][row] for this thread's share of the features (j = jb + NJB * i)
+#pragma unroll
+        for (int i = 0; i < NB2; ++i) {
+          const float4 x = *reinterpret_cast<const float4*>(B3 + (jb + NJB * i) * LDA + 4 * rb);
+          s_b2[i] += (x.x + x.y) + (x.z + x.w);
+        }
+        float4 gv[OUT];
+#pragma unroll
+        for (int a = 0; a < OUT; ++a) {
+          gv[a] = *reinterpret_cast<const float4*>(g3 + a * RC + 4 * rb);
+          if (jb == 0) s_b3[a] += (gv[a].x + gv[a].y) + (gv[a].z + gv[a].w);
+        }
+        const float4 lm = *reinterpret_cast<const float4*>(rlam + 4 * rb);
+        float4 oh[S];
+#pragma unroll
+        for (int c = 0; c < S; ++c) oh[c] = *reinterpret_cast<const float4*>(roh + c * RC + 4 * rb);
 #pragma unroll
         for (int j = 0; j < TJ; ++j) {
+          float* cell = B2 + (TJ * jb + j) * LDA + 4 * rb;
+          const float4 a2 = *reinterpret_cast<const float4*>(cell);   // dW3[a][j] += g_a * a2 before a2 is overwritten
+#pragma unroll
+          for (int a = 0; a < OUT; ++a)
+            s_w3[a][j] += fmaf(gv[a].x, a2.x, gv[a].y * a2.y) + fmaf(gv[a].z, a2.z, gv[a].w * a2.w);
           const float4 a1 = *reinterpret_cast<const float4*>(B1 + (TJ * jb + j) * LDA + 4 * rb);
           float4 o;
           o.x = acc[j][0] * (1.f - a1.x * a1.x);
           o.y = acc[j][1] * (1.f - a1.y * a1.y);
           o.z = acc[j][2] * (1.f - a1.z * a1.z);
           o.w = acc[j][3] * (1.f - a1.w * a1.w);
-          *reinterpret_cast<float4*>(B2 + (TJ * jb + j) * LDA + 4 * rb) = o;
+          s_b1[j] += (o.x + o.y) + (o.z + o.w);
+          s_wl[j] += fmaf(o.x, lm.x, o.y * lm.y) + fmaf(o.z, lm.z, o.w * lm.w);
+#pragma unroll
+          for (int c = 0; c < S; ++c)
+            s_w1[c][j] += fmaf(o.x, oh[c].x, o.y * oh[c].y) + fmaf(o.z, oh[c].z, o.w * oh[c].w);
         }
       }
-      __syncthreads();
-      // ---- P5b: db1, dW1 from d1 (warp per feature, lanes over rows) ----
-#pragma unroll
-      for (int f = 0; f < FPW; ++f) {
-        const int k = warp + 8 * f;
-        if (k < H) {
-          for (int r = lane; r < RC; r += 32) {
-            const int m = m0 + r < M ? m0 + r : M - 1;
-            const int s = m / E, e = m - s * E;
-            const float dd = B2[k * LDA + r];   // zero for the padded rows (their g is zero)
-            s_b1[f] += dd;
-            s_wl[f] = fmaf(dd, slam[e], s_wl[f]);
-#pragma unroll
-            for (int c = 0; c < S; ++c) s_w1[f][c] += (s == c) ? dd : 0.f;
-          }
-        }
-      }
-      __syncthreads();  // the next chunk's P1 overwrites B1
+      __syncthreads();  // the next chunk's P1 overwrites B1 / the row metadata
     }
 
     // ---- reduce the partial sums in a fixed order into G ----
@@ -362,30 +362,32 @@ __global__ void __launch_bounds__(256, (H >= 64 ? 1 : 2)) ppo_table_kernel(TblAr
     for (int i = 0; i < WT; ++i)
 #pragma unroll
       for (int j = 0; j < WT; ++j) park[slice * (H * H) + (WT * tj + i) * H + WT * tk + j] = accW2[i][j];
+    // row sums: threads with the same jb (lanes congruent mod NJB) hold partials of the same features; butterfly over
+    // the row-block bits of the lane, then the 8 warps through shared memory in warp order
+    constexpr int NV = TJ * (OUT + 2 + S) + NB2 + OUT;
+    float* rs = park + NSL * H * H;  // [8 warps][NJB][NV]
+    {
+      float vals[NV];
+      int q = 0;
 #pragma unroll
-    for (int f = 0; f < FPW; ++f) {
-      const int k = warp + 8 * f;
-      float v0 = warp_sum(s_b2[f]), v1 = warp_sum(s_b1[f]), v2 = warp_sum(s_wl[f]);
-      float v3[OUT], v4[S];
+      for (int j = 0; j < TJ; ++j) {
+        vals[q++] = s_b1[j];
+        vals[q++] = s_wl[j];
 #pragma unroll
-      for (int a = 0; a < OUT; ++a) v3[a] = warp_sum(s_w3[f][a]);
+        for (int c = 0; c < S; ++c) vals[q++] = s_w1[c][j];
 #pragma unroll
-      for (int c = 0; c < S; ++c) v4[c] = warp_sum(s_w1[f][c]);
-      if (lane == 0 && k < H) {
-        G[L.ob2 + k] = v0;
-        G[L.ob1 + k] = v1;
-        G[L.oW1 + k * IN + IN - 1] = v2;
-#pragma unroll
-        for (int a = 0; a < OUT; ++a) G[L.oW3 + a * H + k] = v3[a];
-#pragma unroll
-        for (int c = 0; c < S; ++c) G[L.oW1 + k * IN + c] = v4[c];
+        for (int a = 0; a < OUT; ++a) vals[q++] = s_w3[a][j];
       }
-    }
-    if (warp == 0) {
 #pragma unroll
-      for (int a = 0; a < OUT; ++a) {
-        const float v = warp_sum(s_b3[a]);
-        if (lane == 0) G[L.ob3 + a] = v;
+      for (int i = 0; i < NB2; ++i) vals[q++] = s_b2[i];
+#pragma unroll
+      for (int a = 0; a < OUT; ++a) vals[q++] = s_b3[a];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        float x = vals[v];
+#pragma unroll
+        for (int o = 16; o >= NJB; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane < NJB) rs[(warp * NJB + lane) * NV + v] = x;
       }
     }
     const float loss_tot = block_sum(loss_acc, red);  // contains __syncthreads
@@ -396,6 +398,24 @@ __global__ void __launch_bounds__(256, (H >= 64 ? 1 : 2)) ppo_table_kernel(TblAr
       for (int sl = 1; sl < NSL; ++sl) v += park[sl * (H * H) + i];
       G[L.oW2 + i] = v;
     }
+    for (int i = tid; i < NJB * NV; i += 256) {
+      const int b = i / NV, v = i - b * NV;
+      float x = rs[i];
+#pragma unroll
+      for (int wq = 1; wq < 8; ++wq) x += rs[wq * NJB * NV + i];
+      // decode slot v of feature block b (same order as vals[] above)
+      if (v < TJ * (OUT + 2 + S)) {
+        const int j = v / (OUT + 2 + S), r = v - j * (OUT + 2 + S), k = TJ * b + j;
+        if (r == 0) G[L.ob1 + k] = x;
+        else if (r == 1) G[L.oW1 + k * IN + IN - 1] = x;
+        else if (r < 2 + S) G[L.oW1 + k * IN + (r - 2)] = x;
+        else G[L.oW3 + (r - 2 - S) * H + k] = x;
+      } else if (v < TJ * (OUT + 2 + S) + NB2) {
+        G[L.ob2 + b + NJB * (v - TJ * (OUT + 2 + S))] = x;
+      } else if (b == 0) {
+        G[L.ob3 + (v - TJ * (OUT + 2 + S) - NB2)] = x;
+      }
+    }
     if (g.loss_out && tid == 0) {
       float extra = 0.f;
       if (!IS_PI && g.arm_stats) extra = g.arm_stats[4 * (int64_t)n + 2];  // sum (ret - mean_ret[s,e])^2
@@ -404,9 +424,9 @@ __global__ void __launch_bounds__(256, (H >= 64 ? 1 : 2)) ppo_table_kernel(TblAr
     __syncthreads();
 
     // ---- Adam (torch.optim.Adam defaults; _single_tensor_adam form) ----
-    const int step = step0 + it + 1;
-    const double bc1 = 1.0 - pow(g.hp.beta1, (double)step);
-    const double bc2 = 1.0 - pow(g.hp.beta2, (double)step);
+    b1p *= g.hp.beta1;  // beta^step, step = step0 + it + 1
+    b2p *= g.hp.beta2;
+    const double bc1 = 1.0 - b1p, bc2 = 1.0 - b2p;
     const float step_size = (float)(lr / bc1);
     const float bc2s = (float)sqrt(bc2);
     for (int i = tid; i < P; i += 256) {
@@ -435,7 +455,7 @@ static int launch_table(const TblArgs& args, cudaStream_t st) {
   constexpr int OUT = IS_PI ? 2 : 1, SA = S * 2;
   const MlpLayout L(S + 1, H, OUT);
   const int E = g.d.n_envs;
-  size_t fl = 4 * (size_t)L.padded() + H * H + S * H + H + 3 * (size_t)H * C::LDA + OUT * C::RC + (((size_t)E + 3) & ~(size_t)3);
+  size_t fl = 4 * (size_t)L.padded() + H * H + S * H + H + 3 * (size_t)H * C::LDA + (OUT + 1 + S) * C::RC + (((size_t)E + 3) & ~(size_t)3);
   const size_t rows = IS_PI ? 3 * SA + S : 2 * S;
   g.stage_stats = 0;
   if ((fl + rows * E) * sizeof(float) <= 100 * 1024 || (H >= 64 && (fl + rows * E) * sizeof(float) <= 220 * 1024)) {
