@@ -35,8 +35,10 @@ struct TblCfg {
 
 __device__ __forceinline__ float tanh_fast(float x) {
   // 1 - 2 / (exp(2x) + 1) with two MUFU ops; absolute error < 2e-7 (what propagates through the next layer)
-  const float e = __expf(2.f * x);
-  return 1.f - __fdividef(2.f, e + 1.f);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+  return fmaf(-2.f, r, 1.f);
 }
 
 struct TblArgs {

@@ -23,15 +23,20 @@ namespace {
 
 constexpr int kLDT = 40;  // tile row length: 32 rows + pad; 40 = 8 (mod 32) makes the B-fragment loads conflict-free
 
+// tanh(x) = 1 - 2 / (2^(2 log2(e) x) + 1): FMUL, MUFU.EX2, FADD, MUFU.RCP, FFMA.  Absolute error < 2e-7 (what
+// propagates through the next layer); saturates correctly (ex2 -> inf gives 1, ex2 -> 0 gives -1).
 __device__ __forceinline__ float tanh_fast_m(float x) {
-  const float e = __expf(2.f * x);
-  return 1.f - __fdividef(2.f, e + 1.f);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+  return fmaf(-2.f, r, 1.f);
 }
 
+// x = hi + lo with hi = the top 19 bits of x (a valid TF32 operand) and lo = x - hi exactly; the tensor core reads
+// only the TF32 bits of lo, which leaves a relative error of ~2^-21 -- the same order as the dropped lo*lo term.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -236,12 +241,19 @@ __global__ void __launch_bounds__(256, (H >= 32 ? 1 : 2)) ppo_table_mma_kernel(M
         for (int a = 0; a < OUT; ++a) { logit[a] = w[L.ob3 + a]; gl[a] = 0.f; }
         float a2v[H];
 #pragma unroll
-        for (int j = 0; j < H; ++j) {
-          a2v[j] = A2w[j * LDT + lane];
+        for (int j = 0; j < H; ++j) a2v[j] = A2w[j * LDT + lane];
 #pragma unroll
-          for (int a = 0; a < OUT; ++a) logit[a] = fmaf(w[L.oW3 + a * H + j], a2v[j], logit[a]);
-        }
-        const float wrow = st[(int64_t)(3 * SA - ROW0 + srow) * E + erow];  // CntS
+        for (int a = 0; a < OUT; ++a)
+#pragma unroll
+          for (int j4 = 0; j4 < H / 4; ++j4) {
+            const float4 w3 = *reinterpret_cast<const float4*>(w + L.oW3 + a * H + 4 * j4);
+            logit[a] = fmaf(w3.x, a2v[4 * j4], logit[a]);
+            logit[a] = fmaf(w3.y, a2v[4 * j4 + 1], logit[a]);
+            logit[a] = fmaf(w3.z, a2v[4 * j4 + 2], logit[a]);
+            logit[a] = fmaf(w3.w, a2v[4 * j4 + 3], logit[a]);
+          }
+        const float* sp = st + erow;
+        const float wrow = sp[(3 * SA - ROW0 + srow) * E];  // CntS
         if (IS_PI) {
           const float mx = fmaxf(logit[0], logit[OUT - 1]);
           const float e0 = __expf(logit[0] - mx), e1 = __expf(logit[OUT - 1] - mx);
@@ -253,8 +265,8 @@ __global__ void __launch_bounds__(256, (H >= 32 ? 1 : 2)) ppo_table_mma_kernel(M
 #pragma unroll
           for (int a = 0; a < 2; ++a) {
             const int c = srow * A + a;
-            const float Ap = st[(int64_t)c * E + erow], Am = st[(int64_t)(SA + c) * E + erow];
-            const float ratio = __expf(lp[a] - st[(int64_t)(2 * SA + c) * E + erow]);
+            const float Ap = sp[c * E], Am = sp[(SA + c) * E];
+            const float ratio = __expf(lp[a] - sp[(2 * SA + c) * E]);
             lrow -= fminf(ratio, clip_hi) * Ap + fmaxf(ratio, clip_lo) * Am;
             ga[a] = -((ratio <= clip_hi ? ratio * Ap : 0.f) + (ratio >= clip_lo ? ratio * Am : 0.f));
             sumg += ga[a];
@@ -266,7 +278,7 @@ __global__ void __launch_bounds__(256, (H >= 32 ? 1 : 2)) ppo_table_mma_kernel(M
               gl[a < OUT ? a : 0] = invM * (ga[a] - p[a] * sumg + beta_ent * wrow * p[a] * (lp[a] + ent));
           }
         } else {
-          const float diff = logit[0] - st[(int64_t)(3 * SA + S - ROW0 + srow) * E + erow];
+          const float diff = logit[0] - sp[(3 * SA + S - ROW0 + srow) * E];
           if (valid) {
             loss_acc = fmaf(wrow * diff, diff, loss_acc);
             gl[0] = invM * 2.f * wrow * diff;
@@ -278,11 +290,21 @@ __global__ void __launch_bounds__(256, (H >= 32 ? 1 : 2)) ppo_table_mma_kernel(M
           s_b3[a] += gl[a];
         }
 #pragma unroll
-        for (int j = 0; j < H; ++j) {
-          float up = 0.f;
+        for (int j4 = 0; j4 < H / 4; ++j4) {
+          float up[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int a = 0; a < OUT; ++a) up = fmaf(gl[a], w[L.oW3 + a * H + j], up);
-          D2w[j * LDT + lane] = up * (1.f - a2v[j] * a2v[j]);
+          for (int a = 0; a < OUT; ++a) {
+            const float4 w3 = *reinterpret_cast<const float4*>(w + L.oW3 + a * H + 4 * j4);
+            up[0] = fmaf(gl[a], w3.x, up[0]);
+            up[1] = fmaf(gl[a], w3.y, up[1]);
+            up[2] = fmaf(gl[a], w3.z, up[2]);
+            up[3] = fmaf(gl[a], w3.w, up[3]);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float a2 = a2v[4 * j4 + q];
+            D2w[(4 * j4 + q) * LDT + lane] = up[q] * fmaf(-a2, a2, 1.f);
+          }
         }
       }
       __syncwarp();
@@ -311,24 +333,45 @@ __global__ void __launch_bounds__(256, (H >= 32 ? 1 : 2)) ppo_table_mma_kernel(M
             for (int nt = 0; nt < 4; ++nt) mma3(c[mt][nt], ahi, alo, bh[nt][0], bh[nt][1], bl[nt][0], bl[nt][1]);
           }
         }
+        // rows of a block share one state whenever E is a multiple of 32 (warp-uniform test): then dW1[:, s] gets
+        // the same row sum as db1 and the one-hot products are skipped
+        const int s_first = (blk * 32) / E, s_last = (min(blk * 32 + 31, M - 1)) / E;
+        const bool uniform = s_first == s_last;
+        float t_b1[MT][2];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) { t_b1[mt][0] = 0.f; t_b1[mt][1] = 0.f; }
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const float2 lm = *reinterpret_cast<const float2*>(rlw + 8 * nt + 2 * tq);
           float2 oh[S];
+          if (!uniform) {
 #pragma unroll
-          for (int cc = 0; cc < S; ++cc) oh[cc] = *reinterpret_cast<const float2*>(row + cc * 32 + 8 * nt + 2 * tq);
+            for (int cc = 0; cc < S; ++cc) oh[cc] = *reinterpret_cast<const float2*>(row + cc * 32 + 8 * nt + 2 * tq);
+          }
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               const float2 a1 = *reinterpret_cast<const float2*>(A1w + (16 * mt + gq + 8 * hh) * LDT + 8 * nt + 2 * tq);
-              const float dx = c[mt][nt][2 * hh] * (1.f - a1.x * a1.x), dy = c[mt][nt][2 * hh + 1] * (1.f - a1.y * a1.y);
-              s_b1[mt][hh] += dx + dy;
+              const float dx = c[mt][nt][2 * hh] * fmaf(-a1.x, a1.x, 1.f), dy = c[mt][nt][2 * hh + 1] * fmaf(-a1.y, a1.y, 1.f);
+              t_b1[mt][hh] += dx + dy;
               s_wl[mt][hh] += fmaf(dx, lm.x, dy * lm.y);
+              if (!uniform) {
 #pragma unroll
-              for (int cc = 0; cc < S; ++cc) s_w1[cc][mt][hh] += fmaf(dx, oh[cc].x, dy * oh[cc].y);
+                for (int cc = 0; cc < S; ++cc) s_w1[cc][mt][hh] += fmaf(dx, oh[cc].x, dy * oh[cc].y);
+              }
             }
         }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            s_b1[mt][hh] += t_b1[mt][hh];
+            if (uniform) {
+#pragma unroll
+              for (int cc = 0; cc < S; ++cc) s_w1[cc][mt][hh] += (s_first == cc) ? t_b1[mt][hh] : 0.f;
+            }
+          }
       }
       // ---- W: dW2 += d2 a1^T over the block's 32 rows (4 k-steps); db2 and dW3 ride along ----
 #pragma unroll
