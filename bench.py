@@ -41,8 +41,8 @@ def parse():
     ap.add_argument("--pi-iters", type=int, default=20)
     ap.add_argument("--v-iters", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-arms", type=int, default=48)
-    ap.add_argument("--cpu-envs", type=int, default=4)
+    ap.add_argument("--cpu-arms", type=int, default=192)
+    ap.add_argument("--cpu-envs", type=int, default=16)
     return ap.parse_args()
 
 
@@ -146,7 +146,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -202,12 +202,16 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(a.warmup, 3)):
-        tr.epoch()
-    barrier()
     clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()
+        clocks.start()          # samples cover the warm-up and the timed region (both under load)
+    for _ in range(max(a.warmup, 3)):
+        tr.epoch()
+    if world > 1:                      # NCCL picks its algorithm / channels lazily: settle it before the timed region
+        t_w = torch.zeros(2 * E + 1, device=dev)
+        for _ in range(20):
+            dist.all_reduce(t_w)
+    barrier()
     tr.timers = {}
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

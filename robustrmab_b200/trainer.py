@@ -93,12 +93,11 @@ class RMABPPOTrainer:
         f32, u8 = torch.float32, torch.uint8
         self.net = ops.net_desc(N, E, S, A, h, True, 1.0)
         self.Ppi, self.Pv = ops.n_params(S + 1, h, A), ops.n_params(S + 1, h, 1)
-        # every rank draws the full-size init stream and keeps its slice, so sharding does not change the nets
+        # nets are drawn in blocks of 1024 arms from generators keyed by (seed, block), so a rank only draws the
+        # blocks it owns and any sharding gives every arm the same initial weights
+        self.Wpi = self._init_arm_nets(S + 1, h, A, 1).to(dev)
+        self.Wv = self._init_arm_nets(S + 1, h, 1, 2).to(dev)
         g = torch.Generator(device="cpu").manual_seed(self.seed)
-        Wpi = linear_default_init_(torch.empty((self.N_total, self.Ppi)), S + 1, h, A, g)
-        Wv = linear_default_init_(torch.empty((self.N_total, self.Pv)), S + 1, h, 1, g)
-        self.Wpi = Wpi[self.arm0:self.arm0 + N].contiguous().to(dev)
-        self.Wv = Wv[self.arm0:self.arm0 + N].contiguous().to(dev)
         self.lam_params = self._init_lambda_net(g).to(dev)
         self.adam_pi = torch.zeros((N, 2, self.Ppi), dtype=f32, device=dev)
         self.adam_v = torch.zeros((N, 2, self.Pv), dtype=f32, device=dev)
@@ -120,7 +119,9 @@ class RMABPPOTrainer:
         self.last_val = torch.empty((N, E), dtype=f32, device=dev)
         self.stats = torch.empty((N, ops.stat_rows(self.domain), E), dtype=f32, device=dev)
         self.arm_stats = torch.empty((N, 4), dtype=f32, device=dev)
-        self.env_sums = torch.empty((2, E), dtype=f32, device=dev)
+        # one reduction buffer per epoch: per-env reward sum [E], per-env discounted cost-to-go [E], VVals sum [1]
+        self.red_buf = torch.zeros((2 * E + 1,), dtype=f32, device=dev)
+        self.env_sums = self.red_buf[:2 * E].view(2, E)
         self.ws = torch.empty((max(int(_lib.lib().rmab_epoch_ws_bytes(N, E)), 8) + 7) // 8, dtype=torch.float64,
                               device=dev)
         self.adv = self.ret = None
@@ -157,6 +158,17 @@ class RMABPPOTrainer:
         draw = np.sort(rs.rand(*base.shape), axis=-1)
         lo = base.min(-1)[..., None]
         return draw * (base.max(-1)[..., None] - lo) + lo
+
+    def _init_arm_nets(self, in_dim, h, out, salt, block=1024):
+        P = ops.n_params(in_dim, h, out)
+        W = torch.empty((self.N, P))
+        b0, b1 = self.arm0 // block, (self.arm0 + self.N + block - 1) // block
+        for b in range(b0, b1):
+            g = torch.Generator(device="cpu").manual_seed((self.seed * 1000003 + salt) * 1000003 + b)
+            blk = linear_default_init_(torch.empty((block, P)), in_dim, h, out, g)
+            lo, hi = max(b * block, self.arm0), min((b + 1) * block, self.arm0 + self.N)
+            W[lo - self.arm0:hi - self.arm0] = blk[lo - b * block:hi - b * block]
+        return W.contiguous()
 
     def _init_lambda_net(self, g):
         """MLPLambdaNet N -> 8 -> 8 -> 1 (rmabppo_core.py:108-115, :170-171), packed W1 b1 W2 b2 W3 b3."""
@@ -267,16 +279,19 @@ class RMABPPOTrainer:
         self.steps_pi += self.pi_iters
         self.steps_v += self.v_iters
         with self._stage("lambda_sgd_stats"):
-            sums = self._allreduce(self.env_sums) if (want_stats or self.lambda_update_due(ep)) else self.env_sums
-            if self.lambda_update_due(ep):
-                coef = self.B / (1.0 - self.gamma) - sums[1]            # compute_loss_lambda (:360-376)
+            due = self.lambda_update_due(ep)
+            if want_stats:
+                SA = S * A
+                self.red_buf[2 * E] = (self.stats[:, 3 * SA:3 * SA + S] * self.stats[:, 3 * SA + 2 * S:3 * SA + 3 * S]).sum()
+            if want_stats or due:
+                self._allreduce(self.red_buf)                           # the epoch's only cross-rank exchange besides h1
+            if due:
+                coef = self.B / (1.0 - self.gamma) - self.env_sums[1]   # compute_loss_lambda (:360-376)
                 ops.lambda_sgd(self.lam_params, s0, self.N_total, self.arm0, 1.0, h1, coef, self.lm_lr)
             stats = None
             if want_stats:
-                SA = S * A
-                vv = (self.stats[:, 3 * SA:3 * SA + S] * self.stats[:, 3 * SA + 2 * S:3 * SA + 3 * S]).sum()
-                vv = self._allreduce(vv.reshape(1)) / float(self.N_total * T * E)
-                stats = {"EpActualRet": sums[0].clone(), "Lamb": lamb, "VVals": vv}
+                stats = {"EpActualRet": self.env_sums[0].clone(), "Lamb": lamb,
+                         "VVals": self.red_buf[2 * E:] / float(self.N_total * T * E)}
         # env.reset() at the end of the epoch (:568)
         self.epoch_idx += 1
         self.t_global += T

@@ -1,0 +1,74 @@
+"""world_size-2 gloo tests (CPU) of the collective drop-ins (robust_rmab/utils/mpi_tools.py, mpi_pytorch.py
+semantics) and of the arm sharding host logic."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from robustrmab_b200 import mpi_tools as mt
+    res = {}
+    res["ids"] = (mt.proc_id(), mt.num_procs())
+    res["avg"] = float(mt.mpi_avg(float(rank + 1)))
+    x = np.arange(5, dtype=np.float64) + 10 * rank
+    res["stats"] = [float(v) for v in mt.mpi_statistics_scalar(x, with_min_and_max=True)]
+    torch.manual_seed(rank)                       # ranks start with different parameters and gradients
+    m = torch.nn.Sequential(torch.nn.Linear(3, 4), torch.nn.Tanh(), torch.nn.Linear(4, 1))
+    mt.sync_params(m)
+    res["params"] = torch.cat([p.data.reshape(-1) for p in m.parameters()]).numpy().copy()
+    (m(torch.full((2, 3), float(rank + 1))).sum()).backward()
+    res["grad_local"] = torch.cat([p.grad.reshape(-1) for p in m.parameters()]).numpy().copy()
+    mt.mpi_avg_grads(m)
+    res["grad_avg"] = torch.cat([p.grad.reshape(-1) for p in m.parameters()]).numpy().copy()
+    res["shard"] = mt.arm_shard(10)
+    # arm-sharded lambda-net first layer: partial sums over each rank's arms add up to the full product
+    N, E = 10, 3
+    rs = np.random.RandomState(0)
+    W1, s = rs.randn(8, N).astype(np.float32), rs.randint(0, 3, (N, E)).astype(np.float32)
+    a0, n = res["shard"]
+    part = torch.as_tensor(W1[:, a0:a0 + n] @ s[a0:a0 + n])
+    mt.allreduce_(part)
+    res["h1"] = part.numpy().copy()
+    res["h1_full"] = W1 @ s
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+def test_collectives_world2():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    r0, r1 = out[0], out[1]
+    assert r0["ids"] == (0, 2) and r1["ids"] == (1, 2)
+    assert r0["avg"] == r1["avg"] == 1.5
+    allx = np.concatenate([np.arange(5) + 0.0, np.arange(5) + 10.0]).astype(np.float32)
+    np.testing.assert_allclose(r0["stats"], [allx.mean(), allx.std(), 0.0, 14.0], rtol=1e-6)
+    assert r0["stats"] == r1["stats"]
+    assert np.array_equal(r0["params"], r1["params"])                       # sync_params: rank 0's values everywhere
+    np.testing.assert_allclose(r0["grad_avg"], 0.5 * (r0["grad_local"] + r1["grad_local"]), rtol=1e-6)
+    assert np.array_equal(r0["grad_avg"], r1["grad_avg"])
+    assert r0["shard"] == (0, 5) and r1["shard"] == (5, 5)
+    np.testing.assert_allclose(r0["h1"], r0["h1_full"], rtol=1e-5, atol=1e-5)
+
+
+def test_single_process_defaults():
+    from robustrmab_b200 import mpi_tools as mt
+    assert mt.proc_id() == 0 and mt.num_procs() == 1
+    assert mt.mpi_avg(3.0) == 3.0
+    mean, std = mt.mpi_statistics_scalar(np.array([1.0, 2.0, 3.0]))
+    assert abs(mean - 2.0) < 1e-6 and abs(std - np.std([1, 2, 3])) < 1e-6
+    assert [mt.arm_shard(10, r, 3) for r in range(3)] == [(0, 4), (4, 4), (8, 2)]
+    assert mt.arm_shard(2, 3, 4) == (2, 0)

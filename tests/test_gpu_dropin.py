@@ -1,0 +1,195 @@
+"""Drop-in classes (environments, actor-critic, buffer) against the golden fixtures generated from the reference's
+own classes and against the CPU oracle.  GPU only."""
+import io
+
+import numpy as np
+import pytest
+
+from oracle import buffer as obuf
+from oracle import envs as oenv
+from oracle import nets as onets
+from oracle import philox
+from oracle import select as osel
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def test_counterexample_env_matches_oracle(torch_mod):
+    from robustrmab_b200.environments import CounterExampleRobustEnv
+    N = 12
+    env = CounterExampleRobustEnv(N, 4.0, 7)
+    env.sampled_parameter_ranges = env.sample_parameter_ranges()
+    assert env.S == 2 and env.A == 2 and env.action_dim_nature == N and env.T.shape == (N, 2, 2, 2)
+    np.testing.assert_allclose(env.PARAMETER_RANGES, oenv.ce_param_ranges(N))
+    o = env.reset()
+    assert o.shape == (N, 1) and np.array_equal(o[:, 0], oenv.reset_states(7, 0, 2, 1, N)[:, 0])
+    rs = np.random.RandomState(0)
+    R = oenv.rewards_table(0, N, 2)
+    with pytest.warns(RuntimeWarning):
+        env.step(np.zeros(N), np.full(N, 1.5))                       # out of range: warn and clamp (:867-874)
+    assert np.allclose(env.T[:, 1, 1, 1], env.sampled_parameter_ranges[:, 1])
+    s = env.current_full_state.copy()
+    for t in range(1, 6):
+        a = rs.randint(0, 2, N)
+        p = rs.uniform(0.2, 0.8, N).astype(F32)
+        u = philox.uniform_grid(7, philox.STREAM_ENV, t, 1, N)
+        ws, wr = oenv.ce_step(s[:, None], a[:, None], p, env.sampled_parameter_ranges.astype(F32), R, u)
+        so, r, d, info = env.step(a, p.astype(np.float64))
+        assert so.shape == (N, 1) and r.shape == (N,) and d is False and info is None
+        assert np.array_equal(so[:, 0], ws[:, 0]) and np.array_equal(r.astype(F32), wr[:, 0])
+        s = so[:, 0]
+    env.current_full_state = np.ones(N)                              # externally settable (nature_oracle.py:657)
+    assert np.array_equal(env.current_full_state, np.ones(N))
+    with pytest.raises(ValueError):
+        env.get_T_for_a_nature(np.full(N, 2.0))
+    with pytest.raises(AssertionError):
+        CounterExampleRobustEnv(10, 2.0, 0)                          # assert N % 3 == 0 (:755)
+
+
+def test_env_bound_and_golden(torch_mod, golden):
+    from robustrmab_b200.environments import ARMMANRobustEnv, CounterExampleRobustEnv, SISRobustEnv
+    g = golden("env")
+    N = g["ce_ranges"].shape[0]
+    env = CounterExampleRobustEnv(N, 2.0, 0)
+    env.sampled_parameter_ranges = g["ce_ranges"]
+    np.testing.assert_allclose(env.bound_nature_actions(g["ce_bound_raw"], state=g["ce_s0"], reshape=True),
+                               g["ce_bound_out"], rtol=1e-6, atol=1e-7)
+    N = g["armman_ranges"].shape[0]
+    env = ARMMANRobustEnv(N, 2.0, 0)
+    np.testing.assert_allclose(env.PARAMETER_RANGES, g["armman_PARAMETER_RANGES"])
+    env.sampled_parameter_ranges = g["armman_ranges"]
+    np.testing.assert_allclose(env.bound_nature_actions(g["armman_bound_raw"], state=g["armman_bound_state"]),
+                               g["armman_bound_out"], rtol=1e-6, atol=1e-7)
+    # same host RandomState stream as the reference: the sampled sub-ranges are the reference's for the same seed
+    ref = ARMMANRobustEnv(N, 2.0, 0)
+    sub = ref.sample_parameter_ranges()
+    assert (sub[..., 0] >= ref.PARAMETER_RANGES[..., 0]).all() and (sub[..., 1] <= ref.PARAMETER_RANGES[..., 1]).all()
+    N, pop = g["sis_ranges"].shape[0], int(g["sis_pop"])
+    env = SISRobustEnv(N, 2.0, pop, 0)
+    env.sampled_parameter_ranges = g["sis_ranges"]
+    np.testing.assert_allclose(env.bound_nature_actions(g["sis_bound_raw"], state=g["sis_s0"]), g["sis_bound_out"],
+                               rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(env.get_T_for_a_nature(g["sis_nature"][-1]), g["sis_T"], rtol=1e-6, atol=1e-9)
+    with pytest.raises(ValueError):
+        env.step(np.zeros(N), np.full((N, 4), 100.0))                # SIS raises on out-of-range params (:1205-1215)
+    env.reset()
+    so, r, _, _ = env.step(np.ones(N, int), g["sis_nature"][0])
+    assert so.shape == (N, 1) and r.shape == (N,) and (so <= pop).all()
+
+
+def test_armman_env_batched(torch_mod):
+    from robustrmab_b200.environments import ARMMANRobustEnv
+    N, E = 10, 16
+    env = ARMMANRobustEnv(N, 2.0, 3, n_envs=E)
+    env.sampled_parameter_ranges = env.sample_parameter_ranges()
+    s0 = env.reset()
+    assert s0.shape == (N, E)
+    rs = np.random.RandomState(1)
+    a = rs.randint(0, 2, (N, E))
+    rg = env.sampled_parameter_ranges
+    nat = (rg[..., 0] + rs.rand(N, 3, 2) * (rg[..., 1] - rg[..., 0])).astype(F32)
+    nat_now = nat[np.arange(N)[:, None], s0]                        # [N,E,A]: the table looked up at the state
+    so, r, _, _ = env.step(a, np.moveaxis(nat_now, 2, 1))
+    u = philox.uniform_grid(3, philox.STREAM_ENV, 0, E, N)
+    ws, wr = oenv.armman_step(s0, a, nat, rg.astype(F32), oenv.rewards_table(1, N, 3), u)
+    assert np.array_equal(so, ws) and np.array_equal(r.astype(F32), wr)
+
+
+@pytest.mark.parametrize("name", ["oh3", "sis"])
+def test_actor_critic_dropin(torch_mod, golden, name):
+    torch = torch_mod
+    from robustrmab_b200.core import MLPActorCriticRMAB
+    g = golden("ac")
+    N, S, A, h, one_hot, norm = [int(x) for x in g[name + "_meta"]]
+    C = np.arange(A)
+    ac = MLPActorCriticRMAB(np.arange(S), np.arange(A), hidden_sizes=[h, h], C=C, N=N, B=2.0, one_hot_encode=bool(one_hot),
+                            non_ohe_obs_dim=1, state_norm=norm if not one_hot else None)
+    assert repr(ac) == "RMABPPO_0" and ac.act_dim == A and ac.act_type == 'd'
+    ac.Wpi.copy_(torch.as_tensor(g[name + "_Wpi"]))
+    ac.Wv.copy_(torch.as_tensor(g[name + "_Wv"]))
+    lin = [m for m in ac.lambda_net.lambda_net if isinstance(m, torch.nn.Linear)]
+    with torch.no_grad():
+        for i, m in enumerate(lin):
+            m.weight.copy_(torch.as_tensor(g[f"{name}_lam{2 * i}"]))
+            m.bias.copy_(torch.as_tensor(g[f"{name}_lam{2 * i + 1}"]))
+    ac.seed(21)
+    K = g[name + "_obs"].shape[0]
+    for k in range(K):
+        a, v, logp, q, p1 = ac.step(torch.as_tensor(g[name + "_obs"][k], dtype=torch.float32),
+                                    torch.as_tensor(g[name + "_lamb"][k]))
+        assert a.shape == (N,) and a.dtype.kind == "i" and q.shape == (N,) and not q.any()
+        # golden uniforms were generated with the same Philox keying (seed 21, stream ACT, t = call index)
+        assert np.array_equal(a, g[name + "_a"][k])
+        np.testing.assert_allclose(v, g[name + "_v"][k], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(logp, g[name + "_logp"][k], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(p1, g[name + "_p1"][k], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(ac.get_lambda(g[name + "_obs"][k].astype(np.float64)), g[name + "_lam_out"][k],
+                                   rtol=2e-5, atol=2e-6)
+    # per-arm views share storage with the packed rows and evaluate like the reference modules
+    x = torch.zeros(ac.in_dim)
+    x[0], x[-1] = 1.0, 0.3
+    pi, _ = ac.pi_list[1](x)
+    s0 = torch.zeros((N, 1), dtype=torch.uint8, device=ac.Wpi.device) if one_hot else None
+    if one_hot:
+        _, _, _, _, probs = ac.step_device(s0, torch.full((1,), 0.3, device=ac.Wpi.device), want_probs=True)
+        np.testing.assert_allclose(pi.probs.detach().cpu().numpy(), probs[1, :, 0].cpu().numpy(), rtol=1e-5, atol=1e-7)
+    opt = torch.optim.SGD(ac.pi_list[1].parameters(), lr=0.1)
+    before = ac.Wpi[1].clone()
+    pi.probs[0].backward()
+    opt.step()
+    assert not torch.equal(ac.Wpi[1], before) and torch.equal(ac.Wpi[0], torch.as_tensor(g[name + "_Wpi"][0]).to(ac.Wpi.device))
+    # picklable like torch.save(ac) (utils/logx.py:253-275)
+    buf = io.BytesIO()
+    torch.save(ac, buf)
+    buf.seek(0)
+    ac2 = torch.load(buf, weights_only=False)
+    assert torch.equal(ac2.Wpi.cpu(), ac.Wpi.cpu()) and repr(ac2) == repr(ac)
+    a_test = ac2.act_test(g[name + "_obs"][0].astype(np.float64))
+    assert a_test.shape == (N,) and C[a_test].sum() <= 2.0
+
+
+def test_act_test_matches_reference_selection(torch_mod, golden):
+    torch = torch_mod
+    from robustrmab_b200.core import MLPActorCriticRMAB
+    rs = np.random.RandomState(2)
+    N, S, A = 30, 3, 2
+    ac = MLPActorCriticRMAB(np.arange(S), np.arange(A), hidden_sizes=[16, 16], C=np.array([0, 1]), N=N, B=7.0)
+    obs = rs.randint(0, S, N)
+    s = torch.as_tensor(obs[:, None].astype(np.uint8), device=ac.Wpi.device)
+    lamb = ac.get_lambda_device(s)
+    _, _, _, p1, probs = ac.step_device(s, lamb, want_probs=True)
+    want = osel.greedy_multiaction(np.moveaxis(probs.cpu().numpy(), 1, 2)[:, 0], np.array([0, 1]), 7.0)
+    assert np.array_equal(ac.act_test(obs.astype(np.float64)), want)
+    assert want.sum() == 7
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_buffer_dropin_golden(torch_mod, golden, name):
+    from robustrmab_b200.buffer import RMABPPO_Buffer
+    g = golden("buffer")
+    T, N = g[name + "_obs"].shape
+    S = int(g[name + "_obs"].max()) + 1
+    gamma, lam = g[name + "_hyper"]
+    buf = RMABPPO_Buffer(S, 2, N, 'd', T, one_hot_encode=True, gamma=gamma, lam_OTHER=lam)
+    for t in range(T):
+        buf.store(g[name + "_obs"][t], g[name + "_act"][t], g[name + "_rew"][t], g[name + "_cost"][t], g[name + "_val"][t],
+                  np.zeros(N), g[name + "_lamb"][t], g[name + "_logp"][t])
+    with pytest.raises(AssertionError):
+        buf.store(g[name + "_obs"][0], g[name + "_act"][0], g[name + "_rew"][0], g[name + "_cost"][0], g[name + "_val"][0],
+                  np.zeros(N), 0.0, g[name + "_logp"][0])
+    buf.finish_path(g[name + "_last"], np.zeros((50, N)))
+    data = buf.get()
+    for k in ("obs", "act", "ret", "adv", "logp", "qs", "oha", "ohs", "costs", "lambdas"):
+        want = g[f"{name}_get_{k}"]
+        assert tuple(data[k].shape) == want.shape, k
+        tol = dict(rtol=1e-4, atol=1e-5) if k == "adv" else dict(rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(data[k].numpy(), want, err_msg=k, **tol)
+    assert buf.ptr == 0
