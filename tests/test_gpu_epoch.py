@@ -183,3 +183,34 @@ def test_trainer_matches_cpu_epoch_loop(K, domain, h):
     np.testing.assert_allclose(K.n(tr.Wv), cpu.opt.Wv.detach().numpy(), atol=5e-3)
     lam_cpu = np.concatenate([p.detach().numpy().reshape(-1) for p in cpu.lam_params])
     np.testing.assert_allclose(K.n(tr.lam_params), lam_cpu, rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize("name,domain", [("ce", 0), ("armman", 1)])
+def test_trainer_matches_reference_best_response(K, golden, name, domain):
+    """Device trainer (E = 1) against the values logged by the UNMODIFIED reference AgentOracle.best_response run
+    with the same injected uniforms (tests/golden/train.npz, oracle/gen_golden_train.py)."""
+    from robustrmab_b200.trainer import RMABPPOTrainer
+    g = golden("train")
+    N, S, T, epochs, hidden, seed = [int(x) for x in g[name + "_meta"]]
+    kw = dict(zip([str(k) for k in g[name + "_hyper_names"]], [float(v) for v in g[name + "_hyper_values"]]))
+    tr = RMABPPOTrainer(domain, N, 1, T, hidden=hidden, B=float(g[name + "_B"]), gamma=kw["gamma"],
+                        lam_other=kw["lam_OTHER"], clip_ratio=kw["clip_ratio"], pi_lr=kw["pi_lr"], vf_lr=kw["vf_lr"],
+                        lm_lr=kw["lm_lr"], train_pi_iters=int(kw["train_pi_iters"]), train_v_iters=int(kw["train_v_iters"]),
+                        epochs=epochs, lamb_update_freq=int(kw["lamb_update_freq"]),
+                        final_train_lambdas=int(kw["final_train_lambdas"]), start_entropy_coeff=kw["start_entropy_coeff"],
+                        end_entropy_coeff=kw["end_entropy_coeff"], seed=seed, ranges=g[name + "_ranges"],
+                        nature=g[name + "_nature"], device=K.dev)
+    tr.Wpi.copy_(K.t(g[name + "_Wpi0"]))
+    tr.Wv.copy_(K.t(g[name + "_Wv0"]))
+    tr.lam_params.copy_(K.t(np.concatenate([g[f"{name}_lam0_{i}"].reshape(-1) for i in range(6)])))
+    lamb, ret, vv = [], [], []
+    for _ in range(epochs):
+        st = tr.epoch()
+        lamb.append(float(st["Lamb"][0])); ret.append(float(st["EpActualRet"][0])); vv.append(float(st["VVals"][0]))
+    assert np.array_equal(np.array(ret), g[name + "_AverageEpActualRet"])       # same trajectories as the reference
+    np.testing.assert_allclose(lamb, g[name + "_AverageLamb"], rtol=5e-5, atol=2e-6)
+    np.testing.assert_allclose(vv, g[name + "_AverageVVals"], rtol=5e-4, atol=5e-5)
+    np.testing.assert_allclose(K.n(tr.Wpi), g[name + "_Wpi1"], rtol=0, atol=5e-4)
+    np.testing.assert_allclose(K.n(tr.Wv), g[name + "_Wv1"], rtol=0, atol=5e-4)
+    lam1 = np.concatenate([g[f"{name}_lam1_{i}"].reshape(-1) for i in range(6)])
+    np.testing.assert_allclose(K.n(tr.lam_params), lam1, rtol=2e-5, atol=1e-6)

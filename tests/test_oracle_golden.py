@@ -189,3 +189,33 @@ def test_vi_probes(golden, dom, eps):
     ok = it >= 0
     np.testing.assert_allclose(V[ok], g[f"{dom}_V{sfx}"][ok], rtol=1e-12, atol=1e-12)
     assert np.array_equal(pol[ok], g[f"{dom}_pol{sfx}"][ok])
+
+
+@pytest.mark.parametrize("name,domain", [("ce", 0), ("armman", 1)])
+def test_epoch_loop_matches_reference_best_response(golden, name, domain):
+    """oracle/train.py against the unmodified reference AgentOracle.best_response run with the same injected
+    uniforms (oracle/gen_golden_train.py): per-epoch logged values and the weights after all epochs."""
+    from oracle.train import CpuRMABPPO
+    g = golden("train")
+    N, S, T, epochs, hidden, seed = [int(x) for x in g[name + "_meta"]]
+    kw = dict(zip([str(k) for k in g[name + "_hyper_names"]], [float(v) for v in g[name + "_hyper_values"]]))
+    lam0 = [g[f"{name}_lam0_{i}"] for i in range(6)]
+    R = oenv.rewards_table(domain, N, S)
+    cpu = CpuRMABPPO(domain, g[name + "_Wpi0"], g[name + "_Wv0"], lam0, g[name + "_nature"].astype(F32),
+                     g[name + "_ranges"].astype(F32), R, np.array([0, 1], F32), 1, T, hidden, float(g[name + "_B"]),
+                     gamma=kw["gamma"], lam_other=kw["lam_OTHER"], clip_ratio=kw["clip_ratio"], pi_lr=kw["pi_lr"],
+                     vf_lr=kw["vf_lr"], lm_lr=kw["lm_lr"], train_pi_iters=int(kw["train_pi_iters"]),
+                     train_v_iters=int(kw["train_v_iters"]), epochs=epochs, lamb_update_freq=int(kw["lamb_update_freq"]),
+                     final_train_lambdas=int(kw["final_train_lambdas"]), start_entropy_coeff=kw["start_entropy_coeff"],
+                     end_entropy_coeff=kw["end_entropy_coeff"], seed=seed)
+    lamb, ret, vv = [], [], []
+    for _ in range(epochs):
+        w = cpu.epoch()
+        lamb.append(w["lamb"][0]); ret.append(w["rew_sum"][0]); vv.append(w["val"].mean())
+    assert np.array_equal(np.array(ret), g[name + "_AverageEpActualRet"])      # integer path: identical trajectories
+    np.testing.assert_allclose(lamb, g[name + "_AverageLamb"], rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(vv, g[name + "_AverageVVals"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(cpu.opt.Wpi.detach().numpy(), g[name + "_Wpi1"], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(cpu.opt.Wv.detach().numpy(), g[name + "_Wv1"], rtol=0, atol=2e-4)
+    for i, p in enumerate(cpu.lam_params):
+        np.testing.assert_allclose(p.detach().numpy(), g[f"{name}_lam1_{i}"], rtol=1e-5, atol=1e-7)
