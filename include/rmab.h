@@ -15,8 +15,10 @@
  *     [N,P] with P = (in+1)h + (h+1)h + (h+1)out in torch.nn.Linear order W1 b1 W2 b2 W3 b3.
  *   - N is the number of arms held by THIS rank; `arm0` is the global index of its first arm so the
  *     Philox counters (stream, t, env, global_arm) give the same draws under any arm sharding.
- *   - RNG: Philox4x32-10, key = seed, u = (x0 >> 8) * 2^-24; categorical draw k = #{j: cdf_j <= u}
- *     with the cdf accumulated left to right in fp32, clamped to the last category with p > 0.
+ *   - RNG: Philox4x32-10, key = seed, u = (word >> 8) * 2^-24.  Streams ENV and ACT share blocks: the transition
+ *     and action draws of time step t are words 2*(t&1) and 2*(t&1)+1 of the block with counter (0, t>>1, env,
+ *     arm); every other stream uses word 0 of the block (stream, t, env, arm).  Categorical draw
+ *     k = #{j: cdf_j <= u} with the cdf accumulated left to right in fp32, clamped to the last category with p > 0.
  *     If `u_inject` is non-NULL it supplies the uniforms ([N,E]) instead (parity tests).
  */
 #ifndef RMAB_H_

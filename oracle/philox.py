@@ -4,7 +4,7 @@ The reference has no GPU-reproducible RNG (numpy RandomState.multinomial in
 bandit_env_robust.py:886/627/1236 and torch's global generator in rmabppo_core.py:222), so the
 B200 build fixes one: Philox4x32-10 (Salmon et al., SC'11 -- the published
 algorithm, same constants as cuRAND/Random123), key = 64-bit run seed, counter =
-(stream, t, env, global_arm).  One uniform per categorical draw: u = (x0 >> 8) * 2^-24.
+(stream, t, env, global_arm).  One uniform per categorical draw: u = (word >> 8) * 2^-24 (see `uniform`).
 """
 import numpy as np
 
@@ -36,11 +36,24 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
+def _u24(x):
+    return (x >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+
+
 def uniform(seed, stream, t, env, arm):
-    """fp32 uniform in [0,1) for counter (stream, t, env, arm) under 64-bit `seed`."""
+    """fp32 uniform in [0,1) for (stream, t, env, arm) under 64-bit `seed` (t a scalar).
+
+    Streams ENV and ACT share Philox blocks: the transition and action draws of time step t are words 2*(t&1) and
+    2*(t&1)+1 of the block with counter (0, t>>1, env, arm), so a rollout needs one block per two steps.  Every
+    other stream uses word 0 of the block with counter (stream, t, env, arm).
+    """
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-    x0, _, _, _ = philox4x32_10(stream, t, env, arm, seed & 0xFFFFFFFF, seed >> 32)
-    return (x0 >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+    k0, k1 = seed & 0xFFFFFFFF, seed >> 32
+    t = int(t)
+    if stream in (STREAM_ENV, STREAM_ACT):
+        words = philox4x32_10(0, t >> 1, env, arm, k0, k1)
+        return _u24(words[2 * (t & 1) + (1 if stream == STREAM_ACT else 0)])
+    return _u24(philox4x32_10(stream, t, env, arm, k0, k1)[0])
 
 
 def uniform_grid(seed, stream, t, n_envs, n_arms, arm0=0, env0=0):

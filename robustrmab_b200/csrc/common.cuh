@@ -50,11 +50,24 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
   return make_uint4(c0, c1, c2, c3);
 }
 
-// u = (x0 >> 8) * 2^-24 for counter (stream, t, env, arm)
+// One Philox block serves the two draws of two consecutive time steps: the env-transition draw (stream ENV) and the
+// action draw (stream ACT) of step t are words 2*(t&1) and 2*(t&1)+1 of the block with counter (0, t>>1, env, arm).
+// Every other stream uses word 0 of the block with counter (stream, t, env, arm).  u = (word >> 8) * 2^-24.
+__device__ __forceinline__ float u24(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f; }
+
+__device__ __forceinline__ uint4 philox_step_block(uint32_t k0, uint32_t k1, uint32_t t, uint32_t env, uint32_t arm) {
+  return philox4x32_10(0u, t >> 1, env, arm, k0, k1);
+}
+
+__device__ __forceinline__ uint32_t step_word(const uint4& b, uint32_t t, bool act) {
+  return (t & 1u) ? (act ? b.w : b.z) : (act ? b.y : b.x);
+}
+
 __device__ __forceinline__ float philox_uniform(uint32_t k0, uint32_t k1, uint32_t stream, uint32_t t, uint32_t env,
                                                 uint32_t arm) {
-  const uint4 x = philox4x32_10(stream, t, env, arm, k0, k1);
-  return (float)(x.x >> 8) * 5.9604644775390625e-08f;
+  if (stream == RMAB_STREAM_ENV || stream == RMAB_STREAM_ACT)
+    return u24(step_word(philox_step_block(k0, k1, t, env, arm), t, stream == RMAB_STREAM_ACT));
+  return u24(philox4x32_10(stream, t, env, arm, k0, k1).x);
 }
 
 __device__ __forceinline__ float draw_uniform(const Rng& g, const float* __restrict__ u_inject, int64_t idx, int e,

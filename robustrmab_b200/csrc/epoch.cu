@@ -62,7 +62,7 @@ struct EpochArgs {
 };
 
 template <int H, int DOMAIN>
-__global__ void __launch_bounds__(256) epoch_table_kernel(EpochArgs g) {
+__global__ void __launch_bounds__(256, 2) epoch_table_kernel(EpochArgs g) {
   constexpr int S = DOMAIN == RMAB_DOMAIN_CE ? 2 : 3;
   constexpr int A = 2;
   using SR = StatRows<S, A>;
@@ -126,14 +126,15 @@ __global__ void __launch_bounds__(256) epoch_table_kernel(EpochArgs g) {
       int si = tr[0];
       si = si < S ? si : S - 1;
       const uint32_t ge = g.env0 + (uint32_t)e;
+      uint4 blk = make_uint4(0u, 0u, 0u, 0u);
       for (int t = 0; t < T; ++t) {
+        const uint32_t tt = g.t_act0 + (uint32_t)t;
+        if (t == 0 || (tt & 1u) == 0u) blk = philox_step_block(g.k0, g.k1, tt, ge, gn);  // one Philox block per two steps
         float pr[2] = {pick_f<S>(p0t, si), pick_f<S>(p1t, si)};
-        const float ua = philox_uniform(g.k0, g.k1, RMAB_STREAM_ACT, g.t_act0 + (uint32_t)t, ge, gn);
-        const int act = categorical<2>(pr, ua);
+        const int act = categorical<2>(pr, u24(step_word(blk, tt, true)));
         ac[(int64_t)t * E] = (uint8_t)act;
         const float p = act ? pick_f<S>(pn1, si) : pick_f<S>(pn0, si);
-        const float ue = philox_uniform(g.k0, g.k1, RMAB_STREAM_ENV, g.t_env0 + (uint32_t)t, ge, gn);
-        si = table_next<DOMAIN>(si, act, p, ue);
+        si = table_next<DOMAIN>(si, act, p, u24(step_word(blk, tt, false)));
         tr[(int64_t)(t + 1) * E] = (uint8_t)si;
       }
       // backward scan 1 (finish_path :120-130 in fp64 like scipy's lfilter)
@@ -317,6 +318,8 @@ extern "C" int rmab_epoch_table(int domain, const RmabNetDesc* net, int T, const
   RMAB_REQUIRE(net->one_hot && net->n_states == S && net->n_actions == 2 && net->n_extra == 0, RMAB_E_SHAPE,
                "rmab_epoch_table: needs one-hot S=%d, A=2 nets", S);
   RMAB_REQUIRE(T > 0 && net->n_envs > 0 && net->n_arms >= 0, RMAB_E_SHAPE, "rmab_epoch_table: bad T/E/N");
+  RMAB_REQUIRE(t_act0 == t_env0, RMAB_E_BADARG, "rmab_epoch_table: the action and transition draws of a step share one "
+               "Philox block, so t_act0 must equal t_env0");
   RMAB_REQUIRE(Wpi && Wv && lamb && nature && ranges && R && C && s_traj && a && stats, RMAB_E_BADARG,
                "rmab_epoch_table: null pointer");
   RMAB_REQUIRE(!env_sums || (ws && ws_bytes >= rmab_epoch_ws_bytes(net->n_arms, net->n_envs)), RMAB_E_BADARG,
