@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--pi-iters", type=int, default=20)
     ap.add_argument("--v-iters", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-whittle", action="store_true")
+    ap.add_argument("--vi-arms", type=int, default=99999)
+    ap.add_argument("--vi-probes", type=int, default=64)
     ap.add_argument("--cpu-arms", type=int, default=192)
     ap.add_argument("--cpu-envs", type=int, default=16)
     return ap.parse_args()
@@ -133,6 +136,57 @@ def run_reference(a):
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------ Whittle / VI
+def whittle_bench(a, dev, want_cpu):
+    """BASELINE configs[4]: batched value iteration over N arms x L lambda-probes (mdptoolbox ValueIteration per
+    probe, simulator.py:504-521) and the Whittle index by bisection (lp_methods.py:181), counterexample domain.
+    Returns the secondary metric block (Whittle-index arms/sec)."""
+    import numpy as np
+    import torch
+    from robustrmab_b200 import ops
+    from oracle import envs as oenv, vi as ovi
+    N, L = a.vi_arms, a.vi_probes
+    rs = np.random.RandomState(0)
+    rg = oenv.ce_param_ranges(N)
+    p = rg.mean(-1)
+    T = np.zeros((N, 2, 2, 2))
+    T[:, 0] = 0.5
+    T[:, 1, 0, 0] = 1.0
+    T[:, 1, 1, 1], T[:, 1, 1, 0] = p, 1 - p
+    R = np.tile(np.array([0.0, 1.0]), (N, 1))
+    C = np.array([0.0, 1.0])
+    gamma, eps, rounds = 0.9, 1e-1, 20
+    lam_lim = R.max() / (C[C > 0].min() * (1 - gamma))              # agent_baselines.py:61
+    lambdas = np.linspace(0, lam_lim, L)
+    dT, dR, dC, dL = (torch.as_tensor(x, device=dev) for x in (T, R, C, lambdas))
+
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    ms_vi = timed(lambda: ops.vi_batched(dT, dR, dC, dL, gamma, eps))
+    ms_wh = timed(lambda: ops.whittle_bisect(dT, dR, dC, gamma, eps, 0.0, lam_lim, rounds))
+    out = {"metric": "Whittle-index arms/sec", "unit": "arms/s", "value": N / (ms_wh * 1e-3),
+           "vi_probe_solves_per_s": N * L / (ms_vi * 1e-3), "ms_vi_batched": ms_vi, "ms_whittle_bisect": ms_wh,
+           "dtype": "f64",
+           "config": {"workload": f"counterexample domain, N={N} arms x {L} lambda-probes, gamma={gamma}, eps={eps} "
+                                  f"(simulator.py:595 default), Whittle index by {rounds}-round bisection per (arm, state)"}}
+    if want_cpu:
+        n_cpu = 400
+        t0 = time.perf_counter()
+        ovi.batched_vi(T[:n_cpu], R[:n_cpu], C, lambdas, gamma, eps)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n_cpu * L / dt, "unit": "probe solves/s", "cores": 1, "kind": "port",
+                               "sample": f"{n_cpu} arms x {L} probes (oracle port of mdptoolbox ValueIteration, {dt:.1f} s)"}
+    return out
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -277,6 +331,8 @@ def run_ours(a):
         out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
                                "sample": f"1 epoch of N={a.cpu_arms} arms x {a.cpu_envs} envs x T={a.horizon} "
                                          f"(oracle port, 1 thread, {tmax:.1f} s)"}
+    if not a.no_whittle:
+        out["whittle"] = whittle_bench(a, dev, not a.no_cpu_baseline)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -113,7 +113,12 @@ int rmab_bound_nature(int64_t n, const float* x, const float* lo, const float* h
 /* ---- actor-critic ------------------------------------------------------------------------ */
 
 /* MLPActorCriticRMAB.step (rmabppo_core.py:198-244) for all arms x envs.
- * Wpi [N,Ppi], Wv [N,Pv]; s [N,E]; lamb [E]; extra [E,n_extra] or NULL (critic only).
+ * Wpi [N,Ppi], Wv [N,Pv]; s [N,E]; lamb [E].
+ * extra (NULL unless net->n_extra > 0): the MA-RMABPPO agent critics also read the bounded nature action vector
+ * (ma_rmabppo_core.py:312-316, critic input dim = in + n_extra).  Their first layer splits into the packed part
+ * W1[h,in] and W1_nature[h,n_extra]; the caller computes the nature part for all arms and envs as ONE dense GEMM
+ * ([N*h, n_extra] x [n_extra, E], a plain library GEMM) and passes the result extra[N,h,E], which the kernel adds to
+ * the critic's first-layer pre-activation.
  * Outputs a [N,E] u8, v/logp/p1 [N,E] fp32, probs [N,A,E] fp32 (may be NULL). */
 int rmab_ac_step(const RmabNetDesc* net, const float* Wpi, const float* Wv, const uint8_t* s,
                  const float* lamb, const float* extra, const RmabRng* rng, const float* u_inject,
@@ -145,6 +150,23 @@ int rmab_rollout_table(int domain, const RmabNetDesc* net, int T, const float* W
                        const float* lamb, const float* nature, const float* ranges, uint64_t seed,
                        uint32_t t_act0, uint32_t t_env0, uint32_t env0, uint32_t arm0, uint8_t* s_traj,
                        uint8_t* a, float* logp, float* val, float* last_val, rmab_stream_t stream);
+
+/* ---- MA-RMABPPO rollout pieces ------------------------------------------------------------ */
+
+/* Gaussian nature actor sample (ma_rmabppo_core.py:289-291, MLPGaussianActor :98-113): a = mu + exp(log_std) * eps,
+ * logp[e] = sum_d Normal(mu, exp(log_std)).log_prob(a).  mu, a [E,D]; log_std [D]; eps from Philox stream NATURE
+ * (Box-Muller on words 0/1 of the block (NATURE, t, env, d/2)) or eps_inject [E,D]. */
+int rmab_gaussian_sample(int E, int D, const float* mu, const float* log_std, const RmabRng* rng,
+                         const float* eps_inject, float* a, float* logp, rmab_stream_t stream);
+
+/* Counterfactual reward estimate of the nature oracle (nature_oracle.py:685-701): from the SAME state s, take
+ * n_trials independent env steps with action a and the given nature parameters, and return the mean over trials of
+ * the reward R[arm, s'] per (arm, env) in r_mean [N,E] (the caller sums over arms).  Draws: Philox stream CF,
+ * time counter rng->t * n_trials + trial.  domain CE / ARMMAN: nature, ranges as rmab_env_step_table;
+ * domain SIS: nature = params as rmab_env_step_sis, ranges ignored, S = pop + 1. */
+int rmab_env_counterfactual(int domain, int E, int N, int S, const uint8_t* s, const uint8_t* a, const float* nature,
+                            int nature_per_env, const float* ranges, const float* R, const RmabRng* rng, int n_trials,
+                            float* r_mean, rmab_stream_t stream);
 
 /* ---- buffer ------------------------------------------------------------------------------ */
 

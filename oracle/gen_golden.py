@@ -285,8 +285,8 @@ def main(which=None):
     os.makedirs(OUT, exist_ok=True)
     gens = dict(env=gen_env, ac=gen_ac, buffer=gen_buffer, select=gen_select, vi=gen_vi)
     try:
-        from .gen_golden_train import gen_train
-        gens.update(train=gen_train)
+        from .gen_golden_train import gen_train, gen_ma
+        gens.update(train=gen_train, ma=gen_ma)
     except ImportError:
         pass
     for k, f in gens.items():

@@ -127,4 +127,69 @@ def gen_train():
 
 
 def gen_ma():
-    raise NotImplementedError("MA-RMABPPO golden vectors: next round")
+    """RMABLambdaNatureOracle.step (ma_rmabppo_core.py:274-331) on the unmodified reference with injected
+    Categorical / Normal draws, for the counterexample (D = N) and ARMMAN (D = 2N, state-dependent bounds) domains."""
+    import contextlib
+    import torch
+    from torch.distributions.normal import Normal
+    from robust_rmab.algos.ma_rmabppo.ma_rmabppo_core import RMABLambdaNatureOracle
+    from robust_rmab.environments.bandit_env_robust import ARMMANRobustEnv, CounterExampleRobustEnv
+
+    @contextlib.contextmanager
+    def patch_normal(eps_rows):
+        orig = Normal.sample
+        it = iter(eps_rows)
+
+        def sample(self, sample_shape=torch.Size()):
+            return self.loc + self.scale * torch.as_tensor(next(it))
+        Normal.sample = sample
+        try:
+            yield
+        finally:
+            Normal.sample = orig
+
+    def lin(seq):
+        return [m for m in seq if isinstance(m, torch.nn.Linear)]
+
+    out = {}
+    rs = np.random.RandomState(31)
+    for name, Env, N, S, h in [("ce", CounterExampleRobustEnv, 6, 2, 16), ("armman", ARMMANRobustEnv, 5, 3, 8)]:
+        env = Env(N, 2.0, 0)
+        env.sampled_parameter_ranges = env.sample_parameter_ranges().astype(F32).astype(np.float64)
+        D = env.action_dim_nature
+        torch.manual_seed(1)
+        ac = RMABLambdaNatureOracle(env.observation_space, env.action_space, env.sampled_parameter_ranges, D, env,
+                                    hidden_sizes=[h, h], C=env.C, N=N, B=env.B)
+        in_dim = S + 1
+        K = 6
+        obs = rs.randint(0, S, size=(K, N))
+        lamb = rs.uniform(0, 2, size=K).astype(F32)
+        eps = rs.randn(K, D).astype(F32)
+        src = ref_shims.UniformSource(41, philox.STREAM_ACT, N)
+        res = {k: [] for k in "a v logp an vn lpn p1 anb".split()}
+        with ref_shims.patch_categorical_sample(src), patch_normal(list(eps)):
+            for k in range(K):
+                o = torch.as_tensor(obs[k], dtype=torch.float32)
+                a, v, logp, q, an, vn, lpn, qn, p1 = ac.step(o, torch.as_tensor(lamb[k]))
+                res["a"].append(a); res["v"].append(v); res["logp"].append(logp); res["an"].append(an)
+                res["vn"].append(vn); res["lpn"].append(lpn); res["p1"].append(p1)
+                res["anb"].append(np.asarray(env.bound_nature_actions(an, state=obs[k], reshape=False)).reshape(-1))
+        Wv_full = [lin(ac.v_list_agent[i].v_net) for i in range(N)]
+        first = np.stack([l[0].weight.detach().numpy() for l in Wv_full])          # [N,h,in+D]
+        packed_v = []
+        for i, l in enumerate(Wv_full):
+            parts = [first[i][:, :in_dim].reshape(-1), l[0].bias.detach().numpy()]
+            for m in l[1:]:
+                parts += [m.weight.detach().numpy().reshape(-1), m.bias.detach().numpy()]
+            packed_v.append(np.concatenate(parts))
+        out.update({f"{name}_meta": np.array([N, S, h, D]), f"{name}_obs": obs, f"{name}_lamb": lamb, f"{name}_eps": eps,
+                    f"{name}_u": np.array(src.log, F32).reshape(K, N), f"{name}_ranges": env.sampled_parameter_ranges,
+                    f"{name}_Wpi": np.stack([nets.pack_torch_mlp(ac.pi_list_agent[i].logits_net) for i in range(N)]),
+                    f"{name}_Wv": np.stack(packed_v).astype(F32), f"{name}_W1n": first[:, :, in_dim:].astype(F32),
+                    f"{name}_log_std": ac.pi_nature.log_std.detach().numpy()})
+        for tag, seq in (("mu", ac.pi_nature.mu_net), ("vn", ac.v_nature.v_net)):
+            for j, m in enumerate(lin(seq)):
+                out[f"{name}_{tag}_W{j}"] = m.weight.detach().numpy()
+                out[f"{name}_{tag}_b{j}"] = m.bias.detach().numpy()
+        out.update({f"{name}_out_{k}": np.array(v) for k, v in res.items()})
+    np.savez_compressed(os.path.join(OUT, "ma.npz"), **out)

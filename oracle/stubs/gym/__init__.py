@@ -9,11 +9,4 @@ class Env:  # the reference only subclasses it
     pass
 
 
-class _Space:
-    def __init__(self, *a, **k):
-        self.args, self.kwargs = a, k
-
-
-class spaces:
-    Box = _Space
-    Discrete = _Space
+from . import spaces  # noqa: E402,F401

@@ -88,3 +88,24 @@ class CpuRMABPPO:
         self.s = oenv.reset_states(self.seed, self.epoch_idx, S, E, N, self.arm0)
         return dict(lamb=lamb, s_traj=s_traj, a=a, logp=logp, val=val, last_val=last_val, adv=adv_n, ret=ret,
                     cdcost=cdcost, loss_pi=lp, loss_v=lv, rew_sum=rew.sum(axis=(0, 1)))
+
+
+def simulate_reward_cpu(domain, Wpi, Wv, lam_params, nature, ranges, R, C, B, hidden, n_rollouts, steps, gamma, seed):
+    """AgentOracle.simulate_reward (agent_oracle.py:599-652) with the `epochs` rollouts as env replicas and the
+    Philox draws of the device path: reset stream t = 0, transition stream t = step.  Binary-action table domains.
+    Returns the per-rollout discounted returns `[n_rollouts]` (float64)."""
+    from . import select as osel
+    S = 2 if domain == oenv.DOMAIN_CE else 3
+    N, E = Wpi.shape[0], n_rollouts
+    s = oenv.reset_states(seed, 0, S, E, N)
+    step = oenv.ce_step if domain == oenv.DOMAIN_CE else oenv.armman_step
+    ret = np.zeros(E)
+    for t in range(steps):
+        lamb = nets.lambda_net_forward(lam_params, s.T.astype(F32))
+        x = nets.features(s, lamb, S, True)
+        probs, _ = nets.softmax_logits(nets.mlp_forward(Wpi, x, S + 1, hidden, 2))
+        a = np.stack([osel.topk_binary(probs[:, e, 1], C, B) for e in range(E)], axis=1).astype(np.uint8)
+        u = philox.uniform_grid(seed, philox.STREAM_ENV, t, E, N)
+        s, r = step(s, a, nature, ranges, R, u)
+        ret += (gamma ** t) * r.astype(np.float64).sum(axis=0)
+    return ret

@@ -58,6 +58,8 @@ SIGNATURES = {
     "rmab_lambda_sgd": [_I, _I, _P, _I, _I, _P, _F, _P, _P, _F, _P, _P, _P],
     "rmab_rollout_table": [_I, C.POINTER(RmabNetDesc), _I, _P, _P, _P, _P, _P, C.c_uint64, C.c_uint32, C.c_uint32,
                            C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P],
+    "rmab_gaussian_sample": [_I, _I, _P, _P, C.POINTER(RmabRng), _P, _P, _P, _P],
+    "rmab_env_counterfactual": [_I, _I, _I, _I, _P, _P, _P, _I, _P, _P, C.POINTER(RmabRng), _I, _P, _P],
     "rmab_gae": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _D, _D, _I, _P, _P, _P, _P, _P],
     "rmab_gae_explicit": [_I, _I, _I, _P, _P, _P, _P, _P, _D, _D, _I, _P, _P, _P, _P, _P],
     "rmab_cost_togo": [_I, _I, _I, _I, _P, _P, _D, _P, _P, _P],

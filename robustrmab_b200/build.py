@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librmab_b200.so")
-SOURCES = ["common.cu", "env.cu", "ac.cu", "gae.cu", "epoch.cu", "ppo.cu", "ppo_table.cu", "ppo_table_mma.cu", "select.cu", "vi.cu"]
+SOURCES = ["common.cu", "env.cu", "ac.cu", "gae.cu", "epoch.cu", "ppo.cu", "ppo_table.cu", "ppo_table_mma.cu", "ma.cu", "select.cu", "vi.cu"]
 HEADERS = ["common.cuh", "mlp.cuh", os.path.join("..", "..", "include", "rmab.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -54,7 +54,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     if force or procs or _stale(LIB, objs):
-        subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"])
+        subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lcudart"])
     return LIB
 
 

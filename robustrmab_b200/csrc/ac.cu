@@ -14,7 +14,8 @@ namespace rmab {
 template <int H>
 __global__ void __launch_bounds__(128) ac_step_kernel(RmabNetDesc d, const float* __restrict__ Wpi,
                                                       const float* __restrict__ Wv, const uint8_t* __restrict__ s,
-                                                      const float* __restrict__ lamb, Rng g,
+                                                      const float* __restrict__ lamb,
+                                                      const float* __restrict__ z1_extra, Rng g,
                                                       const float* __restrict__ u_inject, uint8_t* __restrict__ a_out,
                                                       float* __restrict__ v_out, float* __restrict__ logp_out,
                                                       float* __restrict__ p1_out, float* __restrict__ probs_out) {
@@ -37,7 +38,8 @@ __global__ void __launch_bounds__(128) ac_step_kernel(RmabNetDesc d, const float
     float logit[kMaxA], vout[kMaxA], a1[H];
     mlp_layer1<H>(sp, Lp, d.one_hot, si, d.state_norm, lam, a1);
     mlp_tail<H>(sp, Lp, a1, A, logit);
-    mlp_layer1<H>(sv, Lv, d.one_hot, si, d.state_norm, lam, a1);
+    // MA agent critic: first-layer addend z1_extra[n][j][e] = (W1_nature[n] . bounded nature vector of env e)[j]
+    mlp_layer1<H>(sv, Lv, d.one_hot, si, d.state_norm, lam, a1, z1_extra ? z1_extra + (int64_t)n * H * E + e : nullptr, E);
     mlp_tail<H>(sv, Lv, a1, 1, vout);
     float p[kMaxA], lp[kMaxA];
     softmax_small(logit, A, p, lp);
@@ -340,8 +342,8 @@ extern "C" int rmab_ac_step(const RmabNetDesc* net, const float* Wpi, const floa
                             uint8_t* a, float* v, float* logp, float* p1, float* probs, rmab_stream_t stream) {
   int rc = check_net(net, "rmab_ac_step");
   if (rc) return rc;
-  RMAB_REQUIRE(net->n_extra == 0 && !extra, RMAB_E_SHAPE,
-               "rmab_ac_step: extra critic inputs are handled by rmab_ma_critic, not here");
+  RMAB_REQUIRE((net->n_extra == 0) == (extra == nullptr), RMAB_E_SHAPE,
+               "rmab_ac_step: the critic addend `extra` [N,h,E] must be given exactly when net->n_extra > 0");
   RMAB_REQUIRE(Wpi && Wv && s && lamb && a && v && logp && (rng || u_inject), RMAB_E_BADARG, "rmab_ac_step: null pointer");
   if (net->n_arms == 0) return RMAB_OK;
   RmabRng z = {0, RMAB_STREAM_ACT, 0, 0, 0};
@@ -352,7 +354,7 @@ extern "C" int rmab_ac_step(const RmabNetDesc* net, const float* Wpi, const floa
 #define LAUNCH(H)                                                                                              \
   {                                                                                                            \
     RMAB_REQUIRE(set_smem(ac_step_kernel<H>, smem) == 0, RMAB_E_LAUNCH, "rmab_ac_step: cannot reserve %zu B smem", smem); \
-    ac_step_kernel<H><<<net->n_arms, 128, smem, st>>>(*net, Wpi, Wv, s, lamb, g, u_inject, a, v, logp, p1, probs); \
+    ac_step_kernel<H><<<net->n_arms, 128, smem, st>>>(*net, Wpi, Wv, s, lamb, extra, g, u_inject, a, v, logp, p1, probs); \
   }
   switch (net->hidden) {
     case 8: LAUNCH(8) break;

@@ -45,23 +45,30 @@ __device__ __forceinline__ void stage_net(float* dst, const SmemNet& L, const fl
   for (int i = threadIdx.x; i < G.P; i += blockDim.x) dst[i < G.oW2 ? i : i + shift] = src[i];
 }
 
-// a1 = tanh(W1 x + b1) for x = onehot(s) ++ [lam]  or  [s/norm, lam]   (rmabppo_core.py:213-218)
+// a1 = tanh(W1 x + b1 [+ add]) for x = onehot(s) ++ [lam]  or  [s/norm, lam]   (rmabppo_core.py:213-218).
+// `add` (may be NULL) is an extra first-layer pre-activation term add[j * add_stride]: the MA-RMABPPO agent critic's
+// W1_nature . bounded_nature_vector (ma_rmabppo_core.py:312-316), computed by the caller as one dense GEMM.
 template <int H>
 __device__ __forceinline__ void mlp_layer1(const float* __restrict__ w, const SmemNet& L, int one_hot, int s,
-                                           float state_norm, float lam, float (&a1)[H]) {
+                                           float state_norm, float lam, float (&a1)[H],
+                                           const float* __restrict__ add = nullptr, int64_t add_stride = 0) {
   const int in = L.in;
   if (one_hot) {
 #pragma unroll
     for (int j = 0; j < H; ++j) {
       const float* row = w + L.oW1 + j * in;
-      a1[j] = tanhf(fmaf(row[in - 1], lam, row[s]) + w[L.ob1 + j]);
+      float z = fmaf(row[in - 1], lam, row[s]) + w[L.ob1 + j];
+      if (add) z += add[j * add_stride];
+      a1[j] = tanhf(z);
     }
   } else {
     const float x0 = __fdiv_rn((float)s, state_norm);
 #pragma unroll
     for (int j = 0; j < H; ++j) {
       const float* row = w + L.oW1 + j * in;
-      a1[j] = tanhf(fmaf(row[1], lam, fmaf(row[0], x0, w[L.ob1 + j])));
+      float z = fmaf(row[1], lam, fmaf(row[0], x0, w[L.ob1 + j]));
+      if (add) z += add[j * add_stride];
+      a1[j] = tanhf(z);
     }
   }
 }

@@ -98,7 +98,7 @@ def bound_nature(x, lo, hi):
 
 
 # ------------------------------------------------------------------------------------- actor-critic
-def ac_step(net, Wpi, Wv, s, lamb, r=None, u=None, want_probs=False):
+def ac_step(net, Wpi, Wv, s, lamb, r=None, u=None, want_probs=False, extra=None):
     N, E = s.shape
     dev = s.device
     a = torch.empty((N, E), dtype=u8, device=dev)
@@ -107,7 +107,7 @@ def ac_step(net, Wpi, Wv, s, lamb, r=None, u=None, want_probs=False):
     p1 = torch.empty((N, E), dtype=f32, device=dev)
     probs = torch.empty((N, net.n_actions, E), dtype=f32, device=dev) if want_probs else None
     check(lib().rmab_ac_step(C.byref(net), _p(Wpi, f32, "Wpi"), _p(Wv, f32, "Wv"), _p(s, u8, "s"),
-                             _p(lamb, f32, "lamb"), None, _rng_ptr(r), _p(u, f32, "u"), _p(a, u8), _p(v, f32),
+                             _p(lamb, f32, "lamb"), _p(extra, f32, "extra"), _rng_ptr(r), _p(u, f32, "u"), _p(a, u8), _p(v, f32),
                              _p(logp, f32), _p(p1, f32), _p(probs, f32), _stream()))
     return a, v, logp, p1, probs
 
@@ -139,6 +139,27 @@ def rollout_table(domain, net, T, Wpi, Wv, lamb, nature, ranges, seed, t_act0, t
                                    int(seed) & 0xFFFFFFFFFFFFFFFF, int(t_act0), int(t_env0), int(env0), int(arm0),
                                    _p(s_traj, u8, "s_traj"), _p(a, u8, "a"), _p(logp, f32, "logp"), _p(val, f32, "val"),
                                    _p(last_val, f32, "last_val"), _stream()))
+
+
+# ------------------------------------------------------------------------------ MA-RMABPPO rollout
+def gaussian_sample(mu, log_std, r=None, eps=None):
+    """a = mu + exp(log_std) * eps, logp = sum_d Normal.log_prob(a).  mu [E,D] -> (a [E,D], logp [E])."""
+    E, D = mu.shape
+    a = torch.empty_like(mu)
+    logp = torch.empty((E,), dtype=f32, device=mu.device)
+    check(lib().rmab_gaussian_sample(E, D, _p(mu, f32, "mu"), _p(log_std, f32, "log_std"), _rng_ptr(r),
+                                     _p(eps, f32, "eps"), _p(a, f32), _p(logp, f32), _stream()))
+    return a, logp
+
+
+def env_counterfactual(domain, s, a, nature, ranges, R, r, n_trials, nature_per_env=False):
+    """Mean over n_trials independent env steps from the same state of the reward, per (arm, env)."""
+    N, E = s.shape
+    out = torch.empty((N, E), dtype=f32, device=s.device)
+    check(lib().rmab_env_counterfactual(int(domain), E, N, R.shape[1], _p(s, u8, "s"), _p(a, u8, "a"),
+                                        _p(nature, f32, "nature"), int(bool(nature_per_env)), _p(ranges, f32, "ranges"),
+                                        _p(R, f32, "R"), _rng_ptr(r), int(n_trials), _p(out, f32), _stream()))
+    return out
 
 
 # -------------------------------------------------------------------------------------------- buffer

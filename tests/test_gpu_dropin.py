@@ -193,3 +193,29 @@ def test_buffer_dropin_golden(torch_mod, golden, name):
         tol = dict(rtol=1e-4, atol=1e-5) if k == "adv" else dict(rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(data[k].numpy(), want, err_msg=k, **tol)
     assert buf.ptr == 0
+
+
+@pytest.mark.parametrize("domain", [0, 1])
+def test_simulate_reward_matches_oracle(torch_mod, domain):
+    torch = torch_mod
+    from robustrmab_b200.core import MLPActorCriticRMAB
+    from robustrmab_b200.environments import ARMMANRobustEnv, CounterExampleRobustEnv
+    from robustrmab_b200.evaluate import PessimisticAgentPolicy, simulate_reward
+    from oracle.train import simulate_reward_cpu
+    N, E, T, h, B = 12, 24, 15, 16, 4.0
+    S = 2 if domain == 0 else 3
+    Env = CounterExampleRobustEnv if domain == 0 else ARMMANRobustEnv
+    env = Env(N, B, 5, n_envs=E)
+    env.sampled_parameter_ranges = env.sample_parameter_ranges()
+    rg = env.sampled_parameter_ranges
+    rs = np.random.RandomState(1)
+    nature = (rg[..., 0] + rs.rand(*rg.shape[:-1]) * (rg[..., 1] - rg[..., 0])).astype(F32)
+    ac = MLPActorCriticRMAB(np.arange(S), np.arange(2), hidden_sizes=[h, h], C=np.array([0, 1]), N=N, B=B, n_envs=E)
+    lam = [p.detach().numpy() for p in ac.lambda_net.parameters()]
+    got = simulate_reward(ac, env, torch.as_tensor(nature, device=env.device), steps_per_epoch=T, epochs=E, gamma=0.9,
+                          seed=11, return_all=True).cpu().numpy()
+    want = simulate_reward_cpu(domain, ac.Wpi.cpu().numpy(), ac.Wv.cpu().numpy(), lam, nature, rg.astype(F32),
+                               oenv.rewards_table(domain, N, S), np.array([0, 1]), B, h, E, T, 0.9, 11)
+    np.testing.assert_allclose(got, want, rtol=1e-12)            # same states and actions -> same returns
+    zero = simulate_reward(PessimisticAgentPolicy(N), env, torch.as_tensor(nature, device=env.device), T, E, 0.9, seed=11)
+    assert np.isfinite(zero)

@@ -1,0 +1,130 @@
+"""MA-RMABPPO rollout pieces on the device: Gaussian nature sample, agent critics with nature inputs, the drop-in
+RMABLambdaNatureOracle.step against the reference golden, and the counterfactual reward estimate.  GPU only."""
+import numpy as np
+import pytest
+
+from oracle import envs as oenv
+from oracle import ma as oma
+from oracle import nets as onets
+from oracle import philox
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def K():
+    import torch
+    assert torch.cuda.is_available()
+    from robustrmab_b200 import _lib, ops
+
+    class NS:
+        pass
+    ns = NS()
+    ns.torch, ns.ops, ns.lib = torch, ops, _lib
+    ns.dev = torch.device("cuda:0")
+    ns.t = lambda x, dt=None: torch.as_tensor(np.ascontiguousarray(x if dt is None else np.asarray(x).astype(dt)),
+                                              device=ns.dev)
+    ns.n = lambda x: x.detach().cpu().numpy()
+    return ns
+
+
+@pytest.mark.parametrize("E,D", [(1, 6), (7, 33), (64, 8192)])
+def test_gaussian_sample(K, E, D):
+    rs = np.random.RandomState(D)
+    mu = rs.randn(E, D).astype(F32)
+    log_std = rs.uniform(-1.5, 0.2, D).astype(F32)
+    eps = rs.randn(E, D).astype(F32)
+    a, lp = K.ops.gaussian_sample(K.t(mu), K.t(log_std), eps=K.t(eps))
+    wa, wlp = oma.gaussian_sample(mu, log_std, eps)
+    np.testing.assert_allclose(K.n(a), wa, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(K.n(lp), wlp, rtol=2e-5, atol=1e-4)
+    # Philox path: same normals as the oracle's Box-Muller on the NATURE stream
+    a2, lp2 = K.ops.gaussian_sample(K.t(mu), K.t(log_std), r=K.ops.rng(99, K.lib.STREAM_NATURE, 5, env0=2))
+    weps = oma.normal_eps(99, 5, E, D, env0=2)
+    wa2, wlp2 = oma.gaussian_sample(mu, log_std, weps)
+    np.testing.assert_allclose(K.n(a2), wa2, rtol=1e-4, atol=2e-5)      # sincos / log ulps between libm and CUDA
+    np.testing.assert_allclose(K.n(lp2), wlp2, rtol=1e-4, atol=1e-2 * max(1, D / 1000))
+    if E * D > 10000:
+        z = (K.n(a2) - mu) / np.exp(log_std)
+        assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
+
+
+@pytest.mark.parametrize("name,domain", [("ce", 0), ("armman", 1)])
+def test_ma_step_dropin_matches_reference(K, golden, name, domain):
+    torch = K.torch
+    from robustrmab_b200.environments import ARMMANRobustEnv, CounterExampleRobustEnv
+    from robustrmab_b200.ma_core import RMABLambdaNatureOracle
+    g = golden("ma")
+    N, S, h, D = [int(x) for x in g[name + "_meta"]]
+    env = (CounterExampleRobustEnv if domain == 0 else ARMMANRobustEnv)(N, 2.0, 0)
+    env.sampled_parameter_ranges = g[name + "_ranges"]
+    ac = RMABLambdaNatureOracle(env.observation_space, env.action_space, env.sampled_parameter_ranges, D, env,
+                                hidden_sizes=[h, h], C=env.C, N=N, B=env.B)
+    assert repr(ac) == "MA-RMABPPO_0" and ac.act_dim_nature == D
+    ac.Wpi.copy_(K.t(g[name + "_Wpi"])); ac.Wv.copy_(K.t(g[name + "_Wv"])); ac.W1n.copy_(K.t(g[name + "_W1n"]))
+    with torch.no_grad():
+        for tag, seq in (("mu", ac.pi_nature.mu_net), ("vn", ac.v_nature.v_net)):
+            for j, m in enumerate([m for m in seq if isinstance(m, torch.nn.Linear)]):
+                m.weight.copy_(K.t(g[f"{name}_{tag}_W{j}"])); m.bias.copy_(K.t(g[f"{name}_{tag}_b{j}"]))
+        ac.pi_nature.log_std.copy_(K.t(g[name + "_log_std"]))
+    for k in range(g[name + "_obs"].shape[0]):
+        s = K.t(g[name + "_obs"][k][:, None], np.uint8)
+        d = ac.step_device(s, K.t(g[name + "_lamb"][k:k + 1]), eps=K.t(g[name + "_eps"][k][None]),
+                           u=K.t(g[name + "_u"][k][:, None]))
+        assert np.array_equal(K.n(d["a_agent"])[:, 0], g[name + "_out_a"][k])
+        np.testing.assert_allclose(K.n(d["a_nature"])[0], g[name + "_out_an"][k], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(K.n(d["a_nature_bounded"])[0], g[name + "_out_anb"][k], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(K.n(d["logp_nature"])[0], g[name + "_out_lpn"][k], rtol=2e-5)
+        np.testing.assert_allclose(K.n(d["v_nature"])[0], g[name + "_out_vn"][k], rtol=1e-4, atol=2e-6)
+        np.testing.assert_allclose(K.n(d["v_agent"])[:, 0], g[name + "_out_v"][k], rtol=1e-4, atol=5e-6)
+        np.testing.assert_allclose(K.n(d["logp_agent"])[:, 0], g[name + "_out_logp"][k], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(K.n(d["p1"])[:, 0], g[name + "_out_p1"][k], rtol=1e-5, atol=1e-7)
+    out = ac.step(g[name + "_obs"][0].astype(np.float32), 0.5)      # the reference's 9-tuple and shapes
+    assert len(out) == 9 and out[0].shape == (N,) and out[4].shape == (D,) and np.ndim(out[5]) == 0
+    mu = ac.get_nature_action(g[name + "_obs"][0])
+    assert mu.shape == (D,)
+
+
+def test_agent_critic_extra_batched(K):
+    rs = np.random.RandomState(3)
+    N, E, S, h, D = 9, 40, 3, 16, 18
+    Wpi = onets.init_linear_default(rs, N, S + 1, h, 2)
+    Wv = onets.init_linear_default(rs, N, S + 1, h, 1)
+    W1n = rs.uniform(-0.3, 0.3, (N, h, D)).astype(F32)
+    s = rs.randint(0, S, (N, E)).astype(np.uint8)
+    lamb = rs.uniform(0, 2, E).astype(F32)
+    nat = rs.uniform(0, 1, (E, D)).astype(F32)
+    u = rs.rand(N, E).astype(F32)
+    extra = (K.t(W1n).reshape(-1, D) @ K.t(nat).t()).reshape(N, h, E).contiguous()
+    net = K.ops.net_desc(N, E, S, 2, h, n_extra=D)
+    a, v, logp, p1, _ = K.ops.ac_step(net, K.t(Wpi), K.t(Wv), K.t(s), K.t(lamb), u=K.t(u), extra=extra)
+    want = oma.agent_critic_extra(Wv, W1n, s, lamb, nat, S, h)
+    np.testing.assert_allclose(K.n(v), want, rtol=1e-4, atol=1e-5)
+    with pytest.raises(K.lib.RmabError):
+        K.ops.ac_step(net, K.t(Wpi), K.t(Wv), K.t(s), K.t(lamb), u=K.t(u))      # n_extra > 0 without the addend
+
+
+@pytest.mark.parametrize("domain,pop", [(0, None), (1, None), (2, 10), (2, 50)])
+def test_counterfactual(K, domain, pop):
+    rs = np.random.RandomState(7 + domain)
+    N, E, trials = 8, 12, 50
+    if domain == 2:
+        S = pop + 1
+        rg = oenv.sis_param_ranges(N)
+        nature = (rg[..., 0] + rs.rand(N, 4) * (rg[..., 1] - rg[..., 0])).astype(F32)
+        ranges = np.zeros((1,), F32)
+        a = rs.randint(0, 3, (N, E)).astype(np.uint8)
+    else:
+        S = 2 if domain == 0 else 3
+        base = oenv.ce_param_ranges(N) if domain == 0 else oenv.armman_param_ranges(N)
+        ranges = oenv.sample_sub_ranges(base, rs).astype(F32)
+        nature = (ranges[..., 0] + rs.rand(*ranges.shape[:-1]) * (ranges[..., 1] - ranges[..., 0])).astype(F32)
+        a = rs.randint(0, 2, (N, E)).astype(np.uint8)
+    s = rs.randint(0, S, (N, E)).astype(np.uint8)
+    R = oenv.rewards_table(domain, N, S)
+    got = K.n(K.ops.env_counterfactual(domain, K.t(s), K.t(a), K.t(nature), K.t(ranges), K.t(R),
+                                       K.ops.rng(5, K.lib.STREAM_CF, 3), trials))
+    want = oma.counterfactual_mean(domain, s, a, nature, ranges, R, 5, 3, trials if domain != 2 or pop <= 10 else trials,
+                                   pop=pop)
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)

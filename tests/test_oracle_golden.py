@@ -219,3 +219,36 @@ def test_epoch_loop_matches_reference_best_response(golden, name, domain):
     np.testing.assert_allclose(cpu.opt.Wv.detach().numpy(), g[name + "_Wv1"], rtol=0, atol=2e-4)
     for i, p in enumerate(cpu.lam_params):
         np.testing.assert_allclose(p.detach().numpy(), g[f"{name}_lam1_{i}"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("name,domain", [("ce", 0), ("armman", 1)])
+def test_ma_step_matches_reference(golden, name, domain):
+    """oracle/ma.py against RMABLambdaNatureOracle.step of the unmodified reference (injected Normal / Categorical draws)."""
+    from oracle import ma as oma
+    g = golden("ma")
+    N, S, h, D = [int(x) for x in g[name + "_meta"]]
+    mu_p = [g[f"{name}_mu_{k}{j}"] for j in range(3) for k in ("W", "b")]
+    vn_p = [g[f"{name}_vn_{k}{j}"] for j in range(3) for k in ("W", "b")]
+    rg = g[name + "_ranges"]
+    for k in range(g[name + "_obs"].shape[0]):
+        obs = g[name + "_obs"][k]
+        s = obs[:, None].astype(np.uint8)
+        lamb = g[name + "_lamb"][k:k + 1]
+        mu = oma.dense_mlp(mu_p, obs[None].astype(F32))
+        a_nat, lp_nat = oma.gaussian_sample(mu, g[name + "_log_std"], g[name + "_eps"][k][None])
+        np.testing.assert_allclose(a_nat[0], g[name + "_out_an"][k], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(lp_nat[0], g[name + "_out_lpn"][k], rtol=1e-5)
+        if domain == 0:
+            lo, hi = rg[:, 0], rg[:, 1]
+        else:
+            lo, hi = rg[np.arange(N), obs, :, 0].reshape(-1), rg[np.arange(N), obs, :, 1].reshape(-1)
+        nat_b = oenv.bound_nature(a_nat[0], lo, hi)
+        np.testing.assert_allclose(nat_b, g[name + "_out_anb"][k], rtol=1e-6, atol=1e-7)
+        a, _, logp, p1, _ = onets.ac_step(g[name + "_Wpi"], g[name + "_Wv"], s, lamb, g[name + "_u"][k][:, None], S, 2, h)
+        assert np.array_equal(a[:, 0], g[name + "_out_a"][k])
+        np.testing.assert_allclose(logp[:, 0], g[name + "_out_logp"][k], rtol=2e-6, atol=1e-6)
+        np.testing.assert_allclose(p1[:, 0], g[name + "_out_p1"][k], rtol=2e-6, atol=1e-7)
+        v = oma.agent_critic_extra(g[name + "_Wv"], g[name + "_W1n"], s, lamb, nat_b[None].astype(F32), S, h)
+        np.testing.assert_allclose(v[:, 0], g[name + "_out_v"][k], rtol=1e-5, atol=2e-6)
+        vn = oma.dense_mlp(vn_p, np.concatenate([obs, a[:, 0]])[None].astype(F32))[0, 0]
+        np.testing.assert_allclose(vn, g[name + "_out_vn"][k], rtol=1e-5, atol=1e-6)
