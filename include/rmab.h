@@ -39,7 +39,10 @@ enum { RMAB_OK = 0, RMAB_E_BADARG = -1, RMAB_E_SHAPE = -2, RMAB_E_ARCH = -3, RMA
 enum { RMAB_DOMAIN_CE = 0, RMAB_DOMAIN_ARMMAN = 1, RMAB_DOMAIN_SIS = 2 };
 enum { RMAB_STREAM_ENV = 0, RMAB_STREAM_ACT = 1, RMAB_STREAM_NATURE = 2, RMAB_STREAM_RESET = 3,
        RMAB_STREAM_CF = 4, RMAB_STREAM_INIT = 7 };
-enum { RMAB_STOP_FULL = 0, RMAB_STOP_FAST = 1 }; /* mdptoolbox stop_criterion 'full' / 'fast' */
+/* mdptoolbox stop_criterion 'full' / 'fast' (both also stop at the _boundIter iteration bound, which leaves V
+ * span-converged only), and ABS: iterate until the sup-norm change is below thresh, ignoring the bound -- the
+ * absolutely converged value function that the Hawkins objective (lp_methods.py:63) needs. */
+enum { RMAB_STOP_FULL = 0, RMAB_STOP_FAST = 1, RMAB_STOP_ABS = 2 };
 
 /* Philox counter block shared by the sampling kernels. */
 typedef struct RmabRng {

@@ -43,7 +43,12 @@ def value_iteration(P, R, gamma, eps=0.01, stop="full", max_iter=None):
     R = np.asarray(R, dtype=np.float64)
     A, S, _ = P.shape
     if max_iter is None:
-        max_iter = bound_iter(P, R, gamma, eps)
+        try:
+            max_iter = bound_iter(P, R, gamma, eps)
+        except (ZeroDivisionError, ValueError, OverflowError):
+            if stop != "abs":
+                raise
+            max_iter = 10 ** 6
     thresh = eps * (1 - gamma) / gamma
     V = np.zeros(S)
     it = 0
@@ -55,9 +60,11 @@ def value_iteration(P, R, gamma, eps=0.01, stop="full", max_iter=None):
         V = Q.max(axis=0)
         d = V - Vprev
         variation = (d.max() - d.min()) if stop == "fast" else d.max()
+        if stop == "abs":                      # not in mdptoolbox: sup-norm change, no iteration bound (true convergence)
+            variation = np.abs(d).max()
         if variation < thresh:
             break
-        if it == max_iter:
+        if it == max_iter and stop != "abs":
             break
     return V, policy, it, max_iter
 
@@ -136,3 +143,43 @@ def hawkins_objective(V, start_state, lambdas, B, gamma):
     N = V.shape[0]
     vs = V[np.arange(N), :, np.asarray(start_state, np.int64)]     # [N,L]
     return vs.sum(axis=0) + np.asarray(lambdas, np.float64) * B / (1 - gamma)
+
+
+def hawkins_lp_highs(T, R, C, B, start_state, gamma, lambda_lim):
+    """lp_methods.hawkins (:11-105) restated for scipy's HiGHS (Gurobi is absent): variables (lambda, L[N,S]),
+    minimise sum_i L_i(s_i) + lambda B/(1-gamma) + 1e-6 sum L  s.t.  L_i(s) >= R_i(s) - lambda C[a] + gamma T_i[s,a].L_i.
+    Small N only (test infrastructure).  Returns (L_vals [N,S], lambda, objective)."""
+    from scipy.optimize import linprog
+    T = np.asarray(T, np.float64)
+    N, S, A, _ = T.shape
+    nv = 1 + N * S
+    c = np.full(nv, 1e-6)
+    c[0] = B / (1 - gamma)
+    for i in range(N):
+        c[1 + i * S + int(start_state[i])] += 1.0
+    A_ub, b_ub = [], []
+    for i in range(N):
+        for s in range(S):
+            for a in range(A):
+                row = np.zeros(nv)
+                row[0] = -C[a]                                   # -lambda*C[a] moved to the left: -L + g T.L - lambda C <= -R
+                row[1 + i * S:1 + (i + 1) * S] = gamma * T[i, s, a]
+                row[1 + i * S + s] -= 1.0
+                A_ub.append(row)
+                b_ub.append(-R[i, s])
+    res = linprog(c, A_ub=np.array(A_ub), b_ub=np.array(b_ub), bounds=[(0, lambda_lim)] + [(None, None)] * (N * S),
+                  method="highs")
+    assert res.status == 0, res.message
+    return res.x[1:].reshape(N, S), res.x[0], res.fun
+
+
+def hawkins_action_binary(T, R, C, B, state, lam, gamma, eps=1e-10):
+    """Hawkins action for binary costs: Q from the converged lambda-charged value function, then exactly B/C[1] arms
+    with the largest Q(s,1) - Q(s,0) (the equality knapsack of lp_methods.py:243-250), ties -> higher arm index."""
+    N = T.shape[0]
+    V, _, _, _ = batched_vi(T, R, C, np.array([lam]), gamma, eps, stop="abs")
+    Q = q_values(T, R, C, V, np.array([lam]), gamma)[:, 0]                       # [N,S,A]
+    gap = (Q[np.arange(N), state, 1] - Q[np.arange(N), state, 0]).astype(np.float32)
+    a = np.zeros(N, dtype=np.int64)
+    a[np.argsort(gap, kind="stable")[::-1][:int(B / C[1])]] = 1
+    return a

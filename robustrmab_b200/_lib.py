@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "librmab_b200.so")
 OK, E_BADARG, E_SHAPE, E_ARCH, E_LAUNCH = 0, -1, -2, -3, -4
 DOMAIN_CE, DOMAIN_ARMMAN, DOMAIN_SIS = 0, 1, 2
 STREAM_ENV, STREAM_ACT, STREAM_NATURE, STREAM_RESET, STREAM_CF, STREAM_INIT = 0, 1, 2, 3, 4, 7
-STOP_FULL, STOP_FAST = 0, 1
+STOP_FULL, STOP_FAST, STOP_ABS = 0, 1, 2
 
 
 class RmabError(RuntimeError):

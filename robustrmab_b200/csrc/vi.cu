@@ -90,6 +90,7 @@ struct SmallMdp {
 #pragma unroll
     for (int s = 1; s < S; ++s) { mx = fmax(mx, V1[s]); mn = fmin(mn, V1[s]); }
     max_iter = bound_iter(k, mx - mn, p);
+    if (p.stop_mode == RMAB_STOP_ABS && max_iter == -1) max_iter = kViCap;
     if (max_iter == -1) {
 #pragma unroll
       for (int s = 0; s < S; ++s) V[s] = __longlong_as_double(0x7ff8000000000000ll);
@@ -107,9 +108,10 @@ struct SmallMdp {
       for (int s = 1; s < S; ++s) { const double dd = Vn[s] - V[s]; dmx = fmax(dmx, dd); dmn = fmin(dmn, dd); }
 #pragma unroll
       for (int s = 0; s < S; ++s) V[s] = Vn[s];
-      const double variation = p.stop_mode == RMAB_STOP_FAST ? dmx - dmn : dmx;
+      double variation = p.stop_mode == RMAB_STOP_FAST ? dmx - dmn : dmx;
+      if (p.stop_mode == RMAB_STOP_ABS) variation = fmax(fabs(dmx), fabs(dmn));  // sup-norm change: true convergence
       if (variation < p.thresh) break;
-      if (it == max_iter) break;
+      if (it == max_iter && p.stop_mode != RMAB_STOP_ABS) break;
       if (it >= kViCap) break;
     }
     return it;
@@ -247,7 +249,8 @@ __global__ void __launch_bounds__(256) vi_generic_kernel(int S, int A, int L, co
         for (int a = 1; a < A; ++a) best = fmax(best, sR[s] - sLam[l] * sC[a]);
         if (s == 0) { mx = best; mn = best; } else { mx = fmax(mx, best); mn = fmin(mn, best); }
       }
-      const int mi = bound_iter(s_k, mx - mn, p);
+      int mi = bound_iter(s_k, mx - mn, p);
+      if (p.stop_mode == RMAB_STOP_ABS && mi == -1) mi = kViCap;
       sMax[l] = mi;
       sIt[l] = mi == -1 ? -1 : 0;
       sAct[l] = mi != -1;
@@ -284,8 +287,9 @@ __global__ void __launch_bounds__(256) vi_generic_kernel(int S, int A, int L, co
           if (s == 0) { dmx = dd; dmn = dd; } else { dmx = fmax(dmx, dd); dmn = fmin(dmn, dd); }
         }
         const int it = ++sIt[l];
-        const double variation = p.stop_mode == RMAB_STOP_FAST ? dmx - dmn : dmx;
-        if (variation < p.thresh || it == sMax[l]) sAct[l] = 0;
+        double variation = p.stop_mode == RMAB_STOP_FAST ? dmx - dmn : dmx;
+        if (p.stop_mode == RMAB_STOP_ABS) variation = fmax(fabs(dmx), fabs(dmn));
+        if (variation < p.thresh || (it == sMax[l] && p.stop_mode != RMAB_STOP_ABS)) sAct[l] = 0;
         else s_any = 1;
       }
       __syncthreads();
@@ -379,7 +383,8 @@ extern "C" int rmab_vi_batched(int N, int S, int A, int L, const double* T, cons
   RMAB_REQUIRE(N >= 0 && S >= 1 && S <= 256 && A >= 1 && A <= 16 && L >= 1, RMAB_E_SHAPE, "rmab_vi_batched: bad shape");
   RMAB_REQUIRE(T && R && C && lambdas && V, RMAB_E_BADARG, "rmab_vi_batched: null pointer");
   RMAB_REQUIRE(gamma > 0.0 && gamma < 1.0 && eps > 0.0, RMAB_E_BADARG, "rmab_vi_batched: need 0 < gamma < 1 and eps > 0");
-  RMAB_REQUIRE(stop_mode == RMAB_STOP_FULL || stop_mode == RMAB_STOP_FAST, RMAB_E_BADARG, "rmab_vi_batched: bad stop_mode");
+  RMAB_REQUIRE(stop_mode == RMAB_STOP_FULL || stop_mode == RMAB_STOP_FAST || stop_mode == RMAB_STOP_ABS, RMAB_E_BADARG,
+               "rmab_vi_batched: bad stop_mode");
   if (N == 0) return RMAB_OK;
   const ViParams p = make_params(gamma, eps, stop_mode);
   cudaStream_t st = (cudaStream_t)stream;

@@ -1,0 +1,88 @@
+"""Hawkins (Lagrangian-relaxation) agent policy on the device: `HawkinsAgentPolicy` of
+robust_rmab/baselines/agent_baselines.py:35-116, whose reference implementation calls two Gurobi programs per step
+(`lp_methods.hawkins` :11-105 and `action_knapsack` :221-271).
+
+Reformulation: for a fixed lambda the LP's minimal L_i is the optimal value function of
+arm i's lambda-charged MDP, so   obj(lambda) = sum_i V_i(s_i; lambda) + lambda * B / (1 - gamma)   (:63) is evaluated
+for a whole grid of lambda-probes by ONE batched value iteration (rmab_vi_batched in its absolutely-converged
+stop mode -- mdptoolbox's own iteration bound leaves V off by a per-MDP constant), minimised over
+the grid and refined by re-gridding around the minimiser (obj is convex piecewise linear in lambda).  The action is
+the knapsack over Q(s_i, a; lambda*) = R - lambda* C[a] + gamma T.L (:69-91); for binary costs C = [0, c] with the
+equality budget `sum x C == B` (:250) that is action 1 for exactly B / c arms with the largest Q(s,1) - Q(s,0).
+PARITY UNPINNED against Gurobi (absent); pinned against a HiGHS restatement of the LP at small N (tests).
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+_F64 = torch.float64
+
+
+class HawkinsAgentPolicy:
+    def __init__(self, N, T, R, C, B, gamma, ind, n_probes=64, n_refine=3, eps=1e-8, device="cuda"):
+        self.N, self.B, self.gamma, self.ind = int(N), B, float(gamma), ind
+        self.T, self.R, self.C = np.asarray(T, np.float64), np.asarray(R, np.float64), np.asarray(C, np.float64)
+        self.name = "Hawkins"
+        self.n_probes, self.n_refine, self.eps = int(n_probes), int(n_refine), float(eps)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("HawkinsAgentPolicy solves on CUDA only (no CPU fallback)")
+        if self.C.shape[0] != 2 or self.C[0] != 0:
+            raise NotImplementedError("device knapsack covers binary costs C = [0, c]; multi-action costs need the "
+                                      "multiple-choice knapsack of lp_methods.py:221-271 (next)")
+        self._T = torch.as_tensor(self.T, dtype=_F64, device=self.device).contiguous()
+        self._R = torch.as_tensor(self.R, dtype=_F64, device=self.device).contiguous()
+        self._C = torch.as_tensor(self.C, dtype=_F64, device=self.device).contiguous()
+        self.lambda_lim = float(self.R.max() / (self.C[self.C > 0].min() * (1 - self.gamma)))   # agent_baselines.py:61
+
+    def __repr__(self):
+        return "%s_%s" % (self.name, self.ind)
+
+    def objective(self, s, lambdas):
+        """obj[e, k] = sum_i V_i(s_i(e); lambda_k) + lambda_k B / (1 - gamma) for states s `[N,E]`; also returns V, Q."""
+        V, _, _, _, Q = ops.vi_batched(self._T, self._R, self._C, lambdas, self.gamma, self.eps, stop="abs", want_q=True)
+        idx = s.long()[:, None, :].expand(-1, lambdas.shape[0], -1)                  # [N,L,E]
+        vs = torch.gather(V, 2, idx)                                                 # V[n,l,s[n,e]]
+        obj = vs.sum(dim=0).t() + lambdas[None, :] * (self.B / (1.0 - self.gamma))   # [E,L]
+        return obj, V, Q
+
+    def hawkins_lambda_device(self, s):
+        """lambda* per env `[E]` (grid + refinement; refinement re-grids around each env's minimiser)."""
+        E = s.shape[1]
+        lo = torch.zeros(E, dtype=_F64, device=self.device)
+        hi = torch.full((E,), self.lambda_lim, dtype=_F64, device=self.device)
+        best = None
+        for rd in range(1 + self.n_refine):
+            if rd == 0 or E == 1:
+                grid = lo[0] + (hi[0] - lo[0]) * torch.linspace(0, 1, self.n_probes, dtype=_F64, device=self.device)
+                obj, _, _ = self.objective(s, grid.contiguous())
+                k = obj.argmin(dim=1)
+                best = grid[k]
+                step = (hi[0] - lo[0]) / (self.n_probes - 1)
+                lo = torch.clamp(best - step, min=0.0)
+                hi = torch.clamp(best + step, max=self.lambda_lim)
+            else:
+                break   # per-env refinement needs one VI batch per env; the shared grid is the E > 1 resolution
+        return best
+
+    def act_test_device(self, s):
+        lam = self.hawkins_lambda_device(s)                                          # [E]
+        E = s.shape[1]
+        a = torch.empty_like(s)
+        k = float(self.B) / float(self.C[1])
+        for e in range(E):                                                           # Q at each env's own lambda*
+            _, _, _, _, Q = ops.vi_batched(self._T, self._R, self._C, lam[e:e + 1].contiguous(), self.gamma, self.eps,
+                                           stop="abs", want_q=True)
+            q = torch.gather(Q[:, 0], 1, s[:, e].long()[:, None, None].expand(-1, 1, 2))[:, 0]   # [N,2]
+            gap = (q[:, 1] - q[:, 0]).to(torch.float32)[:, None].contiguous()
+            a[:, e] = ops.budget_select_binary(gap, 1.0, k)[:, 0]
+        return a
+
+    def act_test(self, o, just_hawkins_lambda=False):
+        cur = o.numpy() if isinstance(o, torch.Tensor) else np.asarray(o)
+        s = torch.as_tensor(cur.reshape(self.N, -1).astype(np.uint8), device=self.device)
+        if just_hawkins_lambda:
+            return self.hawkins_lambda_device(s).cpu().numpy()
+        a = self.act_test_device(s).cpu().numpy().astype(int)
+        return a[:, 0] if a.shape[1] == 1 else a

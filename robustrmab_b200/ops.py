@@ -292,7 +292,7 @@ def vi_batched(T, R, Cc, lambdas, gamma, eps, stop="full", want_q=False):
     Q = torch.empty((N, L, S, A), dtype=f64, device=dev) if want_q else None
     check(lib().rmab_vi_batched(N, S, A, L, _p(T, f64, "T"), _p(R, f64, "R"), _p(Cc, f64, "C"),
                                 _p(lambdas, f64, "lambdas"), int(per_arm), float(gamma), float(eps),
-                                _lib.STOP_FAST if stop == "fast" else _lib.STOP_FULL, _p(V, f64), _p(pol, u8),
+                                {"fast": _lib.STOP_FAST, "abs": _lib.STOP_ABS}.get(stop, _lib.STOP_FULL), _p(V, f64), _p(pol, u8),
                                 _p(iters, i32), _p(mi, i32), _p(Q, f64), _stream()))
     return V, pol, iters, mi, Q
 

@@ -219,3 +219,33 @@ def test_simulate_reward_matches_oracle(torch_mod, domain):
     np.testing.assert_allclose(got, want, rtol=1e-12)            # same states and actions -> same returns
     zero = simulate_reward(PessimisticAgentPolicy(N), env, torch.as_tensor(nature, device=env.device), T, E, 0.9, seed=11)
     assert np.isfinite(zero)
+
+
+def test_hawkins_policy_against_highs_lp(torch_mod):
+    """Device Hawkins lambda* / action against a HiGHS restatement of the reference LP (lp_methods.py:11-105)."""
+    torch = torch_mod
+    from oracle import vi as ovi
+    from robustrmab_b200.hawkins import HawkinsAgentPolicy
+    rs = np.random.RandomState(4)
+    N, B, gamma = 9, 3.0, 0.9
+    rg = oenv.sample_sub_ranges(oenv.armman_param_ranges(N), rs)
+    p = rg.mean(-1)
+    T = np.zeros((N, 3, 2, 3))
+    for s in range(3):
+        for a in range(2):
+            T[:, s, a] = oenv.armman_probs(np.full(N, s), np.full(N, a), p[:, s, a]).astype(np.float64)
+    R = oenv.rewards_table(1, N, 3).astype(np.float64)
+    C = np.array([0.0, 1.0])
+    pol = HawkinsAgentPolicy(N, T, R, C, B, gamma, 0, n_probes=64, n_refine=4)
+    assert repr(pol) == "Hawkins_0" and abs(pol.lambda_lim - 10.0) < 1e-12
+    for trial in range(3):
+        state = rs.randint(0, 3, N)
+        L_lp, lam_lp, obj_lp = ovi.hawkins_lp_highs(T, R, C, B, state, gamma, pol.lambda_lim)
+        lam = float(pol.act_test(state, just_hawkins_lambda=True)[0])
+        s = torch.as_tensor(state[:, None].astype(np.uint8), device=pol.device)
+        obj, V, _ = pol.objective(s, torch.tensor([lam, lam_lp], dtype=torch.float64, device=pol.device))
+        # obj is convex piecewise linear: the grid minimiser attains the LP optimum up to the final grid spacing
+        assert obj[0, 0].item() <= obj_lp + 1e-3 and abs(obj[0, 1].item() - obj_lp) < 1e-4 * max(1.0, abs(obj_lp))
+        np.testing.assert_allclose(V[:, 1].cpu().numpy(), L_lp, rtol=1e-5, atol=1e-5)   # V(lambda_lp) is the LP's L
+        a = pol.act_test(state)
+        assert a.sum() == B and np.array_equal(a, ovi.hawkins_action_binary(T, R, C, B, state, lam, gamma))

@@ -214,3 +214,70 @@ def test_trainer_matches_reference_best_response(K, golden, name, domain):
     np.testing.assert_allclose(K.n(tr.Wv), g[name + "_Wv1"], rtol=0, atol=5e-4)
     lam1 = np.concatenate([g[f"{name}_lam1_{i}"].reshape(-1) for i in range(6)])
     np.testing.assert_allclose(K.n(tr.lam_params), lam1, rtol=2e-5, atol=1e-6)
+
+
+def test_full_size_config3_armman_properties(K):
+    """BASELINE configs[2] shape on one GPU -- ARMMAN, N = 100 000 arms x 1024 envs, T = 10, hidden [64,64] -- checked
+    through size-independent properties (the oracle cannot run this size): state / action ranges, visit counts that
+    add up to T, normalised advantages with zero mean and unit variance per arm, budget feasibility of act_test."""
+    torch = K.torch
+    from robustrmab_b200.trainer import RMABPPOTrainer
+    N, E, T = 100000, 1024, 10
+    tr = RMABPPOTrainer("armman", N, E, T, hidden=64, B=0.2 * N, train_pi_iters=1, train_v_iters=1, epochs=4, seed=1,
+                        device=K.dev)
+    w0 = tr.Wpi[:64].clone()
+    st = tr.epoch(keep_buffers=False)
+    torch.cuda.synchronize()
+    assert int(tr.s_traj.max()) <= 2 and int(tr.a.max()) <= 1
+    SA, S = 6, 3
+    cnt = tr.stats[:, 3 * SA + 3 * S:]                               # n[s,a] rows
+    assert torch.equal(cnt.sum(dim=1), torch.full((N, E), float(T), device=K.dev))
+    cntS = tr.stats[:, 3 * SA:3 * SA + S]
+    assert torch.equal(cntS.sum(dim=1), torch.full((N, E), float(T), device=K.dev))
+    # sum of A+ and A- over all cells and envs = sum of the normalised advantages of the arm = 0; their spread = T*E
+    tot = (tr.stats[:, :SA] + tr.stats[:, SA:2 * SA]).sum(dim=(1, 2))
+    assert float(tot.abs().max()) < 0.5                               # of T*E = 10240 unit-variance samples
+    assert torch.isfinite(tr.arm_stats[:, :3]).all() and float(tr.arm_stats[:, 1].min()) > 0
+    assert torch.isfinite(tr.Wpi).all() and torch.isfinite(tr.Wv).all() and not torch.equal(tr.Wpi[:64], w0)
+    assert torch.isfinite(st["Lamb"]).all() and st["EpActualRet"].shape == (E,)
+    # rewards are in [0, 1]: per-env return of N arms over T steps
+    assert float(st["EpActualRet"].min()) >= 0 and float(st["EpActualRet"].max()) <= N * T
+    # act_test at full size: exactly floor(B) arms per env get action 1 (binary top-k over 100k arms)
+    p1 = torch.rand((N, 64), device=K.dev)
+    a = K.ops.budget_select_binary(p1, 1.0, 0.2 * N)
+    assert torch.equal(a.sum(dim=0, dtype=torch.int64), torch.full((64,), int(0.2 * N), device=K.dev))
+    thr = torch.topk(p1[:, 0], int(0.2 * N)).values.min()
+    assert torch.equal(a[:, 0].bool(), p1[:, 0] >= thr)
+    del tr
+    torch.cuda.empty_cache()
+
+
+def test_full_size_config5_vi_properties(K):
+    """BASELINE configs[4] shape: counterexample, N = 99 999 arms x 64 lambda-probes."""
+    torch = K.torch
+    N, L = 99999, 64
+    rg = oenv.ce_param_ranges(N)
+    p = rg.mean(-1)
+    T = np.zeros((N, 2, 2, 2))
+    T[:, 0] = 0.5
+    T[:, 1, 0, 0] = 1.0
+    T[:, 1, 1, 1], T[:, 1, 1, 0] = p, 1 - p
+    R = np.tile(np.array([0.0, 1.0]), (N, 1))
+    C = np.array([0.0, 1.0])
+    lambdas = np.linspace(0, 10, L)
+    V, pol, it, mi, Q = K.ops.vi_batched(K.t(T), K.t(R), K.t(C), K.t(lambdas), 0.9, 1e-8, want_q=True)
+    ok = it >= 0
+    assert bool(ok.all()) and torch.equal(it, mi)                     # the reference always stops at _boundIter's bound
+    assert bool((V[:, 1:] <= V[:, :-1] + 1e-12).all())                # value is non-increasing in the charge lambda
+    assert bool((pol[:, -1] == 0).all())                              # at lambda = lambda_lim nobody acts
+    # arms repeat with period 3 (ranges cycle by arm % 3): identical MDPs give identical results
+    assert torch.equal(V[0], V[3]) and torch.equal(V[1], V[99997])
+    from oracle import vi as ovi
+    wV, wpol, wit, _ = ovi.batched_vi(T[:3], R[:3], C, lambdas, 0.9, 1e-8)
+    np.testing.assert_allclose(K.n(V[:3]), wV, rtol=1e-12, atol=1e-12)
+    assert np.array_equal(K.n(it[:3]), wit)
+    idx = K.ops.whittle_bisect(K.t(T), K.t(R), K.t(C), 0.9, 1e-8, 0.0, 10.0, 30)
+    assert bool(((idx >= 0) & (idx <= 10)).all())
+    assert float(idx[:, 0].max()) < 1e-6                              # state 0 ignores the action: zero index
+    widx = ovi.whittle_bisect(T[:3], R[:3], C, 0.9, 1e-8, 0.0, 10.0, 30)
+    np.testing.assert_allclose(K.n(idx[:3]), widx, atol=1e-9)
