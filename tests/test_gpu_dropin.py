@@ -249,3 +249,57 @@ def test_hawkins_policy_against_highs_lp(torch_mod):
         np.testing.assert_allclose(V[:, 1].cpu().numpy(), L_lp, rtol=1e-5, atol=1e-5)   # V(lambda_lp) is the LP's L
         a = pol.act_test(state)
         assert a.sum() == B and np.array_equal(a, ovi.hawkins_action_binary(T, R, C, B, state, lam, gamma))
+
+
+class _TableNature:
+    """Stands in for the reference's SampledRandomNaturePolicy (nature_baselines_*.py): a per-arm parameter table."""
+
+    def __init__(self, ranges, seed):
+        rs = np.random.RandomState(seed)
+        self.param_setting = (rs.rand(*ranges.shape[:-1]) * (ranges[..., 1] - ranges[..., 0]) + ranges[..., 0])
+
+    def get_nature_action(self, o):
+        return self.param_setting
+
+    def bound_nature_actions(self, actions, state=None, reshape=True):
+        return actions
+
+
+@pytest.mark.parametrize("data", ["counterexample", "armman"])
+def test_agent_oracle_dropin_and_stepwise_equals_fused(torch_mod, data):
+    """AgentOracle.best_response / simulate_reward drop-in, and the two device loops against each other: with the
+    same seeds the stepwise loop (ac.step + env.step launches, per-sample update) and the fused loop (one launch per
+    epoch, statistics update) must walk the same trajectories and end with the same nets."""
+    torch = torch_mod
+    from robustrmab_b200.agent_oracle import AgentOracle, StepwiseRMABPPO
+    from robustrmab_b200.trainer import RMABPPOTrainer
+    N, E, T, epochs, B = 12, 8, 15, 4, 4.0
+    S = 2 if data == "counterexample" else 3
+    kw = dict(steps_per_epoch=T, epochs=epochs, gamma=0.9, clip_ratio=2.0, pi_lr=2e-3, vf_lr=2e-3, lm_lr=2e-3,
+              train_pi_iters=4, train_v_iters=4, lamb_update_freq=2, final_train_lambdas=1, start_entropy_coeff=0.5,
+              end_entropy_coeff=0.0, ac_kwargs=dict(hidden_sizes=[16, 16]))
+    tmp = AgentOracle(data, N, S, 2, B, 3, 1, agent_kwargs=kw, n_envs=E)
+    ranges = tmp.env.sample_parameter_ranges()
+    nature = _TableNature(ranges, 1)
+    orc = AgentOracle(data, N, S, 2, B, 3, 1, agent_kwargs=kw, sampled_nature_parameter_ranges=ranges, n_envs=E)
+    torch.manual_seed(0)
+    ac = orc.best_response([nature], [1.0], 0)
+    assert repr(ac) == "RMABPPO_1" and len(orc.history) == epochs and orc.history[0]["EpActualRet"].shape == (E,)
+    a = ac.act_test(np.zeros((N, E)))
+    assert a.shape == (N, E) and (a.sum(0) == B).all()
+    val = orc.simulate_reward(ac, nature, seed=5, steps_per_epoch=10, epochs=16, gamma=0.9)
+    assert np.isfinite(val) and 0 <= val <= N * 10
+    # stepwise vs fused on the same initial nets
+    torch.manual_seed(0)
+    from robustrmab_b200.core import MLPActorCriticRMAB
+    env = orc.env_fn()
+    env.sampled_parameter_ranges = ranges
+    ac2 = MLPActorCriticRMAB(env.observation_space, env.action_space, hidden_sizes=[16, 16], N=N, C=env.C, B=B, strat_ind=1,
+                             n_envs=E)
+    sw = StepwiseRMABPPO(env, ac2, T, 0.9, 0.97, 2.0, 2e-3, 2e-3, 2e-3, 4, 4, epochs, 2, 1, 0.5, 0.0, 3)
+    rets = [sw.epoch(nature)["EpActualRet"].cpu().numpy() for _ in range(epochs)]
+    for ep in range(epochs):
+        agree = (rets[ep] == orc.history[ep]["EpActualRet"]).mean()
+        assert agree == 1.0 if ep == 0 else agree > 0.7, (ep, agree)         # epoch 0: identical trajectories
+    np.testing.assert_allclose(ac2.Wpi.cpu().numpy(), ac.Wpi.cpu().numpy(), atol=3e-3)
+    np.testing.assert_allclose(ac2.Wv.cpu().numpy(), ac.Wv.cpu().numpy(), atol=3e-3)
