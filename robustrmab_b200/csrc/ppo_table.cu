@@ -491,6 +491,10 @@ static int run_table(const TblArgs& base, float* Wpi, float* Wv, float* adam_pi,
 int ppo_table_mma_run(const RmabNetDesc* net, const RmabHyper* hp, int T, float* Wpi, float* Wv, float* adam_pi,
                       float* adam_v, const float* stats, const float* arm_stats, const float* lamb, float* loss_pi,
                       float* loss_v, cudaStream_t st);
+// tensor-core variant for H = 64 (ppo_table_mma64.cu)
+int ppo_table_mma64_run(const RmabNetDesc* net, const RmabHyper* hp, int T, float* Wpi, float* Wv, float* adam_pi,
+                        float* adam_v, const float* stats, const float* arm_stats, const float* lamb, float* loss_pi,
+                        float* loss_v, cudaStream_t st);
 
 }  // namespace rmab
 
@@ -513,10 +517,12 @@ extern "C" int rmab_ppo_update_table(const RmabNetDesc* net, const RmabHyper* hp
   TblArgs g = {};
   g.d = *net; g.hp = *hp; g.T = T; g.lamb = lamb; g.stats = stats; g.arm_stats = arm_stats;
   cudaStream_t st = (cudaStream_t)stream;
-  // H = 16 / 32: 3xTF32 mma.sync kernel; H = 8 / 64 (and RMAB_TABLE_FFMA=1, for A/B measurements): FFMA kernel
+  // H = 16 / 32 / 64: 3xTF32 mma.sync kernels; H = 8 (and RMAB_TABLE_FFMA=1, for A/B measurements): FFMA kernel
   static const bool force_ffma = getenv("RMAB_TABLE_FFMA") != nullptr;
   if ((h == 16 || h == 32) && !force_ffma)
     return ppo_table_mma_run(net, hp, T, Wpi, Wv, adam_pi, adam_v, stats, arm_stats, lamb, loss_pi, loss_v, st);
+  if (h == 64 && !force_ffma)
+    return ppo_table_mma64_run(net, hp, T, Wpi, Wv, adam_pi, adam_v, stats, arm_stats, lamb, loss_pi, loss_v, st);
 #define RUN(H)                                                                                   \
   return S == 2 ? run_table<H, 2>(g, Wpi, Wv, adam_pi, adam_v, loss_pi, loss_v, st)              \
                 : run_table<H, 3>(g, Wpi, Wv, adam_pi, adam_v, loss_pi, loss_v, st);
