@@ -171,6 +171,22 @@ int rmab_env_counterfactual(int domain, int E, int N, int S, const uint8_t* s, c
                             int nature_per_env, const float* ranges, const float* R, const RmabRng* rng, int n_trials,
                             float* r_mean, rmab_stream_t stream);
 
+/* One full-batch Adam iteration of the MA-RMABPPO agent critics' value loss (compute_loss_v_agent,
+ * nature_oracle.py:389-416; update loop :520-527).  Critic i = MLP([x_i, bounded nature vector] -> h -> h -> 1); its
+ * first layer splits into the packed block W1[h,in] (in Wv, as rmab_ppo_update) and W1_nature[h,D], which the caller
+ * applies / differentiates with dense GEMMs:
+ *   z1_extra[n, m, :] = W1_nature[n] . nature_bounded[m]      (input,  [N, T*E, h])
+ *   dz1_out [n, m, :] = dLoss_n / d(first-layer pre-activation) (output, [N, T*E, h]) -> dW1_nature[n] = dz1^T . nature
+ * The kernel does the forward / backward of everything else and the Adam step of the packed block (step number
+ * hp->adam_step0_v + 1).  s [N,s_rows,E] u8 (first T rows), ret [N,T,E], lamb [E], loss_v [N] (may be NULL). */
+int rmab_critic_extra_iter(const RmabNetDesc* net, const RmabHyper* hp, int T, int s_rows, float* Wv, float* adam_v,
+                           const uint8_t* s, const float* ret, const float* lamb, const float* z1_extra, float* dz1_out,
+                           float* loss_v, rmab_stream_t stream);
+
+/* Elementwise Adam step (torch.optim.Adam defaults form) on a flat fp32 tensor; `step` is 1-based. */
+int rmab_adam_step(int64_t n, float* p, const float* grad, float* m, float* v, double lr, double beta1, double beta2,
+                   double eps, int step, rmab_stream_t stream);
+
 /* ---- buffer ------------------------------------------------------------------------------ */
 
 /* RMABPPO_Buffer.finish_path + get (agent_oracle.py:90-161): GAE-lambda advantages, rewards-to-go

@@ -3,6 +3,7 @@
 // Reference behaviour: robust_rmab/algos/ma_rmabppo/ma_rmabppo_core.py MLPGaussianActor :98-113, step :289-291
 // (a ~ Normal(mu_net(obs), exp(log_std)), logp = sum over action dims); nature_oracle.py:685-701 (50 env steps
 // from the same state with the test agent action, mean of the summed rewards).
+#include <math.h>
 #include "common.cuh"
 
 namespace rmab {
@@ -164,9 +165,37 @@ __global__ void __launch_bounds__(128) cf_sis_kernel(int E, int N, int pop, cons
   }
 }
 
+// Elementwise Adam step (torch.optim.Adam defaults form, _single_tensor_adam) on a flat tensor: used for the
+// agent critics' first-layer block over the nature inputs, whose gradient comes from a dense GEMM.
+__global__ void adam_step_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ grad, float* __restrict__ m,
+                                 float* __restrict__ v, float lerp_w, float beta2, float omb2, float step_size, float bc2s,
+                                 float eps) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = grad[i];
+    const float mi = m[i] + lerp_w * (gi - m[i]);
+    const float vi = v[i] * beta2 + (omb2 * gi) * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = p[i] - step_size * (mi / (sqrtf(vi) / bc2s + eps));
+  }
+}
+
 }  // namespace rmab
 
 using namespace rmab;
+
+extern "C" int rmab_adam_step(int64_t n, float* p, const float* grad, float* m, float* v, double lr, double beta1,
+                              double beta2, double eps, int step, rmab_stream_t stream) {
+  RMAB_REQUIRE(n >= 0 && p && grad && m && v && step >= 1, RMAB_E_BADARG, "rmab_adam_step: bad argument");
+  if (n == 0) return RMAB_OK;
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  const int64_t b = (n + 255) / 256;
+  const int grid = (int)(b < (int64_t)kNumSMs * 16 ? b : (int64_t)kNumSMs * 16);
+  adam_step_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, p, grad, m, v, (float)(1.0 - beta1), (float)beta2,
+                                                          (float)(1.0 - beta2), (float)(lr / bc1), (float)sqrt(bc2),
+                                                          (float)eps);
+  return check_launch("rmab_adam_step");
+}
 
 extern "C" int rmab_gaussian_sample(int E, int D, const float* mu, const float* log_std, const RmabRng* rng,
                                     const float* eps_inject, float* a, float* logp, rmab_stream_t stream) {

@@ -1,0 +1,231 @@
+"""Drop-in `NatureOracle` (robust_rmab/algos/ma_rmabppo/nature_oracle.py:197-806): MA-RMABPPO best response of the
+nature player against a mixed agent strategy, with the rollout and the agent-side update on the device.
+
+Per time step (nature_oracle.py:673-735): `ac.step` (Gaussian nature action, per-arm agent actions, agent critics over
+the bounded nature vector, nature critic), `env.step`, then the counterfactual reward estimate -- 50 env steps from the
+same state with the sampled agent strategy's `act_test` action -- and
+`r_nature = sum r_agent - mean_test - lambda * sum cost` (:707-719).
+Epoch end: bootstrap `ac.step`, `MA_RMABPPO_Buffer.finish_path` (:107-167: the agent GAE per arm, the nature GAE on
+the scalar stream), `get` (:168-193: per-arm and nature advantage normalisation), `update` (:486-576):
+  agent policies   train_pi_iters Adam steps (rmab_ppo_update, policy loss only)
+  agent critics    train_v_iters Adam steps; every iteration = dense GEMM (nature block of the first layer), one
+                   rmab_critic_extra_iter launch (everything else + Adam of the packed block), dense GEMM for the nature
+                   block's gradient, rmab_adam_step
+  every lamb_update_freq epochs: lambda-net SGD step (rmab_lambda_sgd), nature policy and nature critic
+                   train_pi_iters / train_v_iters Adam steps (dense N -> h -> h -> D nets: torch modules, library GEMMs).
+"""
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .environments import ARMMANRobustEnv, CounterExampleRobustEnv, SISRobustEnv
+from .ma_core import RMABLambdaNatureOracle
+
+_F32 = torch.float32
+NUM_TEST_POLICY_RUNS = 50      # nature_oracle.py:647
+
+
+def nature_env_layout(nat_b, N):
+    """Bounded nature actions `[E,D]` -> the env kernels' per-env layout `[N,E]` (D = N) or `[N,D/N,E]`."""
+    E, D = nat_b.shape
+    return nat_b.t().contiguous() if D == N else nat_b.t().reshape(N, D // N, E).contiguous()
+
+
+class MARolloutTrainer:
+    """Device state and loops of one `best_response_per_cpu` call."""
+
+    def __init__(self, env, ac, T, gamma, lam_other, clip_ratio, pi_lr_agent, pi_lr_nature, vf_lr_agent, vf_lr_nature,
+                 lm_lr, pi_iters, v_iters, epochs, lamb_update_freq, final_train_lambdas, ent0, ent1, seed):
+        self.env, self.ac, self.T = env, ac, int(T)
+        self.gamma, self.lam_other, self.clip = float(gamma), float(lam_other), float(clip_ratio)
+        self.pi_lr_agent, self.vf_lr_agent, self.lm_lr = pi_lr_agent, vf_lr_agent, lm_lr
+        self.pi_iters, self.v_iters, self.epochs = int(pi_iters), int(v_iters), int(epochs)
+        self.freq, self.final, self.ent0, self.ent1 = int(lamb_update_freq), int(final_train_lambdas), ent0, ent1
+        N, E, dev, D = env.N, env.n_envs, env.device, ac.act_dim_nature
+        self.N, self.E, self.D, self.dev = N, E, D, dev
+        T = self.T
+        u8 = torch.uint8
+        self.s_traj = torch.empty((N, T + 1, E), dtype=u8, device=dev)
+        self.a = torch.empty((N, T, E), dtype=u8, device=dev)
+        self.logp = torch.empty((N, T, E), dtype=_F32, device=dev)
+        self.val = torch.empty((N, T, E), dtype=_F32, device=dev)
+        self.a_nat = torch.empty((T, E, D), dtype=_F32, device=dev)       # raw nature actions (buffer act_nature)
+        self.nat_b = torch.empty((T, E, D), dtype=_F32, device=dev)       # bounded (critic inputs, :398-399)
+        self.logp_nat = torch.empty((T, E), dtype=_F32, device=dev)
+        self.val_nat = torch.empty((T, E), dtype=_F32, device=dev)
+        self.rew_nat = torch.empty((T, E), dtype=_F32, device=dev)
+        self.adam_pi = torch.zeros((N, 2, ac.Wpi.shape[1]), dtype=_F32, device=dev)
+        self.adam_v = torch.zeros((N, 2, ac.Wv.shape[1]), dtype=_F32, device=dev)
+        self.m_w1n, self.v_w1n = torch.zeros_like(ac.W1n), torch.zeros_like(ac.W1n)
+        self.steps_pi = self.steps_v = 0
+        self.opt_pi_nat = torch.optim.Adam(ac.pi_nature.parameters(), lr=pi_lr_nature)
+        self.opt_v_nat = torch.optim.Adam(ac.v_nature.parameters(), lr=vf_lr_nature)
+        self.R = torch.as_tensor(np.asarray(env.R), dtype=_F32, device=dev).contiguous()
+        self.C = torch.as_tensor(np.asarray(env.C), dtype=_F32, device=dev).contiguous()
+        self.lam_params = ac.lambda_net.packed().to(dev)
+        self.obs_scale = 1.0 if ac.one_hot_encode else 1.0 / float(ac.state_norm)
+        self.epoch_idx = 0
+        ac.seed(seed)
+        env.seed(seed)
+        self.seed = int(seed)
+        self.s = env.reset_device()
+
+    def _entropy(self, ep):
+        head = float(np.linspace(self.ent0, self.ent1, self.epochs)[min(ep, self.epochs - 1)])
+        if (self.epochs - ep) > self.final:
+            return float(np.linspace(head, 0, self.freq)[ep % self.freq])
+        return 0.0
+
+    # ---------------------------------------------------------------------------------------------
+    def rollout(self, agent_pol):
+        env, ac, T, N, E = self.env, self.ac, self.T, self.N, self.E
+        s0 = self.s.contiguous()
+        lamb, h1 = ops.lambda_forward(self.lam_params, s0, N, 0, self.obs_scale, want_h1=True)
+        self.s_traj[:, 0] = s0
+        ret_agent = torch.zeros((E,), dtype=_F32, device=self.dev)
+        for t in range(T):
+            s = self.s_traj[:, t].contiguous()
+            d = ac.step_device(s, lamb)
+            nat_env = nature_env_layout(d["a_nature_bounded"], N)
+            env._state = s
+            s_next, r = env.step_device(d["a_agent"], nat_env)
+            a_test = agent_pol.act_test_device(s)
+            rng = ops.rng(self.seed, _lib.STREAM_CF, env._t)
+            r_test = ops.env_counterfactual(env.domain, s, a_test, nat_env, env._ranges() if env.domain != _lib.DOMAIN_SIS
+                                            else self.R, self.R, rng, NUM_TEST_POLICY_RUNS, nature_per_env=True)
+            env._t += 1
+            cost_sum = self.C[d["a_agent"].long()].sum(dim=0)
+            r_sum = r.sum(dim=0)
+            self.rew_nat[t] = r_sum - r_test.sum(dim=0) - lamb * cost_sum       # lamb_adjusted_r_nature (:707-719)
+            ret_agent += r_sum
+            self.a[:, t], self.logp[:, t], self.val[:, t], self.s_traj[:, t + 1] = d["a_agent"], d["logp_agent"], d["v_agent"], s_next
+            self.a_nat[t], self.nat_b[t] = d["a_nature"], d["a_nature_bounded"]
+            self.logp_nat[t], self.val_nat[t] = d["logp_nature"], d["v_nature"]
+        d = ac.step_device(self.s_traj[:, T].contiguous(), lamb)               # bootstrap values (:754)
+        ac._steps -= 1
+        return lamb, h1, s0, d["v_agent"], d["v_nature"], ret_agent
+
+    def update(self, lamb, h1, s0, last_v_agent, last_v_nature):
+        ac, T, N, E, D = self.ac, self.T, self.N, self.E, self.D
+        ep = self.epoch_idx
+        # ---- MA_RMABPPO_Buffer.finish_path + get (:107-193) ----
+        adv, ret, _, _ = ops.gae(self.s_traj, self.a, self.val, last_v_agent.contiguous(), lamb, self.C, self.R, self.gamma,
+                                 self.lam_other, normalize=True)
+        zero = torch.zeros((1, T, E), dtype=_F32, device=self.dev)
+        adv_n, ret_n, _, _ = ops.gae_explicit(self.rew_nat[None].contiguous(), zero, self.val_nat[None].contiguous(),
+                                              last_v_nature.reshape(1, E).contiguous(), lamb, self.gamma, self.lam_other,
+                                              normalize=True)
+        # ---- agent policies (:491-502) ----
+        hp = ops.hyper(self.clip, self._entropy(ep), self.pi_lr_agent, self.vf_lr_agent, self.pi_iters, 0, self.steps_pi,
+                       self.steps_v)
+        ops.ppo_update(ac._net(E, False), hp, ac.Wpi, ac.Wv, self.adam_pi, self.adam_v, self.s_traj, self.a, adv, self.logp,
+                       ret, lamb)
+        self.steps_pi += self.pi_iters
+        # ---- agent critics over [x_i, bounded nature vector] (:505-513) ----
+        natM = self.nat_b.reshape(T * E, D)                                      # sample m = t*E + e
+        net = ac._net(E, False)
+        for _ in range(self.v_iters):
+            z1 = torch.matmul(natM, ac.W1n.transpose(1, 2)).contiguous()         # [N, T*E, h] dense GEMM
+            hpv = ops.hyper(self.clip, 0.0, self.pi_lr_agent, self.vf_lr_agent, 0, 1, self.steps_pi, self.steps_v)
+            dz1, _ = ops.critic_extra_iter(net, hpv, ac.Wv, self.adam_v, self.s_traj, ret, lamb, z1)
+            gW1n = torch.matmul(dz1.transpose(1, 2), natM).contiguous()          # [N, h, D] dense GEMM
+            self.steps_v += 1
+            ops.adam_step(ac.W1n, gW1n, self.m_w1n, self.v_w1n, self.vf_lr_agent, self.steps_v)
+        # ---- lambda net and the nature nets, every lamb_update_freq epochs (:516-576) ----
+        if ep % self.freq == 0 and ep > 0:
+            if (self.epochs - ep) > self.final:
+                cd = ops.cost_togo(self.a, self.C, self.gamma)
+                coef = (float(ac.B) / (1.0 - self.gamma) - cd[0]).contiguous()
+                ops.lambda_sgd(self.lam_params, s0, N, 0, self.obs_scale, h1, coef, self.lm_lr)
+            obs = self.s_traj[:, :T].permute(1, 2, 0).reshape(T * E, N).to(_F32) * self.obs_scale
+            obs_n = obs / float(ac.nature_state_norm)
+            act = self.a_nat.reshape(T * E, D)
+            advn, lpo, retn = adv_n.reshape(-1), self.logp_nat.reshape(-1), ret_n.reshape(-1)
+            for _ in range(self.pi_iters):
+                self.opt_pi_nat.zero_grad()
+                mu = ac.pi_nature.mu_net(obs_n)
+                pi = torch.distributions.Normal(mu, torch.exp(ac.pi_nature.log_std))
+                logp = pi.log_prob(act).sum(axis=-1)
+                ratio = torch.exp(logp - lpo)
+                clip_adv = torch.clamp(ratio, 1 - self.clip, 1 + self.clip) * advn
+                loss = -(torch.min(ratio * advn, clip_adv)).mean() - 0.0 * pi.entropy().mean()   # entropy_coeff = 0 (:544)
+                loss.backward()
+                self.opt_pi_nat.step()
+            x = torch.cat([obs, self.a.permute(1, 2, 0).reshape(T * E, N).to(_F32)], dim=1)
+            for _ in range(self.v_iters):
+                self.opt_v_nat.zero_grad()
+                ((ac.v_nature(x) - retn) ** 2).mean().backward()
+                self.opt_v_nat.step()
+        self.epoch_idx += 1
+
+    def epoch(self, agent_pol):
+        lamb, h1, s0, lv, lvn, ret_agent = self.rollout(agent_pol)
+        stats = {"EpActualRetAgent": ret_agent, "EpLambAdjRetNature": self.rew_nat.sum(dim=0), "Lamb": lamb,
+                 "VVals_agent": self.val.mean().reshape(1), "VVals_nature": self.val_nat.mean().reshape(1)}
+        self.update(lamb, h1, s0, lv, lvn)
+        self.s = self.env.reset_device()                                      # :779
+        return stats
+
+    def export_lambda(self):
+        flat, o = self.lam_params.detach().cpu(), 0
+        with torch.no_grad():
+            for p in self.ac.lambda_net.parameters():
+                p.copy_(flat[o:o + p.numel()].reshape(p.shape))
+                o += p.numel()
+
+
+class NatureOracle:
+
+    def __init__(self, data, N, S, A, B, seed, REWARD_BOUND, nature_kwargs=dict(), home_dir="", exp_name="",
+                 sampled_nature_parameter_ranges=None, pop_size=0, one_hot_encode=True, non_ohe_obs_dim=None, state_norm=1,
+                 nature_state_norm=1, n_envs=1, device="cuda"):
+        self.data, self.home_dir, self.exp_name, self.REWARD_BOUND = data, home_dir, exp_name, REWARD_BOUND
+        self.N, self.S, self.A, self.B, self.seed = N, S, A, B, seed
+        self.sampled_nature_parameter_ranges = sampled_nature_parameter_ranges
+        self.nature_state_norm, self.pop_size = nature_state_norm, pop_size
+        self.one_hot_encode, self.non_ohe_obs_dim, self.state_norm = one_hot_encode, non_ohe_obs_dim, state_norm
+        self.n_envs, self.device = int(n_envs), device
+        if data == 'armman':
+            self.env_fn = lambda: ARMMANRobustEnv(N, B, seed, n_envs=self.n_envs, device=device)
+        elif data == 'counterexample':
+            self.env_fn = lambda: CounterExampleRobustEnv(N, B, seed, n_envs=self.n_envs, device=device)
+        elif data == 'sis':
+            self.env_fn = lambda: SISRobustEnv(N, B, pop_size, seed, n_envs=self.n_envs, device=device)
+        else:
+            raise ValueError("data must be 'counterexample', 'armman' or 'sis'")
+        self.ma_actor_critic = RMABLambdaNatureOracle
+        self.nature_kwargs = nature_kwargs
+        self.strat_ind = -1
+        self.env = self.env_fn()
+        self.env.seed(seed)
+        self.env.sampled_parameter_ranges = self.sampled_nature_parameter_ranges
+        self.history = []
+
+    def best_response(self, nature_strats, nature_eq, add_to_seed):
+        self.strat_ind += 1
+        return self.best_response_per_cpu(nature_strats, nature_eq, add_to_seed, seed=self.seed, **self.nature_kwargs)
+
+    def best_response_per_cpu(self, agent_strats, agent_eq, add_to_seed, ma_actor_critic=None, ac_kwargs=dict(), seed=0,
+                              steps_per_epoch=4000, epochs=50, gamma=0.99, clip_ratio=0.2, pi_lr_agent=3e-4,
+                              pi_lr_nature=3e-4, vf_lr_agent=1e-3, vf_lr_nature=1e-3, qf_lr=1e-3, lm_lr=5e-2,
+                              train_pi_iters=80, train_v_iters=80, train_q_iters=80, lam_OTHER=0.97, max_ep_len=1000,
+                              start_entropy_coeff=0.0, end_entropy_coeff=0.0, target_kl=0.01, logger_kwargs=dict(),
+                              save_freq=10, lamb_update_freq=10, init_lambda_trains=0, final_train_lambdas=0):
+        env = self.env
+        ac = RMABLambdaNatureOracle(env.observation_space, env.action_space, env.sampled_parameter_ranges,
+                                    env.action_dim_nature, env=env, N=env.N, C=env.C, B=env.B, strat_ind=self.strat_ind,
+                                    one_hot_encode=self.one_hot_encode, non_ohe_obs_dim=self.non_ohe_obs_dim,
+                                    state_norm=self.state_norm, nature_state_norm=self.nature_state_norm,
+                                    n_envs=self.n_envs, device=self.device, **ac_kwargs)
+        agent_eq = np.array(agent_eq, dtype=np.float64)
+        agent_eq[agent_eq < 0] = 0
+        agent_eq = agent_eq / agent_eq.sum()
+        agent_pol = np.random.choice(agent_strats, p=agent_eq)                   # :651
+        if hasattr(agent_pol, "n_envs"):
+            agent_pol.n_envs = self.n_envs
+        tr = MARolloutTrainer(env, ac, steps_per_epoch, gamma, lam_OTHER, clip_ratio, pi_lr_agent, pi_lr_nature,
+                              vf_lr_agent, vf_lr_nature, lm_lr, train_pi_iters, train_v_iters, epochs, lamb_update_freq,
+                              final_train_lambdas, start_entropy_coeff, end_entropy_coeff, seed)
+        self.history = [{k: v.detach().cpu().numpy() for k, v in tr.epoch(agent_pol).items()} for _ in range(epochs)]
+        tr.export_lambda()
+        return ac

@@ -162,6 +162,22 @@ def env_counterfactual(domain, s, a, nature, ranges, R, r, n_trials, nature_per_
     return out
 
 
+def critic_extra_iter(net, hp, Wv, adam_v, s, ret, lamb, z1_extra, want_loss=False):
+    """One Adam iteration of the agent critics with nature inputs; returns (dz1 [N,T*E,h], loss [N] or None)."""
+    N, T, E = ret.shape
+    dz1 = torch.zeros_like(z1_extra)
+    loss = torch.zeros((N, 1), dtype=f32, device=ret.device) if want_loss else None
+    check(lib().rmab_critic_extra_iter(C.byref(net), C.byref(hp), T, s.shape[1], _p(Wv, f32, "Wv"), _p(adam_v, f32, "adam_v"),
+                                       _p(s, u8, "s"), _p(ret, f32, "ret"), _p(lamb, f32, "lamb"),
+                                       _p(z1_extra, f32, "z1_extra"), _p(dz1, f32), _p(loss, f32), _stream()))
+    return dz1, loss
+
+
+def adam_step(p, grad, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
+    check(lib().rmab_adam_step(p.numel(), _p(p, f32, "p"), _p(grad, f32, "grad"), _p(m, f32, "m"), _p(v, f32, "v"),
+                               float(lr), float(beta1), float(beta2), float(eps), int(step), _stream()))
+
+
 # -------------------------------------------------------------------------------------------- buffer
 def gae(s_traj, a, val, last_val, lamb, Cc, R, gamma, lam, normalize=True, want_q=False, want_stats=False):
     N, T, E = a.shape

@@ -128,3 +128,65 @@ def test_counterfactual(K, domain, pop):
     want = oma.counterfactual_mean(domain, s, a, nature, ranges, R, 5, 3, trials if domain != 2 or pop <= 10 else trials,
                                    pop=pop)
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("data,domain", [("counterexample", 0), ("armman", 1)])
+def test_ma_epoch_loop_matches_oracle(K, data, domain):
+    """Device MA-RMABPPO nature-oracle loop (rollout with counterfactual estimate, agent pi / critic-with-nature-inputs
+    updates, lambda step, nature PPO) against the CPU restatement of nature_oracle.py's loop (oracle/ma_train.py)."""
+    import copy
+    torch = K.torch
+    from oracle.ma_train import CpuMARMABPPO
+    from robustrmab_b200.environments import ARMMANRobustEnv, CounterExampleRobustEnv
+    from robustrmab_b200.evaluate import PessimisticAgentPolicy
+    from robustrmab_b200.ma_core import RMABLambdaNatureOracle
+    from robustrmab_b200.nature_oracle import MARolloutTrainer, NatureOracle
+    N, E, T, h, B, epochs = 6, 4, 8, 16, 2.0, 4
+    S = 2 if domain == 0 else 3
+    env = (CounterExampleRobustEnv if domain == 0 else ARMMANRobustEnv)(N, B, 9, n_envs=E)
+    env.sampled_parameter_ranges = env.sample_parameter_ranges()
+    torch.manual_seed(2)
+    ac = RMABLambdaNatureOracle(env.observation_space, env.action_space, env.sampled_parameter_ranges,
+                                env.action_dim_nature, env, hidden_sizes=[h, h], C=env.C, N=N, B=B, n_envs=E)
+    hyp = dict(gamma=0.9, lam_other=0.97, clip_ratio=2.0, pi_lr_agent=2e-3, pi_lr_nature=2e-3, vf_lr_agent=2e-3,
+               vf_lr_nature=2e-3, lm_lr=2e-3, pi_iters=3, v_iters=3, epochs=epochs, lamb_update_freq=2,
+               final_train_lambdas=1, ent0=0.5, ent1=0.0, seed=9)
+    lam = [p.detach().numpy().copy() for p in ac.lambda_net.parameters()]
+    cpu = CpuMARMABPPO(domain, K.n(ac.Wpi), K.n(ac.Wv), K.n(ac.W1n), lam, copy.deepcopy(ac.pi_nature.mu_net).cpu(),
+                       K.n(ac.pi_nature.log_std), copy.deepcopy(ac.v_nature.v_net).cpu(), env.sampled_parameter_ranges,
+                       oenv.rewards_table(domain, N, S), np.array([0, 1], F32), E, T, h, B, hyp["gamma"], hyp["lam_other"],
+                       hyp["clip_ratio"], hyp["pi_lr_agent"], hyp["pi_lr_nature"], hyp["vf_lr_agent"], hyp["vf_lr_nature"],
+                       hyp["lm_lr"], hyp["pi_iters"], hyp["v_iters"], epochs, hyp["lamb_update_freq"],
+                       hyp["final_train_lambdas"], hyp["ent0"], hyp["ent1"], hyp["seed"])
+    tr = MARolloutTrainer(env, ac, T, hyp["gamma"], hyp["lam_other"], hyp["clip_ratio"], hyp["pi_lr_agent"],
+                          hyp["pi_lr_nature"], hyp["vf_lr_agent"], hyp["vf_lr_nature"], hyp["lm_lr"], hyp["pi_iters"],
+                          hyp["v_iters"], epochs, hyp["lamb_update_freq"], hyp["final_train_lambdas"], hyp["ent0"],
+                          hyp["ent1"], hyp["seed"])
+    pess = PessimisticAgentPolicy(N)
+    for ep in range(3):                                   # epoch 2 runs the lambda step and the nature PPO updates
+        st = tr.epoch(pess)
+        w = cpu.epoch(lambda s: np.zeros_like(s))
+        np.testing.assert_allclose(K.n(st["Lamb"]), w["lamb"], rtol=1e-4, atol=1e-5)
+        agree = (K.n(tr.a) == w["a"]).mean()
+        if ep == 0:
+            assert agree == 1.0 and np.array_equal(K.n(tr.s_traj), w["s_traj"])
+            np.testing.assert_allclose(K.n(tr.a_nat), w["a_nat"], rtol=1e-4, atol=2e-5)
+            np.testing.assert_allclose(K.n(tr.rew_nat), w["rew_nat"], rtol=1e-4, atol=1e-4)
+            np.testing.assert_allclose(K.n(tr.val), w["val"], rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(K.n(tr.val_nat), w["val_nat"], rtol=1e-4, atol=1e-5)
+            assert np.array_equal(K.n(st["EpActualRetAgent"]), w["ret_agent"])
+        else:
+            assert agree > 0.95, (ep, agree)
+    np.testing.assert_allclose(K.n(ac.Wpi), cpu.opt.Wpi.detach().numpy(), atol=3e-3)
+    np.testing.assert_allclose(K.n(ac.Wv), cpu.opt.Wv.detach().numpy(), atol=3e-3)
+    np.testing.assert_allclose(K.n(ac.W1n), cpu.W1n.detach().numpy(), atol=3e-3)
+    np.testing.assert_allclose(K.n(ac.pi_nature.log_std), cpu.log_std.detach().numpy(), atol=3e-3)
+    for p, q in zip(ac.pi_nature.mu_net.parameters(), cpu.mu_net.parameters()):
+        np.testing.assert_allclose(K.n(p), q.detach().numpy(), atol=5e-3)
+    # the drop-in class end to end
+    orc = NatureOracle(data, N, S, 2, B, 9, 1, nature_kwargs=dict(steps_per_epoch=T, epochs=2, gamma=0.9, clip_ratio=2.0,
+                       train_pi_iters=2, train_v_iters=2, lamb_update_freq=1, ac_kwargs=dict(hidden_sizes=[h, h])),
+                       sampled_nature_parameter_ranges=env.sampled_parameter_ranges, n_envs=E)
+    nat_ac = orc.best_response([pess], [1.0], 0)
+    assert repr(nat_ac) == "MA-RMABPPO_0" and len(orc.history) == 2
+    assert nat_ac.get_nature_action(np.zeros((N, E))).shape == (E, nat_ac.act_dim_nature)
