@@ -19,8 +19,7 @@ F32 = np.float32
 
 class _ActSource(ref_shims.UniformSource):
     """Uniforms for Categorical.sample keyed like the oracle: the T rollout steps of epoch e use stream ACT with
-    t = e*T + step; the extra bootstrap ac.step at the end of every epoch (agent_oracle.py:553) consumes draws that
-    do not influence anything and gets a throw-away stream."""
+    t = e*T + step; the extra bootstrap ac.step at the end of every epoch (agent_oracle.py:553) uses t = e*T + T."""
 
     def __init__(self, seed, n_arms, T):
         super().__init__(seed, philox.STREAM_ACT, n_arms)
@@ -29,10 +28,9 @@ class _ActSource(ref_shims.UniformSource):
     def next(self):
         k = self.sweep % (self.T + 1)
         ep = self.sweep // (self.T + 1)
-        if k == self.T:
-            u = np.float32(0.5)
-        else:
-            u = philox.uniform(self.seed, self.stream, ep * self.T + k, 0, np.uint32(self.i))
+        # k == T is the bootstrap step: it draws with the time counter of the next epoch's first step (the device
+        # path and oracle/*train.py do the same; the draw only matters for MA-RMABPPO's nature critic input)
+        u = philox.uniform(self.seed, self.stream, ep * self.T + k, 0, np.uint32(self.i))
         self.i += 1
         if self.i == self.n:
             self.i, self.sweep = 0, self.sweep + 1
@@ -193,3 +191,155 @@ def gen_ma():
                 out[f"{name}_{tag}_b{j}"] = m.bias.detach().numpy()
         out.update({f"{name}_out_{k}": np.array(v) for k, v in res.items()})
     np.savez_compressed(os.path.join(OUT, "ma.npz"), **out)
+
+
+class _MAEnvStream:
+    """`env.random_stream` shim for the nature oracle's rollout: every time step makes 51 env.step calls -- the real
+    one (stream ENV, t = step) and NUM_TEST_POLICY_RUNS = 50 counterfactual ones (stream CF, t = step*50 + trial) --
+    of N multinomial draws each; resets draw from stream RESET (t = reset index)."""
+
+    def __init__(self, seed, n_arms, n_states, trials=50):
+        self.seed, self.N, self.S, self.trials = seed, n_arms, n_states, trials
+        self.calls, self.resets = 0, 0
+
+    def seed(self, seed=None):
+        return None
+
+    def multinomial(self, n, p):
+        step, within = divmod(self.calls, self.N * (1 + self.trials))
+        block, arm = divmod(within, self.N)
+        self.calls += 1
+        if block == 0:
+            u = philox.uniform(self.seed, philox.STREAM_ENV, step, 0, np.uint32(arm))
+        else:
+            u = philox.uniform(self.seed, philox.STREAM_CF, step * self.trials + block - 1, 0, np.uint32(arm))
+        k = int(philox.categorical(np.asarray(p, dtype=np.float32), np.float32(u)))
+        out = np.zeros(len(p), dtype=np.int64)
+        out[k] = 1
+        return out
+
+    def _reset_states(self, size):
+        u = philox.uniform(self.seed, philox.STREAM_RESET, self.resets, 0, np.arange(size, dtype=np.uint32))
+        self.resets += 1
+        return np.minimum((u * np.float32(self.S)).astype(np.int64), self.S - 1)
+
+    def choice(self, space, size):
+        return np.asarray(space)[self._reset_states(size)]
+
+    def randint(self, low=0, high=None, size=None):
+        return low + self._reset_states(size)
+
+
+_MA_REC = {}
+
+
+def _ma_recorder_class(core):
+    if "MARecorder" not in globals():
+        import torch
+
+        class MARecorder(core.RMABLambdaNatureOracle):
+            def __init__(self, *a, **k):
+                super().__init__(*a, **k)
+                lin = lambda seq: [m for m in seq if isinstance(m, torch.nn.Linear)]
+                N, in_dim = self.N, self.obs_dim + 1
+                _MA_REC["Wpi0"] = np.stack([nets.pack_torch_mlp(self.pi_list_agent[i].logits_net) for i in range(N)])
+                _MA_REC["Wv0"], _MA_REC["W1n0"] = _pack_ma_critics(self, in_dim)
+                _MA_REC["lam0"] = [p.detach().numpy().copy() for p in self.lambda_net.parameters()]
+                _MA_REC["mu0"] = [t.detach().numpy().copy() for m in lin(self.pi_nature.mu_net) for t in (m.weight, m.bias)]
+                _MA_REC["vn0"] = [t.detach().numpy().copy() for m in lin(self.v_nature.v_net) for t in (m.weight, m.bias)]
+                _MA_REC["log_std0"] = self.pi_nature.log_std.detach().numpy().copy()
+        MARecorder.__qualname__ = "MARecorder"
+        globals()["MARecorder"] = MARecorder
+    return globals()["MARecorder"]
+
+
+def _pack_ma_critics(ac, in_dim):
+    import torch
+    packed, w1n = [], []
+    for i in range(ac.N):
+        l = [m for m in ac.v_list_agent[i].v_net if isinstance(m, torch.nn.Linear)]
+        first = l[0].weight.detach().numpy()
+        parts = [first[:, :in_dim].reshape(-1), l[0].bias.detach().numpy()]
+        for m in l[1:]:
+            parts += [m.weight.detach().numpy().reshape(-1), m.bias.detach().numpy()]
+        packed.append(np.concatenate(parts))
+        w1n.append(first[:, in_dim:].copy())
+    return np.stack(packed).astype(F32), np.stack(w1n).astype(F32)
+
+
+def gen_ma_train(epochs=5, out_name="ma_train.npz", final_train_lambdas=1):
+    """The UNMODIFIED reference NatureOracle.best_response (nature_oracle.py:252-806) against a Pessimist agent on a
+    tiny counterexample problem with every random draw injected from the Philox convention of the CUDA path."""
+    import contextlib
+    import torch
+    from torch.distributions.normal import Normal
+    from robust_rmab.algos.ma_rmabppo import ma_rmabppo_core as core
+    from robust_rmab.algos.ma_rmabppo import nature_oracle as no
+    from robust_rmab.baselines.agent_baselines import PessimisticAgentPolicy
+    from robust_rmab.environments.bandit_env_robust import CounterExampleRobustEnv
+    from . import ma as oma
+    N, S, B, T, h, seed = 6, 2, 2.0, 7, 16, 4
+    kw = dict(gamma=0.9, clip_ratio=2.0, pi_lr_agent=2e-3, pi_lr_nature=2e-3, vf_lr_agent=2e-3, vf_lr_nature=2e-3, lm_lr=2e-3,
+              train_pi_iters=3, train_v_iters=3, lam_OTHER=0.97, start_entropy_coeff=0.5, end_entropy_coeff=0.0,
+              lamb_update_freq=2, final_train_lambdas=final_train_lambdas)
+    env0 = CounterExampleRobustEnv(N, B, seed)
+    ranges = env0.sample_parameter_ranges().astype(F32).astype(np.float64)
+    D = N
+    sweep = {"k": 0}
+
+    @contextlib.contextmanager
+    def patch_normal():
+        orig = Normal.sample
+
+        def sample(self, sample_shape=torch.Size()):
+            k, ep = sweep["k"] % (T + 1), sweep["k"] // (T + 1)
+            sweep["k"] += 1
+            eps = oma.normal_eps(seed, ep * T + k, 1, D)      # k == T: the bootstrap step (t of the next epoch's first)
+            return self.loc + self.scale * torch.as_tensor(eps[0])
+        Normal.sample = sample
+        try:
+            yield
+        finally:
+            Normal.sample = orig
+
+    home = tempfile.mkdtemp(prefix="rmab_golden_ma_")
+    try:
+        _MA_REC.clear()
+        Rec = _ma_recorder_class(core)
+        nature_kwargs = dict(steps_per_epoch=T, epochs=epochs, ac_kwargs=dict(hidden_sizes=[h, h]), ma_actor_critic=Rec, **kw)
+        orc = no.NatureOracle("counterexample", N, S, 2, B, seed, 1, nature_kwargs=nature_kwargs, home_dir=home,
+                              exp_name="golden_ma", sampled_nature_parameter_ranges=ranges)
+        orc.env.random_stream = _MAEnvStream(seed, N, S)
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        with ref_shims.patch_categorical_sample(_ActSource(seed, N, T)), patch_normal(), ref_shims.quiet():
+            ac = orc.best_response([PessimisticAgentPolicy(N, 0)], [1.0], 0)
+        prog = None
+        for dp, _, fs in os.walk(home):
+            if "progress.txt" in fs:
+                prog = os.path.join(dp, "progress.txt")
+        rows = [l.rstrip("\n").split("\t") for l in open(prog)]
+        cols = {c: np.array([float(r[i]) for r in rows[1:]]) for i, c in enumerate(rows[0])}
+        lin = lambda seq: [m for m in seq if isinstance(m, torch.nn.Linear)]
+        out = dict(meta=np.array([N, S, T, epochs, h, seed, D]), B=np.array(B), ranges=ranges,
+                   Wpi0=_MA_REC["Wpi0"], Wv0=_MA_REC["Wv0"], W1n0=_MA_REC["W1n0"], log_std0=_MA_REC["log_std0"],
+                   Wpi1=np.stack([nets.pack_torch_mlp(ac.pi_list_agent[i].logits_net) for i in range(N)]),
+                   log_std1=ac.pi_nature.log_std.detach().numpy().copy(),
+                   Lamb=cols["Lamb"], EpActualRetAgent=cols["AverageEpActualRetAgent"],
+                   EpLambAdjRetNature=cols["AverageEpLambAdjRetNature"], VVals_agent=cols["AverageVVals_agent"],
+                   VVals_nature=cols["AverageVVals_nature"])
+        out["Wv1"], out["W1n1"] = _pack_ma_critics(ac, S + 1)
+        for tag, lst in (("lam0", _MA_REC["lam0"]), ("mu0", _MA_REC["mu0"]), ("vn0", _MA_REC["vn0"])):
+            for i, p in enumerate(lst):
+                out[f"{tag}_{i}"] = p
+        for i, p in enumerate(ac.lambda_net.parameters()):
+            out[f"lam1_{i}"] = p.detach().numpy().copy()
+        for i, t in enumerate([t for m in lin(ac.pi_nature.mu_net) for t in (m.weight, m.bias)]):
+            out[f"mu1_{i}"] = t.detach().numpy().copy()
+        for i, t in enumerate([t for m in lin(ac.v_nature.v_net) for t in (m.weight, m.bias)]):
+            out[f"vn1_{i}"] = t.detach().numpy().copy()
+        out["hyper_names"] = np.array(sorted(kw))
+        out["hyper_values"] = np.array([float(kw[k]) for k in sorted(kw)])
+        np.savez_compressed(os.path.join(OUT, out_name) if os.sep not in out_name else out_name, **out)
+    finally:
+        shutil.rmtree(home, ignore_errors=True)

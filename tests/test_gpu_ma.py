@@ -190,3 +190,49 @@ def test_ma_epoch_loop_matches_oracle(K, data, domain):
     nat_ac = orc.best_response([pess], [1.0], 0)
     assert repr(nat_ac) == "MA-RMABPPO_0" and len(orc.history) == 2
     assert nat_ac.get_nature_action(np.zeros((N, E))).shape == (E, nat_ac.act_dim_nature)
+
+
+def test_ma_device_loop_matches_reference_nature_oracle(K, golden):
+    """Device MA-RMABPPO loop (E = 1) against the values logged by the UNMODIFIED reference NatureOracle.best_response
+    (vs a Pessimist agent) run with every draw injected (tests/golden/ma_train.npz)."""
+    torch = K.torch
+    from robustrmab_b200.environments import CounterExampleRobustEnv
+    from robustrmab_b200.evaluate import PessimisticAgentPolicy
+    from robustrmab_b200.ma_core import RMABLambdaNatureOracle
+    from robustrmab_b200.nature_oracle import MARolloutTrainer
+    g = golden("ma_train")
+    N, S, T, epochs, h, seed, D = [int(x) for x in g["meta"]]
+    kw = dict(zip([str(k) for k in g["hyper_names"]], [float(v) for v in g["hyper_values"]]))
+    env = CounterExampleRobustEnv(N, float(g["B"]), seed)
+    env.sampled_parameter_ranges = g["ranges"]
+    ac = RMABLambdaNatureOracle(env.observation_space, env.action_space, env.sampled_parameter_ranges, D, env,
+                                hidden_sizes=[h, h], C=env.C, N=N, B=env.B)
+    ac.Wpi.copy_(K.t(g["Wpi0"])); ac.Wv.copy_(K.t(g["Wv0"])); ac.W1n.copy_(K.t(g["W1n0"]))
+    with torch.no_grad():
+        for tag, seq in (("mu0", ac.pi_nature.mu_net), ("vn0", ac.v_nature.v_net)):
+            for j, m in enumerate([m for m in seq if isinstance(m, torch.nn.Linear)]):
+                m.weight.copy_(K.t(g[f"{tag}_{2 * j}"])); m.bias.copy_(K.t(g[f"{tag}_{2 * j + 1}"]))
+        ac.pi_nature.log_std.copy_(K.t(g["log_std0"]))
+        for i, p in enumerate(ac.lambda_net.parameters()):
+            p.copy_(torch.as_tensor(g[f"lam0_{i}"]))
+    tr = MARolloutTrainer(env, ac, T, kw["gamma"], kw["lam_OTHER"], kw["clip_ratio"], kw["pi_lr_agent"], kw["pi_lr_nature"],
+                          kw["vf_lr_agent"], kw["vf_lr_nature"], kw["lm_lr"], int(kw["train_pi_iters"]),
+                          int(kw["train_v_iters"]), epochs, int(kw["lamb_update_freq"]), int(kw["final_train_lambdas"]),
+                          kw["start_entropy_coeff"], kw["end_entropy_coeff"], seed)
+    pess = PessimisticAgentPolicy(N)
+    lamb, ret, rn, vv, vn = [], [], [], [], []
+    for _ in range(epochs):
+        st = tr.epoch(pess)
+        lamb.append(float(st["Lamb"][0])); ret.append(float(st["EpActualRetAgent"][0]))
+        rn.append(float(st["EpLambAdjRetNature"][0])); vv.append(float(st["VVals_agent"][0])); vn.append(float(st["VVals_nature"][0]))
+    assert np.array_equal(np.array(ret), g["EpActualRetAgent"])                   # same trajectories as the reference
+    np.testing.assert_allclose(lamb, g["Lamb"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(rn, g["EpLambAdjRetNature"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(vv, g["VVals_agent"], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(vn, g["VVals_nature"], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(K.n(ac.Wpi), g["Wpi1"], atol=1e-3)
+    np.testing.assert_allclose(K.n(ac.Wv), g["Wv1"], atol=1e-3)
+    np.testing.assert_allclose(K.n(ac.W1n), g["W1n1"], atol=1e-3)
+    tr.export_lambda()
+    for i, p in enumerate(ac.lambda_net.parameters()):
+        np.testing.assert_allclose(p.detach().numpy(), g[f"lam1_{i}"], rtol=1e-4, atol=1e-6)
