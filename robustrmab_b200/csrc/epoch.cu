@@ -137,23 +137,22 @@ __global__ void __launch_bounds__(256, 2) epoch_table_kernel(EpochArgs g) {
         si = table_next<DOMAIN>(si, act, p, u24(step_word(blk, tt, false)));
         tr[(int64_t)(t + 1) * E] = (uint8_t)si;
       }
-      // backward scan 1 (finish_path :120-130 in fp64 like scipy's lfilter)
-      const double lv = (double)pick_f<S>(vt, si);
-      if (g.last_val) g.last_val[(int64_t)n * E + e] = (float)lv;
-      const double lm = (double)lam;
-      double next_v = lv, adv_acc = 0.0;
+      // backward scan 1: only the advantage moments are needed here, so the recurrence runs in fp32 (relative error
+      // ~1e-7 per step, damped by gamma*lam); pass 2 below redoes it in fp64 for the values that are kept
+      const float lvf = pick_f<S>(vt, si);
+      if (g.last_val) g.last_val[(int64_t)n * E + e] = lvf;
+      const float gam_f = (float)gamma, gl_f = (float)gl;
+      float next_v = lvf, adv_acc = 0.f;
       int sn = si;
       for (int t = T - 1; t >= 0; --t) {
         const int a_t = ac[(int64_t)t * E];
         const int s_t = tr[(int64_t)t * E];
-        const double r = (double)pick_f<S>(Rn, sn), c = (double)(a_t ? C1 : C0), v = (double)pick_f<S>(vt, s_t);
-        const double rt = __dsub_rn(r, __dmul_rn(lm, c));
-        const double qv = __dadd_rn(rt, __dmul_rn(gamma, next_v));
-        const double delta = __dsub_rn(qv, v);
-        adv_acc = __dadd_rn(delta, __dmul_rn(gl, adv_acc));
-        const double af = (double)(float)adv_acc;
-        asum += af;
-        asq = fma(af, af, asq);
+        const float v = pick_f<S>(vt, s_t);
+        const float rt = fmaf(-lam, a_t ? C1 : C0, pick_f<S>(Rn, sn));
+        const float delta = fmaf(gam_f, next_v, rt) - v;
+        adv_acc = fmaf(gl_f, adv_acc, delta);
+        asum += (double)adv_acc;
+        asq = fma((double)adv_acc, (double)adv_acc, asq);
         next_v = v;
         sn = s_t;
       }
@@ -179,6 +178,7 @@ __global__ void __launch_bounds__(256, 2) epoch_table_kernel(EpochArgs g) {
     }
     __syncthreads();
     const float mean = s_ms[0], stdv = s_ms[1];
+    const float inv_std = __fdiv_rn(1.f, stdv);  // std = 0 -> inf, and (adv - mean) * inf = NaN like the reference's 0 / 0
 
     // ---- pass 2: backward scan again, normalised advantages into the per-(s,a) statistics ----
     double var_sum = 0.0;
@@ -193,10 +193,11 @@ __global__ void __launch_bounds__(256, 2) epoch_table_kernel(EpochArgs g) {
       int sn = tr[(int64_t)T * E];
       const double lv = (double)pick_f<S>(vt, sn);
       double next_v = lv, adv_acc = 0.0, ret_acc = lv, dcost = 0.0, rsum = 0.0;
-      double Ap[S * A], Am[S * A], Sr[S], Sr2[S];
+      float Ap[S * A], Am[S * A];
+      double Sr[S], Sr2[S];
       int cnt[S * A];
 #pragma unroll
-      for (int c = 0; c < S * A; ++c) { Ap[c] = 0.0; Am[c] = 0.0; cnt[c] = 0; }
+      for (int c = 0; c < S * A; ++c) { Ap[c] = 0.f; Am[c] = 0.f; cnt[c] = 0; }
 #pragma unroll
       for (int s = 0; s < S; ++s) { Sr[s] = 0.0; Sr2[s] = 0.0; }
       for (int t = T - 1; t >= 0; --t) {
@@ -210,17 +211,17 @@ __global__ void __launch_bounds__(256, 2) epoch_table_kernel(EpochArgs g) {
         ret_acc = __dadd_rn(rt, __dmul_rn(gamma, ret_acc));
         dcost = __dadd_rn(c, __dmul_rn(gamma, dcost));
         rsum += r;
-        const float x = __fdiv_rn(__fsub_rn((float)adv_acc, mean), stdv);  // (adv - mean) / std in fp32 (:155)
+        const float x = __fmul_rn(__fsub_rn((float)adv_acc, mean), inv_std);  // (adv - mean) / std in fp32 (:155)
         const float rf = (float)ret_acc;
         if (g.adv) g.adv[step0 + (int64_t)t * E + e] = x;
         if (g.ret) g.ret[step0 + (int64_t)t * E + e] = rf;
         const int cell = s_t * A + a_t;
-        const double xp = x > 0.f ? (double)x : 0.0, xm = x < 0.f ? (double)x : 0.0;
+        const float xp = fmaxf(x, 0.f), xm = fminf(x, 0.f);
 #pragma unroll
         for (int cc = 0; cc < S * A; ++cc) {
           const bool hit = cell == cc;
-          Ap[cc] += hit ? xp : 0.0;
-          Am[cc] += hit ? xm : 0.0;
+          Ap[cc] += hit ? xp : 0.f;
+          Am[cc] += hit ? xm : 0.f;
           cnt[cc] += hit ? 1 : 0;
         }
 #pragma unroll
@@ -234,8 +235,8 @@ __global__ void __launch_bounds__(256, 2) epoch_table_kernel(EpochArgs g) {
       }
 #pragma unroll
       for (int c = 0; c < S * A; ++c) {
-        st[(int64_t)(SR::kAp + c) * E] = (float)Ap[c];
-        st[(int64_t)(SR::kAm + c) * E] = (float)Am[c];
+        st[(int64_t)(SR::kAp + c) * E] = Ap[c];
+        st[(int64_t)(SR::kAm + c) * E] = Am[c];
         st[(int64_t)(SR::kCnt + c) * E] = (float)cnt[c];
       }
 #pragma unroll
