@@ -1,10 +1,12 @@
 // Statistics-based PPO update, tensor-core variant for hidden width 64 (the ARMMAN N = 100k x 1024 envs shape).
 // Same algorithm and fragment conventions as ppo_table_mma.cu (3xTF32 mma.sync m16n8k8, warp-local tiles); what
 // changes is the shared-memory plan, because a 64 x 64 layer does not fit the 8-warp / 32-row tiles in 227 KB:
-//   * 4 warps per CTA, blocks of 16 rows (two n-tiles), tile row length 24 (24t + g hits 32 distinct banks);
+//   * blocks of 16 rows (two n-tiles), tile row length 24 (24t + g hits 32 distinct banks), 8 warps per CTA;
 //   * two lanes per row in the lane-per-row phases: lane half hf owns the features {4i + 2hf, 4i + 2hf + 1};
-//   * Adam moments stay in global memory (read-modify-write once per iteration, L2 resident), weights and the
-//     gradient in shared memory; the statistics rows are read from global (L2).
+//   * W2 lives ONLY in its two pre-split fragment sets (hi + lo is the exact fp32 value): the Adam step of W2 reads
+//     the summed gradient straight from the reduction scratch and writes the new hi / lo back into both sets;
+//   * Adam moments stay in global memory (read-modify-write once per iteration, L2 resident); only the non-W2
+//     weights and their gradient are staged in shared memory; the statistics rows are read from global (L2).
 // Per 16-row block a warp issues 3 x (8 x 4 x 2 + 8 x 4 x 2 + 2 x 4 x 8) x 3 = 576 mma, ~85 % of its instructions'
 // tensor time; FFMA equivalent would be 3 x 64 x 64 x 16 / 32 = 6144 FFMA instructions.
 //
@@ -16,7 +18,14 @@ namespace rmab {
 
 namespace {
 
-constexpr int H = 64, MT = 4, KS = 8, NT8 = 8, RB = 16, NTL = 2, LDT = 24, NW = 4, NTHR = NW * 32;
+constexpr int H = 64, MT = 4, KS = 8, NT8 = 8, RB = 16, NTL = 2, LDT = 24, NW = 8, NTHR = NW * 32, HH = H * H;
+
+// Position of W2[r][c] inside a pre-split fragment set [KS][MT][32 lanes][8] (hi a0..a3, lo a0..a3) whose A operand is
+// A[m = r][k = c] (fragment layout of mma.m16n8k8: a_q at row g + 8 (q & 1), column t + 4 (q >> 1)).
+__host__ __device__ __forceinline__ int frag_pos(int r, int c) {
+  const int mt = r >> 4, rr = r & 15, ks = c >> 3, cc = c & 7;
+  return ((ks * MT + mt) * 32 + (rr & 7) * 4 + (cc & 3)) * 8 + (rr >> 3) + 2 * (cc >> 2);
+}
 
 __device__ __forceinline__ float tanh_fast_6(float x) {
   float e, r;
@@ -66,9 +75,11 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_mma64_kernel(Mma64Args g) {
   const int E = g.d.n_envs, T = g.T;
   const MlpLayout L(IN, H, OUT);
   const int P = L.P, Pp = L.padded();
+  // w / G hold the packed layout WITHOUT the W2 block: index i < oW2 as is, i >= ob2 shifted down by H*H
+  const int Ps = Pp - HH;
   float* w = smem;
-  float* G = w + Pp;
-  float* fragF = G + Pp;
+  float* G = w + Ps;
+  float* fragF = G + Ps;
   float* fragB = fragF + FRAG;
   float* wb = fragB + FRAG;          // [S][H]
   float* wl = wb + S * H;            // [H]
@@ -86,7 +97,20 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_mma64_kernel(Mma64Args g) {
 
   float* Wn = g.W + (int64_t)n * P;
   float* An = g.adam + (int64_t)n * 2 * P;
-  for (int i = tid; i < P; i += NTHR) w[i] = Wn[i];
+  for (int i = tid; i < P; i += NTHR) {
+    const float x = Wn[i];
+    if (i < L.oW2) w[i] = x;
+    else if (i >= L.ob2) w[i - HH] = x;
+    else {
+      const int r = (i - L.oW2) / H, c = (i - L.oW2) - r * H;
+      uint32_t hi, lo;
+      split6(x, hi, lo);
+      fragF[frag_pos(r, c)] = __uint_as_float(hi);
+      fragF[frag_pos(r, c) + 4] = __uint_as_float(lo);
+      fragB[frag_pos(c, r)] = __uint_as_float(hi);    // backward operand A[m = c][k = r] = W2[r][c]
+      fragB[frag_pos(c, r) + 4] = __uint_as_float(lo);
+    }
+  }
   for (int i = tid; i < E; i += NTHR) slam[i] = g.lamb[i];
   const float* st = g.stats + ((int64_t)n * KST + ROW0) * E;
   __syncthreads();
@@ -104,19 +128,6 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_mma64_kernel(Mma64Args g) {
   double b1p = pow(g.hp.beta1, (double)step0), b2p = pow(g.hp.beta2, (double)step0);
 
   for (int it = 0; it < iters; ++it) {
-    for (int i = tid; i < KS * MT * 32 * 4; i += NTHR) {
-      const int q = i & 3, ln = (i >> 2) & 31, fm = i >> 7;  // fm = ks * MT + mt
-      const int mt = fm % MT, ks = fm / MT;
-      const int gg = ln >> 2, tt = ln & 3;
-      const int r = 16 * mt + gg + ((q & 1) ? 8 : 0), c = 8 * ks + tt + ((q & 2) ? 4 : 0);
-      uint32_t hi, lo;
-      split6(w[L.oW2 + r * H + c], hi, lo);
-      fragF[(fm * 32 + ln) * 8 + q] = __uint_as_float(hi);
-      fragF[(fm * 32 + ln) * 8 + 4 + q] = __uint_as_float(lo);
-      split6(w[L.oW2 + c * H + r], hi, lo);
-      fragB[(fm * 32 + ln) * 8 + q] = __uint_as_float(hi);
-      fragB[(fm * 32 + ln) * 8 + 4 + q] = __uint_as_float(lo);
-    }
     for (int i = tid; i < S * H; i += NTHR) {
       const int s = i / H, k = i - s * H;
       wb[i] = w[L.oW1 + k * IN + s] + w[L.ob1 + k];
@@ -174,7 +185,7 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_mma64_kernel(Mma64Args g) {
         float c[MT][NTL][4];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-          const float blo = w[L.ob2 + 16 * mt + gq], bhi = w[L.ob2 + 16 * mt + gq + 8];
+          const float blo = w[L.ob2 - HH + 16 * mt + gq], bhi = w[L.ob2 - HH + 16 * mt + gq + 8];
 #pragma unroll
           for (int nt = 0; nt < NTL; ++nt) { c[mt][nt][0] = blo; c[mt][nt][1] = blo; c[mt][nt][2] = bhi; c[mt][nt][3] = bhi; }
         }
@@ -223,12 +234,12 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_mma64_kernel(Mma64Args g) {
         for (int a = 0; a < OUT; ++a) {
 #pragma unroll
           for (int k4 = 0; k4 < H / 4; ++k4) {
-            const float4 w3 = *reinterpret_cast<const float4*>(w + L.oW3 + a * H + 4 * k4);
+            const float4 w3 = *reinterpret_cast<const float4*>(w + L.oW3 - HH + a * H + 4 * k4);
             logit[a] = fmaf(hf ? w3.z : w3.x, a2v[2 * k4], logit[a]);
             logit[a] = fmaf(hf ? w3.w : w3.y, a2v[2 * k4 + 1], logit[a]);
           }
           logit[a] += __shfl_xor_sync(0xffffffffu, logit[a], 16);
-          logit[a] += w[L.ob3 + a];
+          logit[a] += w[L.ob3 - HH + a];
         }
         const float* sp = st + erow;
         const float wrow = sp[(3 * SA - ROW0 + srow) * E];  // CntS
@@ -274,7 +285,7 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_mma64_kernel(Mma64Args g) {
           float up0 = 0.f, up1 = 0.f;
 #pragma unroll
           for (int a = 0; a < OUT; ++a) {
-            const float4 w3 = *reinterpret_cast<const float4*>(w + L.oW3 + a * H + 4 * k4);
+            const float4 w3 = *reinterpret_cast<const float4*>(w + L.oW3 - HH + a * H + 4 * k4);
             up0 = fmaf(gl[a], hf ? w3.z : w3.x, up0);
             up1 = fmaf(gl[a], hf ? w3.w : w3.y, up1);
           }
@@ -427,12 +438,6 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_mma64_kernel(Mma64Args g) {
 #pragma unroll
       for (int a = 0; a < OUT; ++a) red[8 + warp * OUT + a] = b3tot[a];
     __syncthreads();
-    for (int i = tid; i < H * H; i += NTHR) {
-      float v = pW2[i];
-#pragma unroll
-      for (int wq = 1; wq < NW; ++wq) v += pW2[wq * (H * H) + i];
-      G[L.oW2 + i] = v;
-    }
     for (int i = tid; i < H * NRS; i += NTHR) {
       const int k = i / NRS, v = i - k * NRS;
       float x = pRS[i];
@@ -441,13 +446,13 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_mma64_kernel(Mma64Args g) {
       if (v == 0) G[L.ob1 + k] = x;
       else if (v == 1) G[L.oW1 + k * IN + IN - 1] = x;
       else if (v < 2 + S) G[L.oW1 + k * IN + (v - 2)] = x;
-      else if (v < 2 + S + OUT) G[L.oW3 + (v - 2 - S) * H + k] = x;
-      else G[L.ob2 + k] = x;
+      else if (v < 2 + S + OUT) G[L.oW3 - HH + (v - 2 - S) * H + k] = x;
+      else G[L.ob2 - HH + k] = x;
     }
     if (tid < OUT) {
       float x = 0.f;
       for (int wq = 0; wq < NW; ++wq) x += red[8 + wq * OUT + tid];
-      G[L.ob3 + tid] = x;
+      G[L.ob3 - HH + tid] = x;
     }
     if (g.loss_out && tid == 0) {
       float extra = 0.f;
@@ -463,18 +468,49 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_mma64_kernel(Mma64Args g) {
     const float step_size = (float)(lr / bc1);
     const float bc2s = (float)sqrt(bc2);
     for (int i = tid; i < P; i += NTHR) {
-      const float gi = G[i];
+      const bool in_w2 = i >= L.oW2 && i < L.ob2;
+      float gi, x;
+      int r = 0, c = 0;
+      if (in_w2) {
+        const int j = i - L.oW2;
+        r = j / H; c = j - r * H;
+        gi = pW2[j];
+#pragma unroll
+        for (int wq = 1; wq < NW; ++wq) gi += pW2[wq * HH + j];     // fixed warp order
+        x = fragF[frag_pos(r, c)] + fragF[frag_pos(r, c) + 4];      // hi + lo is the exact fp32 weight
+      } else {
+        const int k = i < L.oW2 ? i : i - HH;
+        gi = G[k];
+        x = w[k];
+      }
       const float m0 = An[i], v0 = An[P + i];
       const float mi = m0 + lerp_w * (gi - m0);
       const float vi = v0 * beta2f + (omb2 * gi) * gi;
       An[i] = mi;
       An[P + i] = vi;
       const float denom = sqrtf(vi) / bc2s + epsf;
-      w[i] = w[i] - step_size * (mi / denom);
+      const float xn = x - step_size * (mi / denom);
+      if (in_w2) {
+        uint32_t hi, lo;
+        split6(xn, hi, lo);
+        fragF[frag_pos(r, c)] = __uint_as_float(hi);
+        fragF[frag_pos(r, c) + 4] = __uint_as_float(lo);
+        fragB[frag_pos(c, r)] = __uint_as_float(hi);
+        fragB[frag_pos(c, r) + 4] = __uint_as_float(lo);
+      } else {
+        w[i < L.oW2 ? i : i - HH] = xn;
+      }
     }
     __syncthreads();
   }
-  for (int i = tid; i < P; i += NTHR) Wn[i] = w[i];
+  for (int i = tid; i < P; i += NTHR) {
+    if (i < L.oW2) Wn[i] = w[i];
+    else if (i >= L.ob2) Wn[i] = w[i - HH];
+    else {
+      const int r = (i - L.oW2) / H, c = (i - L.oW2) - r * H;
+      Wn[i] = fragF[frag_pos(r, c)] + fragF[frag_pos(r, c) + 4];
+    }
+  }
 }
 
 template <int S, bool IS_PI>
@@ -482,7 +518,7 @@ static int launch_mma64(const Mma64Args& g, cudaStream_t st) {
   constexpr int OUT = IS_PI ? 2 : 1;
   const MlpLayout L(S + 1, H, OUT);
   const int E = g.d.n_envs;
-  const size_t fl = 2 * (size_t)L.padded() + 2 * (size_t)(KS * MT * 32 * 8) + S * H + H +
+  const size_t fl = 2 * (size_t)(L.padded() - HH) + 2 * (size_t)(KS * MT * 32 * 8) + S * H + H +
                     NW * (size_t)(3 * H * LDT + (OUT + 1 + S) * RB) + (((size_t)E + 3) & ~(size_t)3);
   const size_t smem = fl * sizeof(float);
   if (smem > 227 * 1024) return fail(RMAB_E_SHAPE, "rmab_ppo_update_table: E=%d needs %zu B of shared memory", E, smem);
