@@ -257,10 +257,14 @@ int rmab_ppo_update_table(const RmabNetDesc* net, const RmabHyper* hp, int T, fl
 
 size_t rmab_select_ws_bytes(int E, int N, int A);
 
-/* act_test for binary actions (rmabppo_core.py:289-334 == :338-445 when C=[0,1]): action 1 for the
- * top-k arms by p1 per env, k = number of C[1]-cost actions that fit in B; ties -> higher arm index.
- * p1 [N,E] -> actions [N,E]. */
-int rmab_budget_select_binary(int E, int N, const float* p1, float cost1, float B, uint8_t* actions,
+/* Top-k selection for binary actions: action 1 for the top-k arms by key p1 per env, k = number of C[1]-cost actions
+ * that fit in B; ties -> higher arm index.  p1 [N,E] -> actions [N,E].
+ *   positive_only = 0: act_test_deterministic (rmabppo_core.py:289-334) and top-B by index (simulator.py:309-325;
+ *                      keys may be <= 0).
+ *   positive_only = 1: act_test_deterministic_multiaction (:338-445) for C = [0,1], which never assigns an action whose
+ *                      probability is exactly 0 (the sweep ends when no positive entry is left, :434), so fewer than k
+ *                      arms act if fewer than k have p1 > 0. */
+int rmab_budget_select_binary(int E, int N, const float* p1, float cost1, float B, int positive_only, uint8_t* actions,
                               void* ws, size_t ws_bytes, rmab_stream_t stream);
 
 /* act_test_deterministic_multiaction (rmabppo_core.py:338-445), one CTA per env, stepwise argmax

@@ -17,8 +17,10 @@ def _order_desc(keys):
     return np.argsort(keys, kind="stable")[::-1]
 
 
-def topk_binary(p1, C, B):
-    """rmabppo_core.py:289-334 for one env.  p1 `[N]` -> actions `[N]` int64."""
+def topk_binary(p1, C, B, positive_only=False):
+    """rmabppo_core.py:289-334 for one env.  p1 `[N]` -> actions `[N]` int64.
+    positive_only: the binary case of the multi-action greedy (:338-445), which never assigns a zero-probability
+    action: the selected arms with p1 <= 0 are dropped (their budget stays unused)."""
     p1 = np.asarray(p1)
     N = p1.shape[0]
     a = np.zeros(N, dtype=np.int64)
@@ -30,6 +32,8 @@ def topk_binary(p1, C, B):
         a[order[i]] = 1
         spent += C[1]
         i += 1
+    if positive_only:
+        a[~(p1 > 0)] = 0
     return a
 
 

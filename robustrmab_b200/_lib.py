@@ -74,7 +74,7 @@ SIGNATURES = {
     "rmab_ppo_update_table": [C.POINTER(RmabNetDesc), C.POINTER(RmabHyper), _I, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                               _P],
     "rmab_select_ws_bytes": [_I, _I, _I],
-    "rmab_budget_select_binary": [_I, _I, _P, _F, _F, _P, _P, C.c_size_t, _P],
+    "rmab_budget_select_binary": [_I, _I, _P, _F, _F, _I, _P, _P, C.c_size_t, _P],
     "rmab_budget_select_multi": [_I, _I, _I, _P, _P, _F, _P, _P, C.c_size_t, _P],
     "rmab_vi_batched": [_I, _I, _I, _I, _P, _P, _P, _P, _I, _D, _D, _I, _P, _P, _P, _P, _P, _P],
     "rmab_whittle_bisect": [_I, _I, _I, _P, _P, _P, _D, _D, _I, _D, _D, _I, _P, _P],

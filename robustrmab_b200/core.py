@@ -233,7 +233,7 @@ class MLPActorCriticRMAB(nn.Module):
         self._steps -= 1
         Cc = torch.as_tensor(self.C.astype(np.float32), device=self.device_)
         if self.act_dim == 2 and float(self.C[0]) == 0.0:
-            return ops.budget_select_binary(p1, float(self.C[1]), float(self.B))
+            return ops.budget_select_binary(p1, float(self.C[1]), float(self.B), positive_only=True)
         return ops.budget_select_multi(probs, Cc, float(self.B))
 
     def act_test(self, obs):

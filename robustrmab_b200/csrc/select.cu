@@ -21,7 +21,8 @@ constexpr int kSelEnvs = 32;
 constexpr int kSelWarps = 8;
 
 __global__ void __launch_bounds__(kSelEnvs* kSelWarps) select_binary_kernel(int E, int N, const float* __restrict__ p1,
-                                                                           int k, uint8_t* __restrict__ actions) {
+                                                                           int k, int positive_only,
+                                                                           uint8_t* __restrict__ actions) {
   __shared__ uint32_t hist[kSelEnvs][257];
   __shared__ uint32_t prefix[kSelEnvs];   // key bits fixed so far
   __shared__ uint32_t remain[kSelEnvs];   // how many still to take among keys matching the prefix
@@ -33,7 +34,8 @@ __global__ void __launch_bounds__(kSelEnvs* kSelWarps) select_binary_kernel(int 
   const int n0 = min(N, w * chunk), n1 = min(N, n0 + chunk);
   if (k <= 0 || k >= N) {
     if (live)
-      for (int n = n0; n < n1; ++n) actions[(int64_t)n * E + e] = (k >= N) ? 1 : 0;
+      for (int n = n0; n < n1; ++n)
+        actions[(int64_t)n * E + e] = (k >= N && (!positive_only || p1[(int64_t)n * E + e] > 0.f)) ? 1 : 0;
     return;
   }
   if (w == 0) { prefix[lane] = 0u; remain[lane] = (uint32_t)k; }
@@ -75,10 +77,13 @@ __global__ void __launch_bounds__(kSelEnvs* kSelWarps) select_binary_kernel(int 
   for (int ww = w + 1; ww < kSelWarps; ++ww) above += eqcnt[ww][lane];
   if (live)
     for (int n = n1 - 1; n >= n0; --n) {
-      const uint32_t key = sortable(p1[(int64_t)n * E + e]);
+      const float pv = p1[(int64_t)n * E + e];
+      const uint32_t key = sortable(pv);
       uint8_t a = 0;
       if (key > tau) a = 1;
       else if (key == tau) { a = (above < r) ? 1 : 0; ++above; }
+      // the multi-action greedy never assigns an action whose probability is exactly 0 (rmabppo_core.py:434)
+      if (positive_only && !(pv > 0.f)) a = 0;
       actions[(int64_t)n * E + e] = a;
     }
 }
@@ -206,8 +211,8 @@ extern "C" size_t rmab_select_ws_bytes(int E, int N, int A) {
   return 16;  // both kernels keep their working set in shared memory; a token workspace keeps the ABI stable
 }
 
-extern "C" int rmab_budget_select_binary(int E, int N, const float* p1, float cost1, float B, uint8_t* actions, void* ws,
-                                         size_t ws_bytes, rmab_stream_t stream) {
+extern "C" int rmab_budget_select_binary(int E, int N, const float* p1, float cost1, float B, int positive_only,
+                                         uint8_t* actions, void* ws, size_t ws_bytes, rmab_stream_t stream) {
   (void)ws; (void)ws_bytes;
   RMAB_REQUIRE(E > 0 && N >= 0 && p1 && actions, RMAB_E_BADARG, "rmab_budget_select_binary: bad argument");
   if (N == 0) return RMAB_OK;
@@ -219,8 +224,8 @@ extern "C" int rmab_budget_select_binary(int E, int N, const float* p1, float co
     spent += (double)cost1;
     ++k;
   }
-  select_binary_kernel<<<(E + kSelEnvs - 1) / kSelEnvs, kSelEnvs * kSelWarps, 0, (cudaStream_t)stream>>>(E, N, p1, k,
-                                                                                                       actions);
+  select_binary_kernel<<<(E + kSelEnvs - 1) / kSelEnvs, kSelEnvs * kSelWarps, 0, (cudaStream_t)stream>>>(
+      E, N, p1, k, positive_only, actions);
   return check_launch("rmab_budget_select_binary");
 }
 

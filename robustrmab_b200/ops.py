@@ -279,11 +279,11 @@ def ppo_update_table(net, hp, T, Wpi, Wv, adam_pi, adam_v, stats, arm_stats, lam
 
 
 # ------------------------------------------------------------------------------------------ selection
-def budget_select_binary(p1, cost1, B):
+def budget_select_binary(p1, cost1, B, positive_only=False):
     N, E = p1.shape
     out = torch.empty((N, E), dtype=u8, device=p1.device)
-    check(lib().rmab_budget_select_binary(E, N, _p(p1, f32, "p1"), float(cost1), float(B), _p(out, u8), None, 0,
-                                          _stream()))
+    check(lib().rmab_budget_select_binary(E, N, _p(p1, f32, "p1"), float(cost1), float(B), int(bool(positive_only)),
+                                          _p(out, u8), None, 0, _stream()))
     return out
 
 

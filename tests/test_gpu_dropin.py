@@ -303,3 +303,30 @@ def test_agent_oracle_dropin_and_stepwise_equals_fused(torch_mod, data):
         assert agree == 1.0 if ep == 0 else agree > 0.7, (ep, agree)         # epoch 0: identical trajectories
     np.testing.assert_allclose(ac2.Wpi.cpu().numpy(), ac.Wpi.cpu().numpy(), atol=3e-3)
     np.testing.assert_allclose(ac2.Wv.cpu().numpy(), ac.Wv.cpu().numpy(), atol=3e-3)
+
+
+def test_checkpoint_roundtrip_and_resume(torch_mod, tmp_path):
+    """Pickle-free model file: save -> load reproduces act_test; a resumed trainer continues exactly."""
+    torch = torch_mod
+    from robustrmab_b200 import checkpoint
+    from robustrmab_b200.core import MLPActorCriticRMAB
+    from robustrmab_b200.trainer import RMABPPOTrainer
+    kw = dict(hidden=16, B=4, train_pi_iters=2, train_v_iters=2, epochs=6, seed=2)
+    tr = RMABPPOTrainer("armman", 12, 8, 6, **kw)
+    tr.epoch(); tr.epoch()
+    ac = MLPActorCriticRMAB(np.arange(3), np.arange(2), hidden_sizes=[16, 16], C=np.array([0, 1]), N=12, B=4, n_envs=8)
+    ac.Wpi.copy_(tr.Wpi); ac.Wv.copy_(tr.Wv)
+    flat, o = tr.lam_params.cpu(), 0
+    with torch.no_grad():
+        for p in ac.lambda_net.parameters():
+            p.copy_(flat[o:o + p.numel()].reshape(p.shape)); o += p.numel()
+    f = str(tmp_path / "model.npz")
+    checkpoint.save(f, ac, trainer=tr)
+    ac2, extra = checkpoint.load(f, n_envs=8)
+    obs = np.random.RandomState(0).randint(0, 3, (12, 8))
+    assert np.array_equal(ac.act_test(obs), ac2.act_test(obs)) and repr(ac2) == repr(ac)
+    tr2 = RMABPPOTrainer("armman", 12, 8, 6, **kw)
+    checkpoint.restore_trainer(tr2, ac2, extra)
+    tr2.s_traj[:, 0] = tr.s_traj[:, 0]
+    a, b = tr.epoch(), tr2.epoch()
+    assert torch.equal(a["EpActualRet"], b["EpActualRet"]) and torch.equal(tr.Wpi, tr2.Wpi) and torch.equal(tr.Wv, tr2.Wv)

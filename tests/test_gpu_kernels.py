@@ -511,3 +511,21 @@ def test_errors_are_loud(K):
     before = K.lib.launch_count()
     K.ops.reset_states(4, 4, 2, K.ops.rng(1, 3, 0))
     assert K.lib.launch_count() == before + 1
+
+
+def test_select_binary_positive_only(K):
+    """The multi-action greedy never assigns a zero-probability action (rmabppo_core.py:434): with positive_only the
+    binary top-k drops selected arms whose key is <= 0, exactly like greedy_multiaction on C = [0,1]."""
+    rs = np.random.RandomState(12)
+    N, E = 40, 6
+    p1 = rs.rand(N, E).astype(F32)
+    p1[rs.rand(N, E) < 0.6] = 0.0
+    for B in (0, 3, 10, 39, 40, 50):
+        got = K.n(K.ops.budget_select_binary(K.t(p1), 1.0, float(B), positive_only=True))
+        for e in range(E):
+            probs = np.stack([1 - p1[:, e], p1[:, e]], axis=1)
+            want = osel.greedy_multiaction(probs, np.array([0, 1]), B)
+            assert np.array_equal(got[:, e], want), (B, e)
+            assert np.array_equal(got[:, e], osel.topk_binary(p1[:, e], [0, 1], B, positive_only=True))
+    assert np.array_equal(K.n(K.ops.budget_select_binary(K.t(p1[:1, :1] * 0), 1.0, 1.0)), [[1]])        # :289-334 semantics
+    assert np.array_equal(K.n(K.ops.budget_select_binary(K.t(p1[:1, :1] * 0), 1.0, 1.0, positive_only=True)), [[0]])
