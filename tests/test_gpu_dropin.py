@@ -330,3 +330,28 @@ def test_checkpoint_roundtrip_and_resume(torch_mod, tmp_path):
     tr2.s_traj[:, 0] = tr.s_traj[:, 0]
     a, b = tr.epoch(), tr2.epoch()
     assert torch.equal(a["EpActualRet"], b["EpActualRet"]) and torch.equal(tr.Wpi, tr2.Wpi) and torch.equal(tr.Wv, tr2.Wv)
+
+
+def test_agent_oracle_sis_stepwise(torch_mod):
+    """SIS (S = pop + 1 = 21, A = 3, non-one-hot inputs) goes through the stepwise device loop: ac.step, env.step,
+    rmab_gae, per-sample rmab_ppo_update, multi-action budget selection."""
+    torch = torch_mod
+    from robustrmab_b200.agent_oracle import AgentOracle
+    N, E, T, pop, B = 9, 8, 12, 20, 4.0
+    kw = dict(steps_per_epoch=T, epochs=3, gamma=0.9, clip_ratio=2.0, pi_lr=2e-3, vf_lr=2e-3, lm_lr=2e-3,
+              train_pi_iters=3, train_v_iters=3, lamb_update_freq=1, final_train_lambdas=0, start_entropy_coeff=0.5,
+              end_entropy_coeff=0.0, ac_kwargs=dict(hidden_sizes=[16, 16]))
+    tmp = AgentOracle("sis", N, pop + 1, 3, B, 1, 1, agent_kwargs=kw, pop_size=pop, one_hot_encode=False, non_ohe_obs_dim=1,
+                      state_norm=pop, n_envs=E)
+    ranges = tmp.env.sample_parameter_ranges()
+    orc = AgentOracle("sis", N, pop + 1, 3, B, 1, 1, agent_kwargs=kw, sampled_nature_parameter_ranges=ranges, pop_size=pop,
+                      one_hot_encode=False, non_ohe_obs_dim=1, state_norm=pop, n_envs=E)
+    nature = _TableNature(ranges, 2)
+    torch.manual_seed(0)
+    ac = orc.best_response([nature], [1.0], 0)
+    assert len(orc.history) == 3 and all(np.isfinite(h["EpActualRet"]).all() for h in orc.history)
+    assert torch.isfinite(ac.Wpi).all() and torch.isfinite(ac.Wv).all()
+    a = ac.act_test(np.random.RandomState(0).randint(0, pop + 1, (N, E)))
+    assert a.shape == (N, E) and a.max() <= 2 and (np.array([0, 1, 2])[a].sum(0) <= B).all()
+    val = orc.simulate_reward(ac, nature, seed=3, steps_per_epoch=8, epochs=8, gamma=0.9)
+    assert np.isfinite(val)
