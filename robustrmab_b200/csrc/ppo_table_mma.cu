@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256, (H >= 32 ? 1 : 2)) ppo_table_mma_kernel(M
       const int m = blk * 32 + lane;
       const bool valid = m < M;
       const int mm = valid ? m : M - 1;
-      const int srow = mm / E, erow = mm - srow * E;
+      const int srow = (mm >= E) + (mm >= 2 * E), erow = mm - srow * E;  // S <= 3: no integer division
       {
         const float lam = slam[erow];
         rlw[lane] = valid ? lam : 0.f;
@@ -335,43 +335,54 @@ __global__ void __launch_bounds__(256, (H >= 32 ? 1 : 2)) ppo_table_mma_kernel(M
         }
         // rows of a block share one state whenever E is a multiple of 32 (warp-uniform test): then dW1[:, s] gets
         // the same row sum as db1 and the one-hot products are skipped
-        const int s_first = (blk * 32) / E, s_last = (min(blk * 32 + 31, M - 1)) / E;
+        const int m_first = blk * 32, m_last = min(blk * 32 + 31, M - 1);
+        const int s_first = (m_first >= E) + (m_first >= 2 * E), s_last = (m_last >= E) + (m_last >= 2 * E);
         const bool uniform = s_first == s_last;
         float t_b1[MT][2];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) { t_b1[mt][0] = 0.f; t_b1[mt][1] = 0.f; }
+        if (uniform) {   // warp-uniform branch: all rows of the block are in state s_first
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          const float2 lm = *reinterpret_cast<const float2*>(rlw + 8 * nt + 2 * tq);
-          float2 oh[S];
-          if (!uniform) {
+          for (int nt = 0; nt < 4; ++nt) {
+            const float2 lm = *reinterpret_cast<const float2*>(rlw + 8 * nt + 2 * tq);
 #pragma unroll
-            for (int cc = 0; cc < S; ++cc) oh[cc] = *reinterpret_cast<const float2*>(row + cc * 32 + 8 * nt + 2 * tq);
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const float2 a1 = *reinterpret_cast<const float2*>(A1w + (16 * mt + gq + 8 * hh) * LDT + 8 * nt + 2 * tq);
+                const float dx = c[mt][nt][2 * hh] * fmaf(-a1.x, a1.x, 1.f), dy = c[mt][nt][2 * hh + 1] * fmaf(-a1.y, a1.y, 1.f);
+                t_b1[mt][hh] += dx + dy;
+                s_wl[mt][hh] += fmaf(dx, lm.x, dy * lm.y);
+              }
           }
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-              const float2 a1 = *reinterpret_cast<const float2*>(A1w + (16 * mt + gq + 8 * hh) * LDT + 8 * nt + 2 * tq);
-              const float dx = c[mt][nt][2 * hh] * fmaf(-a1.x, a1.x, 1.f), dy = c[mt][nt][2 * hh + 1] * fmaf(-a1.y, a1.y, 1.f);
-              t_b1[mt][hh] += dx + dy;
-              s_wl[mt][hh] += fmaf(dx, lm.x, dy * lm.y);
-              if (!uniform) {
-#pragma unroll
-                for (int cc = 0; cc < S; ++cc) s_w1[cc][mt][hh] += fmaf(dx, oh[cc].x, dy * oh[cc].y);
-              }
-            }
-        }
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            s_b1[mt][hh] += t_b1[mt][hh];
-            if (uniform) {
+              s_b1[mt][hh] += t_b1[mt][hh];
 #pragma unroll
               for (int cc = 0; cc < S; ++cc) s_w1[cc][mt][hh] += (s_first == cc) ? t_b1[mt][hh] : 0.f;
             }
+        } else {
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            const float2 lm = *reinterpret_cast<const float2*>(rlw + 8 * nt + 2 * tq);
+            float2 oh[S];
+#pragma unroll
+            for (int cc = 0; cc < S; ++cc) oh[cc] = *reinterpret_cast<const float2*>(row + cc * 32 + 8 * nt + 2 * tq);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const float2 a1 = *reinterpret_cast<const float2*>(A1w + (16 * mt + gq + 8 * hh) * LDT + 8 * nt + 2 * tq);
+                const float dx = c[mt][nt][2 * hh] * fmaf(-a1.x, a1.x, 1.f), dy = c[mt][nt][2 * hh + 1] * fmaf(-a1.y, a1.y, 1.f);
+                s_b1[mt][hh] += dx + dy;
+                s_wl[mt][hh] += fmaf(dx, lm.x, dy * lm.y);
+#pragma unroll
+                for (int cc = 0; cc < S; ++cc) s_w1[cc][mt][hh] += fmaf(dx, oh[cc].x, dy * oh[cc].y);
+              }
           }
+        }
       }
       // ---- W: dW2 += d2 a1^T over the block's 32 rows (4 k-steps); db2 and dW3 ride along ----
 #pragma unroll
@@ -448,7 +459,7 @@ __global__ void __launch_bounds__(256, (H >= 32 ? 1 : 2)) ppo_table_mma_kernel(M
     float b3tot[OUT];
 #pragma unroll
     for (int a = 0; a < OUT; ++a) b3tot[a] = warp_sum(s_b3[a]);
-    const float loss_tot = block_sum(loss_acc, red);  // contains __syncthreads
+    const float loss_tot = g.loss_out ? block_sum(loss_acc, red) : 0.f;  // block-wide; skipped when nobody reads it
     if (lane == 0)
 #pragma unroll
       for (int a = 0; a < OUT; ++a) red[8 + warp * OUT + a] = b3tot[a];
@@ -485,9 +496,12 @@ __global__ void __launch_bounds__(256, (H >= 32 ? 1 : 2)) ppo_table_mma_kernel(M
     // ---- Adam (torch.optim.Adam defaults; _single_tensor_adam form) ----
     b1p *= g.hp.beta1;
     b2p *= g.hp.beta2;
-    const double bc1 = 1.0 - b1p, bc2 = 1.0 - b2p;
-    const float step_size = (float)(lr / bc1);
-    const float bc2s = (float)sqrt(bc2);
+    if (tid == 0) {  // the double-precision bias corrections once per iteration, not once per thread
+      red[30] = (float)(lr / (1.0 - b1p));
+      red[31] = (float)sqrt(1.0 - b2p);
+    }
+    __syncthreads();
+    const float step_size = red[30], bc2s = red[31];
     for (int i = tid; i < P; i += 256) {
       const float gi = G[i];
       const float mi = am[i] + lerp_w * (gi - am[i]);

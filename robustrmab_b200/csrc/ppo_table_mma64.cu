@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_mma64_kernel(Mma64Args g) {
       const int m = blk * RB + rr;
       const bool valid = m < M;
       const int mm = valid ? m : M - 1;
-      const int srow = mm / E, erow = mm - srow * E;
+      const int srow = (mm >= E) + (mm >= 2 * E), erow = mm - srow * E;  // S <= 3: no integer division
       {
         const float lam = slam[erow];
         if (hf == 0) {
@@ -320,43 +320,54 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_mma64_kernel(Mma64Args g) {
             for (int nt = 0; nt < NTL; ++nt) mma6x3(c[mt][nt], ahi, alo, bh[nt][0], bh[nt][1], bl[nt][0], bl[nt][1]);
           }
         }
-        const int s_first = (blk * RB) / E, s_last = (min(blk * RB + RB - 1, M - 1)) / E;
+        const int m_first = blk * RB, m_last = min(blk * RB + RB - 1, M - 1);
+        const int s_first = (m_first >= E) + (m_first >= 2 * E), s_last = (m_last >= E) + (m_last >= 2 * E);
         const bool uniform = s_first == s_last;
         float t_b1[MT][2];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) { t_b1[mt][0] = 0.f; t_b1[mt][1] = 0.f; }
+        if (uniform) {   // warp-uniform branch: all rows of the block are in state s_first
 #pragma unroll
-        for (int nt = 0; nt < NTL; ++nt) {
-          const float2 lm = *reinterpret_cast<const float2*>(rlw + 8 * nt + 2 * tq);
-          float2 oh[S];
-          if (!uniform) {
+          for (int nt = 0; nt < NTL; ++nt) {
+            const float2 lm = *reinterpret_cast<const float2*>(rlw + 8 * nt + 2 * tq);
 #pragma unroll
-            for (int cc = 0; cc < S; ++cc) oh[cc] = *reinterpret_cast<const float2*>(row + cc * RB + 8 * nt + 2 * tq);
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const float2 a1 = *reinterpret_cast<const float2*>(A1w + (16 * mt + gq + 8 * hh) * LDT + 8 * nt + 2 * tq);
+                const float dx = c[mt][nt][2 * hh] * fmaf(-a1.x, a1.x, 1.f), dy = c[mt][nt][2 * hh + 1] * fmaf(-a1.y, a1.y, 1.f);
+                t_b1[mt][hh] += dx + dy;
+                s_wl[mt][hh] += fmaf(dx, lm.x, dy * lm.y);
+              }
           }
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-              const float2 a1 = *reinterpret_cast<const float2*>(A1w + (16 * mt + gq + 8 * hh) * LDT + 8 * nt + 2 * tq);
-              const float dx = c[mt][nt][2 * hh] * fmaf(-a1.x, a1.x, 1.f), dy = c[mt][nt][2 * hh + 1] * fmaf(-a1.y, a1.y, 1.f);
-              t_b1[mt][hh] += dx + dy;
-              s_wl[mt][hh] += fmaf(dx, lm.x, dy * lm.y);
-              if (!uniform) {
-#pragma unroll
-                for (int cc = 0; cc < S; ++cc) s_w1[cc][mt][hh] += fmaf(dx, oh[cc].x, dy * oh[cc].y);
-              }
-            }
-        }
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            s_b1[mt][hh] += t_b1[mt][hh];
-            if (uniform) {
+              s_b1[mt][hh] += t_b1[mt][hh];
 #pragma unroll
               for (int cc = 0; cc < S; ++cc) s_w1[cc][mt][hh] += (s_first == cc) ? t_b1[mt][hh] : 0.f;
             }
+        } else {
+#pragma unroll
+          for (int nt = 0; nt < NTL; ++nt) {
+            const float2 lm = *reinterpret_cast<const float2*>(rlw + 8 * nt + 2 * tq);
+            float2 oh[S];
+#pragma unroll
+            for (int cc = 0; cc < S; ++cc) oh[cc] = *reinterpret_cast<const float2*>(row + cc * RB + 8 * nt + 2 * tq);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const float2 a1 = *reinterpret_cast<const float2*>(A1w + (16 * mt + gq + 8 * hh) * LDT + 8 * nt + 2 * tq);
+                const float dx = c[mt][nt][2 * hh] * fmaf(-a1.x, a1.x, 1.f), dy = c[mt][nt][2 * hh + 1] * fmaf(-a1.y, a1.y, 1.f);
+                s_b1[mt][hh] += dx + dy;
+                s_wl[mt][hh] += fmaf(dx, lm.x, dy * lm.y);
+#pragma unroll
+                for (int cc = 0; cc < S; ++cc) s_w1[cc][mt][hh] += fmaf(dx, oh[cc].x, dy * oh[cc].y);
+              }
           }
+        }
       }
       // ---- W: dW2 += d2 a1^T over the block's 16 rows (2 k-steps); db2 and dW3 ride along ----
 #pragma unroll
@@ -433,7 +444,7 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_mma64_kernel(Mma64Args g) {
     float b3tot[OUT];
 #pragma unroll
     for (int a = 0; a < OUT; ++a) b3tot[a] = warp_sum(s_b3[a]);
-    const float loss_tot = block_sum(loss_acc, red);
+    const float loss_tot = g.loss_out ? block_sum(loss_acc, red) : 0.f;  // block-wide; skipped when nobody reads it
     if (lane == 0)
 #pragma unroll
       for (int a = 0; a < OUT; ++a) red[8 + warp * OUT + a] = b3tot[a];
@@ -464,9 +475,12 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_mma64_kernel(Mma64Args g) {
     // ---- Adam; moments live in global memory (one read-modify-write per iteration) ----
     b1p *= g.hp.beta1;
     b2p *= g.hp.beta2;
-    const double bc1 = 1.0 - b1p, bc2 = 1.0 - b2p;
-    const float step_size = (float)(lr / bc1);
-    const float bc2s = (float)sqrt(bc2);
+    if (tid == 0) {  // the double-precision bias corrections once per iteration, not once per thread
+      red[30] = (float)(lr / (1.0 - b1p));
+      red[31] = (float)sqrt(1.0 - b2p);
+    }
+    __syncthreads();
+    const float step_size = red[30], bc2s = red[31];
     for (int i = tid; i < P; i += NTHR) {
       const bool in_w2 = i >= L.oW2 && i < L.ob2;
       float gi, x;
