@@ -62,7 +62,7 @@ struct EpochArgs {
 };
 
 template <int H, int DOMAIN>
-__global__ void __launch_bounds__(256, 2) epoch_table_kernel(EpochArgs g) {
+__global__ void __launch_bounds__(256, (H >= 32 ? 1 : 2)) epoch_table_kernel(EpochArgs g) {
   constexpr int S = DOMAIN == RMAB_DOMAIN_CE ? 2 : 3;
   constexpr int A = 2;
   using SR = StatRows<S, A>;
@@ -271,13 +271,17 @@ __global__ void __launch_bounds__(256, 2) epoch_table_kernel(EpochArgs g) {
   }
 }
 
-// out[k, e] = sum_b in[b, k, e] in fp64, fixed order (deterministic).
+// out[i] = sum_b in[b, i] in fp64 (i over the 2*E sums).  One warp per output: lane l adds partials l, l+32, ... in
+// order, then a fixed butterfly -- deterministic for a given grid size.
 __global__ void part_sum_kernel(int nb, int64_t ke, const double* __restrict__ in, float* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= ke) return;
   double acc = 0.0;
-  for (int b = 0; b < nb; ++b) acc += in[(int64_t)b * ke + i];
-  out[i] = (float)acc;
+  for (int b = lane; b < nb; b += 32) acc += in[(int64_t)b * ke + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[i] = (float)acc;
 }
 
 template <typename K>
@@ -356,6 +360,6 @@ extern "C" int rmab_epoch_table(int domain, const RmabNetDesc* net, int T, const
   int rc = check_launch("rmab_epoch_table");
   if (rc || !env_sums) return rc;
   const int64_t ke = 2 * (int64_t)net->n_envs;
-  part_sum_kernel<<<(int)((ke + 127) / 128), 128, 0, st>>>(grid, ke, (const double*)ws, env_sums);
+  part_sum_kernel<<<(int)((ke + 7) / 8), 256, 0, st>>>(grid, ke, (const double*)ws, env_sums);
   return check_launch("rmab_epoch_table(sum)");
 }
