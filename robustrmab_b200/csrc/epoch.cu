@@ -62,7 +62,7 @@ struct EpochArgs {
 };
 
 template <int H, int DOMAIN>
-__global__ void __launch_bounds__(256, (H >= 32 ? 1 : 2)) epoch_table_kernel(EpochArgs g) {
+__global__ void __launch_bounds__(256, 2) epoch_table_kernel(EpochArgs g) {
   constexpr int S = DOMAIN == RMAB_DOMAIN_CE ? 2 : 3;
   constexpr int A = 2;
   using SR = StatRows<S, A>;
