@@ -286,6 +286,12 @@ int rmab_vi_batched(int N, int S, int A, int L, const double* T, const double* R
                     double* V, uint8_t* policy, int32_t* iters, int32_t* max_iter, double* Q,
                     rmab_stream_t stream);
 
+/* mdptoolbox.mdp.ValueIteration with a general reward: T [N,S,A,S], Rsa [N,S,A] (the matrix MDP._computeReward
+ * collapses any accepted reward shape to, mdp.py:292-302), one solve per arm.  V [N,S], policy [N,S] (may be NULL),
+ * iters / max_iter [N] (may be NULL).  Used by the drop-in `ValueIteration` class (robustrmab_b200/mdp.py). */
+int rmab_vi_general(int N, int S, int A, const double* T, const double* Rsa, double gamma, double eps, int stop_mode,
+                    double* V, uint8_t* policy, int32_t* iters, int32_t* max_iter, rmab_stream_t stream);
+
 /* Whittle index by bisection on the indifference condition Q(s,1;l) = Q(s,0;l) (lp_methods.py:181),
  * n_rounds halvings of [lam_lo, lam_hi] per (arm, state), each probe one ValueIteration as above.
  * index [N,S] fp64. */

@@ -38,17 +38,36 @@ struct SmallMdp {
   double R[S];
   double C[A];
   double k;           // 1 - sum_ss min_{a,s} P[a][s][ss]
-  __device__ void load(const double* __restrict__ T, const double* __restrict__ Rg, const double* __restrict__ Cg) {
+  double Ra[S][A];    // general reward R[s][a] (rmab_vi_general); used instead of R[s] - lam * C[a] when use_ra
+  bool use_ra;
+  __device__ __forceinline__ double rew(int s, int a, double lam) const {
+    double v = 0.0;
+#pragma unroll
+    for (int ss = 0; ss < S; ++ss)
+#pragma unroll
+      for (int aa = 0; aa < A; ++aa)
+        if (ss == s && aa == a) v = use_ra ? Ra[ss][aa] : (R[ss] - lam * C[aa]);
+    return v;
+  }
+  __device__ void load(const double* __restrict__ T, const double* __restrict__ Rg, const double* __restrict__ Cg,
+                       const double* __restrict__ Rsa = nullptr) {
+    use_ra = Rsa != nullptr;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      R[s] = Rg[s];
+#pragma unroll
+      for (int a = 0; a < A; ++a) Ra[s][a] = use_ra ? Rsa[s * A + a] : 0.0;
+    }
+    if (use_ra) Rg = nullptr;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      R[s] = Rg ? Rg[s] : 0.0;
 #pragma unroll
       for (int a = 0; a < A; ++a)
 #pragma unroll
         for (int t = 0; t < S; ++t) P[a][s][t] = T[(s * A + a) * S + t];
     }
 #pragma unroll
-    for (int a = 0; a < A; ++a) C[a] = Cg[a];
+    for (int a = 0; a < A; ++a) C[a] = Cg ? Cg[a] : 0.0;
     double hs = 0.0;
 #pragma unroll
     for (int t = 0; t < S; ++t) {
@@ -73,7 +92,7 @@ struct SmallMdp {
         double ev = 0.0;
 #pragma unroll
         for (int t = 0; t < S; ++t) ev += P[a][s][t] * V[t];
-        const double q = (R[s] - lam * C[a]) + p.gamma * ev;
+        const double q = rew(s, a, lam) + p.gamma * ev;
         if (a == 0 || q > best) { best = q; ba = a; }
       }
       Vn[s] = best;
@@ -128,7 +147,7 @@ struct SmallMdp {
           if (ss == s && aa == a) pv = P[aa][ss][t];
       ev += pv * V[t];
     }
-    return (R[s] - lam * C[a]) + p.gamma * ev;
+    return rew(s, a, lam) + p.gamma * ev;
   }
 };
 
@@ -138,13 +157,13 @@ __global__ void __launch_bounds__(128) vi_small_kernel(int N, int L, const doubl
                                                        const double* __restrict__ lambdas, int per_arm, ViParams p,
                                                        double* __restrict__ Vout, uint8_t* __restrict__ pol_out,
                                                        int32_t* __restrict__ iters, int32_t* __restrict__ max_iter_out,
-                                                       double* __restrict__ Qout) {
+                                                       double* __restrict__ Qout, const double* __restrict__ Rsa) {
   const int64_t total = (int64_t)N * L;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int n = (int)(i / L), l = (int)(i - (int64_t)n * L);
     SmallMdp<S, A> m;
-    m.load(T + (int64_t)n * S * A * S, R + (int64_t)n * S, C);
-    const double lam = per_arm ? lambdas[i] : lambdas[l];
+    m.load(T + (int64_t)n * S * A * S, R ? R + (int64_t)n * S : nullptr, C, Rsa ? Rsa + (int64_t)n * S * A : nullptr);
+    const double lam = Rsa ? 0.0 : (per_arm ? lambdas[i] : lambdas[l]);
     double V[S];
     int pol[S], mi;
     const int it = m.solve(lam, p, V, pol, mi);
@@ -195,7 +214,8 @@ __global__ void __launch_bounds__(256) vi_generic_kernel(int S, int A, int L, co
                                                          int mode, double lam_lo, double lam_hi, int n_rounds,
                                                          double* __restrict__ Vout, uint8_t* __restrict__ pol_out,
                                                          int32_t* __restrict__ iters, int32_t* __restrict__ max_iter_out,
-                                                         double* __restrict__ Qout, double* __restrict__ index) {
+                                                         double* __restrict__ Qout, double* __restrict__ index,
+                                                         const double* __restrict__ Rsa) {
   extern __shared__ __align__(16) unsigned char sraw[];
   double* sT = reinterpret_cast<double*>(sraw);        // [S][A][S]
   double* sR = sT + (size_t)S * A * S;                 // [S]
@@ -206,7 +226,8 @@ __global__ void __launch_bounds__(256) vi_generic_kernel(int S, int A, int L, co
   double* sLo = sLam + L;                              // [L]
   double* sHi = sLo + L;                               // [L]
   double* sMin = sHi + L;                              // [S] column minima
-  int* sIt = reinterpret_cast<int*>(sMin + S);         // [L] iteration counters
+  double* sRa = sMin + S;                              // [S][A] general reward (rmab_vi_general), else unused
+  int* sIt = reinterpret_cast<int*>(sRa + (size_t)S * A);  // [L] iteration counters
   int* sMax = sIt + L;                                 // [L] max_iter (-1 invalid)
   int* sAct = sMax + L;                                // [L] still iterating
   uint8_t* sPol = reinterpret_cast<uint8_t*>(sAct + L);  // [L][S]
@@ -215,12 +236,15 @@ __global__ void __launch_bounds__(256) vi_generic_kernel(int S, int A, int L, co
   const int n = blockIdx.x, tid = threadIdx.x;
   const double* Tn = T + (int64_t)n * S * A * S;
   for (int i = tid; i < S * A * S; i += blockDim.x) sT[i] = Tn[i];
-  for (int i = tid; i < S; i += blockDim.x) sR[i] = R[(int64_t)n * S + i];
-  for (int i = tid; i < A; i += blockDim.x) sC[i] = C[i];
+  const bool use_ra = Rsa != nullptr;
+  for (int i = tid; i < S; i += blockDim.x) sR[i] = use_ra ? 0.0 : R[(int64_t)n * S + i];
+  for (int i = tid; i < A; i += blockDim.x) sC[i] = use_ra ? 0.0 : C[i];
+  for (int i = tid; i < S * A; i += blockDim.x) sRa[i] = use_ra ? Rsa[(int64_t)n * S * A + i] : 0.0;
+#define RMAB_REW(s_, a_, l_) (use_ra ? sRa[(s_) * A + (a_)] : (sR[s_] - sLam[l_] * sC[a_]))
   for (int l = tid; l < L; l += blockDim.x) {
     sLo[l] = lam_lo;
     sHi[l] = lam_hi;
-    if (mode == 0) sLam[l] = per_arm ? lambdas[(int64_t)n * L + l] : lambdas[l];
+    if (mode == 0) sLam[l] = use_ra ? 0.0 : (per_arm ? lambdas[(int64_t)n * L + l] : lambdas[l]);
   }
   __syncthreads();
   // k = 1 - sum_t min_{a,s} P[a][s,t]   (:1344-1354)
@@ -245,8 +269,8 @@ __global__ void __launch_bounds__(256) vi_generic_kernel(int S, int A, int L, co
     for (int l = tid; l < L; l += blockDim.x) {
       double mx = 0.0, mn = 0.0;
       for (int s = 0; s < S; ++s) {
-        double best = sR[s] - sLam[l] * sC[0];
-        for (int a = 1; a < A; ++a) best = fmax(best, sR[s] - sLam[l] * sC[a]);
+        double best = RMAB_REW(s, 0, l);
+        for (int a = 1; a < A; ++a) best = fmax(best, RMAB_REW(s, a, l));
         if (s == 0) { mx = best; mn = best; } else { mx = fmax(mx, best); mn = fmin(mn, best); }
       }
       int mi = bound_iter(s_k, mx - mn, p);
@@ -272,7 +296,7 @@ __global__ void __launch_bounds__(256) vi_generic_kernel(int S, int A, int L, co
           const double* row = sT + ((size_t)s * A + a) * S;
           double ev = 0.0;
           for (int t = 0; t < S; ++t) ev += row[t] * Vl[t];
-          const double q = (sR[s] - sLam[l] * sC[a]) + p.gamma * ev;
+          const double q = RMAB_REW(s, a, l) + p.gamma * ev;
           if (a == 0 || q > best) { best = q; ba = a; }
         }
         Vn[i] = best;
@@ -308,7 +332,7 @@ __global__ void __launch_bounds__(256) vi_generic_kernel(int S, int A, int L, co
             const double* row = sT + ((size_t)l * A + a) * S;
             double ev = 0.0;
             for (int t = 0; t < S; ++t) ev += row[t] * Vc[(size_t)l * S + t];
-            q[a] = (sR[l] - sLam[l] * sC[a]) + p.gamma * ev;
+            q[a] = RMAB_REW(l, a, l) + p.gamma * ev;
           }
           act = (q[1] - q[0]) > 0.0;
         }
@@ -328,7 +352,7 @@ __global__ void __launch_bounds__(256) vi_generic_kernel(int S, int A, int L, co
             const double* row = sT + ((size_t)s * A + a) * S;
             double ev = 0.0;
             for (int t = 0; t < S; ++t) ev += row[t] * Vc[(size_t)l * S + t];
-            Qout[o * A + a] = ok ? (sR[s] - sLam[l] * sC[a]) + p.gamma * ev : nan;
+            Qout[o * A + a] = ok ? RMAB_REW(s, a, l) + p.gamma * ev : nan;
           }
       }
       for (int l = tid; l < L; l += blockDim.x) {
@@ -341,8 +365,10 @@ __global__ void __launch_bounds__(256) vi_generic_kernel(int S, int A, int L, co
     for (int l = tid; l < L; l += blockDim.x) index[(int64_t)n * S + l] = 0.5 * (sLo[l] + sHi[l]);
 }
 
+#undef RMAB_REW
+
 static size_t vi_generic_smem(int S, int A, int L) {
-  size_t d = (size_t)S * A * S + S + A + 2 * (size_t)L * S + 3 * (size_t)L + S;
+  size_t d = (size_t)S * A * S + S + A + 2 * (size_t)L * S + 3 * (size_t)L + S + (size_t)S * A;
   size_t b = d * 8 + 3 * (size_t)L * 4 + (size_t)L * S;
   return (b + 15) & ~(size_t)15;
 }
@@ -350,7 +376,7 @@ static size_t vi_generic_smem(int S, int A, int L) {
 static int launch_generic(int N, int S, int A, int L, const double* T, const double* R, const double* C,
                           const double* lambdas, int per_arm, const ViParams& p, int mode, double lo, double hi,
                           int rounds, double* V, uint8_t* pol, int32_t* iters, int32_t* mi, double* Q, double* index,
-                          cudaStream_t st, const char* who) {
+                          cudaStream_t st, const char* who, const double* Rsa = nullptr) {
   const size_t smem = vi_generic_smem(S, A, L);
   RMAB_REQUIRE(smem <= 227 * 1024, RMAB_E_SHAPE, "%s: S=%d A=%d L=%d needs %zu B of shared memory (> 227 KB)", who, S, A, L,
                smem);
@@ -359,7 +385,7 @@ static int launch_generic(int N, int S, int A, int L, const double* T, const dou
                      cudaSuccess,
                  RMAB_E_LAUNCH, "%s: cannot reserve %zu B smem", who, smem);
   vi_generic_kernel<<<N, 256, smem, st>>>(S, A, L, T, R, C, lambdas, per_arm, p, mode, lo, hi, rounds, V, pol, iters, mi, Q,
-                                         index);
+                                         index, Rsa);
   return check_launch(who);
 }
 
@@ -391,11 +417,13 @@ extern "C" int rmab_vi_batched(int N, int S, int A, int L, const double* T, cons
   const int64_t total = (int64_t)N * L;
   const int grid = (int)((total + 127) / 128 < (int64_t)kNumSMs * 32 ? (total + 127) / 128 : (int64_t)kNumSMs * 32);
   if (S == 2 && A == 2) {
-    vi_small_kernel<2, 2><<<grid, 128, 0, st>>>(N, L, T, R, C, lambdas, lambdas_per_arm, p, V, policy, iters, max_iter, Q);
+    vi_small_kernel<2, 2><<<grid, 128, 0, st>>>(N, L, T, R, C, lambdas, lambdas_per_arm, p, V, policy, iters, max_iter, Q,
+                                                nullptr);
     return check_launch("rmab_vi_batched<2,2>");
   }
   if (S == 3 && A == 2) {
-    vi_small_kernel<3, 2><<<grid, 128, 0, st>>>(N, L, T, R, C, lambdas, lambdas_per_arm, p, V, policy, iters, max_iter, Q);
+    vi_small_kernel<3, 2><<<grid, 128, 0, st>>>(N, L, T, R, C, lambdas, lambdas_per_arm, p, V, policy, iters, max_iter, Q,
+                                                nullptr);
     return check_launch("rmab_vi_batched<3,2>");
   }
   return launch_generic(N, S, A, L, T, R, C, lambdas, lambdas_per_arm, p, 0, 0.0, 0.0, 1, V, policy, iters, max_iter, Q,
@@ -424,4 +452,30 @@ extern "C" int rmab_whittle_bisect(int N, int S, int A, const double* T, const d
   }
   return launch_generic(N, S, A, S, T, R, C, nullptr, 0, p, 1, lam_lo, lam_hi, n_rounds, nullptr, nullptr, nullptr, nullptr,
                         nullptr, index, st, "rmab_whittle_bisect");
+}
+
+extern "C" int rmab_vi_general(int N, int S, int A, const double* T, const double* Rsa, double gamma, double eps,
+                               int stop_mode, double* V, uint8_t* policy, int32_t* iters, int32_t* max_iter,
+                               rmab_stream_t stream) {
+  RMAB_REQUIRE(N >= 0 && S >= 1 && S <= 256 && A >= 1 && A <= 16, RMAB_E_SHAPE, "rmab_vi_general: bad shape");
+  RMAB_REQUIRE(T && Rsa && V, RMAB_E_BADARG, "rmab_vi_general: null pointer");
+  RMAB_REQUIRE(gamma > 0.0 && gamma < 1.0 && eps > 0.0, RMAB_E_BADARG, "rmab_vi_general: need 0 < gamma < 1 and eps > 0");
+  RMAB_REQUIRE(stop_mode == RMAB_STOP_FULL || stop_mode == RMAB_STOP_FAST || stop_mode == RMAB_STOP_ABS, RMAB_E_BADARG,
+               "rmab_vi_general: bad stop_mode");
+  if (N == 0) return RMAB_OK;
+  const ViParams p = make_params(gamma, eps, stop_mode);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = (int)(((int64_t)N + 127) / 128 < (int64_t)kNumSMs * 32 ? ((int64_t)N + 127) / 128 : (int64_t)kNumSMs * 32);
+  if (S == 2 && A == 2) {
+    vi_small_kernel<2, 2><<<grid, 128, 0, st>>>(N, 1, T, nullptr, nullptr, nullptr, 0, p, V, policy, iters, max_iter, nullptr,
+                                                Rsa);
+    return check_launch("rmab_vi_general<2,2>");
+  }
+  if (S == 3 && A == 2) {
+    vi_small_kernel<3, 2><<<grid, 128, 0, st>>>(N, 1, T, nullptr, nullptr, nullptr, 0, p, V, policy, iters, max_iter, nullptr,
+                                                Rsa);
+    return check_launch("rmab_vi_general<3,2>");
+  }
+  return launch_generic(N, S, A, 1, T, nullptr, nullptr, nullptr, 0, p, 0, 0.0, 0.0, 1, V, policy, iters, max_iter, nullptr,
+                        nullptr, st, "rmab_vi_general", Rsa);
 }

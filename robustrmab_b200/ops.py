@@ -313,6 +313,20 @@ def vi_batched(T, R, Cc, lambdas, gamma, eps, stop="full", want_q=False):
     return V, pol, iters, mi, Q
 
 
+def vi_general(T, Rsa, gamma, eps, stop="full"):
+    """ValueIteration for N MDPs with general rewards: T [N,S,A,S], Rsa [N,S,A] -> (V [N,S], policy, iters, max_iter)."""
+    N, S, A, _ = T.shape
+    dev = T.device
+    V = torch.empty((N, S), dtype=f64, device=dev)
+    pol = torch.empty((N, S), dtype=u8, device=dev)
+    iters = torch.empty((N,), dtype=i32, device=dev)
+    mi = torch.empty((N,), dtype=i32, device=dev)
+    check(lib().rmab_vi_general(N, S, A, _p(T, f64, "T"), _p(Rsa, f64, "Rsa"), float(gamma), float(eps),
+                                {"fast": _lib.STOP_FAST, "abs": _lib.STOP_ABS}.get(stop, _lib.STOP_FULL), _p(V, f64),
+                                _p(pol, u8), _p(iters, i32), _p(mi, i32), _stream()))
+    return V, pol, iters, mi
+
+
 def whittle_bisect(T, R, Cc, gamma, eps, lam_lo, lam_hi, n_rounds, stop="full"):
     N, S, A, _ = T.shape
     idx = torch.empty((N, S), dtype=f64, device=T.device)

@@ -355,3 +355,35 @@ def test_agent_oracle_sis_stepwise(torch_mod):
     assert a.shape == (N, E) and a.max() <= 2 and (np.array([0, 1, 2])[a].sum(0) <= B).all()
     val = orc.simulate_reward(ac, nature, seed=3, steps_per_epoch=8, epochs=8, gamma=0.9)
     assert np.isfinite(val)
+
+
+def test_value_iteration_dropin(torch_mod, golden):
+    """mdptoolbox.mdp.ValueIteration drop-in: the docstring known answers (mdp.py:1248-1290, span rule), the
+    reference's own 'full' default on the forest example, and the simulator.py:504-521 call shape."""
+    from robustrmab_b200.mdp import ValueIteration, ValueIterationBatch
+    g = golden("vi")
+    P, R = g["forest_P"], g["forest_R"]
+    vi = ValueIteration(P, R, 0.96, stop_criterion='fast')
+    vi.run()
+    assert np.allclose(vi.V, (5.93215488, 9.38815488, 13.38815488), atol=1e-8) and vi.policy == (0, 0, 0) and vi.iter == 4
+    vi = ValueIteration(np.array([[[0.5, 0.5], [0.8, 0.2]], [[0, 1], [0.1, 0.9]]]), np.array([[5, 10], [-1, 2]]), 0.9,
+                        stop_criterion='fast')
+    vi.run()
+    assert np.allclose(vi.V, (40.048625392716815, 33.65371175967546), atol=1e-12) and vi.policy == (1, 0) and vi.iter == 26
+    vi = ValueIteration(P, R, 0.96)
+    vi.run()
+    assert np.allclose(vi.V, g["forest_V_full"], atol=1e-10) and vi.iter == int(g["forest_iter_full"]) == vi.max_iter
+    assert isinstance(vi.V, tuple) and isinstance(vi.policy, tuple) and abs(vi.thresh - 0.01 * 0.04 / 0.96) < 1e-15
+    # the simulator.py call shape: T_i = swapaxes(T[i], 0, 1), R_i[a, s, s'] = R[i][s]
+    T, Rr = g["armman_T"], g["armman_R"]
+    N = T.shape[0]
+    Ts = np.swapaxes(T, 1, 2)
+    R3 = np.broadcast_to(Rr[:, None, :, None], Ts.shape).copy()
+    b = ValueIterationBatch(Ts, R3, 0.9, epsilon=1e-4).run()
+    np.testing.assert_allclose(b.V, g["armman_V_0.0001"][:, 0], rtol=1e-12, atol=1e-12)      # lambda = 0 probe of the golden
+    assert np.array_equal(b.iter, g["armman_it_0.0001"][:, 0]) and np.array_equal(b.policy, g["armman_pol_0.0001"][:, 0])
+    # degenerate MDPs fail in the constructor exactly where the reference's _boundIter does (:1358-1364):
+    with pytest.raises(OverflowError):      # zero span -> inf / log(gamma k) -> int(ceil(-inf))
+        ValueIteration(np.array([[[0.9, 0.1], [0.2, 0.8]], [[0.5, 0.5], [0.3, 0.7]]]), np.ones((2, 2)), 0.9)
+    with pytest.raises(ValueError):         # k = 0 -> math.log(0)
+        ValueIteration(np.array([[[0.5, 0.5], [0.5, 0.5]]] * 2), np.array([[1.0, 1.0], [2.0, 2.0]]), 0.9)
