@@ -132,8 +132,11 @@ int rmab_ac_step(const RmabNetDesc* net, const float* Wpi, const float* Wv, cons
  * h1_partial (may be NULL) receives the first-layer pre-activation partial sums [E,8] WITHOUT bias so
  * that arm-sharded ranks can all-reduce them; when sharded, pass h1_in = the reduced sums instead of s. */
 int rmab_lambda_forward(int E, int N, const float* params, int n_total, int arm0, const uint8_t* s,
-                        float obs_scale, const float* h1_in, float* h1_partial, float* lamb,
+                        float obs_scale, const float* h1_in, float* h1_partial, float* lamb, void* ws, size_t ws_bytes,
                         rmab_stream_t stream);
+/* Optional workspace of rmab_lambda_forward (ws may be NULL): with it the first layer is computed by arm splits in
+ * parallel and summed in split order. */
+size_t rmab_lambda_ws_bytes(int E, int N);
 
 /* SGD step on the lambda net for loss = mean_e lamb_e * coef_e  (compute_loss_lambda,
  * agent_oracle.py:360-376, :440-454; coef_e = B/(1-gamma) - cdcost_e[0]; the mean over envs is what

@@ -54,7 +54,8 @@ SIGNATURES = {
     "rmab_sis_table": [_I, _I, _P, _P, _P],
     "rmab_bound_nature": [C.c_int64, _P, _P, _P, _P, _P],
     "rmab_ac_step": [C.POINTER(RmabNetDesc), _P, _P, _P, _P, _P, C.POINTER(RmabRng), _P, _P, _P, _P, _P, _P, _P],
-    "rmab_lambda_forward": [_I, _I, _P, _I, _I, _P, _F, _P, _P, _P, _P],
+    "rmab_lambda_forward": [_I, _I, _P, _I, _I, _P, _F, _P, _P, _P, _P, C.c_size_t, _P],
+    "rmab_lambda_ws_bytes": [_I, _I],
     "rmab_lambda_sgd": [_I, _I, _P, _I, _I, _P, _F, _P, _P, _F, _P, _P, _P],
     "rmab_rollout_table": [_I, C.POINTER(RmabNetDesc), _I, _P, _P, _P, _P, _P, C.c_uint64, C.c_uint32, C.c_uint32,
                            C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P],
@@ -81,7 +82,7 @@ SIGNATURES = {
     "rmab_whittle_bisect": [_I, _I, _I, _P, _P, _P, _D, _D, _I, _D, _D, _I, _P, _P],
 }
 _RESTYPES = {"rmab_last_error": C.c_char_p, "rmab_launch_count": C.c_uint64, "rmab_select_ws_bytes": C.c_size_t,
-             "rmab_epoch_ws_bytes": C.c_size_t}
+             "rmab_epoch_ws_bytes": C.c_size_t, "rmab_lambda_ws_bytes": C.c_size_t}
 
 _lib = None
 

@@ -166,7 +166,7 @@ constexpr int kLamH = 8;
 __global__ void __launch_bounds__(1024) lambda_forward_kernel(int E, int N, const float* __restrict__ params,
                                                               int n_total, int arm0, const uint8_t* __restrict__ s,
                                                               float obs_scale, const float* __restrict__ h1_in,
-                                                              float* __restrict__ h1_partial,
+                                                              int n_split, float* __restrict__ h1_partial,
                                                               float* __restrict__ lamb) {
   __shared__ float red[32][kLamH][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -182,8 +182,9 @@ __global__ void __launch_bounds__(1024) lambda_forward_kernel(int E, int N, cons
   for (int j = 0; j < kLamH; ++j) h[j] = 0.f;
   if (h1_in) {
     if (w == 0 && e < E)
+      for (int k = 0; k < n_split; ++k)  // partial sums of the arm splits, added in split order (deterministic)
 #pragma unroll
-      for (int j = 0; j < kLamH; ++j) h[j] = h1_in[(int64_t)e * kLamH + j];
+        for (int j = 0; j < kLamH; ++j) h[j] += h1_in[((int64_t)k * E + e) * kLamH + j];
   } else {
     for (int n = w; n < N; n += nw) {
       const float x = (e < E) ? (float)s[(int64_t)n * E + e] * obs_scale : 0.f;
@@ -218,6 +219,42 @@ __global__ void __launch_bounds__(1024) lambda_forward_kernel(int E, int N, cons
     out = fmaf(__ldg(W3 + j), tanhf(z), out);
   }
   lamb[e] = out;
+}
+
+// First-layer partial sums of one arm split: grid (ceil(E/32), n_split), 8 warps stride the split's arms, lane = env.
+// part[split][e][j] = sum_{n in split} W1[j, arm0 + n] * s[n, e] * scale, warps merged in a fixed order.
+__global__ void __launch_bounds__(256) lambda_partial_kernel(int E, int N, const float* __restrict__ W1, int n_total,
+                                                             int arm0, const uint8_t* __restrict__ s, float obs_scale,
+                                                             int chunk, float* __restrict__ part) {
+  __shared__ float red[8][kLamH][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + lane;
+  const int n0 = blockIdx.y * chunk, n1 = min(N, n0 + chunk);
+  float h[kLamH];
+#pragma unroll
+  for (int j = 0; j < kLamH; ++j) h[j] = 0.f;
+  for (int n = n0 + w; n < n1; n += 8) {
+    const float x = (e < E) ? (float)s[(int64_t)n * E + e] * obs_scale : 0.f;
+#pragma unroll
+    for (int j = 0; j < kLamH; ++j) h[j] = fmaf(__ldg(W1 + (int64_t)j * n_total + arm0 + n), x, h[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < kLamH; ++j) red[w][j][lane] = h[j];
+  __syncthreads();
+  if (w == 0 && e < E) {
+#pragma unroll
+    for (int j = 0; j < kLamH; ++j) {
+      float acc = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < 8; ++ww) acc += red[ww][j][lane];
+      part[((int64_t)blockIdx.y * E + e) * kLamH + j] = acc;
+    }
+  }
+}
+
+static int lambda_splits(int N) {
+  const int k = N / 256;
+  return k < 1 ? 1 : (k > 64 ? 64 : k);
 }
 
 // Backward of mean_e lamb_e * coef_e through the two small layers (single CTA, thread per env, fixed-order
@@ -402,15 +439,31 @@ extern "C" int rmab_rollout_table(int domain, const RmabNetDesc* net, int T, con
   return check_launch("rmab_rollout_table");
 }
 
+extern "C" size_t rmab_lambda_ws_bytes(int E, int N) { return (size_t)lambda_splits(N) * (size_t)E * kLamH * sizeof(float); }
+
 extern "C" int rmab_lambda_forward(int E, int N, const float* params, int n_total, int arm0, const uint8_t* s,
-                                   float obs_scale, const float* h1_in, float* h1_partial, float* lamb,
-                                   rmab_stream_t stream) {
+                                   float obs_scale, const float* h1_in, float* h1_partial, float* lamb, void* ws,
+                                   size_t ws_bytes, rmab_stream_t stream) {
   RMAB_REQUIRE(E > 0 && N >= 0 && params && n_total >= N && arm0 >= 0 && arm0 + N <= n_total && (s || h1_in) &&
                    (lamb || h1_partial),
                RMAB_E_BADARG, "rmab_lambda_forward: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nsp = lambda_splits(N);
+  if (!h1_in && ws && nsp > 1 && ws_bytes >= rmab_lambda_ws_bytes(E, N)) {
+    // arm-split path: the first layer is spread over (E/32) x nsp CTAs, then one small kernel adds the splits in
+    // order and runs the 8 -> 8 -> 1 tail (same summation order for a given N, so results are reproducible)
+    const int chunk = (N + nsp - 1) / nsp;
+    lambda_partial_kernel<<<dim3((E + 31) / 32, nsp), 256, 0, st>>>(E, N, params, n_total, arm0, s, obs_scale, chunk,
+                                                                   (float*)ws);
+    int rc = check_launch("rmab_lambda_forward(partial)");
+    if (rc) return rc;
+    lambda_forward_kernel<<<(E + 31) / 32, 32, 0, st>>>(E, N, params, n_total, arm0, s, obs_scale, (const float*)ws, nsp,
+                                                       h1_partial, lamb);
+    return check_launch("rmab_lambda_forward(tail)");
+  }
   const int threads = h1_in ? 32 : 1024;
-  lambda_forward_kernel<<<(E + 31) / 32, threads, 0, (cudaStream_t)stream>>>(E, N, params, n_total, arm0, s, obs_scale,
-                                                                           h1_in, h1_partial, lamb);
+  lambda_forward_kernel<<<(E + 31) / 32, threads, 0, st>>>(E, N, params, n_total, arm0, s, obs_scale, h1_in, 1, h1_partial,
+                                                          lamb);
   return check_launch("rmab_lambda_forward");
 }
 

@@ -112,13 +112,21 @@ def ac_step(net, Wpi, Wv, s, lamb, r=None, u=None, want_probs=False, extra=None)
     return a, v, logp, p1, probs
 
 
+_LAMBDA_WS = {}
+
+
 def lambda_forward(params, s, n_total, arm0=0, obs_scale=1.0, h1_in=None, want_h1=False, want_lamb=True):
     N, E = s.shape
     dev = s.device
     h1 = torch.empty((E, 8), dtype=f32, device=dev) if want_h1 else None
     lamb = torch.empty((E,), dtype=f32, device=dev) if want_lamb else None
+    need = int(lib().rmab_lambda_ws_bytes(E, N))
+    ws = _LAMBDA_WS.get((dev, need))
+    if ws is None:
+        ws = _LAMBDA_WS[(dev, need)] = torch.empty((need + 3) // 4, dtype=f32, device=dev)
     check(lib().rmab_lambda_forward(E, N, _p(params, f32, "params"), int(n_total), int(arm0), _p(s, u8, "s"),
-                                    float(obs_scale), _p(h1_in, f32, "h1_in"), _p(h1, f32), _p(lamb, f32), _stream()))
+                                    float(obs_scale), _p(h1_in, f32, "h1_in"), _p(h1, f32), _p(lamb, f32), _p(ws, f32),
+                                    ws.numel() * 4, _stream()))
     return lamb, h1
 
 
