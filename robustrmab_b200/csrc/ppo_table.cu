@@ -495,6 +495,11 @@ int ppo_table_mma_run(const RmabNetDesc* net, const RmabHyper* hp, int T, float*
 int ppo_table_mma64_run(const RmabNetDesc* net, const RmabHyper* hp, int T, float* Wpi, float* Wv, float* adam_pi,
                         float* adam_v, const float* stats, const float* arm_stats, const float* lamb, float* loss_pi,
                         float* loss_v, cudaStream_t st);
+// tcgen05 / TMEM variant for H = 64 (ppo_table_umma64.cu)
+bool ppo_table_umma64_fits(const RmabNetDesc* net);
+int ppo_table_umma64_run(const RmabNetDesc* net, const RmabHyper* hp, int T, float* Wpi, float* Wv, float* adam_pi,
+                         float* adam_v, const float* stats, const float* arm_stats, const float* lamb, float* loss_pi,
+                         float* loss_v, cudaStream_t st);
 
 }  // namespace rmab
 
@@ -517,10 +522,14 @@ extern "C" int rmab_ppo_update_table(const RmabNetDesc* net, const RmabHyper* hp
   TblArgs g = {};
   g.d = *net; g.hp = *hp; g.T = T; g.lamb = lamb; g.stats = stats; g.arm_stats = arm_stats;
   cudaStream_t st = (cudaStream_t)stream;
-  // H = 16 / 32 / 64: 3xTF32 mma.sync kernels; H = 8 (and RMAB_TABLE_FFMA=1, for A/B measurements): FFMA kernel
+  // H = 16 / 32: 3xTF32 mma.sync kernels; H = 64: tcgen05 kernel (RMAB_H64_MMA_SYNC=1 selects the mma.sync one, also
+  // used when E is too large for its shared-memory plan); H = 8 (and RMAB_TABLE_FFMA=1, for A/B measurements): FFMA kernel
   static const bool force_ffma = getenv("RMAB_TABLE_FFMA") != nullptr;
+  static const bool h64_mma_sync = getenv("RMAB_H64_MMA_SYNC") != nullptr;
   if ((h == 16 || h == 32) && !force_ffma)
     return ppo_table_mma_run(net, hp, T, Wpi, Wv, adam_pi, adam_v, stats, arm_stats, lamb, loss_pi, loss_v, st);
+  if (h == 64 && !force_ffma && !h64_mma_sync && ppo_table_umma64_fits(net))
+    return ppo_table_umma64_run(net, hp, T, Wpi, Wv, adam_pi, adam_v, stats, arm_stats, lamb, loss_pi, loss_v, st);
   if (h == 64 && !force_ffma)
     return ppo_table_mma64_run(net, hp, T, Wpi, Wv, adam_pi, adam_v, stats, arm_stats, lamb, loss_pi, loss_v, st);
 #define RUN(H)                                                                                   \
