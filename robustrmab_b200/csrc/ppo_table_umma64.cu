@@ -25,6 +25,7 @@ namespace rmab {
 namespace {
 
 constexpr int H = 64, HH = H * H, TM = 128, NW = 16, NTHR = NW * 32, FW = 16;
+constexpr float kTanhScale = 2.885390081777927f;   // 2 / ln 2: tanh(x) = 1 - 2 / (2^(x * kTanhScale) + 1)
 // shared-memory tiles (byte offsets from a 1024-byte aligned base)
 constexpr uint32_t T_A1H = 0, T_A1L = 32768, T_D2H = 65536, T_D2L = 98304;             // 128 x 64, swizzled MN-major
 constexpr uint32_t T_W2H = 131072, T_W2L = 147456, T_WTH = 163840, T_WTL = 180224;     // 64 x 64, K-major core matrices
@@ -110,6 +111,17 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%4], {%0,%1,%2,%3};\n" ::"r"(a), "r"(b), "r"(c), "r"(d), "r"(taddr) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
@@ -119,6 +131,14 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ float tanh_fast_u(float x) {
   float e, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+  return fmaf(-2.f, r, 1.f);
+}
+
+// tanh(x) given y = x * 2 / ln 2 (callers fold the scale into the layer's weights / the accumulator read)
+__device__ __forceinline__ float tanh_scaled_u(float y) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(y));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
   return fmaf(-2.f, r, 1.f);
 }
@@ -180,9 +200,10 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
   const int P = L.P, Ps = L.padded() - HH;   // w / G hold the packed layout WITHOUT the W2 block
   float* w = reinterpret_cast<float*>(base + T_END);
   float* G = w + Ps;
-  float* wb = G + Ps;                 // [S][H]  W1[:, s] + b1
-  float* wl = wb + S * H;             // [H]     W1[:, lambda]
-  float* plog = wl + H;               // [4 cq][128 rows][OUT] partial logits
+  float* wb = G + Ps;                 // [S][H]  (W1[:, s] + b1) * kTanhScale
+  float* wl = wb + S * H;             // [H]     W1[:, lambda] * kTanhScale
+  float* b2s = wl + H;                // [H]     b2 * kTanhScale
+  float* plog = b2s + H;              // [4 cq][128 rows][OUT] partial logits
   float* redw = plog + 4 * TM * OUT;  // [NW][NQ][16]
   float* slam = redw + NW * NQ * FW;  // [E]
   float* W2H = reinterpret_cast<float*>(base + T_W2H);
@@ -243,15 +264,18 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
   for (int it = 0; it < iters; ++it) {
     for (int i = tid; i < S * H; i += NTHR) {
       const int s = i >> 6, k = i & 63;
-      wb[i] = w[L.oW1 + k * IN + s] + w[L.ob1 + k];
+      wb[i] = kTanhScale * (w[L.oW1 + k * IN + s] + w[L.ob1 + k]);
     }
-    for (int i = tid; i < H; i += NTHR) wl[i] = w[L.oW1 + i * IN + IN - 1];
+    for (int i = tid; i < H; i += NTHR) {
+      wl[i] = kTanhScale * w[L.oW1 + i * IN + IN - 1];
+      b2s[i] = kTanhScale * w[L.ob2 - HH + i];
+    }
     __syncthreads();
 
-    float s_b2[FW], s_wl[FW], t_b1[FW], s_w3[OUT][FW], s_w1r[S], s_b3[OUT];
+    float s_b2[FW], s_wl[FW], s_w3[OUT][FW], s_w1r[S], s_b3[OUT];
 #pragma unroll
     for (int k = 0; k < FW; ++k) {
-      s_b2[k] = 0.f; s_wl[k] = 0.f; t_b1[k] = 0.f;
+      s_b2[k] = 0.f; s_wl[k] = 0.f;
 #pragma unroll
       for (int a = 0; a < OUT; ++a) s_w3[a][k] = 0.f;
     }
@@ -260,7 +284,6 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
 #pragma unroll
     for (int a = 0; a < OUT; ++a) s_b3[a] = 0.f;
     float loss_acc = 0.f;
-    int cur_s = 0;   // state whose rows t_b1 is currently summing (warp-uniform)
 
     // E1: a1 = tanh(W1 x + b1) for this thread's 16 features of tile tt; hi/lo into TMEM buffer tt & 1 (operand of G1)
     auto layer1_to_tmem = [&](int tt) {
@@ -269,20 +292,22 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
       const int mm = valid ? m : M - 1;
       const int srow = (mm >= E) + (mm >= 2 * E), erow = mm - srow * E;   // S <= 3: no integer division
       const float lam = slam[erow];
-      uint32_t hi[FW], lo[FW];
+      const float keep = valid ? 1.f : 0.f;   // rows past the end contribute a1 = 0 (and so d2 = d1 = 0)
       const float4* wb4 = reinterpret_cast<const float4*>(wb + srow * H + f0);
       const float4* wl4 = reinterpret_cast<const float4*>(wl + f0);
+      const uint32_t buf = (uint32_t)(tt & 1) * C_A1BUF;
+      const bool last = tt == n_tiles - 1;    // only the last tile can hold rows past the end
 #pragma unroll
       for (int k4 = 0; k4 < FW / 4; ++k4) {
         const float4 b = wb4[k4], l = wl4[k4];
-        const float x0 = valid ? tanh_fast_u(fmaf(l.x, lam, b.x)) : 0.f, x1 = valid ? tanh_fast_u(fmaf(l.y, lam, b.y)) : 0.f;
-        const float x2 = valid ? tanh_fast_u(fmaf(l.z, lam, b.z)) : 0.f, x3 = valid ? tanh_fast_u(fmaf(l.w, lam, b.w)) : 0.f;
-        split_u(x0, hi[4 * k4], lo[4 * k4]); split_u(x1, hi[4 * k4 + 1], lo[4 * k4 + 1]);
-        split_u(x2, hi[4 * k4 + 2], lo[4 * k4 + 2]); split_u(x3, hi[4 * k4 + 3], lo[4 * k4 + 3]);
+        float x0 = tanh_scaled_u(fmaf(l.x, lam, b.x)), x1 = tanh_scaled_u(fmaf(l.y, lam, b.y));
+        float x2 = tanh_scaled_u(fmaf(l.z, lam, b.z)), x3 = tanh_scaled_u(fmaf(l.w, lam, b.w));
+        if (last) { x0 *= keep; x1 *= keep; x2 *= keep; x3 *= keep; }
+        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+        split_u(x0, h0, l0); split_u(x1, h1, l1); split_u(x2, h2, l2); split_u(x3, h3, l3);
+        tmem_st4(tl + C_A1H + buf + f0 + 4 * k4, h0, h1, h2, h3);
+        tmem_st4(tl + C_A1L + buf + f0 + 4 * k4, l0, l1, l2, l3);
       }
-      const uint32_t buf = (uint32_t)(tt & 1) * C_A1BUF;
-      tmem_st16(tl + C_A1H + buf + f0, hi);
-      tmem_st16(tl + C_A1L + buf + f0, lo);
     };
     // G1(tt): z2 = a1 . W2^T into the shared accumulator, three tf32 products (lo.hi, hi.lo, hi.hi)
     auto issue_g1 = [&](int tt) {
@@ -339,14 +364,14 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
         uint32_t v[FW];
         tmem_ld16(tl + C_D + f0, v);
         tmem_wait_ld();
-        const float4* b24 = reinterpret_cast<const float4*>(w + L.ob2 - HH + f0);
+        const float4* b24 = reinterpret_cast<const float4*>(b2s + f0);   // b2 * kTanhScale
 #pragma unroll
         for (int k4 = 0; k4 < FW / 4; ++k4) {
           const float4 b = b24[k4];
-          a2[4 * k4] = tanh_fast_u(__uint_as_float(v[4 * k4]) + b.x);
-          a2[4 * k4 + 1] = tanh_fast_u(__uint_as_float(v[4 * k4 + 1]) + b.y);
-          a2[4 * k4 + 2] = tanh_fast_u(__uint_as_float(v[4 * k4 + 2]) + b.z);
-          a2[4 * k4 + 3] = tanh_fast_u(__uint_as_float(v[4 * k4 + 3]) + b.w);
+          a2[4 * k4] = tanh_scaled_u(fmaf(__uint_as_float(v[4 * k4]), kTanhScale, b.x));
+          a2[4 * k4 + 1] = tanh_scaled_u(fmaf(__uint_as_float(v[4 * k4 + 1]), kTanhScale, b.y));
+          a2[4 * k4 + 2] = tanh_scaled_u(fmaf(__uint_as_float(v[4 * k4 + 2]), kTanhScale, b.z));
+          a2[4 * k4 + 3] = tanh_scaled_u(fmaf(__uint_as_float(v[4 * k4 + 3]), kTanhScale, b.w));
         }
       }
 #pragma unroll
@@ -403,52 +428,46 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
 #pragma unroll
           for (int a = 0; a < OUT; ++a) s_b3[a] += gl[a];
       }
-      {
-        uint32_t hi[FW], lo[FW];
+      if (gt > 0) mbar_wait(bar3, (gt - 1) & 1);   // the previous tile's G3 has finished reading the a1 / d2 tiles
 #pragma unroll
-        for (int k4 = 0; k4 < FW / 4; ++k4) {
-          float up[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int k4 = 0; k4 < FW / 4; ++k4) {
+        float up[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int a = 0; a < OUT; ++a) {
-            const float4 w3 = *reinterpret_cast<const float4*>(w + L.oW3 - HH + a * H + f0 + 4 * k4);
-            up[0] = fmaf(gl[a], w3.x, up[0]); up[1] = fmaf(gl[a], w3.y, up[1]);
-            up[2] = fmaf(gl[a], w3.z, up[2]); up[3] = fmaf(gl[a], w3.w, up[3]);
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int k = 4 * k4 + j;
-            const float x = a2[k], d2 = up[j] * fmaf(-x, x, 1.f);
-            s_b2[k] += d2;
-#pragma unroll
-            for (int a = 0; a < OUT; ++a) s_w3[a][k] = fmaf(gl[a], x, s_w3[a][k]);
-            split_u(d2, hi[k], lo[k]);
-          }
+        for (int a = 0; a < OUT; ++a) {
+          const float4 w3 = *reinterpret_cast<const float4*>(w + L.oW3 - HH + a * H + f0 + 4 * k4);
+          up[0] = fmaf(gl[a], w3.x, up[0]); up[1] = fmaf(gl[a], w3.y, up[1]);
+          up[2] = fmaf(gl[a], w3.z, up[2]); up[3] = fmaf(gl[a], w3.w, up[3]);
         }
-        tmem_st16(tl + C_D2H + f0, hi);
-        tmem_st16(tl + C_D2L + f0, lo);
-        if (gt > 0) mbar_wait(bar3, (gt - 1) & 1);   // the previous tile's G3 has finished reading the a1 / d2 tiles
-        *reinterpret_cast<uint4*>(base + T_D2H + off_c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(base + T_D2H + off_c0 + 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-        *reinterpret_cast<uint4*>(base + T_D2H + off_c1) = make_uint4(hi[8], hi[9], hi[10], hi[11]);
-        *reinterpret_cast<uint4*>(base + T_D2H + off_c1 + 16) = make_uint4(hi[12], hi[13], hi[14], hi[15]);
-        *reinterpret_cast<uint4*>(base + T_D2L + off_c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        *reinterpret_cast<uint4*>(base + T_D2L + off_c0 + 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-        *reinterpret_cast<uint4*>(base + T_D2L + off_c1) = make_uint4(lo[8], lo[9], lo[10], lo[11]);
-        *reinterpret_cast<uint4*>(base + T_D2L + off_c1 + 16) = make_uint4(lo[12], lo[13], lo[14], lo[15]);
-        // this tile's a1 (still in its TMEM buffer) -> the smem tile G3 contracts over
-        tmem_ld16(tl + C_A1H + abuf + f0, hi);
-        tmem_ld16(tl + C_A1L + abuf + f0, lo);
-        tmem_wait_ld();
-        *reinterpret_cast<uint4*>(base + T_A1H + off_c0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(base + T_A1H + off_c0 + 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-        *reinterpret_cast<uint4*>(base + T_A1H + off_c1) = make_uint4(hi[8], hi[9], hi[10], hi[11]);
-        *reinterpret_cast<uint4*>(base + T_A1H + off_c1 + 16) = make_uint4(hi[12], hi[13], hi[14], hi[15]);
-        *reinterpret_cast<uint4*>(base + T_A1L + off_c0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        *reinterpret_cast<uint4*>(base + T_A1L + off_c0 + 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-        *reinterpret_cast<uint4*>(base + T_A1L + off_c1) = make_uint4(lo[8], lo[9], lo[10], lo[11]);
-        *reinterpret_cast<uint4*>(base + T_A1L + off_c1 + 16) = make_uint4(lo[12], lo[13], lo[14], lo[15]);
-        tmem_wait_st();
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = 4 * k4 + j;
+          const float x = a2[k], d2 = up[j] * fmaf(-x, x, 1.f);
+          s_b2[k] += d2;
+#pragma unroll
+          for (int a = 0; a < OUT; ++a) s_w3[a][k] = fmaf(gl[a], x, s_w3[a][k]);
+          split_u(d2, h[j], l[j]);
+        }
+        tmem_st4(tl + C_D2H + f0 + 4 * k4, h[0], h[1], h[2], h[3]);
+        tmem_st4(tl + C_D2L + f0 + 4 * k4, l[0], l[1], l[2], l[3]);
+        const uint32_t off = (k4 < 2 ? off_c0 : off_c1) + 16 * (k4 & 1);
+        *reinterpret_cast<uint4*>(base + T_D2H + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(base + T_D2L + off) = make_uint4(l[0], l[1], l[2], l[3]);
       }
+      // this tile's a1 (still in its TMEM buffer) -> the smem tile G3 contracts over
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t h[8], l[8];
+        tmem_ld8(tl + C_A1H + abuf + f0 + 8 * c, h);
+        tmem_ld8(tl + C_A1L + abuf + f0 + 8 * c, l);
+        tmem_wait_ld();
+        const uint32_t off = c == 0 ? off_c0 : off_c1;
+        *reinterpret_cast<uint4*>(base + T_A1H + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(base + T_A1H + off + 16) = make_uint4(h[4], h[5], h[6], h[7]);
+        *reinterpret_cast<uint4*>(base + T_A1L + off) = make_uint4(l[0], l[1], l[2], l[3]);
+        *reinterpret_cast<uint4*>(base + T_A1L + off + 16) = make_uint4(l[4], l[5], l[6], l[7]);
+      }
+      tmem_wait_st();
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
@@ -488,19 +507,13 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
           d1[k] = __uint_as_float(v[k]) * fmaf(-a1, a1, 1.f);
           s_wl[k] = fmaf(d1[k], lam, s_wl[k]);
         }
+        // db1 / dW1[:, s]: the tile's column sums go straight to one register per state (lane l holds feature f0 + l / 2)
         const int m_lo = min(t * TM + 32 * q, M - 1), m_hi = min(t * TM + 32 * q + 31, M - 1);
         const int s_lo = (m_lo >= E) + (m_lo >= 2 * E), s_hi = (m_hi >= E) + (m_hi >= 2 * E);
         if (s_lo == s_hi) {   // warp-uniform: all 32 rows are in one state
-          if (s_lo != cur_s) {
-            const float x = colsum16(t_b1, lane);
+          const float x = colsum16(d1, lane);
 #pragma unroll
-            for (int c = 0; c < S; ++c) s_w1r[c] += (c == cur_s) ? x : 0.f;
-#pragma unroll
-            for (int k = 0; k < FW; ++k) t_b1[k] = 0.f;
-            cur_s = s_lo;
-          }
-#pragma unroll
-          for (int k = 0; k < FW; ++k) t_b1[k] += d1[k];
+          for (int c = 0; c < S; ++c) s_w1r[c] += (c == s_lo) ? x : 0.f;
         } else {              // the warp's rows straddle a state boundary: masked sums for this tile
 #pragma unroll
           for (int c = 0; c < S; ++c) {
@@ -537,9 +550,6 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
 
     // ---- end of the pass over the rows: per-warp row sums -> smem, dW2 from TMEM -> smem ----
     {
-      const float x = colsum16(t_b1, lane);
-#pragma unroll
-      for (int c = 0; c < S; ++c) s_w1r[c] += (c == cur_s) ? x : 0.f;
       float vals[NQ];
       vals[0] = colsum16(s_b2, lane);
       vals[1] = colsum16(s_wl, lane);
@@ -659,7 +669,7 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
 static size_t umma64_smem_bytes(int S, int OUT, int E) {
   const MlpLayout L(S + 1, H, OUT);
   const int NQ = 2 + S + OUT;
-  const size_t fl = 2 * (size_t)(L.padded() - HH) + S * H + H + 4 * TM * OUT + NW * NQ * FW + (((size_t)E + 3) & ~(size_t)3);
+  const size_t fl = 2 * (size_t)(L.padded() - HH) + S * H + 2 * H + 4 * TM * OUT + NW * NQ * FW + (((size_t)E + 3) & ~(size_t)3);
   return 1024 + T_END + fl * sizeof(float);
 }
 
