@@ -11,10 +11,9 @@
 // each as three tf32 products (lo.hi + hi.lo + hi.hi).  tools/umma_probe.cu pins every descriptor encoding used here
 // against a CPU product on the device.  Everything else (layer 1, tanh, softmax / clip terms, the row sums that make
 // db1 / dW1 / db2 / dW3) runs on the CUDA cores between the GEMMs; a1/d2 tiles are single-buffered (192 of 227 KB).
-// Schedule (the tensor pipe runs GEMMs in issue order, so the order is chosen to keep it busy under CUDA-core work):
-//   ... E2(t) | G2(t) || E1(t+1), E3(t) | G1(t+1), G3(t) || E2(t+1) | ...        ("|" = block barrier + issue)
-// G2 runs under the next tile's layer 1 and this tile's row sums, G3 under the next tile's E2; only G1 is waited for.
-// a1 hi/lo are double-buffered in TMEM (E1 of the next tile overlaps E3 of this one); G1 and G2 share one accumulator.
+// Schedule: ONE block barrier per tile.  E2(t) computes d2 (FMA pipe) interleaved with layer 1 of tile t+1 (MUFU pipe), then
+//   | barrier, issue G2(t), G1(t+1), G3(t) |  E3(t) (row sums of d1, needs G2)  ->  E2(t+1) (needs G1)  ->  ...
+// so the tensor pipe works under E3 and E2; G3 is never waited for inside the pass.
 //
 // Reference behaviour: agent_oracle.py compute_loss_pi :285-322, compute_loss_v :325-339, update :399-436.
 #include "common.cuh"
@@ -32,7 +31,7 @@ constexpr uint32_t T_W2H = 131072, T_W2L = 147456, T_WTH = 163840, T_WTL = 18022
 constexpr uint32_t T_END = 196608;
 constexpr uint32_t BLK = 16384;   // bytes per 32-feature block of a 128-row MN-major tile
 // TMEM columns (512 allocated: the CTA owns its SM)
-constexpr uint32_t C_D = 0, C_DW2 = 64, C_A1H = 128, C_A1L = 192, C_A1BUF = 128, C_D2H = 384, C_D2L = 448;   // a1 buffer b at +128 b
+constexpr uint32_t C_D1 = 0, C_D1P = 64, C_DW2 = 128, C_A1H = 192, C_A1L = 256, C_D2H = 320, C_D2L = 384, C_OM1 = 448;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -272,10 +271,10 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
     }
     __syncthreads();
 
-    float s_b2[FW], s_wl[FW], s_w3[OUT][FW], s_w1r[S], s_b3[OUT];
+    float s_b2[FW], s_w3[OUT][FW], s_w1r[S], s_b3[OUT], s_wlr = 0.f;
 #pragma unroll
     for (int k = 0; k < FW; ++k) {
-      s_b2[k] = 0.f; s_wl[k] = 0.f;
+      s_b2[k] = 0.f;
 #pragma unroll
       for (int a = 0; a < OUT; ++a) s_w3[a][k] = 0.f;
     }
@@ -285,53 +284,87 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
     for (int a = 0; a < OUT; ++a) s_b3[a] = 0.f;
     float loss_acc = 0.f;
 
-    // E1: a1 = tanh(W1 x + b1) for this thread's 16 features of tile tt; hi/lo into TMEM buffer tt & 1 (operand of G1)
-    auto layer1_to_tmem = [&](int tt) {
+    // E1 chunk: a1 = tanh(W1 x + b1) for features f0 + 4 k4 .. + 3 of row (srow1, lam1); hi/lo into TMEM (operand of G1)
+    auto layer1_chunk = [&](int k4, int srow1, float lam1, float keep1, bool last1) {
+      const float4 b = *reinterpret_cast<const float4*>(wb + srow1 * H + f0 + 4 * k4);
+      const float4 l = *reinterpret_cast<const float4*>(wl + f0 + 4 * k4);
+      float x0 = tanh_scaled_u(fmaf(l.x, lam1, b.x)), x1 = tanh_scaled_u(fmaf(l.y, lam1, b.y));
+      float x2 = tanh_scaled_u(fmaf(l.z, lam1, b.z)), x3 = tanh_scaled_u(fmaf(l.w, lam1, b.w));
+      if (last1) { x0 *= keep1; x1 *= keep1; x2 *= keep1; x3 *= keep1; }   // rows past the end: a1 = 0 (so d2 = d1 = 0)
+      uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+      split_u(x0, h0, l0); split_u(x1, h1, l1); split_u(x2, h2, l2); split_u(x3, h3, l3);
+      tmem_st4(tl + C_A1H + f0 + 4 * k4, h0, h1, h2, h3);
+      tmem_st4(tl + C_A1L + f0 + 4 * k4, l0, l1, l2, l3);
+    };
+    // row of this thread in tile tt: state, lambda, validity
+    auto row_of = [&](int tt, int& srow1, float& lam1, float& keep1) {
       const int m = tt * TM + r;
-      const bool valid = m < M;
-      const int mm = valid ? m : M - 1;
-      const int srow = (mm >= E) + (mm >= 2 * E), erow = mm - srow * E;   // S <= 3: no integer division
-      const float lam = slam[erow];
-      const float keep = valid ? 1.f : 0.f;   // rows past the end contribute a1 = 0 (and so d2 = d1 = 0)
-      const float4* wb4 = reinterpret_cast<const float4*>(wb + srow * H + f0);
-      const float4* wl4 = reinterpret_cast<const float4*>(wl + f0);
-      const uint32_t buf = (uint32_t)(tt & 1) * C_A1BUF;
-      const bool last = tt == n_tiles - 1;    // only the last tile can hold rows past the end
+      const int mm = m < M ? m : M - 1;
+      srow1 = (mm >= E) + (mm >= 2 * E);   // S <= 3: no integer division
+      lam1 = slam[mm - srow1 * E];
+      keep1 = m < M ? 1.f : 0.f;
+    };
+    // E3 of tile tt (its G2 has been issued): d1 = d1' (1 - a1^2); column sums for db1 / dW1.
+    auto backward_rowsums = [&](int tt) {
+      int srow1; float lam1, keep1;
+      row_of(tt, srow1, lam1, keep1);
+      mbar_wait(bar2, (gt - 1) & 1);
+      tc_fence_after();
+      uint32_t v[FW], om[FW];
+      tmem_ld16(tl + C_D1P + f0, v);
+      tmem_ld16(tl + C_OM1 + f0, om);   // 1 - a1^2, parked in TMEM by E2 of the same tile
+      tmem_wait_ld();
+      float d1[FW], d1l[FW];
 #pragma unroll
-      for (int k4 = 0; k4 < FW / 4; ++k4) {
-        const float4 b = wb4[k4], l = wl4[k4];
-        float x0 = tanh_scaled_u(fmaf(l.x, lam, b.x)), x1 = tanh_scaled_u(fmaf(l.y, lam, b.y));
-        float x2 = tanh_scaled_u(fmaf(l.z, lam, b.z)), x3 = tanh_scaled_u(fmaf(l.w, lam, b.w));
-        if (last) { x0 *= keep; x1 *= keep; x2 *= keep; x3 *= keep; }
-        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-        split_u(x0, h0, l0); split_u(x1, h1, l1); split_u(x2, h2, l2); split_u(x3, h3, l3);
-        tmem_st4(tl + C_A1H + buf + f0 + 4 * k4, h0, h1, h2, h3);
-        tmem_st4(tl + C_A1L + buf + f0 + 4 * k4, l0, l1, l2, l3);
+      for (int k = 0; k < FW; ++k) {
+        d1[k] = __uint_as_float(v[k]) * __uint_as_float(om[k]);
+        d1l[k] = d1[k] * lam1;
+      }
+      s_wlr += colsum16(d1l, lane);
+      // db1 / dW1[:, s]: the tile's column sums go straight to one register per state (lane l holds feature f0 + l / 2)
+      const int m_lo = min(tt * TM + 32 * q, M - 1), m_hi = min(tt * TM + 32 * q + 31, M - 1);
+      const int s_lo = (m_lo >= E) + (m_lo >= 2 * E), s_hi = (m_hi >= E) + (m_hi >= 2 * E);
+      if (s_lo == s_hi) {   // warp-uniform: all 32 rows are in one state
+        const float x = colsum16(d1, lane);
+#pragma unroll
+        for (int c = 0; c < S; ++c) s_w1r[c] += (c == s_lo) ? x : 0.f;
+      } else {              // the warp's rows straddle a state boundary: masked sums for this tile
+#pragma unroll
+        for (int c = 0; c < S; ++c) {
+          float msk[FW];
+#pragma unroll
+          for (int k = 0; k < FW; ++k) msk[k] = (srow1 == c) ? d1[k] : 0.f;
+          s_w1r[c] += colsum16(msk, lane);
+        }
       }
     };
-    // G1(tt): z2 = a1 . W2^T into the shared accumulator, three tf32 products (lo.hi, hi.lo, hi.hi)
-    auto issue_g1 = [&](int tt) {
+    // G1: z2 = a1 . W2^T, three tf32 products (lo.hi, hi.lo, hi.hi)
+    auto issue_g1 = [&]() {
       constexpr uint32_t idesc = make_idesc(128, 64, 0, 0);
-      const uint32_t buf = (uint32_t)(tt & 1) * C_A1BUF;
       const uint32_t wh = desc_lo_k(sbase + T_W2H), wlo = desc_lo_k(sbase + T_W2L);
 #pragma unroll
       for (int term = 0; term < 3; ++term) {
-        const uint32_t acol = tmem + buf + (term == 0 ? C_A1L : C_A1H);
+        const uint32_t acol = tmem + (term == 0 ? C_A1L : C_A1H);
         const uint32_t bt = term == 1 ? wlo : wh;
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) umma_ts(tmem + C_D, acol + 8 * ks, bt + 16 * ks, DESC_HI_K, idesc, (term | ks) != 0);
+        for (int ks = 0; ks < 8; ++ks) umma_ts(tmem + C_D1, acol + 8 * ks, bt + 16 * ks, DESC_HI_K, idesc, (term | ks) != 0);
       }
       umma_commit(bar1);
     };
 
-    layer1_to_tmem(0);
+    {
+      int srow1; float lam1, keep1;
+      row_of(0, srow1, lam1, keep1);
+#pragma unroll
+      for (int k4 = 0; k4 < FW / 4; ++k4) layer1_chunk(k4, srow1, lam1, keep1, n_tiles == 1);
+    }
     tmem_wait_st();
     fence_async_smem();   // the W2 tiles (initial load / Adam) were written through the generic proxy
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
       tc_fence_after();
-      if (elect_one()) issue_g1(0);
+      if (elect_one()) issue_g1();
       __syncwarp();
     }
 
@@ -340,7 +373,6 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
       const bool valid = m < M;
       const int mm = valid ? m : M - 1;
       const int srow = (mm >= E) + (mm >= 2 * E), erow = mm - srow * E;
-      const float lam = slam[erow];
       // statistics of this row (L2 resident), in flight while G1 runs
       const float* sp = st + erow;
       const float wrow = sp[(3 * SA - ROW0 + srow) * E];   // CntS
@@ -354,7 +386,9 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
       } else {
         stA[0] = sp[(3 * SA + S - ROW0 + srow) * E];
       }
-      const uint32_t abuf = (uint32_t)(t & 1) * C_A1BUF;
+
+      // ---- E3 of the previous tile, under this tile's G1 ----
+      if (t > 0) backward_rowsums(t - 1);
 
       // ---- E2: a2 = tanh(z2 + b2); logits (partials meet through smem); loss terms; d2 ----
       mbar_wait(bar1, gt & 1);
@@ -362,7 +396,7 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
       float a2[FW];
       {
         uint32_t v[FW];
-        tmem_ld16(tl + C_D + f0, v);
+        tmem_ld16(tl + C_D1 + f0, v);
         tmem_wait_ld();
         const float4* b24 = reinterpret_cast<const float4*>(b2s + f0);   // b2 * kTanhScale
 #pragma unroll
@@ -385,6 +419,28 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
           pl = fmaf(w3.z, a2[4 * k4 + 2], pl); pl = fmaf(w3.w, a2[4 * k4 + 3], pl);
         }
         plog[(cq * TM + r) * OUT + a] = pl;
+      }
+      // this tile's a1 (still in TMEM) -> the smem tile G3 contracts over; filler while the row's other warps catch up
+      if (gt > 0) mbar_wait(bar3, (gt - 1) & 1);   // the previous tile's G3 has finished reading the a1 / d2 tiles
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t h[8], l[8];
+        tmem_ld8(tl + C_A1H + f0 + 8 * c, h);
+        tmem_ld8(tl + C_A1L + f0 + 8 * c, l);
+        tmem_wait_ld();
+        const uint32_t off = c == 0 ? off_c0 : off_c1;
+        *reinterpret_cast<uint4*>(base + T_A1H + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(base + T_A1H + off + 16) = make_uint4(h[4], h[5], h[6], h[7]);
+        *reinterpret_cast<uint4*>(base + T_A1L + off) = make_uint4(l[0], l[1], l[2], l[3]);
+        *reinterpret_cast<uint4*>(base + T_A1L + off + 16) = make_uint4(l[4], l[5], l[6], l[7]);
+        uint32_t om[8];   // 1 - a1^2 for E3 of this tile (hi + lo is the exact fp32 activation)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float a1 = __uint_as_float(h[j]) + __uint_as_float(l[j]);
+          om[j] = __float_as_uint(fmaf(-a1, a1, 1.f));
+        }
+        tmem_st4(tl + C_OM1 + f0 + 8 * c, om[0], om[1], om[2], om[3]);
+        tmem_st4(tl + C_OM1 + f0 + 8 * c + 4, om[4], om[5], om[6], om[7]);
       }
       asm volatile("bar.sync %0, 128;\n" ::"r"(1 + q) : "memory");   // the four warps that share these 32 rows
       float gl[OUT];
@@ -428,44 +484,37 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
 #pragma unroll
           for (int a = 0; a < OUT; ++a) s_b3[a] += gl[a];
       }
-      if (gt > 0) mbar_wait(bar3, (gt - 1) & 1);   // the previous tile's G3 has finished reading the a1 / d2 tiles
+      // d2 (FMA pipe) interleaved with the NEXT tile's layer 1 (MUFU pipe); z2's a1 operand in TMEM is free once G1 is done
+      {
+        const bool more = t + 1 < n_tiles;
+        int srow1 = 0; float lam1 = 0.f, keep1 = 0.f;
+        if (more) row_of(t + 1, srow1, lam1, keep1);
 #pragma unroll
-      for (int k4 = 0; k4 < FW / 4; ++k4) {
-        float up[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k4 = 0; k4 < FW / 4; ++k4) {
+          float up[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int a = 0; a < OUT; ++a) {
-          const float4 w3 = *reinterpret_cast<const float4*>(w + L.oW3 - HH + a * H + f0 + 4 * k4);
-          up[0] = fmaf(gl[a], w3.x, up[0]); up[1] = fmaf(gl[a], w3.y, up[1]);
-          up[2] = fmaf(gl[a], w3.z, up[2]); up[3] = fmaf(gl[a], w3.w, up[3]);
+          for (int a = 0; a < OUT; ++a) {
+            const float4 w3 = *reinterpret_cast<const float4*>(w + L.oW3 - HH + a * H + f0 + 4 * k4);
+            up[0] = fmaf(gl[a], w3.x, up[0]); up[1] = fmaf(gl[a], w3.y, up[1]);
+            up[2] = fmaf(gl[a], w3.z, up[2]); up[3] = fmaf(gl[a], w3.w, up[3]);
+          }
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = 4 * k4 + j;
+            const float x = a2[k], d2 = up[j] * fmaf(-x, x, 1.f);
+            s_b2[k] += d2;
+#pragma unroll
+            for (int a = 0; a < OUT; ++a) s_w3[a][k] = fmaf(gl[a], x, s_w3[a][k]);
+            split_u(d2, h[j], l[j]);
+          }
+          tmem_st4(tl + C_D2H + f0 + 4 * k4, h[0], h[1], h[2], h[3]);
+          tmem_st4(tl + C_D2L + f0 + 4 * k4, l[0], l[1], l[2], l[3]);
+          const uint32_t off = (k4 < 2 ? off_c0 : off_c1) + 16 * (k4 & 1);
+          *reinterpret_cast<uint4*>(base + T_D2H + off) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(base + T_D2L + off) = make_uint4(l[0], l[1], l[2], l[3]);
+          if (more) layer1_chunk(k4, srow1, lam1, keep1, t + 2 == n_tiles);
         }
-        uint32_t h[4], l[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = 4 * k4 + j;
-          const float x = a2[k], d2 = up[j] * fmaf(-x, x, 1.f);
-          s_b2[k] += d2;
-#pragma unroll
-          for (int a = 0; a < OUT; ++a) s_w3[a][k] = fmaf(gl[a], x, s_w3[a][k]);
-          split_u(d2, h[j], l[j]);
-        }
-        tmem_st4(tl + C_D2H + f0 + 4 * k4, h[0], h[1], h[2], h[3]);
-        tmem_st4(tl + C_D2L + f0 + 4 * k4, l[0], l[1], l[2], l[3]);
-        const uint32_t off = (k4 < 2 ? off_c0 : off_c1) + 16 * (k4 & 1);
-        *reinterpret_cast<uint4*>(base + T_D2H + off) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(base + T_D2L + off) = make_uint4(l[0], l[1], l[2], l[3]);
-      }
-      // this tile's a1 (still in its TMEM buffer) -> the smem tile G3 contracts over
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t h[8], l[8];
-        tmem_ld8(tl + C_A1H + abuf + f0 + 8 * c, h);
-        tmem_ld8(tl + C_A1L + abuf + f0 + 8 * c, l);
-        tmem_wait_ld();
-        const uint32_t off = c == 0 ? off_c0 : off_c1;
-        *reinterpret_cast<uint4*>(base + T_A1H + off) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(base + T_A1H + off + 16) = make_uint4(h[4], h[5], h[6], h[7]);
-        *reinterpret_cast<uint4*>(base + T_A1L + off) = make_uint4(l[0], l[1], l[2], l[3]);
-        *reinterpret_cast<uint4*>(base + T_A1L + off + 16) = make_uint4(l[4], l[5], l[6], l[7]);
       }
       tmem_wait_st();
       fence_async_smem();
@@ -473,86 +522,45 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
       __syncthreads();
       if (warp == 0) {
         tc_fence_after();
-        if (elect_one()) {   // G2(t): d1' = d2 . W2 into the shared accumulator (E2 has consumed z2)
-          constexpr uint32_t idesc = make_idesc(128, 64, 0, 0);
-          const uint32_t wh = desc_lo_k(sbase + T_WTH), wlo = desc_lo_k(sbase + T_WTL);
-#pragma unroll
-          for (int term = 0; term < 3; ++term) {
-            const uint32_t acol = tmem + (term == 0 ? C_D2L : C_D2H);
-            const uint32_t bt = term == 1 ? wlo : wh;
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) umma_ts(tmem + C_D, acol + 8 * ks, bt + 16 * ks, DESC_HI_K, idesc, (term | ks) != 0);
-          }
-          umma_commit(bar2);
-        }
-        __syncwarp();
-      }
-
-      // ---- E1 of the next tile runs under G2 ----
-      if (t + 1 < n_tiles) layer1_to_tmem(t + 1);
-
-      // ---- E3: d1 = d1' (1 - a1^2); running sums for db1 / dW1 ----
-      mbar_wait(bar2, gt & 1);
-      tc_fence_after();
-      {
-        uint32_t v[FW], ah[FW], al[FW];
-        tmem_ld16(tl + C_D + f0, v);
-        tmem_ld16(tl + C_A1H + abuf + f0, ah);
-        tmem_ld16(tl + C_A1L + abuf + f0, al);
-        tmem_wait_ld();
-        float d1[FW];
-#pragma unroll
-        for (int k = 0; k < FW; ++k) {
-          const float a1 = __uint_as_float(ah[k]) + __uint_as_float(al[k]);   // hi + lo is the exact fp32 activation
-          d1[k] = __uint_as_float(v[k]) * fmaf(-a1, a1, 1.f);
-          s_wl[k] = fmaf(d1[k], lam, s_wl[k]);
-        }
-        // db1 / dW1[:, s]: the tile's column sums go straight to one register per state (lane l holds feature f0 + l / 2)
-        const int m_lo = min(t * TM + 32 * q, M - 1), m_hi = min(t * TM + 32 * q + 31, M - 1);
-        const int s_lo = (m_lo >= E) + (m_lo >= 2 * E), s_hi = (m_hi >= E) + (m_hi >= 2 * E);
-        if (s_lo == s_hi) {   // warp-uniform: all 32 rows are in one state
-          const float x = colsum16(d1, lane);
-#pragma unroll
-          for (int c = 0; c < S; ++c) s_w1r[c] += (c == s_lo) ? x : 0.f;
-        } else {              // the warp's rows straddle a state boundary: masked sums for this tile
-#pragma unroll
-          for (int c = 0; c < S; ++c) {
-            float msk[FW];
-#pragma unroll
-            for (int k = 0; k < FW; ++k) msk[k] = (srow == c) ? d1[k] : 0.f;
-            s_w1r[c] += colsum16(msk, lane);
-          }
-        }
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      __syncthreads();
-      if (warp == 0) {
-        tc_fence_after();
         if (elect_one()) {
-          if (t + 1 < n_tiles) issue_g1(t + 1);   // first, so that only G1 is ever waited for
-          // G3(t): dW2 += d2^T . a1 over this tile's 128 rows (16 k-steps of 8 rows), accumulated across the pass
-          constexpr uint32_t idesc3 = make_idesc(64, 64, 1, 1);
-          const uint32_t dh = desc_lo_mn(sbase + T_D2H), dl = desc_lo_mn(sbase + T_D2L);
-          const uint32_t ah = desc_lo_mn(sbase + T_A1H), al = desc_lo_mn(sbase + T_A1L);
+          {   // G2(t): d1' = d2 . W2
+            constexpr uint32_t idesc = make_idesc(128, 64, 0, 0);
+            const uint32_t wh = desc_lo_k(sbase + T_WTH), wlo = desc_lo_k(sbase + T_WTL);
 #pragma unroll
-          for (int term = 0; term < 3; ++term) {
-            const uint32_t at = term == 0 ? dl : dh, bt = term == 1 ? al : ah;
+            for (int term = 0; term < 3; ++term) {
+              const uint32_t acol = tmem + (term == 0 ? C_D2L : C_D2H);
+              const uint32_t bt = term == 1 ? wlo : wh;
 #pragma unroll
-            for (int ks = 0; ks < 16; ++ks)
-              umma_ss(tmem + C_DW2, at + 64 * ks, bt + 64 * ks, DESC_HI_MN, idesc3, (term | ks) != 0 ? 1u : (uint32_t)(t != 0));
+              for (int ks = 0; ks < 8; ++ks) umma_ts(tmem + C_D1P, acol + 8 * ks, bt + 16 * ks, DESC_HI_K, idesc, (term | ks) != 0);
+            }
+            umma_commit(bar2);
           }
-          umma_commit(bar3);
+          if (t + 1 < n_tiles) issue_g1();   // G1(t + 1)
+          {   // G3(t): dW2 += d2^T . a1 over this tile's 128 rows (16 k-steps of 8 rows), accumulated across the pass
+            constexpr uint32_t idesc3 = make_idesc(64, 64, 1, 1);
+            const uint32_t dh = desc_lo_mn(sbase + T_D2H), dl = desc_lo_mn(sbase + T_D2L);
+            const uint32_t ah = desc_lo_mn(sbase + T_A1H), al = desc_lo_mn(sbase + T_A1L);
+#pragma unroll
+            for (int term = 0; term < 3; ++term) {
+              const uint32_t at = term == 0 ? dl : dh, bt = term == 1 ? al : ah;
+#pragma unroll
+              for (int ks = 0; ks < 16; ++ks)
+                umma_ss(tmem + C_DW2, at + 64 * ks, bt + 64 * ks, DESC_HI_MN, idesc3, (term | ks) != 0 ? 1u : (uint32_t)(t != 0));
+            }
+            umma_commit(bar3);
+          }
         }
         __syncwarp();
       }
     }
+    backward_rowsums(n_tiles - 1);   // E3 of the last tile
+
 
     // ---- end of the pass over the rows: per-warp row sums -> smem, dW2 from TMEM -> smem ----
     {
       float vals[NQ];
       vals[0] = colsum16(s_b2, lane);
-      vals[1] = colsum16(s_wl, lane);
+      vals[1] = s_wlr;
 #pragma unroll
       for (int c = 0; c < S; ++c) vals[2 + c] = s_w1r[c];
 #pragma unroll
@@ -570,6 +578,7 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
       for (int a = 0; a < OUT; ++a) red[40 + q * OUT + a] = b3tot[a];
     mbar_wait(bar3, (gt - 1) & 1);   // every G3 of this pass has landed in TMEM
     tc_fence_after();
+    __syncthreads();                 // all E3 reads of the a1 tile are done: its space becomes the dW2 scratch
     {
       uint32_t v[FW];
       tmem_ld16(tl + C_DW2 + f0, v);
