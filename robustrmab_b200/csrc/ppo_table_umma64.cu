@@ -114,6 +114,10 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b,
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%4], {%0,%1,%2,%3};\n" ::"r"(a), "r"(b), "r"(c), "r"(d), "r"(taddr) : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -229,7 +233,7 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
   }
   for (int i = tid; i < E; i += NTHR) slam[i] = g.lamb[i];
   if (tid == 0) {
-    for (int b = 0; b < 3; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bars[b])));
+    for (int b = 0; b < 3; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&bars[b])), "r"(b == 2 ? 2 : 1));
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {
@@ -304,12 +308,43 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
       lam1 = slam[mm - srow1 * E];
       keep1 = m < M ? 1.f : 0.f;
     };
+    // G1: z2 = a1 . W2^T, three tf32 products (lo.hi, hi.lo, hi.hi)
+    auto issue_g1 = [&]() {
+      constexpr uint32_t idesc = make_idesc(128, 64, 0, 0);
+      const uint32_t wh = desc_lo_k(sbase + T_W2H), wlo = desc_lo_k(sbase + T_W2L);
+#pragma unroll
+      for (int term = 0; term < 3; ++term) {
+        const uint32_t acol = tmem + (term == 0 ? C_A1L : C_A1H);
+        const uint32_t bt = term == 1 ? wlo : wh;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) umma_ts(tmem + C_D1, acol + 8 * ks, bt + 16 * ks, DESC_HI_K, idesc, (term | ks) != 0);
+      }
+      umma_commit(bar1);
+    };
+
+    // G3 half (k-steps ks0 .. ks0+7 of this tile's 16): dW2 += d2^T . a1; DW2 is zeroed at the start of the pass
+    auto issue_g3_half = [&](int ks0) {
+      constexpr uint32_t idesc3 = make_idesc(64, 64, 1, 1);
+      const uint32_t dh = desc_lo_mn(sbase + T_D2H), dl = desc_lo_mn(sbase + T_D2L);
+      const uint32_t ah = desc_lo_mn(sbase + T_A1H), al = desc_lo_mn(sbase + T_A1L);
+#pragma unroll
+      for (int term = 0; term < 3; ++term) {
+        const uint32_t at = term == 0 ? dl : dh, bt = term == 1 ? al : ah;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) umma_ss(tmem + C_DW2, at + 64 * (ks0 + ks), bt + 64 * (ks0 + ks), DESC_HI_MN, idesc3, 1u);
+      }
+      umma_commit(bar3);
+    };
     // E3 of tile tt (its G2 has been issued): d1 = d1' (1 - a1^2); column sums for db1 / dW1.
     auto backward_rowsums = [&](int tt) {
       int srow1; float lam1, keep1;
       row_of(tt, srow1, lam1, keep1);
       mbar_wait(bar2, (gt - 1) & 1);
       tc_fence_after();
+      if (warp == 1 && tt + 1 < n_tiles) {   // G1 of the next tile goes behind the finished G2, ahead of G3
+        if (elect_one()) issue_g1();
+        __syncwarp();
+      }
       uint32_t v[FW], om[FW];
       tmem_ld16(tl + C_D1P + f0, v);
       tmem_ld16(tl + C_OM1 + f0, om);   // 1 - a1^2, parked in TMEM by E2 of the same tile
@@ -337,26 +372,18 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
           s_w1r[c] += colsum16(msk, lane);
         }
       }
-    };
-    // G1: z2 = a1 . W2^T, three tf32 products (lo.hi, hi.lo, hi.hi)
-    auto issue_g1 = [&]() {
-      constexpr uint32_t idesc = make_idesc(128, 64, 0, 0);
-      const uint32_t wh = desc_lo_k(sbase + T_W2H), wlo = desc_lo_k(sbase + T_W2L);
-#pragma unroll
-      for (int term = 0; term < 3; ++term) {
-        const uint32_t acol = tmem + (term == 0 ? C_A1L : C_A1H);
-        const uint32_t bt = term == 1 ? wlo : wh;
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) umma_ts(tmem + C_D1, acol + 8 * ks, bt + 16 * ks, DESC_HI_K, idesc, (term | ks) != 0);
+      if (warp == 2 || warp == 3) {   // G3(tt) behind G1(tt + 1): never waited for before the next tile's d2 is ready
+        if (elect_one()) issue_g3_half(warp == 2 ? 0 : 8);
+        __syncwarp();
       }
-      umma_commit(bar1);
     };
-
     {
       int srow1; float lam1, keep1;
       row_of(0, srow1, lam1, keep1);
 #pragma unroll
       for (int k4 = 0; k4 < FW / 4; ++k4) layer1_chunk(k4, srow1, lam1, keep1, n_tiles == 1);
+      const uint32_t z[FW] = {};
+      tmem_st16(tl + C_DW2 + f0, z);   // G3 only ever accumulates
     }
     tmem_wait_st();
     fence_async_smem();   // the W2 tiles (initial load / Adam) were written through the generic proxy
@@ -420,28 +447,6 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
         }
         plog[(cq * TM + r) * OUT + a] = pl;
       }
-      // this tile's a1 (still in TMEM) -> the smem tile G3 contracts over; filler while the row's other warps catch up
-      if (gt > 0) mbar_wait(bar3, (gt - 1) & 1);   // the previous tile's G3 has finished reading the a1 / d2 tiles
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t h[8], l[8];
-        tmem_ld8(tl + C_A1H + f0 + 8 * c, h);
-        tmem_ld8(tl + C_A1L + f0 + 8 * c, l);
-        tmem_wait_ld();
-        const uint32_t off = c == 0 ? off_c0 : off_c1;
-        *reinterpret_cast<uint4*>(base + T_A1H + off) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(base + T_A1H + off + 16) = make_uint4(h[4], h[5], h[6], h[7]);
-        *reinterpret_cast<uint4*>(base + T_A1L + off) = make_uint4(l[0], l[1], l[2], l[3]);
-        *reinterpret_cast<uint4*>(base + T_A1L + off + 16) = make_uint4(l[4], l[5], l[6], l[7]);
-        uint32_t om[8];   // 1 - a1^2 for E3 of this tile (hi + lo is the exact fp32 activation)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float a1 = __uint_as_float(h[j]) + __uint_as_float(l[j]);
-          om[j] = __float_as_uint(fmaf(-a1, a1, 1.f));
-        }
-        tmem_st4(tl + C_OM1 + f0 + 8 * c, om[0], om[1], om[2], om[3]);
-        tmem_st4(tl + C_OM1 + f0 + 8 * c + 4, om[4], om[5], om[6], om[7]);
-      }
       asm volatile("bar.sync %0, 128;\n" ::"r"(1 + q) : "memory");   // the four warps that share these 32 rows
       float gl[OUT];
       {
@@ -489,8 +494,25 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
         const bool more = t + 1 < n_tiles;
         int srow1 = 0; float lam1 = 0.f, keep1 = 0.f;
         if (more) row_of(t + 1, srow1, lam1, keep1);
+        if (gt > 0) mbar_wait(bar3, (gt - 1) & 1);   // the previous tile's G3 has finished reading the a1 / d2 tiles
 #pragma unroll
         for (int k4 = 0; k4 < FW / 4; ++k4) {
+          const uint32_t off = (k4 < 2 ? off_c0 : off_c1) + 16 * (k4 & 1);
+          {   // this tile's a1 (still in TMEM) -> the smem tile G3 contracts over; 1 - a1^2 parked in TMEM for E3
+            uint32_t ah[4], al[4];
+            tmem_ld4(tl + C_A1H + f0 + 4 * k4, ah);
+            tmem_ld4(tl + C_A1L + f0 + 4 * k4, al);
+            tmem_wait_ld();
+            *reinterpret_cast<uint4*>(base + T_A1H + off) = make_uint4(ah[0], ah[1], ah[2], ah[3]);
+            *reinterpret_cast<uint4*>(base + T_A1L + off) = make_uint4(al[0], al[1], al[2], al[3]);
+            uint32_t om[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float a1 = __uint_as_float(ah[j]) + __uint_as_float(al[j]);   // hi + lo is the exact fp32 activation
+              om[j] = __float_as_uint(fmaf(-a1, a1, 1.f));
+            }
+            tmem_st4(tl + C_OM1 + f0 + 4 * k4, om[0], om[1], om[2], om[3]);
+          }
           float up[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int a = 0; a < OUT; ++a) {
@@ -510,7 +532,6 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
           }
           tmem_st4(tl + C_D2H + f0 + 4 * k4, h[0], h[1], h[2], h[3]);
           tmem_st4(tl + C_D2L + f0 + 4 * k4, l[0], l[1], l[2], l[3]);
-          const uint32_t off = (k4 < 2 ? off_c0 : off_c1) + 16 * (k4 & 1);
           *reinterpret_cast<uint4*>(base + T_D2H + off) = make_uint4(h[0], h[1], h[2], h[3]);
           *reinterpret_cast<uint4*>(base + T_D2L + off) = make_uint4(l[0], l[1], l[2], l[3]);
           if (more) layer1_chunk(k4, srow1, lam1, keep1, t + 2 == n_tiles);
@@ -534,20 +555,6 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
               for (int ks = 0; ks < 8; ++ks) umma_ts(tmem + C_D1P, acol + 8 * ks, bt + 16 * ks, DESC_HI_K, idesc, (term | ks) != 0);
             }
             umma_commit(bar2);
-          }
-          if (t + 1 < n_tiles) issue_g1();   // G1(t + 1)
-          {   // G3(t): dW2 += d2^T . a1 over this tile's 128 rows (16 k-steps of 8 rows), accumulated across the pass
-            constexpr uint32_t idesc3 = make_idesc(64, 64, 1, 1);
-            const uint32_t dh = desc_lo_mn(sbase + T_D2H), dl = desc_lo_mn(sbase + T_D2L);
-            const uint32_t ah = desc_lo_mn(sbase + T_A1H), al = desc_lo_mn(sbase + T_A1L);
-#pragma unroll
-            for (int term = 0; term < 3; ++term) {
-              const uint32_t at = term == 0 ? dl : dh, bt = term == 1 ? al : ah;
-#pragma unroll
-              for (int ks = 0; ks < 16; ++ks)
-                umma_ss(tmem + C_DW2, at + 64 * ks, bt + 64 * ks, DESC_HI_MN, idesc3, (term | ks) != 0 ? 1u : (uint32_t)(t != 0));
-            }
-            umma_commit(bar3);
           }
         }
         __syncwarp();
