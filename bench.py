@@ -340,6 +340,21 @@ def run_ours(a):
                                 "issue bound (ncu: issue active 56-61 %, DRAM < 1 %) and frac is small by construction",
                         "stages": stage_roofs},
            "stage_ms_per_step": stage_ms, "clocks": clk}
+    if a.hidden == 64 and dom_name == "ppo_update":
+        # hidden 64: the update runs its three 64 x 64 GEMMs per row on tcgen05 as 3 tf32 products each (3xTF32), so the
+        # dominant kernel is reported against the tensor roofline.  peak = tf32 dense = half the measured bf16 rate.
+        S_dom = 2 if a.domain == "counterexample" else 3
+        rows = ((S_dom * E + 127) // 128) * 128
+        flops = float(a.arms) * (a.pi_iters + a.v_iters) * rows * 3 * 3 * 2 * 64 * 64
+        tf32_peak = peaks.get("bf16_tflops_sustained", 2250.0 * 0.6) / 2
+        ach = flops / (dom_ms * 1e-3) / 1e12
+        out["roofline"] = {"bound": "tensor", "kernel": "ppo_table_umma64_kernel (pi + v)", "achieved": ach, "peak": tf32_peak,
+                           "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None,
+                           "peak_source": "measured bf16 sustained / 2 (tf32)" if "bf16_tflops_sustained" in peaks else "fallback",
+                           "tf32_flops_per_launch": flops, "fp32_equivalent_TFLOPs": ach / 3, "ms_per_launch": dom_ms,
+                           "note": "executed tf32 MMA flops (3 GEMMs x 3 split products per row and Adam step) over the two "
+                                   "update kernels' time; the CUDA-core work between the GEMMs (tanh, softmax terms, row sums) "
+                                   "bounds the kernel, see DESIGN.md 3.2", "stages": stage_roofs}
     if not a.no_cpu_baseline:
         t0 = time.perf_counter()
         rate, tmax, _ = cpu_port_rate(a, 1, 1)

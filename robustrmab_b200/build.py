@@ -55,7 +55,20 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed")
     if force or procs or _stale(LIB, objs):
         subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lcudart"])
+    build_probe(force)
     return LIB
+
+
+def build_probe(force=False):
+    """tools/umma_probe.cu -> tools/bin/umma_probe: the stand-alone check of the tcgen05 descriptor encodings
+    ppo_table_umma64.cu uses (run by tests/test_gpu_kernels.py on the GPU box)."""
+    root = os.path.dirname(HERE)
+    src = os.path.join(root, "tools", "umma_probe.cu")
+    out = os.path.join(root, "tools", "bin", "umma_probe")
+    if os.path.exists(src) and (force or _stale(out, [src])):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O2", "-o", out, src])
+    return out
 
 
 if __name__ == "__main__":

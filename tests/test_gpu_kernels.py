@@ -529,3 +529,16 @@ def test_select_binary_positive_only(K):
             assert np.array_equal(got[:, e], osel.topk_binary(p1[:, e], [0, 1], B, positive_only=True))
     assert np.array_equal(K.n(K.ops.budget_select_binary(K.t(p1[:1, :1] * 0), 1.0, 1.0)), [[1]])        # :289-334 semantics
     assert np.array_equal(K.n(K.ops.budget_select_binary(K.t(p1[:1, :1] * 0), 1.0, 1.0, positive_only=True)), [[0]])
+
+
+def test_umma_descriptor_probe(K):
+    """The tcgen05 encodings the hidden-64 update kernel relies on (K-major smem operands, A from TMEM, the swizzled
+    MN-major layout with M = 64 accumulators, 3xTF32 accuracy), each checked against a CPU product by tools/umma_probe."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "bin", "umma_probe")
+    assert os.path.exists(exe), "tools/bin/umma_probe missing: run python -m robustrmab_b200.build"
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
+    lines = {ln.split(":")[0]: ln for ln in out.splitlines() if ln.startswith("mode")}
+    for key in ("mode 0 variant 0", "mode 3 variant 0", "mode 4 variant 0", "mode 5 variant 0"):
+        assert key in lines and lines[key].rstrip().endswith("PASS"), out
