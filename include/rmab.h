@@ -181,10 +181,12 @@ int rmab_env_counterfactual(int domain, int E, int N, int S, const uint8_t* s, c
  *   z1_extra[n, m, :] = W1_nature[n] . nature_bounded[m]      (input,  [N, T*E, h])
  *   dz1_out [n, m, :] = dLoss_n / d(first-layer pre-activation) (output, [N, T*E, h]) -> dW1_nature[n] = dz1^T . nature
  * The kernel does the forward / backward of everything else and the Adam step of the packed block (step number
- * hp->adam_step0_v + 1).  s [N,s_rows,E] u8 (first T rows), ret [N,T,E], lamb [E], loss_v [N] (may be NULL). */
+ * hp->adam_step0_v + 1).  s [N,s_rows,E] u8 (first T rows), ret [N,T,E], lamb [E], loss_v [N] (may be NULL).
+ * z1_sample_major != 0: both buffers are [T*E, N, h] -- the row-major result of ONE dense GEMM over all arms,
+ * nature[T*E, D] . W1_nature[N*h, D]^T, instead of N batched ones. */
 int rmab_critic_extra_iter(const RmabNetDesc* net, const RmabHyper* hp, int T, int s_rows, float* Wv, float* adam_v,
                            const uint8_t* s, const float* ret, const float* lamb, const float* z1_extra, float* dz1_out,
-                           float* loss_v, rmab_stream_t stream);
+                           int z1_sample_major, float* loss_v, rmab_stream_t stream);
 
 /* Elementwise Adam step (torch.optim.Adam defaults form) on a flat fp32 tensor; `step` is 1-based. */
 int rmab_adam_step(int64_t n, float* p, const float* grad, float* m, float* v, double lr, double beta1, double beta2,

@@ -61,7 +61,7 @@ SIGNATURES = {
                            C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P],
     "rmab_gaussian_sample": [_I, _I, _P, _P, C.POINTER(RmabRng), _P, _P, _P, _P],
     "rmab_env_counterfactual": [_I, _I, _I, _I, _P, _P, _P, _I, _P, _P, C.POINTER(RmabRng), _I, _P, _P],
-    "rmab_critic_extra_iter": [C.POINTER(RmabNetDesc), C.POINTER(RmabHyper), _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "rmab_critic_extra_iter": [C.POINTER(RmabNetDesc), C.POINTER(RmabHyper), _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P],
     "rmab_adam_step": [C.c_int64, _P, _P, _P, _P, _D, _D, _D, _D, _I, _P],
     "rmab_gae": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _D, _D, _I, _P, _P, _P, _P, _P],
     "rmab_gae_explicit": [_I, _I, _I, _P, _P, _P, _P, _P, _D, _D, _I, _P, _P, _P, _P, _P],

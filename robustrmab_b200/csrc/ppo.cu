@@ -33,7 +33,8 @@ ppo_update_kernel(RmabNetDesc d, RmabHyper hp, int T, int s_rows, float* __restr
                   const uint8_t* __restrict__ s_buf, const uint8_t* __restrict__ a_buf, const float* __restrict__ adv,
                   const float* __restrict__ logp_old, const float* __restrict__ ret, const float* __restrict__ lamb,
                   const float* __restrict__ stats, const float* __restrict__ arm_stats, int stage_stats,
-                  float* __restrict__ loss_out, const float* __restrict__ z1_extra, float* __restrict__ dz1_out) {
+                  float* __restrict__ loss_out, const float* __restrict__ z1_extra, float* __restrict__ dz1_out,
+                  int64_t z1_arm_stride, int64_t z1_sample_stride) {
   using Cfg = PpoCfg<H>;
   constexpr int LPS = Cfg::LPS, FPL = Cfg::FPL, SPW = Cfg::SPW;
   constexpr int NW = 8;
@@ -138,8 +139,9 @@ ppo_update_kernel(RmabNetDesc d, RmabHyper hp, int T, int s_rows, float* __restr
         float z;
         if (d.one_hot) z = fmaf(row[in - 1], lam, row[si]) + w[L.ob1 + f];
         else z = fmaf(row[1], lam, fmaf(row[0], x0, w[L.ob1 + f]));
-        // MA agent critic: first-layer term of the nature inputs, z1_extra[n][sample][f] (one dense GEMM by the caller)
-        if (z1_extra) z += z1_extra[((int64_t)n * M + mm) * H + f];
+        // MA agent critic: first-layer term of the nature inputs (one dense GEMM by the caller), arm-major
+        // z1_extra[n][sample][f] or sample-major z1_extra[sample][n][f]
+        if (z1_extra) z += z1_extra[n * z1_arm_stride + mm * z1_sample_stride + f];
         a1[i] = tanhf(z);
         sa1[f] = a1[i];
       }
@@ -295,7 +297,7 @@ ppo_update_kernel(RmabNetDesc d, RmabHyper hp, int T, int s_rows, float* __restr
 #pragma unroll
       for (int i = 0; i < FPL; ++i) {
         d1[i] *= (1.f - a1[i] * a1[i]);
-        if (dz1_out && valid) dz1_out[((int64_t)n * M + mm) * H + f0 + LPS * i] = d1[i];  // dL/dz1 for dW1_nature
+        if (dz1_out && valid) dz1_out[n * z1_arm_stride + mm * z1_sample_stride + f0 + LPS * i] = d1[i];  // dL/dz1 for dW1_nature
         gb1[i] += d1[i];
         if (d.one_hot) {
 #pragma unroll
@@ -399,7 +401,7 @@ template <int H, bool IS_PI, bool TABLE>
 static int launch_ppo(const RmabNetDesc& d, const RmabHyper& hp, int T, int s_rows, float* W, float* adam,
                       const uint8_t* s, const uint8_t* a, const float* adv, const float* logp_old, const float* ret,
                       const float* lamb, const float* stats, const float* arm_stats, float* loss, cudaStream_t st,
-                      const float* z1_extra = nullptr, float* dz1_out = nullptr) {
+                      const float* z1_extra = nullptr, float* dz1_out = nullptr, int z1_sample_major = 0) {
   using Cfg = PpoCfg<H>;
   const int in = (d.one_hot ? d.n_states : 1) + 1;
   const MlpLayout L(in, H, IS_PI ? d.n_actions : 1);
@@ -416,7 +418,9 @@ static int launch_ppo(const RmabNetDesc& d, const RmabHyper& hp, int T, int s_ro
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return fail(RMAB_E_LAUNCH, "rmab_ppo_update: cannot reserve %zu B of shared memory", smem);
   kern<<<d.n_arms, 256, smem, st>>>(d, hp, T, s_rows, W, adam, s, a, adv, logp_old, ret, lamb, stats, arm_stats, stage,
-                                    loss, z1_extra, dz1_out);
+                                    loss, z1_extra, dz1_out,
+                                    z1_sample_major ? (int64_t)H : (int64_t)T * d.n_envs * H,
+                                    z1_sample_major ? (int64_t)d.n_arms * H : (int64_t)H);
   return check_launch(IS_PI ? "rmab_ppo_update(pi)" : "rmab_ppo_update(v)");
 }
 
@@ -471,7 +475,8 @@ extern "C" int rmab_ppo_update(const RmabNetDesc* net, const RmabHyper* hp, int 
 
 extern "C" int rmab_critic_extra_iter(const RmabNetDesc* net, const RmabHyper* hp, int T, int s_rows, float* Wv,
                                       float* adam_v, const uint8_t* s, const float* ret, const float* lamb,
-                                      const float* z1_extra, float* dz1_out, float* loss_v, rmab_stream_t stream) {
+                                      const float* z1_extra, float* dz1_out, int z1_sample_major, float* loss_v,
+                                      rmab_stream_t stream) {
   RMAB_REQUIRE(net && hp, RMAB_E_BADARG, "rmab_critic_extra_iter: null descriptor");
   RmabNetDesc d = *net;
   d.n_extra = 0;  // the packed part of the critic has the plain (state, lambda) inputs
@@ -485,7 +490,7 @@ extern "C" int rmab_critic_extra_iter(const RmabNetDesc* net, const RmabHyper* h
   if (d.n_arms == 0) return RMAB_OK;
   cudaStream_t st = (cudaStream_t)stream;
 #define RUN(H) rc = launch_ppo<H, false, false>(d, h1, T, s_rows, Wv, adam_v, s, nullptr, nullptr, nullptr, ret, lamb, \
-                                                nullptr, nullptr, loss_v, st, z1_extra, dz1_out);
+                                                nullptr, nullptr, loss_v, st, z1_extra, dz1_out, z1_sample_major);
   switch (d.hidden) {
     case 8: RUN(8) break;
     case 16: RUN(16) break;

@@ -122,9 +122,10 @@ class RMABLambdaNatureOracle(nn.Module):
         return mu[0] if mu.shape[0] == 1 else mu
 
     # -- step --------------------------------------------------------------------------------------
-    def step_device(self, s, lamb, eps=None, u=None):
+    def step_device(self, s, lamb, eps=None, u=None, w1n_split=None):
         """s `[N,E]` u8, lamb `[E]`.  Returns dict of device tensors: a_agent, v_agent, logp_agent, p1 `[N,E]`;
-        a_nature, a_nature_bounded `[E,D]`; logp_nature, v_nature `[E]`."""
+        a_nature, a_nature_bounded `[E,D]`; logp_nature, v_nature `[E]`.  `w1n_split` = ops.split_tf32(W1n.reshape(-1, D))
+        when the caller keeps it across steps (W1n is constant during a rollout)."""
         E = s.shape[1]
         with torch.no_grad():
             mu = self.pi_nature.mu_net(self._nature_obs(s)).contiguous()
@@ -133,7 +134,8 @@ class RMABLambdaNatureOracle(nn.Module):
                                                   r=None if eps is not None else r_n, eps=eps)
             nat_b = self.bound_nature_device(a_nat, s)
             # first-layer nature term of every agent critic as one dense GEMM: [N*h, D] x [D, E] -> [N, h, E]
-            extra = (self.W1n.reshape(-1, self.act_dim_nature) @ nat_b.t()).reshape(self.N, -1, E).contiguous()
+            w1 = w1n_split if w1n_split is not None else self.W1n.reshape(-1, self.act_dim_nature)
+            extra = ops.matmul_3xtf32(w1, nat_b.t()).reshape(self.N, -1, E).contiguous()
             r_a = ops.rng(self._seed, _lib.STREAM_ACT, self._steps)
             a, v, logp, p1, _ = ops.ac_step(self._net(E, True), self.Wpi, self.Wv, s, lamb,
                                             r=None if u is not None else r_a, u=u, extra=extra)

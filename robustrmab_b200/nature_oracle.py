@@ -31,8 +31,30 @@ def nature_env_layout(nat_b, N):
     return nat_b.t().contiguous() if D == N else nat_b.t().reshape(N, D // N, E).contiguous()
 
 
+class _Stages:
+    """CUDA-event stage timers (off unless `MARolloutTrainer.profile` is set): name -> accumulated ms."""
+
+    def __init__(self, on):
+        self.on, self.ms, self._open = on, {}, None
+
+    def mark(self, name):
+        if not self.on:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        if self._open is not None:
+            prev_name, prev_ev = self._open
+            self.ms.setdefault(prev_name, []).append((prev_ev, ev))
+        self._open = (name, ev) if name else None
+
+    def report(self):
+        torch.cuda.synchronize()
+        return {k: sum(a.elapsed_time(b) for a, b in v) for k, v in self.ms.items()}
+
+
 class MARolloutTrainer:
     """Device state and loops of one `best_response_per_cpu` call."""
+    profile = False
 
     def __init__(self, env, ac, T, gamma, lam_other, clip_ratio, pi_lr_agent, pi_lr_nature, vf_lr_agent, vf_lr_nature,
                  lm_lr, pi_iters, v_iters, epochs, lamb_update_freq, final_train_lambdas, ent0, ent1, seed):
@@ -83,9 +105,10 @@ class MARolloutTrainer:
         lamb, h1 = ops.lambda_forward(self.lam_params, s0, N, 0, self.obs_scale, want_h1=True)
         self.s_traj[:, 0] = s0
         ret_agent = torch.zeros((E,), dtype=_F32, device=self.dev)
+        w1n_split = ops.split_tf32(ac.W1n.reshape(-1, self.D))                 # constant over the rollout
         for t in range(T):
             s = self.s_traj[:, t].contiguous()
-            d = ac.step_device(s, lamb)
+            d = ac.step_device(s, lamb, w1n_split=w1n_split)
             nat_env = nature_env_layout(d["a_nature_bounded"], N)
             env._state = s
             s_next, r = env.step_device(d["a_agent"], nat_env)
@@ -101,13 +124,15 @@ class MARolloutTrainer:
             self.a[:, t], self.logp[:, t], self.val[:, t], self.s_traj[:, t + 1] = d["a_agent"], d["logp_agent"], d["v_agent"], s_next
             self.a_nat[t], self.nat_b[t] = d["a_nature"], d["a_nature_bounded"]
             self.logp_nat[t], self.val_nat[t] = d["logp_nature"], d["v_nature"]
-        d = ac.step_device(self.s_traj[:, T].contiguous(), lamb)               # bootstrap values (:754)
+        d = ac.step_device(self.s_traj[:, T].contiguous(), lamb, w1n_split=w1n_split)   # bootstrap values (:754)
         ac._steps -= 1
         return lamb, h1, s0, d["v_agent"], d["v_nature"], ret_agent
 
     def update(self, lamb, h1, s0, last_v_agent, last_v_nature):
         ac, T, N, E, D = self.ac, self.T, self.N, self.E, self.D
         ep = self.epoch_idx
+        st = self.stages = _Stages(self.profile)
+        st.mark("gae")
         # ---- MA_RMABPPO_Buffer.finish_path + get (:107-193) ----
         adv, ret, _, _ = ops.gae(self.s_traj, self.a, self.val, last_v_agent.contiguous(), lamb, self.C, self.R, self.gamma,
                                  self.lam_other, normalize=True)
@@ -116,22 +141,36 @@ class MARolloutTrainer:
                                               last_v_nature.reshape(1, E).contiguous(), lamb, self.gamma, self.lam_other,
                                               normalize=True)
         # ---- agent policies (:491-502) ----
+        st.mark("agent_policies")
         hp = ops.hyper(self.clip, self._entropy(ep), self.pi_lr_agent, self.vf_lr_agent, self.pi_iters, 0, self.steps_pi,
                        self.steps_v)
         ops.ppo_update(ac._net(E, False), hp, ac.Wpi, ac.Wv, self.adam_pi, self.adam_v, self.s_traj, self.a, adv, self.logp,
                        ret, lamb)
         self.steps_pi += self.pi_iters
         # ---- agent critics over [x_i, bounded nature vector] (:505-513) ----
-        natM = self.nat_b.reshape(T * E, D)                                      # sample m = t*E + e
+        st.mark("agent_critics")
+        natM = ops.split_tf32(self.nat_b.reshape(T * E, D))                      # sample m = t*E + e; (hi, lo) for 3xTF32
         net = ac._net(E, False)
+        h = ac.hidden_sizes[0]
         for _ in range(self.v_iters):
-            z1 = torch.matmul(natM, ac.W1n.transpose(1, 2)).contiguous()         # [N, T*E, h] dense GEMM
+            # nature block of all N first layers as ONE dense GEMM: [T*E, D] x [D, N*h] -> sample-major [T*E, N, h]
+            st.mark("critics.z1_gemm")
+            w1h, w1l = ops.split_tf32(ac.W1n.reshape(N * h, D))
+            z1 = ops.matmul_3xtf32(natM, (w1h.t(), w1l.t())).reshape(T * E, N, h)
+            del w1h, w1l
+            st.mark("critics.kernel")
             hpv = ops.hyper(self.clip, 0.0, self.pi_lr_agent, self.vf_lr_agent, 0, 1, self.steps_pi, self.steps_v)
-            dz1, _ = ops.critic_extra_iter(net, hpv, ac.Wv, self.adam_v, self.s_traj, ret, lamb, z1)
-            gW1n = torch.matmul(dz1.transpose(1, 2), natM).contiguous()          # [N, h, D] dense GEMM
+            dz1, _ = ops.critic_extra_iter(net, hpv, ac.Wv, self.adam_v, self.s_traj, ret, lamb, z1, sample_major=True)
+            del z1
+            st.mark("critics.grad_gemm")
+            dh, dl = ops.split_tf32(dz1.reshape(T * E, N * h))
+            gW1n = ops.matmul_3xtf32((dh.t(), dl.t()), natM).reshape(N, h, D)    # dW1_nature = dz1^T . nature, one GEMM
+            del dh, dl, dz1
+            st.mark("critics.adam")
             self.steps_v += 1
             ops.adam_step(ac.W1n, gW1n, self.m_w1n, self.v_w1n, self.vf_lr_agent, self.steps_v)
         # ---- lambda net and the nature nets, every lamb_update_freq epochs (:516-576) ----
+        st.mark("lambda_and_nature_nets")
         if ep % self.freq == 0 and ep > 0:
             if (self.epochs - ep) > self.final:
                 cd = ops.cost_togo(self.a, self.C, self.gamma)
@@ -156,6 +195,7 @@ class MARolloutTrainer:
                 self.opt_v_nat.zero_grad()
                 ((ac.v_nature(x) - retn) ** 2).mean().backward()
                 self.opt_v_nat.step()
+        st.mark(None)
         self.epoch_idx += 1
 
     def epoch(self, agent_pol):

@@ -170,15 +170,42 @@ def env_counterfactual(domain, s, a, nature, ranges, R, r, n_trials, nature_per_
     return out
 
 
-def critic_extra_iter(net, hp, Wv, adam_v, s, ret, lamb, z1_extra, want_loss=False):
-    """One Adam iteration of the agent critics with nature inputs; returns (dz1 [N,T*E,h], loss [N] or None)."""
+def critic_extra_iter(net, hp, Wv, adam_v, s, ret, lamb, z1_extra, want_loss=False, sample_major=False):
+    """One Adam iteration of the agent critics with nature inputs; returns (dz1, loss [N] or None).  z1_extra and dz1 are
+    `[N,T*E,h]`, or `[T*E,N,h]` with sample_major (the row-major result of one dense GEMM over all arms)."""
     N, T, E = ret.shape
+    h = net.hidden
+    assert tuple(z1_extra.shape) == ((T * E, N, h) if sample_major else (N, T * E, h)), "z1_extra shape"
     dz1 = torch.zeros_like(z1_extra)
     loss = torch.zeros((N, 1), dtype=f32, device=ret.device) if want_loss else None
     check(lib().rmab_critic_extra_iter(C.byref(net), C.byref(hp), T, s.shape[1], _p(Wv, f32, "Wv"), _p(adam_v, f32, "adam_v"),
                                        _p(s, u8, "s"), _p(ret, f32, "ret"), _p(lamb, f32, "lamb"),
-                                       _p(z1_extra, f32, "z1_extra"), _p(dz1, f32), _p(loss, f32), _stream()))
+                                       _p(z1_extra, f32, "z1_extra"), _p(dz1, f32), int(bool(sample_major)), _p(loss, f32),
+                                       _stream()))
     return dz1, loss
+
+
+# Dense GEMMs of the MA agent critics' nature block (library GEMMs, not kernels of this package): fp32 accuracy at
+# tensor-core speed by the same 3xTF32 split the update kernels use -- x = hi + lo with hi exactly representable in tf32,
+# a.b ~ lo_a.hi_b + hi_a.lo_b + hi_a.hi_b, each product a TF32 library GEMM with fp32 accumulation.
+def split_tf32(x):
+    hi = (x.contiguous().view(torch.int32) & -8192).view(f32)
+    return hi, x - hi
+
+
+def matmul_3xtf32(a, b):
+    """a @ b (torch.matmul broadcasting rules); a / b are tensors or (hi, lo) pairs from split_tf32."""
+    ah, al = a if isinstance(a, tuple) else split_tf32(a)
+    bh, bl = b if isinstance(b, tuple) else split_tf32(b)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        out = torch.matmul(al, bh)
+        out += torch.matmul(ah, bl)
+        out += torch.matmul(ah, bh)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return out
 
 
 def adam_step(p, grad, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):

@@ -24,6 +24,7 @@ ac = RMABLambdaNatureOracle(env.observation_space, env.action_space, env.sampled
                             state_norm=pop, nature_state_norm=1, n_envs=E)
 tr = MARolloutTrainer(env, ac, T, 0.9, 0.97, 2.0, 2e-3, 2e-3, 2e-3, 2e-3, 2e-3, pi_iters, v_iters, 4, 1, 0, 0.5, 0.0, 0)
 pess = PessimisticAgentPolicy(N)
+tr.profile = True
 
 
 def timed(fn):
@@ -44,4 +45,5 @@ for ep in range(3):
     print(f"epoch {ep}: rollout {ms_roll:.1f} ms ({N * E * T / ms_roll / 1e3:.1f} M arm-steps/s incl. 50 counterfactual steps each), "
           f"update ({pi_iters}+{v_iters} iters, nature nets every epoch) {ms_upd:.1f} ms, finite={ok}, "
           f"mean return/env {float(ret.mean()):.1f}, mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
+    print("   update stages (ms):", {k: round(v, 1) for k, v in tr.stages.report().items()})
     assert ok and int(tr.s_traj.max()) <= pop
