@@ -61,6 +61,24 @@ class _RobustEnvBase:
         self._resets = 0     # resets taken (Philox time counter of stream RESET)
         self.seed(seed=seed)
 
+    def shard(self, arm0, arm1):
+        """The env of the arm window [arm0, arm1) of this one: same per-arm tables, ranges and Philox counters (global
+        arm index), so its transitions are exactly rows arm0..arm1 of this env's (shards by arm)."""
+        import copy
+        e = copy.copy(self)
+        n, per = arm1 - arm0, self.action_dim_nature // self.N
+        e.N, e.arm0, e.action_dim_nature = n, self.arm0 + arm0, n * per
+        for name in ("PARAMETER_RANGES", "R", "sampled_parameter_ranges", "param_setting"):
+            v = getattr(self, name, None)
+            if v is not None:
+                setattr(e, name, np.ascontiguousarray(np.asarray(v)[arm0:arm1]))
+        e.T = FakeT((n,) + tuple(self.T.shape[1:])) if isinstance(self.T, FakeT) else np.ascontiguousarray(self.T[arm0:arm1])
+        e._R_dev = self._R_dev[arm0:arm1].contiguous()
+        e._state = self._state[arm0:arm1].contiguous()
+        e._ranges_dev = e._ranges_src = None
+        e.random_stream = np.random.RandomState()
+        return e
+
     # -- state ---------------------------------------------------------------------------------
     @property
     def current_full_state(self):

@@ -44,7 +44,7 @@ class RMABLambdaNatureOracle(nn.Module):
 
     def __init__(self, observation_space, action_space_agent, nature_parameter_ranges, action_dim_nature, env,
                  hidden_sizes=(64, 64), C=None, N=None, B=None, one_hot_encode=True, non_ohe_obs_dim=None, state_norm=1,
-                 nature_state_norm=1, strat_ind=0, activation=nn.Tanh, n_envs=1, device="cuda"):
+                 nature_state_norm=1, strat_ind=0, activation=nn.Tanh, n_envs=1, device="cuda", arm_shard=None):
         super().__init__()
         self.observation_space, self.action_space_agent = observation_space, action_space_agent
         self.nature_parameter_ranges = nature_parameter_ranges
@@ -72,6 +72,13 @@ class RMABLambdaNatureOracle(nn.Module):
         Wv[:, :h * self.in_dim + h].uniform_(-b, b)
         self.Wv = Wv.to(self.device_)
         self.W1n = torch.empty(self.N, h, D).uniform_(-b, b).to(self.device_)
+        # arm shard: the per-arm nets of arms [arm0, arm0 + n_local) only; the dense nature nets and the
+        # lambda net stay whole on every rank.  All ranks draw the same full tensors (same torch seed) and keep a slice.
+        self.arm0, self.n_local = 0, self.N
+        if arm_shard is not None:
+            a0, a1 = int(arm_shard[0]), int(arm_shard[1])
+            self.arm0, self.n_local = a0, a1 - a0
+            self.Wpi, self.Wv, self.W1n = (self.Wpi[a0:a1].clone(), self.Wv[a0:a1].clone(), self.W1n[a0:a1].clone())
         self.lambda_net = MLPLambdaNet(self.N, [8, 8])
         self.name = "MA-RMABPPO"
         self.ind = strat_ind
@@ -84,7 +91,7 @@ class RMABLambdaNatureOracle(nn.Module):
         self._seed, self._steps = int(seed), 0
 
     def _net(self, E, extra):
-        return ops.net_desc(self.N, E, self.n_states, self.act_dim_agent, self.hidden_sizes[0], self.one_hot_encode,
+        return ops.net_desc(self.n_local, E, self.n_states, self.act_dim_agent, self.hidden_sizes[0], self.one_hot_encode,
                             float(self.state_norm) if self.state_norm else 1.0, n_extra=self.act_dim_nature if extra else 0)
 
     # -- nature ------------------------------------------------------------------------------------
@@ -121,26 +128,33 @@ class RMABLambdaNatureOracle(nn.Module):
         mu = self.get_nature_action_device(s).cpu().numpy()
         return mu[0] if mu.shape[0] == 1 else mu
 
+    def nature_critic_input(self, s, a):
+        """[obs, a_agent] rows of the nature critic (ma_rmabppo_core.py:318-325): s, a `[N,E]` u8 -> `[E,2N]`."""
+        return torch.cat([s.t().to(_F32) / (1.0 if self.one_hot_encode else float(self.state_norm)), a.t().to(_F32)], dim=1)
+
     # -- step --------------------------------------------------------------------------------------
-    def step_device(self, s, lamb, eps=None, u=None, w1n_split=None):
+    def step_device(self, s, lamb, eps=None, u=None, w1n_split=None, s_full=None):
         """s `[N,E]` u8, lamb `[E]`.  Returns dict of device tensors: a_agent, v_agent, logp_agent, p1 `[N,E]`;
         a_nature, a_nature_bounded `[E,D]`; logp_nature, v_nature `[E]`.  `w1n_split` = ops.split_tf32(W1n.reshape(-1, D))
-        when the caller keeps it across steps (W1n is constant during a rollout)."""
+        when the caller keeps it across steps (W1n is constant during a rollout).  Arm-sharded: s holds the local arms,
+        `s_full` `[N_total,E]` all of them (input of the nature nets); v_nature needs every arm's action and is left to
+        the caller (None)."""
         E = s.shape[1]
+        sharded = s_full is not None
+        s_all = s_full if sharded else s
         with torch.no_grad():
-            mu = self.pi_nature.mu_net(self._nature_obs(s)).contiguous()
+            mu = self.pi_nature.mu_net(self._nature_obs(s_all)).contiguous()
             r_n = ops.rng(self._seed, _lib.STREAM_NATURE, self._steps)
             a_nat, logp_nat = ops.gaussian_sample(mu, self.pi_nature.log_std.detach().contiguous(),
                                                   r=None if eps is not None else r_n, eps=eps)
-            nat_b = self.bound_nature_device(a_nat, s)
+            nat_b = self.bound_nature_device(a_nat, s_all)
             # first-layer nature term of every agent critic as one dense GEMM: [N*h, D] x [D, E] -> [N, h, E]
             w1 = w1n_split if w1n_split is not None else self.W1n.reshape(-1, self.act_dim_nature)
-            extra = ops.matmul_3xtf32(w1, nat_b.t()).reshape(self.N, -1, E).contiguous()
-            r_a = ops.rng(self._seed, _lib.STREAM_ACT, self._steps)
+            extra = ops.matmul_3xtf32(w1, nat_b.t()).reshape(self.n_local, -1, E).contiguous()
+            r_a = ops.rng(self._seed, _lib.STREAM_ACT, self._steps, arm0=self.arm0)
             a, v, logp, p1, _ = ops.ac_step(self._net(E, True), self.Wpi, self.Wv, s, lamb,
                                             r=None if u is not None else r_a, u=u, extra=extra)
-            x = torch.cat([s.t().to(_F32) / (1.0 if self.one_hot_encode else float(self.state_norm)), a.t().to(_F32)], dim=1)
-            v_nat = self.v_nature(x)
+            v_nat = None if sharded else self.v_nature(self.nature_critic_input(s, a))
         self._steps += 1
         return dict(a_agent=a, v_agent=v, logp_agent=logp, p1=p1, a_nature=a_nat, a_nature_bounded=nat_b,
                     logp_nature=logp_nat, v_nature=v_nat)

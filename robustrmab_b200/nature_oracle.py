@@ -53,17 +53,37 @@ class _Stages:
 
 
 class MARolloutTrainer:
-    """Device state and loops of one `best_response_per_cpu` call."""
+    """Device state and loops of one `best_response_per_cpu` call.
+
+    Arm-sharded over `world_size` ranks when `ac` was built with `arm_shard`: every rank keeps all E envs
+    of its arm range -- env transitions, per-arm agent actors / critics (and the nature block W1n of its critics), the
+    50 counterfactual steps, GAE and the agent updates are local.  Exchanged over NCCL: the state vector (all-gather of
+    `[N,E]` u8, once per step: it is the input of the dense nature nets, which every rank evaluates and trains
+    identically), per-step reward / cost partial sums (`[T,3,E]`, one all-reduce per epoch), the agent actions (one
+    all-gather per epoch, input of the nature critic), the lambda-net's first-layer partial sums and the discounted
+    cost at t = 0 as in the RMABPPO trainer."""
     profile = False
 
     def __init__(self, env, ac, T, gamma, lam_other, clip_ratio, pi_lr_agent, pi_lr_nature, vf_lr_agent, vf_lr_nature,
-                 lm_lr, pi_iters, v_iters, epochs, lamb_update_freq, final_train_lambdas, ent0, ent1, seed):
-        self.env, self.ac, self.T = env, ac, int(T)
+                 lm_lr, pi_iters, v_iters, epochs, lamb_update_freq, final_train_lambdas, ent0, ent1, seed,
+                 rank=0, world_size=1, process_group=None):
+        self.ac, self.T = ac, int(T)
         self.gamma, self.lam_other, self.clip = float(gamma), float(lam_other), float(clip_ratio)
         self.pi_lr_agent, self.vf_lr_agent, self.lm_lr = pi_lr_agent, vf_lr_agent, lm_lr
         self.pi_iters, self.v_iters, self.epochs = int(pi_iters), int(v_iters), int(epochs)
         self.freq, self.final, self.ent0, self.ent1 = int(lamb_update_freq), int(final_train_lambdas), ent0, ent1
-        N, E, dev, D = env.N, env.n_envs, env.device, ac.act_dim_nature
+        self.rank, self.world, self.pg = int(rank), int(world_size), process_group
+        self.N_total, self.arm0 = ac.N, ac.arm0
+        N, E, dev, D = ac.n_local, env.n_envs, env.device, ac.act_dim_nature
+        if self.world > 1:
+            assert N < ac.N or self.world == 1, "build the actor-critic with arm_shard=mpi_tools.arm_shard(N, rank, world)"
+            self.env = env.shard(ac.arm0, ac.arm0 + N)   # the rank's arms; `env` itself keeps the global ranges for ac
+            self.per = (self.N_total + self.world - 1) // self.world
+            self.gather_buf = torch.zeros((self.world, self.per, E), dtype=torch.uint8, device=dev)
+            self.s_full_traj = torch.empty((self.N_total, T + 1, E), dtype=torch.uint8, device=dev)
+        else:
+            self.env = env
+        env = self.env
         self.N, self.E, self.D, self.dev = N, E, D, dev
         T = self.T
         u8 = torch.uint8
@@ -76,6 +96,7 @@ class MARolloutTrainer:
         self.logp_nat = torch.empty((T, E), dtype=_F32, device=dev)
         self.val_nat = torch.empty((T, E), dtype=_F32, device=dev)
         self.rew_nat = torch.empty((T, E), dtype=_F32, device=dev)
+        self.part = torch.zeros((T, 3, E), dtype=_F32, device=dev)        # per step: sum r, sum counterfactual r, sum cost
         self.adam_pi = torch.zeros((N, 2, ac.Wpi.shape[1]), dtype=_F32, device=dev)
         self.adam_v = torch.zeros((N, 2, ac.Wv.shape[1]), dtype=_F32, device=dev)
         self.m_w1n, self.v_w1n = torch.zeros_like(ac.W1n), torch.zeros_like(ac.W1n)
@@ -98,43 +119,95 @@ class MARolloutTrainer:
             return float(np.linspace(head, 0, self.freq)[ep % self.freq])
         return 0.0
 
+    # -- cross-rank plumbing (no-ops on one rank) --------------------------------------------------
+    def _allreduce(self, t):
+        if self.world > 1:
+            torch.distributed.all_reduce(t, group=self.pg)
+        return t
+
+    def _gather_arms(self, x):
+        """Local `[N_local, ...]` u8 rows of every rank -> `[N_total, ...]` in global arm order (ragged last shard padded)."""
+        if self.world == 1:
+            return x
+        tail = tuple(x.shape[1:])
+        pad = torch.zeros((self.per,) + tail, dtype=x.dtype, device=x.device)
+        pad[:x.shape[0]] = x
+        out = torch.empty((self.world * self.per,) + tail, dtype=x.dtype, device=x.device)
+        torch.distributed.all_gather_into_tensor(out, pad, group=self.pg)
+        return out[:self.N_total]
+
+    def _lambda(self, s0):
+        if self.world == 1:
+            return ops.lambda_forward(self.lam_params, s0, self.N_total, 0, self.obs_scale, want_h1=True)
+        _, h1 = ops.lambda_forward(self.lam_params, s0, self.N_total, self.arm0, self.obs_scale, want_h1=True, want_lamb=False)
+        self._allreduce(h1)
+        lamb, _ = ops.lambda_forward(self.lam_params, s0, self.N_total, self.arm0, self.obs_scale, h1_in=h1)
+        return lamb, h1
+
     # ---------------------------------------------------------------------------------------------
     def rollout(self, agent_pol):
         env, ac, T, N, E = self.env, self.ac, self.T, self.N, self.E
+        sharded = self.world > 1
         s0 = self.s.contiguous()
-        lamb, h1 = ops.lambda_forward(self.lam_params, s0, N, 0, self.obs_scale, want_h1=True)
+        lamb, h1 = self._lambda(s0)
         self.s_traj[:, 0] = s0
-        ret_agent = torch.zeros((E,), dtype=_F32, device=self.dev)
         w1n_split = ops.split_tf32(ac.W1n.reshape(-1, self.D))                 # constant over the rollout
-        for t in range(T):
+        sl = slice(self.arm0, self.arm0 + N)
+        ret_local = torch.zeros((E,), dtype=_F32, device=self.dev)
+        for t in range(T + 1):                                                  # step T = the bootstrap ac.step (:754)
             s = self.s_traj[:, t].contiguous()
-            d = ac.step_device(s, lamb, w1n_split=w1n_split)
-            nat_env = nature_env_layout(d["a_nature_bounded"], N)
+            s_full = self._gather_arms(s) if sharded else None
+            d = ac.step_device(s, lamb, w1n_split=w1n_split, s_full=s_full)
+            if sharded:
+                self.s_full_traj[:, t] = s_full
+            if t == T:
+                ac._steps -= 1
+                break
+            self.a[:, t] = d["a_agent"]
+            nat_env = nature_env_layout(d["a_nature_bounded"], self.N_total)
+            if sharded:
+                nat_env = nat_env[sl].contiguous()
             env._state = s
             s_next, r = env.step_device(d["a_agent"], nat_env)
-            a_test = agent_pol.act_test_device(s)
-            rng = ops.rng(self.seed, _lib.STREAM_CF, env._t)
+            a_test = agent_pol.act_test_device(s_full if sharded else s)
+            if sharded:
+                a_test = a_test[sl].contiguous()
+            rng = ops.rng(self.seed, _lib.STREAM_CF, env._t, arm0=self.arm0)
             r_test = ops.env_counterfactual(env.domain, s, a_test, nat_env, env._ranges() if env.domain != _lib.DOMAIN_SIS
                                             else self.R, self.R, rng, NUM_TEST_POLICY_RUNS, nature_per_env=True)
             env._t += 1
-            cost_sum = self.C[d["a_agent"].long()].sum(dim=0)
-            r_sum = r.sum(dim=0)
-            self.rew_nat[t] = r_sum - r_test.sum(dim=0) - lamb * cost_sum       # lamb_adjusted_r_nature (:707-719)
-            ret_agent += r_sum
-            self.a[:, t], self.logp[:, t], self.val[:, t], self.s_traj[:, t + 1] = d["a_agent"], d["logp_agent"], d["v_agent"], s_next
+            self.part[t, 0], self.part[t, 1] = r.sum(dim=0), r_test.sum(dim=0)
+            ret_local += self.part[t, 0]
+            self.part[t, 2] = self.C[d["a_agent"].long()].sum(dim=0)
+            self.logp[:, t], self.val[:, t], self.s_traj[:, t + 1] = d["logp_agent"], d["v_agent"], s_next
             self.a_nat[t], self.nat_b[t] = d["a_nature"], d["a_nature_bounded"]
-            self.logp_nat[t], self.val_nat[t] = d["logp_nature"], d["v_nature"]
-        d = ac.step_device(self.s_traj[:, T].contiguous(), lamb, w1n_split=w1n_split)   # bootstrap values (:754)
-        ac._steps -= 1
-        return lamb, h1, s0, d["v_agent"], d["v_nature"], ret_agent
+            self.logp_nat[t] = d["logp_nature"]
+            if not sharded:
+                self.val_nat[t] = d["v_nature"]
+        last_v_nature = d["v_nature"]
+        if sharded:
+            # nature critic over [obs, a_agent] of ALL arms (:318-325): one batch over the gathered trajectories
+            self._allreduce(self.part)
+            self._allreduce(ret_local)
+            self.a_full = self._gather_arms(self.a)
+            a_full = torch.cat([self.a_full, self._gather_arms(d["a_agent"])[:, None]], dim=1)   # + the bootstrap step's actions
+            with torch.no_grad():
+                x = torch.cat([self.s_full_traj.permute(1, 2, 0).reshape((T + 1) * E, self.N_total).to(_F32) * self.obs_scale,
+                               a_full.permute(1, 2, 0).reshape((T + 1) * E, self.N_total).to(_F32)], dim=1)
+                vn = ac.v_nature(x).reshape(T + 1, E)
+            self.val_nat.copy_(vn[:T])
+            last_v_nature = vn[T].contiguous()
+        torch.sub(self.part[:, 0] - self.part[:, 1], lamb * self.part[:, 2], out=self.rew_nat)   # lamb_adjusted_r_nature (:707-719)
+        return lamb, h1, s0, d["v_agent"], last_v_nature, ret_local
 
     def update(self, lamb, h1, s0, last_v_agent, last_v_nature):
         ac, T, N, E, D = self.ac, self.T, self.N, self.E, self.D
         ep = self.epoch_idx
         st = self.stages = _Stages(self.profile)
         st.mark("gae")
+        a = self.a
         # ---- MA_RMABPPO_Buffer.finish_path + get (:107-193) ----
-        adv, ret, _, _ = ops.gae(self.s_traj, self.a, self.val, last_v_agent.contiguous(), lamb, self.C, self.R, self.gamma,
+        adv, ret, _, _ = ops.gae(self.s_traj, a, self.val, last_v_agent.contiguous(), lamb, self.C, self.R, self.gamma,
                                  self.lam_other, normalize=True)
         zero = torch.zeros((1, T, E), dtype=_F32, device=self.dev)
         adv_n, ret_n, _, _ = ops.gae_explicit(self.rew_nat[None].contiguous(), zero, self.val_nat[None].contiguous(),
@@ -144,7 +217,7 @@ class MARolloutTrainer:
         st.mark("agent_policies")
         hp = ops.hyper(self.clip, self._entropy(ep), self.pi_lr_agent, self.vf_lr_agent, self.pi_iters, 0, self.steps_pi,
                        self.steps_v)
-        ops.ppo_update(ac._net(E, False), hp, ac.Wpi, ac.Wv, self.adam_pi, self.adam_v, self.s_traj, self.a, adv, self.logp,
+        ops.ppo_update(ac._net(E, False), hp, ac.Wpi, ac.Wv, self.adam_pi, self.adam_v, self.s_traj, a, adv, self.logp,
                        ret, lamb)
         self.steps_pi += self.pi_iters
         # ---- agent critics over [x_i, bounded nature vector] (:505-513) ----
@@ -172,11 +245,16 @@ class MARolloutTrainer:
         # ---- lambda net and the nature nets, every lamb_update_freq epochs (:516-576) ----
         st.mark("lambda_and_nature_nets")
         if ep % self.freq == 0 and ep > 0:
+            sharded = self.world > 1
             if (self.epochs - ep) > self.final:
-                cd = ops.cost_togo(self.a, self.C, self.gamma)
-                coef = (float(ac.B) / (1.0 - self.gamma) - cd[0]).contiguous()
-                ops.lambda_sgd(self.lam_params, s0, N, 0, self.obs_scale, h1, coef, self.lm_lr)
-            obs = self.s_traj[:, :T].permute(1, 2, 0).reshape(T * E, N).to(_F32) * self.obs_scale
+                cd0 = ops.cost_togo(a, self.C, self.gamma)[0].contiguous()
+                self._allreduce(cd0)
+                coef = (float(ac.B) / (1.0 - self.gamma) - cd0).contiguous()
+                ops.lambda_sgd(self.lam_params, s0, self.N_total, self.arm0, self.obs_scale, h1, coef, self.lm_lr)
+            s_all = self.s_full_traj if sharded else self.s_traj
+            a_all = self.a_full if sharded else a
+            NT = self.N_total
+            obs = s_all[:, :T].permute(1, 2, 0).reshape(T * E, NT).to(_F32) * self.obs_scale
             obs_n = obs / float(ac.nature_state_norm)
             act = self.a_nat.reshape(T * E, D)
             advn, lpo, retn = adv_n.reshape(-1), self.logp_nat.reshape(-1), ret_n.reshape(-1)
@@ -190,24 +268,35 @@ class MARolloutTrainer:
                 loss = -(torch.min(ratio * advn, clip_adv)).mean() - 0.0 * pi.entropy().mean()   # entropy_coeff = 0 (:544)
                 loss.backward()
                 self.opt_pi_nat.step()
-            x = torch.cat([obs, self.a.permute(1, 2, 0).reshape(T * E, N).to(_F32)], dim=1)
+            x = torch.cat([obs, a_all.permute(1, 2, 0).reshape(T * E, NT).to(_F32)], dim=1)
             for _ in range(self.v_iters):
                 self.opt_v_nat.zero_grad()
                 ((ac.v_nature(x) - retn) ** 2).mean().backward()
                 self.opt_v_nat.step()
+            if sharded:   # every rank ran the same steps on the same data; rank 0's copy is the reference
+                for p_ in list(ac.pi_nature.parameters()) + list(ac.v_nature.parameters()):
+                    torch.distributed.broadcast(p_.data, src=0, group=self.pg)
         st.mark(None)
         self.epoch_idx += 1
 
     def epoch(self, agent_pol):
         lamb, h1, s0, lv, lvn, ret_agent = self.rollout(agent_pol)
+        vv = self._allreduce(self.val.sum().reshape(1)) / float(self.N_total * self.T * self.E)
         stats = {"EpActualRetAgent": ret_agent, "EpLambAdjRetNature": self.rew_nat.sum(dim=0), "Lamb": lamb,
-                 "VVals_agent": self.val.mean().reshape(1), "VVals_nature": self.val_nat.mean().reshape(1)}
+                 "VVals_agent": vv, "VVals_nature": self.val_nat.mean().reshape(1)}
         self.update(lamb, h1, s0, lv, lvn)
         self.s = self.env.reset_device()                                      # :779
         return stats
 
     def export_lambda(self):
-        flat, o = self.lam_params.detach().cpu(), 0
+        flat = self.lam_params.detach().clone()
+        if self.world > 1:   # each rank trained the first-layer columns of its own arms
+            w1 = flat[:8 * self.N_total].view(8, self.N_total)
+            own = torch.zeros_like(w1)
+            own[:, self.arm0:self.arm0 + self.N] = w1[:, self.arm0:self.arm0 + self.N]
+            self._allreduce(own)
+            w1.copy_(own)
+        flat, o = flat.cpu(), 0
         with torch.no_grad():
             for p in self.ac.lambda_net.parameters():
                 p.copy_(flat[o:o + p.numel()].reshape(p.shape))
@@ -218,7 +307,8 @@ class NatureOracle:
 
     def __init__(self, data, N, S, A, B, seed, REWARD_BOUND, nature_kwargs=dict(), home_dir="", exp_name="",
                  sampled_nature_parameter_ranges=None, pop_size=0, one_hot_encode=True, non_ohe_obs_dim=None, state_norm=1,
-                 nature_state_norm=1, n_envs=1, device="cuda"):
+                 nature_state_norm=1, n_envs=1, device="cuda", rank=0, world_size=1, process_group=None):
+        self.rank, self.world, self.pg = int(rank), int(world_size), process_group
         self.data, self.home_dir, self.exp_name, self.REWARD_BOUND = data, home_dir, exp_name, REWARD_BOUND
         self.N, self.S, self.A, self.B, self.seed = N, S, A, B, seed
         self.sampled_nature_parameter_ranges = sampled_nature_parameter_ranges
@@ -252,11 +342,18 @@ class NatureOracle:
                               start_entropy_coeff=0.0, end_entropy_coeff=0.0, target_kl=0.01, logger_kwargs=dict(),
                               save_freq=10, lamb_update_freq=10, init_lambda_trains=0, final_train_lambdas=0):
         env = self.env
+        shard = None
+        if self.world > 1:   # arm-sharded ranks must draw the same nets and pick the same agent strategy
+            from .mpi_tools import arm_shard
+            a0, n_loc = arm_shard(env.N, self.rank, self.world)
+            shard = (a0, a0 + n_loc)
+            torch.manual_seed(int(seed) + 7919 * (self.strat_ind + 1))
+            np.random.seed((int(seed) + 7919 * (self.strat_ind + 1)) % (2 ** 31))
         ac = RMABLambdaNatureOracle(env.observation_space, env.action_space, env.sampled_parameter_ranges,
                                     env.action_dim_nature, env=env, N=env.N, C=env.C, B=env.B, strat_ind=self.strat_ind,
                                     one_hot_encode=self.one_hot_encode, non_ohe_obs_dim=self.non_ohe_obs_dim,
                                     state_norm=self.state_norm, nature_state_norm=self.nature_state_norm,
-                                    n_envs=self.n_envs, device=self.device, **ac_kwargs)
+                                    n_envs=self.n_envs, device=self.device, arm_shard=shard, **ac_kwargs)
         agent_eq = np.array(agent_eq, dtype=np.float64)
         agent_eq[agent_eq < 0] = 0
         agent_eq = agent_eq / agent_eq.sum()
@@ -265,7 +362,8 @@ class NatureOracle:
             agent_pol.n_envs = self.n_envs
         tr = MARolloutTrainer(env, ac, steps_per_epoch, gamma, lam_OTHER, clip_ratio, pi_lr_agent, pi_lr_nature,
                               vf_lr_agent, vf_lr_nature, lm_lr, train_pi_iters, train_v_iters, epochs, lamb_update_freq,
-                              final_train_lambdas, start_entropy_coeff, end_entropy_coeff, seed)
+                              final_train_lambdas, start_entropy_coeff, end_entropy_coeff, seed, rank=self.rank,
+                              world_size=self.world, process_group=self.pg)
         self.history = [{k: v.detach().cpu().numpy() for k, v in tr.epoch(agent_pol).items()} for _ in range(epochs)]
         tr.export_lambda()
         return ac
