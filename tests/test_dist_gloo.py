@@ -72,3 +72,46 @@ def test_single_process_defaults():
     assert abs(mean - 2.0) < 1e-6 and abs(std - np.std([1, 2, 3])) < 1e-6
     assert [mt.arm_shard(10, r, 3) for r in range(3)] == [(0, 4), (4, 4), (8, 2)]
     assert mt.arm_shard(2, 3, 4) == (2, 0)
+
+
+def _ma_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from types import SimpleNamespace
+    from robustrmab_b200 import mpi_tools as mt
+    from robustrmab_b200.nature_oracle import MARolloutTrainer
+    N, E, T = 7, 3, 4                                   # ragged: 4 + 3 arms
+    a0, n = mt.arm_shard(N, rank, world)
+    me = SimpleNamespace(world=world, pg=None, per=(N + world - 1) // world, N_total=N, N=n, arm0=a0)
+    full = torch.arange(N * T * E, dtype=torch.int64).remainder(251).to(torch.uint8).reshape(N, T, E)
+    got = MARolloutTrainer._gather_arms(me, full[a0:a0 + n].contiguous())
+    res = {"gather_ok": bool(torch.equal(got, full))}
+    part = torch.full((T, 3, E), float(rank + 1))
+    MARolloutTrainer._allreduce(me, part)
+    res["part"] = float(part[0, 0, 0])
+    # export_lambda: every rank trained only its own first-layer columns; the merge takes each column from its owner
+    lam = torch.zeros(8 * N + 89)
+    lam[:8 * N].view(8, N)[:, a0:a0 + n] = float(rank + 1)
+    lam[8 * N:] = 5.0
+    net = torch.nn.Sequential(torch.nn.Linear(N, 8), torch.nn.Linear(8, 8), torch.nn.Linear(8, 1))
+    me.lam_params, me.ac = lam, SimpleNamespace(lambda_net=net)
+    me._allreduce = lambda t: MARolloutTrainer._allreduce(me, t)
+    MARolloutTrainer.export_lambda(me)
+    res["w1"] = net[0].weight.detach().numpy().copy()
+    res["b1"] = net[0].bias.detach().numpy().copy()
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+def test_ma_sharding_host_logic_world2():
+    """MARolloutTrainer's cross-rank plumbing on CPU: ragged arm all-gather, partial-sum all-reduce, lambda-net merge."""
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_ma_worker, args=(world, port, out), nprocs=world, join=True)
+    for r in (0, 1):
+        assert out[r]["gather_ok"]
+        assert out[r]["part"] == 3.0
+        w1 = out[r]["w1"]
+        assert np.array_equal(w1[:, :4], np.full((8, 4), 1.0)) and np.array_equal(w1[:, 4:], np.full((8, 3), 2.0))
+        assert np.array_equal(out[r]["b1"], np.full(8, 5.0))
