@@ -27,6 +27,28 @@ METRIC = "RMABPPO arm-steps/sec (rollout+update)"
 UNIT = "arm-steps/s"
 
 
+def measure_tf32_gemm(dev, n=8192, reps=5):
+    """Library TF32 GEMM rate on this GPU (torch.matmul fp32 with TF32 allowed, n^3, best of `reps`, CUDA events): the
+    denominator SURVEY.md 8(d) asks for beside MEASURED_PEAKS.json, which has no tf32 line."""
+    import torch
+    a = torch.randn((n, n), device=dev)
+    b = torch.randn((n, n), device=dev)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    best = 0.0
+    try:
+        for _ in range(reps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return best
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -347,11 +369,13 @@ def run_ours(a):
         rows = ((S_dom * E + 127) // 128) * 128
         flops = float(a.arms) * (a.pi_iters + a.v_iters) * rows * 3 * 3 * 2 * 64 * 64
         tf32_peak = peaks.get("bf16_tflops_sustained", 2250.0 * 0.6) / 2
+        tf32_measured = measure_tf32_gemm(dev)   # cuBLAS TF32 8192^3, same recipe as MEASURED_PEAKS' bf16 line (reported beside)
         ach = flops / (dom_ms * 1e-3) / 1e12
         out["roofline"] = {"bound": "tensor", "kernel": "ppo_table_umma64_kernel (pi + v)", "achieved": ach, "peak": tf32_peak,
                            "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None,
                            "peak_source": "measured bf16 sustained / 2 (tf32)" if "bf16_tflops_sustained" in peaks else "fallback",
                            "tf32_flops_per_launch": flops, "fp32_equivalent_TFLOPs": ach / 3, "ms_per_launch": dom_ms,
+                           "cublas_tf32_8192_TFLOPs": tf32_measured, "frac_of_cublas_tf32": ach / tf32_measured if tf32_measured else None,
                            "note": "executed tf32 MMA flops (3 GEMMs x 3 split products per row and Adam step) over the two "
                                    "update kernels' time; the CUDA-core work between the GEMMs (tanh, softmax terms, row sums) "
                                    "bounds the kernel, see DESIGN.md 3.2", "stages": stage_roofs}
