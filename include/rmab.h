@@ -278,6 +278,15 @@ int rmab_budget_select_binary(int E, int N, const float* p1, float cost1, float 
 int rmab_budget_select_multi(int E, int N, int A, const float* probs, const float* C, float B,
                              uint8_t* actions, void* ws, size_t ws_bytes, rmab_stream_t stream);
 
+/* Exact multiple-choice knapsack = the ILP of lp_methods.py:221-271 behind HawkinsAgentPolicy.act_test
+ * (agent_baselines.py:89): maximise sum_i values[i, a_i] subject to sum_i costs[a_i] == B with one action per arm.
+ * Integer costs; dynamic programme over arms with all budgets in parallel, one CTA per env; ties -> lowest action.
+ * values [N,A,E] fp64, costs [A] int32, actions [N,E]; status [E] = 0, or 1 when the budget cannot be met exactly
+ * (the reference's model is infeasible there; actions are then all 0).  ws: rmab_knapsack_ws_bytes(E, N, B) bytes. */
+size_t rmab_knapsack_ws_bytes(int E, int N, int B);
+int rmab_knapsack_multichoice(int E, int N, int A, const double* values, const int32_t* costs, int B, uint8_t* actions,
+                              int32_t* status, void* ws, size_t ws_bytes, rmab_stream_t stream);
+
 /* ---- value iteration / Whittle index ----------------------------------------------------- */
 
 /* mdptoolbox.mdp.ValueIteration (mdp.py:1293-1410 incl. _boundIter) for all arms x lambda-probes, on the

@@ -123,3 +123,39 @@ def topk_by_index(index, B):
     a = np.zeros(index.shape[0], dtype=np.int64)
     a[_order_desc(index)[:int(B)]] = 1
     return a
+
+
+def knapsack_multichoice(values, C, B):
+    """lp_methods.action_knapsack (:221-271) for one env as an exact dynamic programme (Gurobi is absent; pinned to
+    scipy's HiGHS MILP and to brute force in tests): maximise sum_i values[i, a_i] s.t. sum_i C[a_i] == B, one action
+    per arm.  Integer costs.  f_i[b] = max_a f_{i-1}[b - C[a]] + values[i, a], ties -> lowest action (the CUDA kernel
+    follows the same recurrence and tie rule, so the two agree bit for bit).  Returns (actions `[N]` int64, feasible)."""
+    values = np.asarray(values, dtype=np.float64)
+    N, A = values.shape
+    c = [int(round(float(x))) for x in C]
+    B = int(round(float(B)))
+    NEG = -1.0e300
+    f = np.full(B + 1, NEG)
+    f[0] = 0.0
+    choice = np.full((N, B + 1), 255, dtype=np.uint8)
+    for i in range(N):
+        best = np.full(B + 1, NEG)
+        arg = np.full(B + 1, 255, dtype=np.uint8)
+        for a in range(A):
+            if c[a] > B:
+                continue
+            prev = f[:B + 1 - c[a]]
+            cand = np.where(prev > NEG, prev + values[i, a], NEG)
+            tgt = slice(c[a], B + 1)
+            better = cand > best[tgt]
+            best[tgt] = np.where(better, cand, best[tgt])
+            arg[tgt] = np.where(better, a, arg[tgt])
+        f, choice[i] = best, arg
+    feasible = bool(f[B] > NEG) if N else B == 0
+    actions = np.zeros(N, dtype=np.int64)
+    if feasible:
+        b = B
+        for i in range(N - 1, -1, -1):
+            actions[i] = choice[i, b]
+            b -= c[actions[i]]
+    return actions, feasible

@@ -183,3 +183,13 @@ def hawkins_action_binary(T, R, C, B, state, lam, gamma, eps=1e-10):
     a = np.zeros(N, dtype=np.int64)
     a[np.argsort(gap, kind="stable")[::-1][:int(B / C[1])]] = 1
     return a
+
+
+def hawkins_action_knapsack(T, R, C, B, state, lam, gamma, eps=1e-10):
+    """Hawkins action for general integer costs (agent_baselines.py:69-91): Q(s_i, a; lambda) from the converged
+    lambda-charged value function, then the exact equality knapsack of lp_methods.py:221-271."""
+    from .select import knapsack_multichoice
+    N = T.shape[0]
+    V, _, _, _ = batched_vi(T, R, C, np.array([lam]), gamma, eps, stop="abs")
+    Q = q_values(T, R, C, V, np.array([lam]), gamma)[:, 0]                       # [N,S,A]
+    return knapsack_multichoice(Q[np.arange(N), state], C, B)

@@ -77,11 +77,13 @@ SIGNATURES = {
     "rmab_select_ws_bytes": [_I, _I, _I],
     "rmab_budget_select_binary": [_I, _I, _P, _F, _F, _I, _P, _P, C.c_size_t, _P],
     "rmab_budget_select_multi": [_I, _I, _I, _P, _P, _F, _P, _P, C.c_size_t, _P],
+    "rmab_knapsack_ws_bytes": [_I, _I, _I],
+    "rmab_knapsack_multichoice": [_I, _I, _I, _P, _P, _I, _P, _P, _P, C.c_size_t, _P],
     "rmab_vi_batched": [_I, _I, _I, _I, _P, _P, _P, _P, _I, _D, _D, _I, _P, _P, _P, _P, _P, _P],
     "rmab_vi_general": [_I, _I, _I, _P, _P, _D, _D, _I, _P, _P, _P, _P, _P],
     "rmab_whittle_bisect": [_I, _I, _I, _P, _P, _P, _D, _D, _I, _D, _D, _I, _P, _P],
 }
-_RESTYPES = {"rmab_last_error": C.c_char_p, "rmab_launch_count": C.c_uint64, "rmab_select_ws_bytes": C.c_size_t,
+_RESTYPES = {"rmab_last_error": C.c_char_p, "rmab_launch_count": C.c_uint64, "rmab_select_ws_bytes": C.c_size_t, "rmab_knapsack_ws_bytes": C.c_size_t,
              "rmab_epoch_ws_bytes": C.c_size_t, "rmab_lambda_ws_bytes": C.c_size_t}
 
 _lib = None

@@ -206,6 +206,64 @@ __global__ void __launch_bounds__(kMultiThreads) select_multi_kernel(int E, int 
 
 using namespace rmab;
 
+// ---- exact multiple-choice knapsack (lp_methods.py:221-271, the ILP behind HawkinsAgentPolicy.act_test) ----
+// maximise sum_i values[i, a_i]  s.t.  sum_i C[a_i] == B, one action per arm; integer costs.  One CTA per env runs the
+// textbook DP over arms, f_i[b] = max_a f_{i-1}[b - C[a]] + values[i, a] (ties -> lowest action), all budgets b in
+// parallel; the argmax table [N, B+1] (caller workspace) is walked back by one thread.  fp64 like the values it gets.
+constexpr int kKnapThreads = 256;
+constexpr int kKnapMaxA = 8;
+constexpr uint8_t kKnapNone = 255;
+
+__global__ void __launch_bounds__(kKnapThreads) knapsack_mc_kernel(int E, int N, int A, const double* __restrict__ values,
+                                                                    const int* __restrict__ costs, int B,
+                                                                    uint8_t* __restrict__ actions, int* __restrict__ status,
+                                                                    uint8_t* __restrict__ choice_ws) {
+  extern __shared__ __align__(16) double knap_smem[];
+  __shared__ int c_s[kKnapMaxA];
+  __shared__ double v_s[kKnapMaxA];
+  const int e = blockIdx.x, tid = threadIdx.x;
+  const int W = B + 1;
+  double* f_prev = knap_smem;
+  double* f_cur = knap_smem + W;
+  uint8_t* choice = choice_ws + (size_t)e * N * W;
+  const double NEG = -1.0e300;
+  if (tid < A) c_s[tid] = costs[tid];
+  for (int b = tid; b < W; b += kKnapThreads) f_prev[b] = b == 0 ? 0.0 : NEG;
+  __syncthreads();
+  for (int i = 0; i < N; ++i) {
+    if (tid < A) v_s[tid] = values[((size_t)i * A + tid) * E + e];
+    __syncthreads();
+    for (int b = tid; b < W; b += kKnapThreads) {
+      double best = NEG;
+      uint8_t arg = kKnapNone;
+      for (int a = 0; a < A; ++a) {
+        const int c = c_s[a];
+        if (b >= c) {
+          const double prev = f_prev[b - c];
+          if (prev > NEG) {
+            const double cand = prev + v_s[a];
+            if (cand > best) { best = cand; arg = (uint8_t)a; }
+          }
+        }
+      }
+      f_cur[b] = best;
+      choice[(size_t)i * W + b] = arg;
+    }
+    __syncthreads();
+    double* t = f_prev; f_prev = f_cur; f_cur = t;
+  }
+  if (tid == 0) {
+    const bool feasible = N == 0 ? B == 0 : f_prev[B] > NEG;
+    status[e] = feasible ? 0 : 1;
+    int b = B;
+    for (int i = N - 1; i >= 0; --i) {
+      const uint8_t a = feasible ? choice[(size_t)i * W + b] : 0;
+      actions[(size_t)i * E + e] = a;
+      if (feasible) b -= c_s[a];
+    }
+  }
+}
+
 extern "C" size_t rmab_select_ws_bytes(int E, int N, int A) {
   (void)E; (void)N; (void)A;
   return 16;  // both kernels keep their working set in shared memory; a token workspace keeps the ABI stable
@@ -244,4 +302,27 @@ extern "C" int rmab_budget_select_multi(int E, int N, int A, const float* probs,
                  RMAB_E_LAUNCH, "rmab_budget_select_multi: cannot reserve %zu B smem", smem);
   select_multi_kernel<<<E, kMultiThreads, smem, (cudaStream_t)stream>>>(E, N, A, probs, C, (double)B, actions);
   return check_launch("rmab_budget_select_multi");
+}
+
+extern "C" size_t rmab_knapsack_ws_bytes(int E, int N, int B) {
+  if (E <= 0 || N <= 0 || B < 0) return 16;
+  return (size_t)E * (size_t)N * (size_t)(B + 1);
+}
+
+extern "C" int rmab_knapsack_multichoice(int E, int N, int A, const double* values, const int32_t* costs, int B,
+                                         uint8_t* actions, int32_t* status, void* ws, size_t ws_bytes,
+                                         rmab_stream_t stream) {
+  RMAB_REQUIRE(E > 0 && N >= 0 && A >= 1 && A <= kKnapMaxA && B >= 0 && values && costs && actions && status, RMAB_E_BADARG,
+               "rmab_knapsack_multichoice: bad argument");
+  if (N == 0) return RMAB_OK;
+  RMAB_REQUIRE(ws && ws_bytes >= rmab_knapsack_ws_bytes(E, N, B), RMAB_E_BADARG,
+               "rmab_knapsack_multichoice: workspace of %zu B needed (rmab_knapsack_ws_bytes)", rmab_knapsack_ws_bytes(E, N, B));
+  const size_t smem = 2 * (size_t)(B + 1) * sizeof(double);
+  RMAB_REQUIRE(smem <= 200 * 1024, RMAB_E_SHAPE, "rmab_knapsack_multichoice: budget %d exceeds the shared-memory DP rows", B);
+  if (smem > 48 * 1024)
+    RMAB_REQUIRE(cudaFuncSetAttribute(knapsack_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess,
+                 RMAB_E_LAUNCH, "rmab_knapsack_multichoice: cannot reserve %zu B smem", smem);
+  knapsack_mc_kernel<<<E, kKnapThreads, smem, (cudaStream_t)stream>>>(E, N, A, values, costs, B, actions, status,
+                                                                      static_cast<uint8_t*>(ws));
+  return check_launch("rmab_knapsack_multichoice");
 }

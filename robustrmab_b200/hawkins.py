@@ -7,9 +7,11 @@ arm i's lambda-charged MDP, so   obj(lambda) = sum_i V_i(s_i; lambda) + lambda *
 for a whole grid of lambda-probes by ONE batched value iteration (rmab_vi_batched in its absolutely-converged
 stop mode -- mdptoolbox's own iteration bound leaves V off by a per-MDP constant), minimised over
 the grid and refined by re-gridding around the minimiser (obj is convex piecewise linear in lambda).  The action is
-the knapsack over Q(s_i, a; lambda*) = R - lambda* C[a] + gamma T.L (:69-91); for binary costs C = [0, c] with the
-equality budget `sum x C == B` (:250) that is action 1 for exactly B / c arms with the largest Q(s,1) - Q(s,0).
-PARITY UNPINNED against Gurobi (absent); pinned against a HiGHS restatement of the LP at small N (tests).
+the knapsack over Q(s_i, a; lambda*) = R - lambda* C[a] + gamma T.L (:69-91) with the equality budget
+`sum x C == B` (lp_methods.py:250): for binary costs C = [0, c] that is action 1 for exactly B / c arms with the largest
+Q(s,1) - Q(s,0) (rmab_budget_select_binary); for general integer costs (SIS: C = [0,1,2]) the exact multiple-choice
+knapsack dynamic programme rmab_knapsack_multichoice.  Q for all envs comes from ONE batched VI at the envs' lambdas.
+PARITY UNPINNED against Gurobi (absent); pinned against HiGHS restatements of the LP and of the ILP at small N (tests).
 """
 import numpy as np
 import torch
@@ -28,9 +30,9 @@ class HawkinsAgentPolicy:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("HawkinsAgentPolicy solves on CUDA only (no CPU fallback)")
-        if self.C.shape[0] != 2 or self.C[0] != 0:
-            raise NotImplementedError("device knapsack covers binary costs C = [0, c]; multi-action costs need the "
-                                      "multiple-choice knapsack of lp_methods.py:221-271 (next)")
+        self.binary = self.C.shape[0] == 2 and self.C[0] == 0
+        if not self.binary and not (np.abs(self.C - np.round(self.C)) < 1e-12).all():
+            raise ValueError("the multiple-choice knapsack needs integer action costs")
         self._T = torch.as_tensor(self.T, dtype=_F64, device=self.device).contiguous()
         self._R = torch.as_tensor(self.R, dtype=_F64, device=self.device).contiguous()
         self._C = torch.as_tensor(self.C, dtype=_F64, device=self.device).contiguous()
@@ -68,15 +70,20 @@ class HawkinsAgentPolicy:
 
     def act_test_device(self, s):
         lam = self.hawkins_lambda_device(s)                                          # [E]
-        E = s.shape[1]
-        a = torch.empty_like(s)
-        k = float(self.B) / float(self.C[1])
-        for e in range(E):                                                           # Q at each env's own lambda*
-            _, _, _, _, Q = ops.vi_batched(self._T, self._R, self._C, lam[e:e + 1].contiguous(), self.gamma, self.eps,
-                                           stop="abs", want_q=True)
-            q = torch.gather(Q[:, 0], 1, s[:, e].long()[:, None, None].expand(-1, 1, 2))[:, 0]   # [N,2]
-            gap = (q[:, 1] - q[:, 0]).to(torch.float32)[:, None].contiguous()
-            a[:, e] = ops.budget_select_binary(gap, 1.0, k)[:, 0]
+        N, E = s.shape
+        A = self.C.shape[0]
+        # Q at each env's own lambda*: one batched VI with the envs' lambdas as the probes
+        _, _, _, _, Q = ops.vi_batched(self._T, self._R, self._C, lam.contiguous(), self.gamma, self.eps, stop="abs", want_q=True)
+        idx = s.long()[:, :, None, None].expand(-1, -1, 1, A)                        # Q[n, e, s[n,e], :]
+        q = torch.gather(Q, 2, idx)[:, :, 0]                                         # [N,E,A]
+        if self.binary:
+            gap = (q[..., 1] - q[..., 0]).to(torch.float32).contiguous()             # [N,E]
+            return ops.budget_select_binary(gap, 1.0, float(self.B) / float(self.C[1]))
+        if abs(float(self.B) - round(float(self.B))) > 1e-9:
+            raise ValueError("budget %r cannot be met with equality by integer costs (lp_methods.py:250 is infeasible)" % (self.B,))
+        a, status = ops.knapsack_multichoice(q.permute(0, 2, 1).contiguous(), self.C, self.B)
+        if bool(status.any()):
+            raise ValueError("knapsack infeasible: no action vector spends exactly B = %r" % (self.B,))
         return a
 
     def act_test(self, o, just_hawkins_lambda=False):

@@ -330,6 +330,22 @@ def budget_select_multi(probs, Cc, B):
     return out
 
 
+def knapsack_multichoice(values, costs, B):
+    """Exact multiple-choice knapsack per env (lp_methods.py:221-271): values `[N,A,E]` fp64, integer costs `[A]`, integer
+    budget met with equality.  Returns (actions `[N,E]` u8, status `[E]` int32: 1 = infeasible)."""
+    N, A, E = values.shape
+    dev = values.device
+    c = torch.as_tensor([int(round(float(x))) for x in costs], dtype=i32, device=dev)
+    Bi = int(round(float(B)))
+    need = int(lib().rmab_knapsack_ws_bytes(E, N, Bi))
+    ws = torch.empty(need, dtype=u8, device=dev)
+    actions = torch.empty((N, E), dtype=u8, device=dev)
+    status = torch.empty((E,), dtype=i32, device=dev)
+    check(lib().rmab_knapsack_multichoice(E, N, A, _p(values, f64, "values"), _p(c, i32), Bi, _p(actions, u8), _p(status, i32),
+                                          _p(ws, u8), need, _stream()))
+    return actions, status
+
+
 # ------------------------------------------------------------------------------------ value iteration
 def vi_batched(T, R, Cc, lambdas, gamma, eps, stop="full", want_q=False):
     N, S, A, _ = T.shape

@@ -251,6 +251,57 @@ def test_hawkins_policy_against_highs_lp(torch_mod):
         assert a.sum() == B and np.array_equal(a, ovi.hawkins_action_binary(T, R, C, B, state, lam, gamma))
 
 
+@pytest.mark.parametrize("N,A,E,B", [(7, 3, 5, 6), (40, 3, 9, 16), (300, 3, 4, 120), (12, 2, 3, 5), (5, 3, 2, 11)])
+def test_knapsack_multichoice_kernel(torch_mod, N, A, E, B):
+    """rmab_knapsack_multichoice against the oracle's DP (same recurrence and tie rule: bit-exact actions), the ILP of
+    lp_methods.py:221-271; (5, 3, 2, 11) is infeasible (max spend 10)."""
+    torch = torch_mod
+    from oracle import select as osel
+    from robustrmab_b200 import ops
+    rs = np.random.RandomState(N * 7 + B)
+    vals = np.round(rs.randn(N, A, E) * 4) / 4            # quarter-integers: plenty of exact ties
+    C = np.arange(A)
+    a, status = ops.knapsack_multichoice(torch.as_tensor(vals, device="cuda"), C, B)
+    a, status = a.cpu().numpy(), status.cpu().numpy()
+    for e in range(E):
+        want, feas = osel.knapsack_multichoice(vals[:, :, e], C, B)
+        assert status[e] == (0 if feas else 1)
+        assert np.array_equal(a[:, e], want)
+        if feas:
+            assert C[a[:, e]].sum() == B
+
+
+def test_hawkins_policy_multiaction_sis(torch_mod):
+    """Hawkins on the SIS domain (C = [0,1,2]): lambda* against the HiGHS LP, the action against the oracle's
+    knapsack over Q(s, a; lambda*) (agent_baselines.py:69-91)."""
+    torch = torch_mod
+    from oracle import vi as ovi
+    from robustrmab_b200 import ops
+    from robustrmab_b200.hawkins import HawkinsAgentPolicy
+    rs = np.random.RandomState(9)
+    N, pop, B, gamma = 8, 6, 5.0, 0.9
+    prm = np.stack([rs.uniform(0.5, 0.99, N), rs.uniform(1, 10, N), rs.uniform(1, 10, N), rs.uniform(1, 10, N)], 1)
+    T = ops.sis_table(pop, torch.as_tensor(prm.astype(np.float32), device="cuda")).cpu().numpy().astype(np.float64)
+    R = np.tile(np.linspace(0, 1, pop + 1), (N, 1))
+    C = np.array([0.0, 1.0, 2.0])
+    pol = HawkinsAgentPolicy(N, T, R, C, B, gamma, 1, n_probes=64, n_refine=4)
+    for trial in range(3):
+        state = rs.randint(0, pop + 1, N)
+        _, lam_lp, obj_lp = ovi.hawkins_lp_highs(T, R, C, B, state, gamma, pol.lambda_lim)
+        lam = float(pol.act_test(state, just_hawkins_lambda=True)[0])
+        s = torch.as_tensor(state[:, None].astype(np.uint8), device=pol.device)
+        obj, _, _ = pol.objective(s, torch.tensor([lam, lam_lp], dtype=torch.float64, device=pol.device))
+        assert obj[0, 0].item() <= obj_lp + 1e-3 and abs(obj[0, 1].item() - obj_lp) < 1e-4 * max(1.0, abs(obj_lp))
+        a = pol.act_test(state)
+        want, feas = ovi.hawkins_action_knapsack(T, R, C, B, state, lam, gamma)
+        assert feas and C[a].sum() == B and np.array_equal(a, want)
+    # several envs at once: each env's action is the single-env answer
+    states = rs.randint(0, pop + 1, (N, 4))
+    a_all = pol.act_test(states)
+    for e in range(4):
+        assert np.array_equal(a_all[:, e], pol.act_test(states[:, e]))
+
+
 class _TableNature:
     """Stands in for the reference's SampledRandomNaturePolicy (nature_baselines_*.py): a per-arm parameter table."""
 
