@@ -443,6 +443,24 @@ static int check_ppo_args(const RmabNetDesc* net, const RmabHyper* hp, int T, co
 
 using namespace rmab;
 
+namespace rmab {
+// tcgen05 / TMEM kernels for hidden 64 with the scalar state input (ppo_table_umma64.cu, per-sample row modes)
+bool ppo_sample_umma64_fits(const RmabNetDesc* net);
+int ppo_sample_umma64_run(const RmabNetDesc* net, const RmabHyper* hp, int T, int s_rows, float* Wpi, float* Wv,
+                          float* adam_pi, float* adam_v, const uint8_t* s, const uint8_t* a, const float* adv,
+                          const float* logp_old, const float* ret, const float* lamb, float* loss_pi, float* loss_v,
+                          cudaStream_t st);
+int ppo_sample_umma64_critic_extra(const RmabNetDesc* net, const RmabHyper* hp, int T, int s_rows, float* Wv, float* adam_v,
+                                   const uint8_t* s, const float* ret, const float* lamb, const float* z1_extra,
+                                   float* dz1_out, float* loss_v, cudaStream_t st);
+// RMAB_H64_MMA_SYNC=1 keeps hidden 64 off the tcgen05 kernels (A/B measurements)
+static bool h64_legacy() {
+  static const bool v = getenv("RMAB_H64_MMA_SYNC") != nullptr;
+  return v;
+}
+
+}  // namespace rmab
+
 extern "C" int rmab_ppo_update(const RmabNetDesc* net, const RmabHyper* hp, int T, int s_rows, float* Wpi, float* Wv,
                                float* adam_pi, float* adam_v, const uint8_t* s, const uint8_t* a, const float* adv,
                                const float* logp_old, const float* ret, const float* lamb, float* loss_pi,
@@ -454,6 +472,9 @@ extern "C" int rmab_ppo_update(const RmabNetDesc* net, const RmabHyper* hp, int 
                "rmab_ppo_update: null pointer");
   if (net->n_arms == 0) return RMAB_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (net->hidden == 64 && net->n_extra == 0 && !h64_legacy() && ppo_sample_umma64_fits(net))
+    return ppo_sample_umma64_run(net, hp, T, s_rows, Wpi, Wv, adam_pi, adam_v, s, a, adv, logp_old, ret, lamb, loss_pi,
+                                 loss_v, st);
 #define RUN(H)                                                                                                    \
   {                                                                                                               \
     if (hp->pi_iters > 0)                                                                                         \
@@ -489,6 +510,8 @@ extern "C" int rmab_critic_extra_iter(const RmabNetDesc* net, const RmabHyper* h
                "rmab_critic_extra_iter: null pointer or s_rows < T");
   if (d.n_arms == 0) return RMAB_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (d.hidden == 64 && z1_sample_major && !h64_legacy() && ppo_sample_umma64_fits(&d))
+    return ppo_sample_umma64_critic_extra(&d, &h1, T, s_rows, Wv, adam_v, s, ret, lamb, z1_extra, dz1_out, loss_v, st);
 #define RUN(H) rc = launch_ppo<H, false, false>(d, h1, T, s_rows, Wv, adam_v, s, nullptr, nullptr, nullptr, ret, lamb, \
                                                 nullptr, nullptr, loss_v, st, z1_extra, dz1_out, z1_sample_major);
   switch (d.hidden) {

@@ -18,163 +18,13 @@
 // Reference behaviour: agent_oracle.py compute_loss_pi :285-322, compute_loss_v :325-339, update :399-436.
 #include "common.cuh"
 #include "mlp.cuh"
+#include "umma.cuh"
 
 namespace rmab {
 
 namespace {
 
-constexpr int H = 64, HH = H * H, TM = 128, NW = 16, NTHR = NW * 32, FW = 16;
-constexpr float kTanhScale = 2.885390081777927f;   // 2 / ln 2: tanh(x) = 1 - 2 / (2^(x * kTanhScale) + 1)
-// shared-memory tiles (byte offsets from a 1024-byte aligned base)
-constexpr uint32_t T_A1H = 0, T_A1L = 32768, T_D2H = 65536, T_D2L = 98304;             // 128 x 64, swizzled MN-major
-constexpr uint32_t T_W2H = 131072, T_W2L = 147456, T_WTH = 163840, T_WTL = 180224;     // 64 x 64, K-major core matrices
-constexpr uint32_t T_END = 196608;
-constexpr uint32_t BLK = 16384;   // bytes per 32-feature block of a 128-row MN-major tile
-// TMEM columns (512 allocated: the CTA owns its SM)
-constexpr uint32_t C_D1 = 0, C_D1P = 64, C_DW2 = 128, C_A1H = 192, C_A1L = 256, C_D2H = 320, C_D2L = 384, C_OM1 = 448;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// K-major 8-row x 16-byte core matrices: element (r, f) of a [rows][64] tile, in floats
-__host__ __device__ __forceinline__ int kmaj_off(int r, int f) { return (r >> 3) * 512 + (f >> 2) * 32 + (r & 7) * 4 + (f & 3); }
-
-// Shared-memory matrix descriptors, as (lo, hi) words: start address >> 4 | LBO >> 4 << 16 ; SBO >> 4 | version 1 << 14 | layout << 29.
-// K-major core matrices: LBO = 128 (next 4 k), SBO = 2048 (next 8 rows), no swizzle; one k-step (8 k) = +256 B.
-// MN-major swizzled tiles: LBO = BLK (next 32 features), SBO = 512 (next 4 rows), layout type 1; one k-step (8 rows) = +1024 B.
-constexpr uint32_t DESC_HI_K = (2048u >> 4) | (1u << 14);
-constexpr uint32_t DESC_HI_MN = (512u >> 4) | (1u << 14) | (1u << 29);
-__device__ __forceinline__ uint32_t desc_lo_k(uint32_t saddr) { return (saddr >> 4) | ((128u >> 4) << 16); }
-__device__ __forceinline__ uint32_t desc_lo_mn(uint32_t saddr) { return (saddr >> 4) | ((BLK >> 4) << 16); }
-
-// kind::tf32, fp32 accumulate: c_format F32 (bit 4), a/b format TF32 (bits 7, 10), majors (bits 15, 16), N>>3, M>>4
-constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 ad, {%1, %3};\n\tmov.b64 bd, {%2, %3};\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], ad, bd, %4, p;\n\t}\n" ::"r"(d_tmem),
-      "r"(alo), "r"(blo), "r"(hi), "r"(idesc), "r"(acc)
-      : "memory");
-}
-
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 bd, {%2, %3};\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n\t}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc)
-      : "memory");
-}
-
-// One lane of a converged warp (the compiler then knows a single thread issues, and keeps the operands uniform).
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
-  return pred != 0;
-}
-
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
-}
-
-// Bounded wait: a wrong phase must fail the launch, not hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-#pragma unroll 1
-  for (int spin = 0; spin < (1 << 26); ++spin) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                 : "=r"(ok)
-                 : "r"(bar), "r"(parity)
-                 : "memory");
-    if (ok) return;
-  }
-  __trap();
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};\n" ::"r"(v[0]),
-      "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
-      "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(taddr)
-      : "memory");
-}
-
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%4], {%0,%1,%2,%3};\n" ::"r"(a), "r"(b), "r"(c), "r"(d), "r"(taddr) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(taddr)
-               : "memory");
-}
-
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-
-__device__ __forceinline__ float tanh_fast_u(float x) {
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
-  return fmaf(-2.f, r, 1.f);
-}
-
-// tanh(x) given y = x * 2 / ln 2 (callers fold the scale into the layer's weights / the accumulator read)
-__device__ __forceinline__ float tanh_scaled_u(float y) {
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(y));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
-  return fmaf(-2.f, r, 1.f);
-}
-
-__device__ __forceinline__ void split_u(float x, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(x) & 0xffffe000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
-}
-
-// Column sums over the 32 lanes of 16 per-lane values: lane l returns the sum of column l >> 1 (both lanes of a pair).
-__device__ __forceinline__ float colsum16(const float (&v)[16], int lane) {
-  float a[8], b[4], c[2];
-  const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float keep = h4 ? v[i + 8] : v[i], send = h4 ? v[i] : v[i + 8];
-    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float keep = h3 ? a[i + 4] : a[i], send = h3 ? a[i] : a[i + 4];
-    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float keep = h2 ? b[i + 2] : b[i], send = h2 ? b[i] : b[i + 2];
-    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  const float keep = h1 ? c[1] : c[0], send = h1 ? c[0] : c[1];
-  float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  d += __shfl_xor_sync(0xffffffffu, d, 1);
-  return d;
-}
+using namespace umma;
 
 struct UmmaArgs {
   RmabNetDesc d;
@@ -183,15 +33,29 @@ struct UmmaArgs {
   float* W; float* adam;
   const float* lamb; const float* stats; const float* arm_stats;
   float* loss_out;
+  // per-sample rows (MODE >= 1): the buffers of rmab_ppo_update / rmab_critic_extra_iter
+  int s_rows;
+  const uint8_t* s_buf; const uint8_t* a_buf;
+  const float* adv; const float* logp_old; const float* ret;
+  const float* z1_extra; float* dz1_out;   // MODE 2, sample-major [T*E, N, h]
 };
+
+// Row sources.  MODE 0: one row per (state, env) carrying the loss statistics of rmab_epoch_table (one-hot inputs, S <= 3).
+// MODE 1: one row per sample (t, env) of the [N,T,E] buffers, scalar state input s / state_norm (the SIS domain).
+// MODE 2: MODE 1 for the MA agent critics: the caller's dense-GEMM term is added to the first layer, dLoss/dz1 is written.
+constexpr int kRowsTable = 0, kRowsSample = 1, kRowsSampleExtra = 2;
 
 }  // namespace
 
-template <int S, bool IS_PI>
+template <int S, int A, bool IS_PI, int MODE>
 __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
-  constexpr int A = 2, OUT = IS_PI ? A : 1, IN = S + 1, SA = S * A;
+  constexpr bool TABLE = MODE == kRowsTable, EXTRA = MODE == kRowsSampleExtra;
+  static_assert(TABLE ? (A == 2 && (S == 2 || S == 3)) : (S == 1 && A >= 2 && A <= 3), "row mode / shape");
+  constexpr int OUT = IS_PI ? A : 1, IN = S + 1, SA = S * A;   // sample rows: IN = 2 = (s / state_norm, lambda)
   constexpr int ROW0 = IS_PI ? 0 : 3 * SA, KST = 4 * SA + 3 * S;
-  constexpr int NQ = 2 + S + OUT;   // per-feature row sums: db2, dW1[:, lambda], dW1[:, s] x S, dW3 x OUT
+  // per-feature row sums: db2, dW1[:, lambda], then table: dW1[:, s] x S (db1 is their sum) | sample: dW1[:, 0], db1; dW3 x OUT
+  constexpr int NW1 = TABLE ? S : 2;
+  constexpr int NQ = 2 + NW1 + OUT;
   extern __shared__ unsigned char smraw[];
   __shared__ __align__(8) uint64_t bars[3];
   __shared__ uint32_t tmem_s;
@@ -203,10 +67,11 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
   const int P = L.P, Ps = L.padded() - HH;   // w / G hold the packed layout WITHOUT the W2 block
   float* w = reinterpret_cast<float*>(base + T_END);
   float* G = w + Ps;
-  float* wb = G + Ps;                 // [S][H]  (W1[:, s] + b1) * kTanhScale
+  float* wb = G + Ps;                 // [S][H]  (W1[:, s] + b1) * kTanhScale        (sample rows: b1 * kTanhScale)
   float* wl = wb + S * H;             // [H]     W1[:, lambda] * kTanhScale
   float* b2s = wl + H;                // [H]     b2 * kTanhScale
-  float* plog = b2s + H;              // [4 cq][128 rows][OUT] partial logits
+  float* wa = b2s + H;                // [H]     W1[:, 0] * kTanhScale (sample rows)
+  float* plog = wa + H;              // [4 cq][128 rows][OUT] partial logits
   float* redw = plog + 4 * TM * OUT;  // [NW][NQ][16]
   float* slam = redw + NW * NQ * FW;  // [E]
   float* W2H = reinterpret_cast<float*>(base + T_W2H);
@@ -250,8 +115,13 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
   const uint32_t rowb = (uint32_t)(cq >> 1) * BLK + (uint32_t)(r >> 2) * 512 + (uint32_t)(r & 3) * 128;
   const uint32_t off_c0 = rowb + (uint32_t)(((2 * (cq & 1)) ^ (r & 3)) * 32), off_c1 = rowb + (uint32_t)(((2 * (cq & 1) + 1) ^ (r & 3)) * 32);
 
-  const float* st = g.stats + ((int64_t)n * KST + ROW0) * E;
-  const int M = S * E;
+  const float* st = TABLE ? g.stats + ((int64_t)n * KST + ROW0) * E : nullptr;
+  const int M = TABLE ? S * E : T * E;
+  const uint32_t e_magic = (uint32_t)(0x100000000ull / (uint32_t)E);   // floor(2^32 / E): m / E with one correction step
+  const int64_t smp_base = (int64_t)n * T * E, st_base = (int64_t)n * g.s_rows * E;
+  const int64_t z_stride = (int64_t)g.d.n_arms * H;                    // sample-major [T*E, N, h]
+  const int s_max = g.d.n_states - 1;
+  const float state_norm = g.d.state_norm;
   const int n_tiles = (M + TM - 1) / TM;
   const float invM = 1.f / (float)((int64_t)T * E);
   const int iters = IS_PI ? g.hp.pi_iters : g.hp.v_iters;
@@ -267,15 +137,16 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
   for (int it = 0; it < iters; ++it) {
     for (int i = tid; i < S * H; i += NTHR) {
       const int s = i >> 6, k = i & 63;
-      wb[i] = kTanhScale * (w[L.oW1 + k * IN + s] + w[L.ob1 + k]);
+      wb[i] = kTanhScale * (TABLE ? w[L.oW1 + k * IN + s] + w[L.ob1 + k] : w[L.ob1 + k]);
     }
     for (int i = tid; i < H; i += NTHR) {
       wl[i] = kTanhScale * w[L.oW1 + i * IN + IN - 1];
       b2s[i] = kTanhScale * w[L.ob2 - HH + i];
+      wa[i] = kTanhScale * w[L.oW1 + i * IN];
     }
     __syncthreads();
 
-    float s_b2[FW], s_w3[OUT][FW], s_w1r[S], s_b3[OUT], s_wlr = 0.f;
+    float s_b2[FW], s_w3[OUT][FW], s_w1r[NW1], s_b3[OUT], s_wlr = 0.f;
 #pragma unroll
     for (int k = 0; k < FW; ++k) {
       s_b2[k] = 0.f;
@@ -283,30 +154,51 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
       for (int a = 0; a < OUT; ++a) s_w3[a][k] = 0.f;
     }
 #pragma unroll
-    for (int c = 0; c < S; ++c) s_w1r[c] = 0.f;
+    for (int c = 0; c < NW1; ++c) s_w1r[c] = 0.f;
 #pragma unroll
     for (int a = 0; a < OUT; ++a) s_b3[a] = 0.f;
     float loss_acc = 0.f;
+    struct Row { int srow; int mm; float x0, lam, keep; };   // table: state of the row | sample: index and scalar input
 
-    // E1 chunk: a1 = tanh(W1 x + b1) for features f0 + 4 k4 .. + 3 of row (srow1, lam1); hi/lo into TMEM (operand of G1)
-    auto layer1_chunk = [&](int k4, int srow1, float lam1, float keep1, bool last1) {
-      const float4 b = *reinterpret_cast<const float4*>(wb + srow1 * H + f0 + 4 * k4);
+    // E1 chunk: a1 = tanh(W1 x + b1) for features f0 + 4 k4 .. + 3 of row rw; hi/lo into TMEM (operand of G1)
+    auto layer1_chunk = [&](int k4, const Row& rw, bool last1) {
+      const float4 b = *reinterpret_cast<const float4*>(wb + rw.srow * H + f0 + 4 * k4);
       const float4 l = *reinterpret_cast<const float4*>(wl + f0 + 4 * k4);
-      float x0 = tanh_scaled_u(fmaf(l.x, lam1, b.x)), x1 = tanh_scaled_u(fmaf(l.y, lam1, b.y));
-      float x2 = tanh_scaled_u(fmaf(l.z, lam1, b.z)), x3 = tanh_scaled_u(fmaf(l.w, lam1, b.w));
-      if (last1) { x0 *= keep1; x1 *= keep1; x2 *= keep1; x3 *= keep1; }   // rows past the end: a1 = 0 (so d2 = d1 = 0)
+      float z0 = fmaf(l.x, rw.lam, b.x), z1 = fmaf(l.y, rw.lam, b.y), z2 = fmaf(l.z, rw.lam, b.z), z3 = fmaf(l.w, rw.lam, b.w);
+      if (!TABLE) {
+        const float4 c = *reinterpret_cast<const float4*>(wa + f0 + 4 * k4);
+        z0 = fmaf(c.x, rw.x0, z0); z1 = fmaf(c.y, rw.x0, z1); z2 = fmaf(c.z, rw.x0, z2); z3 = fmaf(c.w, rw.x0, z3);
+      }
+      if (EXTRA) {   // the caller's dense GEMM over the nature inputs (ma_rmabppo_core.py:312-316)
+        const float4 x = *reinterpret_cast<const float4*>(g.z1_extra + rw.mm * z_stride + (int64_t)n * H + f0 + 4 * k4);
+        z0 = fmaf(kTanhScale, x.x, z0); z1 = fmaf(kTanhScale, x.y, z1); z2 = fmaf(kTanhScale, x.z, z2); z3 = fmaf(kTanhScale, x.w, z3);
+      }
+      float x0 = tanh_scaled_u(z0), x1 = tanh_scaled_u(z1), x2 = tanh_scaled_u(z2), x3 = tanh_scaled_u(z3);
+      if (last1) { x0 *= rw.keep; x1 *= rw.keep; x2 *= rw.keep; x3 *= rw.keep; }   // rows past the end: a1 = 0 (so d2 = d1 = 0)
       uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
       split_u(x0, h0, l0); split_u(x1, h1, l1); split_u(x2, h2, l2); split_u(x3, h3, l3);
       tmem_st4(tl + C_A1H + f0 + 4 * k4, h0, h1, h2, h3);
       tmem_st4(tl + C_A1L + f0 + 4 * k4, l0, l1, l2, l3);
     };
-    // row of this thread in tile tt: state, lambda, validity
-    auto row_of = [&](int tt, int& srow1, float& lam1, float& keep1) {
+    // row of this thread in tile tt
+    auto row_of = [&](int tt, Row& rw) {
       const int m = tt * TM + r;
       const int mm = m < M ? m : M - 1;
-      srow1 = (mm >= E) + (mm >= 2 * E);   // S <= 3: no integer division
-      lam1 = slam[mm - srow1 * E];
-      keep1 = m < M ? 1.f : 0.f;
+      rw.mm = mm;
+      rw.keep = m < M ? 1.f : 0.f;
+      if (TABLE) {
+        rw.srow = (mm >= E) + (mm >= 2 * E);   // S <= 3: no integer division
+        rw.lam = slam[mm - rw.srow * E];
+        rw.x0 = 0.f;
+      } else {
+        uint32_t ts = __umulhi((uint32_t)mm, e_magic);
+        int e = mm - (int)ts * E;
+        if (e >= E) e -= E;
+        const int si = min((int)g.s_buf[st_base + mm], s_max);   // sample m = t * E + e of the first T rows of s
+        rw.srow = 0;
+        rw.lam = slam[e];
+        rw.x0 = __fdiv_rn((float)si, state_norm);
+      }
     };
     // G1: z2 = a1 . W2^T, three tf32 products (lo.hi, hi.lo, hi.hi)
     auto issue_g1 = [&]() {
@@ -337,8 +229,8 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
     };
     // E3 of tile tt (its G2 has been issued): d1 = d1' (1 - a1^2); column sums for db1 / dW1.
     auto backward_rowsums = [&](int tt) {
-      int srow1; float lam1, keep1;
-      row_of(tt, srow1, lam1, keep1);
+      Row rw;
+      row_of(tt, rw);
       mbar_wait(bar2, (gt - 1) & 1);
       tc_fence_after();
       if (warp == 1 && tt + 1 < n_tiles) {   // G1 of the next tile goes behind the finished G2, ahead of G3
@@ -353,24 +245,36 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
 #pragma unroll
       for (int k = 0; k < FW; ++k) {
         d1[k] = __uint_as_float(v[k]) * __uint_as_float(om[k]);
-        d1l[k] = d1[k] * lam1;
+        d1l[k] = d1[k] * rw.lam;
       }
       s_wlr += colsum16(d1l, lane);
-      // db1 / dW1[:, s]: the tile's column sums go straight to one register per state (lane l holds feature f0 + l / 2)
-      const int m_lo = min(tt * TM + 32 * q, M - 1), m_hi = min(tt * TM + 32 * q + 31, M - 1);
-      const int s_lo = (m_lo >= E) + (m_lo >= 2 * E), s_hi = (m_hi >= E) + (m_hi >= 2 * E);
-      if (s_lo == s_hi) {   // warp-uniform: all 32 rows are in one state
-        const float x = colsum16(d1, lane);
+      if (TABLE) {
+        // db1 / dW1[:, s]: the tile's column sums go straight to one register per state (lane l holds feature f0 + l / 2)
+        const int m_lo = min(tt * TM + 32 * q, M - 1), m_hi = min(tt * TM + 32 * q + 31, M - 1);
+        const int s_lo = (m_lo >= E) + (m_lo >= 2 * E), s_hi = (m_hi >= E) + (m_hi >= 2 * E);
+        if (s_lo == s_hi) {   // warp-uniform: all 32 rows are in one state
+          const float x = colsum16(d1, lane);
 #pragma unroll
-        for (int c = 0; c < S; ++c) s_w1r[c] += (c == s_lo) ? x : 0.f;
-      } else {              // the warp's rows straddle a state boundary: masked sums for this tile
+          for (int c = 0; c < NW1; ++c) s_w1r[c] += (c == s_lo) ? x : 0.f;
+        } else {              // the warp's rows straddle a state boundary: masked sums for this tile
 #pragma unroll
-        for (int c = 0; c < S; ++c) {
-          float msk[FW];
+          for (int c = 0; c < NW1; ++c) {
+            float msk[FW];
 #pragma unroll
-          for (int k = 0; k < FW; ++k) msk[k] = (srow1 == c) ? d1[k] : 0.f;
-          s_w1r[c] += colsum16(msk, lane);
+            for (int k = 0; k < FW; ++k) msk[k] = (rw.srow == c) ? d1[k] : 0.f;
+            s_w1r[c] += colsum16(msk, lane);
+          }
         }
+      } else {
+        if (EXTRA && rw.keep != 0.f) {   // dLoss / d(first-layer pre-activation) for the caller's dW1_nature GEMM
+          float4* o = reinterpret_cast<float4*>(g.dz1_out + rw.mm * z_stride + (int64_t)n * H + f0);
+#pragma unroll
+          for (int k4 = 0; k4 < FW / 4; ++k4) o[k4] = make_float4(d1[4 * k4], d1[4 * k4 + 1], d1[4 * k4 + 2], d1[4 * k4 + 3]);
+        }
+        s_w1r[1] += colsum16(d1, lane);                       // db1
+#pragma unroll
+        for (int k = 0; k < FW; ++k) d1l[k] = d1[k] * rw.x0;
+        s_w1r[0] += colsum16(d1l, lane);                      // dW1[:, 0]
       }
       if (warp == 2 || warp == 3) {   // G3(tt) behind G1(tt + 1): never waited for before the next tile's d2 is ready
         if (elect_one()) issue_g3_half(warp == 2 ? 0 : 8);
@@ -378,10 +282,10 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
       }
     };
     {
-      int srow1; float lam1, keep1;
-      row_of(0, srow1, lam1, keep1);
+      Row rw;
+      row_of(0, rw);
 #pragma unroll
-      for (int k4 = 0; k4 < FW / 4; ++k4) layer1_chunk(k4, srow1, lam1, keep1, n_tiles == 1);
+      for (int k4 = 0; k4 < FW / 4; ++k4) layer1_chunk(k4, rw, n_tiles == 1);
       const uint32_t z[FW] = {};
       tmem_st16(tl + C_DW2 + f0, z);   // G3 only ever accumulates
     }
@@ -399,19 +303,30 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
       const int m = t * TM + r;
       const bool valid = m < M;
       const int mm = valid ? m : M - 1;
-      const int srow = (mm >= E) + (mm >= 2 * E), erow = mm - srow * E;
-      // statistics of this row (L2 resident), in flight while G1 runs
-      const float* sp = st + erow;
-      const float wrow = sp[(3 * SA - ROW0 + srow) * E];   // CntS
+      // loss inputs of this row (L2 resident), in flight while G1 runs.  Table rows: statistics Ap Am Lp per action, CntS
+      // (policy) / RetMean, CntS (value).  Sample rows: action, advantage, old log-prob (policy) / return (value).
+      float wrow = 1.f;
       float stA[IS_PI ? 6 : 1];
-      if (IS_PI) {
+      int act = 0;
+      if (TABLE) {
+        const int srow = (mm >= E) + (mm >= 2 * E), erow = mm - srow * E;
+        const float* sp = st + erow;
+        wrow = sp[(3 * SA - ROW0 + srow) * E];   // CntS
+        if (IS_PI) {
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
-          const int c = srow * A + a;
-          stA[a] = sp[c * E]; stA[2 + a] = sp[(SA + c) * E]; stA[4 + a] = sp[(2 * SA + c) * E];
+          for (int a = 0; a < 2; ++a) {
+            const int c = srow * A + a;
+            stA[a] = sp[c * E]; stA[2 + a] = sp[(SA + c) * E]; stA[4 + a] = sp[(2 * SA + c) * E];
+          }
+        } else {
+          stA[0] = sp[(3 * SA + S - ROW0 + srow) * E];
         }
+      } else if (IS_PI) {
+        act = g.a_buf[smp_base + mm];
+        stA[0] = g.adv[smp_base + mm];
+        stA[1] = g.logp_old[smp_base + mm];
       } else {
-        stA[0] = sp[(3 * SA + S - ROW0 + srow) * E];
+        stA[0] = g.ret[smp_base + mm];
       }
 
       // ---- E3 of the previous tile, under this tile's G1 ----
@@ -458,25 +373,51 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
           gl[a] = 0.f;
         }
         if (IS_PI) {
-          const float mx = fmaxf(logit[0], logit[OUT - 1]);
-          const float e0 = __expf(logit[0] - mx), e1 = __expf(logit[OUT - 1] - mx);
-          const float sum = e0 + e1, lse = __logf(sum), inv = __fdividef(1.f, sum);
-          const float p[2] = {e0 * inv, e1 * inv};
-          const float lp[2] = {(logit[0] - mx) - lse, (logit[OUT - 1] - mx) - lse};
-          const float ent = -(p[0] * lp[0] + p[1] * lp[1]);
-          float ga[2], sumg = 0.f, lrow = 0.f;
+          float mx = logit[0];
 #pragma unroll
-          for (int a = 0; a < 2; ++a) {
-            const float Ap = stA[a], Am = stA[IS_PI ? 2 + a : 0];
-            const float ratio = __expf(lp[a] - stA[IS_PI ? 4 + a : 0]);
-            lrow -= fminf(ratio, clip_hi) * Ap + fmaxf(ratio, clip_lo) * Am;
-            ga[a] = -((ratio <= clip_hi ? ratio * Ap : 0.f) + (ratio >= clip_lo ? ratio * Am : 0.f));
-            sumg += ga[a];
+          for (int a = 1; a < OUT; ++a) mx = fmaxf(mx, logit[a]);
+          float ex[OUT], sum = 0.f;
+#pragma unroll
+          for (int a = 0; a < OUT; ++a) { ex[a] = __expf(logit[a] - mx); sum += ex[a]; }
+          const float lse = __logf(sum), inv = __fdividef(1.f, sum);
+          float p[OUT], lp[OUT], ent = 0.f;
+#pragma unroll
+          for (int a = 0; a < OUT; ++a) {
+            p[a] = ex[a] * inv;
+            lp[a] = (logit[a] - mx) - lse;
+            ent = fmaf(-p[a], lp[a], ent);
           }
-          if (valid) {
-            if (cq == 0) loss_acc += lrow - beta_ent * wrow * ent;
+          if (TABLE) {
+            float ga[OUT], sumg = 0.f, lrow = 0.f;
 #pragma unroll
-            for (int a = 0; a < 2; ++a) gl[a < OUT ? a : 0] = invM * (ga[a] - p[a] * sumg + beta_ent * wrow * p[a] * (lp[a] + ent));
+            for (int a = 0; a < OUT; ++a) {
+              const float Ap = stA[a], Am = stA[TABLE ? 2 + a : 0];
+              const float ratio = __expf(lp[a] - stA[TABLE ? 4 + a : 0]);
+              lrow -= fminf(ratio, clip_hi) * Ap + fmaxf(ratio, clip_lo) * Am;
+              ga[a] = -((ratio <= clip_hi ? ratio * Ap : 0.f) + (ratio >= clip_lo ? ratio * Am : 0.f));
+              sumg += ga[a];
+            }
+            if (valid) {
+              if (cq == 0) loss_acc += lrow - beta_ent * wrow * ent;
+#pragma unroll
+              for (int a = 0; a < OUT; ++a) gl[a] = invM * (ga[a] - p[a] * sumg + beta_ent * wrow * p[a] * (lp[a] + ent));
+            }
+          } else {   // one sample: compute_loss_pi (agent_oracle.py:285-322) on (act, adv, logp_old)
+            float lpa = lp[0];
+#pragma unroll
+            for (int a = 1; a < OUT; ++a) lpa = act == a ? lp[a] : lpa;
+            const float advv = stA[0];
+            const float ratio = __expf(lpa - stA[IS_PI && !TABLE ? 1 : 0]);
+            const float surr1 = ratio * advv;
+            const float surr2 = fminf(fmaxf(ratio, clip_lo), clip_hi) * advv;
+            const bool pass = (ratio >= clip_lo && ratio <= clip_hi) || (surr1 < surr2);
+            const float coef = pass ? -advv * ratio : 0.f;
+            if (valid) {
+              if (cq == 0) loss_acc += -fminf(surr1, surr2) - beta_ent * ent;
+#pragma unroll
+              for (int a = 0; a < OUT; ++a)
+                gl[a] = invM * (coef * ((act == a ? 1.f : 0.f) - p[a]) + beta_ent * p[a] * (lp[a] + ent));
+            }
           }
         } else {
           const float diff = logit[0] - stA[0];
@@ -492,8 +433,8 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
       // d2 (FMA pipe) interleaved with the NEXT tile's layer 1 (MUFU pipe); z2's a1 operand in TMEM is free once G1 is done
       {
         const bool more = t + 1 < n_tiles;
-        int srow1 = 0; float lam1 = 0.f, keep1 = 0.f;
-        if (more) row_of(t + 1, srow1, lam1, keep1);
+        Row rw1 = {};
+        if (more) row_of(t + 1, rw1);
         if (gt > 0) mbar_wait(bar3, (gt - 1) & 1);   // the previous tile's G3 has finished reading the a1 / d2 tiles
 #pragma unroll
         for (int k4 = 0; k4 < FW / 4; ++k4) {
@@ -534,7 +475,7 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
           tmem_st4(tl + C_D2L + f0 + 4 * k4, l[0], l[1], l[2], l[3]);
           *reinterpret_cast<uint4*>(base + T_D2H + off) = make_uint4(h[0], h[1], h[2], h[3]);
           *reinterpret_cast<uint4*>(base + T_D2L + off) = make_uint4(l[0], l[1], l[2], l[3]);
-          if (more) layer1_chunk(k4, srow1, lam1, keep1, t + 2 == n_tiles);
+          if (more) layer1_chunk(k4, rw1, t + 2 == n_tiles);
         }
       }
       tmem_wait_st();
@@ -569,9 +510,9 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
       vals[0] = colsum16(s_b2, lane);
       vals[1] = s_wlr;
 #pragma unroll
-      for (int c = 0; c < S; ++c) vals[2 + c] = s_w1r[c];
+      for (int c = 0; c < NW1; ++c) vals[2 + c] = s_w1r[c];
 #pragma unroll
-      for (int a = 0; a < OUT; ++a) vals[2 + S + a] = colsum16(s_w3[a], lane);
+      for (int a = 0; a < OUT; ++a) vals[2 + NW1 + a] = colsum16(s_w3[a], lane);
       if ((lane & 1) == 0)
 #pragma unroll
         for (int v = 0; v < NQ; ++v) redw[(warp * NQ + v) * FW + (lane >> 1)] = vals[v];
@@ -607,8 +548,10 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
       for (int qq = 1; qq < 4; ++qq) x += redw[((kc * 4 + qq) * NQ + v) * FW + kk];   // fixed order over the row quarters
       if (v == 0) G[L.ob2 - HH + k] = x;
       else if (v == 1) G[L.oW1 + k * IN + IN - 1] = x;
-      else if (v < 2 + S) G[L.oW1 + k * IN + (v - 2)] = x;
-      else G[L.oW3 - HH + (v - 2 - S) * H + k] = x;
+      else if (v < 2 + NW1) {
+        if (TABLE || v == 2) G[L.oW1 + k * IN + (v - 2)] = x;   // table: dW1[:, state]; sample: dW1[:, 0]
+        else G[L.ob1 + k] = x;                                   // sample: db1
+      } else G[L.oW3 - HH + (v - 2 - NW1) * H + k] = x;
     }
     if (tid < OUT) {
       float x = 0.f;
@@ -617,16 +560,17 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
     }
     if (g.loss_out && tid == 0) {
       float extra = 0.f;
-      if (!IS_PI && g.arm_stats) extra = g.arm_stats[4 * (int64_t)n + 2];
+      if (TABLE && !IS_PI && g.arm_stats) extra = g.arm_stats[4 * (int64_t)n + 2];
       g.loss_out[(int64_t)n * iters + it] = (loss_tot + extra) * invM;
     }
     __syncthreads();
-    for (int k = tid; k < H; k += NTHR) {   // db1 = sum over states of dW1[:, s]
-      float x = 0.f;
+    if (TABLE)
+      for (int k = tid; k < H; k += NTHR) {   // db1 = sum over states of dW1[:, s]
+        float x = 0.f;
 #pragma unroll
-      for (int c = 0; c < S; ++c) x += G[L.oW1 + k * IN + c];
-      G[L.ob1 + k] = x;
-    }
+        for (int c = 0; c < S; ++c) x += G[L.oW1 + k * IN + c];
+        G[L.ob1 + k] = x;
+      }
 
     // ---- Adam; moments live in global memory (one read-modify-write per iteration) ----
     b1p *= g.hp.beta1;
@@ -682,27 +626,27 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
 }
 
-static size_t umma64_smem_bytes(int S, int OUT, int E) {
+static size_t umma64_smem_bytes(int S, int OUT, bool table, int E) {
   const MlpLayout L(S + 1, H, OUT);
-  const int NQ = 2 + S + OUT;
-  const size_t fl = 2 * (size_t)(L.padded() - HH) + S * H + 2 * H + 4 * TM * OUT + NW * NQ * FW + (((size_t)E + 3) & ~(size_t)3);
+  const int NQ = 2 + (table ? S : 2) + OUT;
+  const size_t fl = 2 * (size_t)(L.padded() - HH) + S * H + 3 * H + 4 * TM * OUT + NW * NQ * FW + (((size_t)E + 3) & ~(size_t)3);
   return 1024 + T_END + fl * sizeof(float);
 }
 
-template <int S, bool IS_PI>
-static int launch_umma64(const UmmaArgs& g, cudaStream_t st) {
-  constexpr int OUT = IS_PI ? 2 : 1;
-  const size_t smem = umma64_smem_bytes(S, OUT, g.d.n_envs);
-  auto kern = ppo_table_umma64_kernel<S, IS_PI>;
+template <int S, int A, bool IS_PI, int MODE>
+static int launch_umma64(const UmmaArgs& g, cudaStream_t st, const char* what) {
+  constexpr int OUT = IS_PI ? A : 1;
+  const size_t smem = umma64_smem_bytes(S, OUT, MODE == kRowsTable, g.d.n_envs);
+  auto kern = ppo_table_umma64_kernel<S, A, IS_PI, MODE>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-    return fail(RMAB_E_LAUNCH, "rmab_ppo_update_table: cannot reserve %zu B of shared memory", smem);
+    return fail(RMAB_E_LAUNCH, "%s: cannot reserve %zu B of shared memory", what, smem);
   kern<<<g.d.n_arms, NTHR, smem, st>>>(g);
-  return check_launch(IS_PI ? "rmab_ppo_update_table(pi, tcgen05)" : "rmab_ppo_update_table(v, tcgen05)");
+  return check_launch(what);
 }
 
 // Does the tcgen05 kernel's shared-memory plan fit this shape?  (E bounds the staged lambda vector.)
 bool ppo_table_umma64_fits(const RmabNetDesc* net) {
-  return umma64_smem_bytes(net->n_states, 2, net->n_envs) <= 227 * 1024 - 512;   // 512 B of static __shared__
+  return umma64_smem_bytes(net->n_states, 2, true, net->n_envs) <= 227 * 1024 - 512;   // 512 B of static __shared__
 }
 
 // Entry used by rmab_ppo_update_table (ppo_table.cu) for H = 64.
@@ -716,13 +660,48 @@ int ppo_table_umma64_run(const RmabNetDesc* net, const RmabHyper* hp, int T, flo
   gv.W = Wv; gv.adam = adam_v; gv.loss_out = loss_v;
   int rc = RMAB_OK;
   if (net->n_states == 2) {
-    if (hp->pi_iters > 0) rc = launch_umma64<2, true>(gp, st);
-    if (rc == RMAB_OK && hp->v_iters > 0) rc = launch_umma64<2, false>(gv, st);
+    if (hp->pi_iters > 0) rc = launch_umma64<2, 2, true, kRowsTable>(gp, st, "rmab_ppo_update_table(pi, tcgen05)");
+    if (rc == RMAB_OK && hp->v_iters > 0) rc = launch_umma64<2, 2, false, kRowsTable>(gv, st, "rmab_ppo_update_table(v, tcgen05)");
   } else {
-    if (hp->pi_iters > 0) rc = launch_umma64<3, true>(gp, st);
-    if (rc == RMAB_OK && hp->v_iters > 0) rc = launch_umma64<3, false>(gv, st);
+    if (hp->pi_iters > 0) rc = launch_umma64<3, 2, true, kRowsTable>(gp, st, "rmab_ppo_update_table(pi, tcgen05)");
+    if (rc == RMAB_OK && hp->v_iters > 0) rc = launch_umma64<3, 2, false, kRowsTable>(gv, st, "rmab_ppo_update_table(v, tcgen05)");
   }
   return rc;
+}
+
+// ---- per-sample rows, scalar state input (rmab_ppo_update / rmab_critic_extra_iter with hidden 64, one_hot = 0) ----
+bool ppo_sample_umma64_fits(const RmabNetDesc* net) {
+  return !net->one_hot && net->hidden == H && net->n_actions >= 2 && net->n_actions <= 3 &&
+         umma64_smem_bytes(1, 3, false, net->n_envs) <= 227 * 1024 - 512;
+}
+
+// One policy pass (hp->pi_iters Adam steps) and / or one value pass over the [N,T,E] sample buffers.
+int ppo_sample_umma64_run(const RmabNetDesc* net, const RmabHyper* hp, int T, int s_rows, float* Wpi, float* Wv,
+                          float* adam_pi, float* adam_v, const uint8_t* s, const uint8_t* a, const float* adv,
+                          const float* logp_old, const float* ret, const float* lamb, float* loss_pi, float* loss_v,
+                          cudaStream_t st) {
+  UmmaArgs g = {};
+  g.d = *net; g.hp = *hp; g.T = T; g.lamb = lamb; g.s_rows = s_rows; g.s_buf = s; g.a_buf = a; g.adv = adv;
+  g.logp_old = logp_old; g.ret = ret;
+  UmmaArgs gp = g, gv = g;
+  gp.W = Wpi; gp.adam = adam_pi; gp.loss_out = loss_pi;
+  gv.W = Wv; gv.adam = adam_v; gv.loss_out = loss_v;
+  int rc = RMAB_OK;
+  if (hp->pi_iters > 0)
+    rc = net->n_actions == 2 ? launch_umma64<1, 2, true, kRowsSample>(gp, st, "rmab_ppo_update(pi, tcgen05)")
+                             : launch_umma64<1, 3, true, kRowsSample>(gp, st, "rmab_ppo_update(pi, tcgen05)");
+  if (rc == RMAB_OK && hp->v_iters > 0) rc = launch_umma64<1, 2, false, kRowsSample>(gv, st, "rmab_ppo_update(v, tcgen05)");
+  return rc;
+}
+
+// One Adam step of the MA agent critics (first-layer term of the nature inputs from / to the caller's dense GEMMs).
+int ppo_sample_umma64_critic_extra(const RmabNetDesc* net, const RmabHyper* hp, int T, int s_rows, float* Wv, float* adam_v,
+                                   const uint8_t* s, const float* ret, const float* lamb, const float* z1_extra,
+                                   float* dz1_out, float* loss_v, cudaStream_t st) {
+  UmmaArgs g = {};
+  g.d = *net; g.hp = *hp; g.T = T; g.lamb = lamb; g.s_rows = s_rows; g.s_buf = s; g.ret = ret;
+  g.z1_extra = z1_extra; g.dz1_out = dz1_out; g.W = Wv; g.adam = adam_v; g.loss_out = loss_v;
+  return launch_umma64<1, 2, false, kRowsSampleExtra>(g, st, "rmab_critic_extra_iter(tcgen05)");
 }
 
 }  // namespace rmab

@@ -341,7 +341,10 @@ def test_gae_oracle(K, domain, N, T, E):
 # ---------------------------------------------------------------------------------- PPO update
 @pytest.mark.parametrize("S,A,h,one_hot,N,T,E", [(2, 2, 16, True, 4, 20, 8), (3, 2, 64, True, 3, 10, 32),
                                                  (3, 2, 8, True, 3, 7, 5), (3, 2, 32, True, 2, 9, 16),
-                                                 (11, 3, 16, False, 3, 12, 8)])
+                                                 (11, 3, 16, False, 3, 12, 8),
+                                                 # hidden 64 + scalar state input: the tcgen05 per-sample kernel
+                                                 (11, 3, 64, False, 3, 12, 8), (51, 3, 64, False, 2, 20, 40),
+                                                 (6, 2, 64, False, 2, 5, 3)])
 def test_ppo_update(K, S, A, h, one_hot, N, T, E):
     rs = np.random.RandomState(S + h + T)
     in_dim = (S if one_hot else 1) + 1

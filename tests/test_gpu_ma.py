@@ -105,6 +105,39 @@ def test_agent_critic_extra_batched(K):
         K.ops.ac_step(net, K.t(Wpi), K.t(Wv), K.t(s), K.t(lamb), u=K.t(u))      # n_extra > 0 without the addend
 
 
+@pytest.mark.parametrize("N,T,E,S", [(3, 6, 8, 11), (2, 20, 40, 51), (4, 3, 50, 7)])
+def test_critic_extra_iter_tcgen05_vs_per_sample_kernel(K, N, T, E, S):
+    """rmab_critic_extra_iter at hidden 64 with the scalar state input: the sample-major call runs the tcgen05 kernel,
+    the arm-major call the per-sample FFMA kernel (itself pinned to the oracle by the MA loop tests); same loss, dLoss/dz1
+    and critic after three Adam steps."""
+    torch = K.torch
+    rs = np.random.RandomState(N * 100 + E)
+    h = 64
+    Wv0 = onets.init_linear_default(rs, N, 2, h, 1)
+    s = rs.randint(0, S, size=(N, T + 1, E)).astype(np.uint8)
+    ret = (rs.randn(N, T, E) * 2).astype(F32)
+    lamb = rs.uniform(0, 2, size=E).astype(F32)
+    net = K.ops.net_desc(N, E, S, 3, h, False, float(S - 1))
+    z1 = (rs.randn(N, T * E, h) * 0.3).astype(F32)
+    outs = []
+    for sample_major in (False, True):
+        Wv = K.t(Wv0.copy())
+        adam = torch.zeros((N, 2, Wv0.shape[1]), device=K.dev)
+        z = K.t(z1.transpose(1, 0, 2).copy()) if sample_major else K.t(z1)
+        losses, dz = [], None
+        for it in range(3):
+            hp = K.ops.hyper(0.2, 0.0, 2e-3, 2e-3, 0, 1, 0, it)
+            dz, loss = K.ops.critic_extra_iter(net, hp, Wv, adam, K.t(s), K.t(ret), K.t(lamb), z, want_loss=True,
+                                               sample_major=sample_major)
+            losses.append(K.n(loss)[:, 0])
+        dz = K.n(dz)
+        outs.append((np.array(losses), dz.transpose(1, 0, 2) if sample_major else dz, K.n(Wv)))
+    (l0, d0, w0), (l1, d1, w1) = outs
+    np.testing.assert_allclose(l1, l0, rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(d1, d0, rtol=1e-3, atol=2e-8)
+    np.testing.assert_allclose(w1, w0, rtol=0, atol=1e-4)
+
+
 @pytest.mark.parametrize("domain,pop", [(0, None), (1, None), (2, 10), (2, 50)])
 def test_counterfactual(K, domain, pop):
     rs = np.random.RandomState(7 + domain)
