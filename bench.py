@@ -403,6 +403,20 @@ def run_ours(a):
                                 "issue bound (ncu: issue active 56-61 %, DRAM < 1 %) and frac is small by construction",
                         "stages": stage_roofs},
            "stage_ms_per_step": stage_ms, "clocks": clk}
+    if dom_name == "ppo_update" and dom_ms:
+        # the flop side of the same kernel, for context: SURVEY 8(d) counts the update at 6 (K_pi P_pi + K_v P_v) flops per
+        # arm-step (one forward + backward per sample and Adam step); the statistics reformulation executes those on
+        # S*E rows instead of T*E samples, i.e. T/S times fewer, as 3xTF32 tensor-core products
+        S_dom = 2 if a.domain == "counterexample" else 3
+        per_sample = 6.0 * (a.pi_iters * tr.Ppi + a.v_iters * tr.Pv)
+        alg = per_sample * N * T * E
+        h = a.hidden
+        tf32_exec = float(N) * (a.pi_iters + a.v_iters) * S_dom * E * 3 * 3 * 2 * h * h
+        out["roofline"]["flops_view"] = {
+            "algorithmic_TFLOPs": alg / (dom_ms * 1e-3) / 1e12, "executed_tf32_TFLOPs": tf32_exec / (dom_ms * 1e-3) / 1e12,
+            "rows_per_arm": S_dom * E, "samples_per_arm": T * E,
+            "note": "algorithmic = per-sample autograd flops of the reference update; executed = tensor-core products of the "
+                    "3 h x h GEMMs per row and Adam step (the rest of the kernel is CUDA-core work)"}
     if a.hidden == 64 and dom_name == "ppo_update":
         # hidden 64: the update runs its three 64 x 64 GEMMs per row on tcgen05 as 3 tf32 products each (3xTF32), so the
         # dominant kernel is reported against the tensor roofline.  peak = tf32 dense = half the measured bf16 rate.
