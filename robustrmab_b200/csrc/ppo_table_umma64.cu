@@ -531,12 +531,12 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
       uint32_t v[FW];
       tmem_ld16(tl + C_DW2 + f0, v);
       tmem_wait_ld();
-      if (lane < 16) {   // M = 64 accumulator: row j = 16q + lane sits on lane 32q + lane
-        float4* o = reinterpret_cast<float4*>(scratch + (16 * q + lane) * H + f0);
-        o[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
-        o[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
-        o[2] = make_float4(__uint_as_float(v[8]), __uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
-        o[3] = make_float4(__uint_as_float(v[12]), __uint_as_float(v[13]), __uint_as_float(v[14]), __uint_as_float(v[15]));
+      if (lane < 16) {   // M = 64 accumulator: row j = 16q + lane sits on lane 32q + lane; scratch in K-major tile order
+        const int j = 16 * q + lane;
+#pragma unroll
+        for (int k4 = 0; k4 < FW / 4; ++k4)
+          *reinterpret_cast<float4*>(scratch + kmaj_off(j, f0 + 4 * k4)) =
+              make_float4(__uint_as_float(v[4 * k4]), __uint_as_float(v[4 * k4 + 1]), __uint_as_float(v[4 * k4 + 2]), __uint_as_float(v[4 * k4 + 3]));
       }
     }
     tc_fence_before();
@@ -581,34 +581,39 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
     }
     __syncthreads();
     const float step_size = red[62], bc2s = red[63];
-    for (int i = tid; i < P; i += NTHR) {
-      const bool in_w2 = i >= L.oW2 && i < L.ob2;
-      float gi, x;
-      int j = 0, c = 0;
-      if (in_w2) {
-        j = (i - L.oW2) >> 6; c = (i - L.oW2) & 63;
-        gi = scratch[i - L.oW2];
-        x = W2H[kmaj_off(j, c)] + W2L[kmaj_off(j, c)];   // hi + lo is the exact fp32 weight
-      } else {
-        const int k = i < L.oW2 ? i : i - HH;
-        gi = G[k];
-        x = w[k];
-      }
-      const float m0 = An[i], v0 = An[P + i];
+    auto adam = [&](float x, float gi, float m0, float v0, int i) {
       const float mi = m0 + lerp_w * (gi - m0);
       const float vi = v0 * beta2f + (omb2 * gi) * gi;
       An[i] = mi;
       An[P + i] = vi;
       const float denom = sqrtf(vi) / bc2s + epsf;
-      const float xn = x - step_size * (mi / denom);
-      if (in_w2) {
+      return x - step_size * (mi / denom);
+    };
+    // W2 block, walked in the order of the K-major tile (conflict-free shared-memory access; the gradient scratch has the
+    // same layout): tile position p <-> W2[j][c]
+    {
+      float m0[HH / NTHR], v0[HH / NTHR];
+#pragma unroll
+      for (int k = 0; k < HH / NTHR; ++k) {   // all moment loads in flight before the first use
+        const int p = tid + k * NTHR;
+        const int j = ((p >> 9) << 3) | ((p >> 2) & 7), c = (((p >> 5) & 15) << 2) | (p & 3);
+        m0[k] = An[L.oW2 + j * H + c];
+        v0[k] = An[P + L.oW2 + j * H + c];
+      }
+#pragma unroll
+      for (int k = 0; k < HH / NTHR; ++k) {
+        const int p = tid + k * NTHR;
+        const int j = ((p >> 9) << 3) | ((p >> 2) & 7), c = (((p >> 5) & 15) << 2) | (p & 3);
+        const float xn = adam(W2H[p] + W2L[p], scratch[p], m0[k], v0[k], L.oW2 + j * H + c);   // hi + lo = exact fp32 weight
         uint32_t hi, lo;
         split_u(xn, hi, lo);
-        W2H[kmaj_off(j, c)] = __uint_as_float(hi); W2L[kmaj_off(j, c)] = __uint_as_float(lo);
+        W2H[p] = __uint_as_float(hi); W2L[p] = __uint_as_float(lo);
         WTH[kmaj_off(c, j)] = __uint_as_float(hi); WTL[kmaj_off(c, j)] = __uint_as_float(lo);
-      } else {
-        w[i < L.oW2 ? i : i - HH] = xn;
       }
+    }
+    for (int k = tid; k < P - HH; k += NTHR) {   // everything else, packed order without the W2 block
+      const int i = k < L.oW2 ? k : k + HH;
+      w[k] = adam(w[k], G[k], An[i], An[P + i], i);
     }
     fence_async_smem();   // the new W2 tiles are read by the tensor core in the next pass
     __syncthreads();
