@@ -38,6 +38,7 @@ struct UmmaArgs {
   const uint8_t* s_buf; const uint8_t* a_buf;
   const float* adv; const float* logp_old; const float* ret;
   const float* z1_extra; float* dz1_out;   // MODE 2, sample-major [T*E, N, h]
+  int stage_lamb;                          // lambda [E] staged in shared memory (else read through L1 / L2)
 };
 
 // Row sources.  MODE 0: one row per (state, env) carrying the loss statistics of rmab_epoch_table (one-hot inputs, S <= 3).
@@ -73,7 +74,8 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
   float* wa = b2s + H;                // [H]     W1[:, 0] * kTanhScale (sample rows)
   float* plog = wa + H;              // [4 cq][128 rows][OUT] partial logits
   float* redw = plog + 4 * TM * OUT;  // [NW][NQ][16]
-  float* slam = redw + NW * NQ * FW;  // [E]
+  float* slam_s = redw + NW * NQ * FW;  // [E] when it fits
+  const float* slam = g.stage_lamb ? slam_s : g.lamb;
   float* W2H = reinterpret_cast<float*>(base + T_W2H);
   float* W2L = reinterpret_cast<float*>(base + T_W2L);
   float* WTH = reinterpret_cast<float*>(base + T_WTH);
@@ -96,7 +98,8 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
       WTH[kmaj_off(c, j)] = __uint_as_float(hi); WTL[kmaj_off(c, j)] = __uint_as_float(lo);
     }
   }
-  for (int i = tid; i < E; i += NTHR) slam[i] = g.lamb[i];
+  if (g.stage_lamb)
+    for (int i = tid; i < E; i += NTHR) slam_s[i] = g.lamb[i];
   if (tid == 0) {
     for (int b = 0; b < 3; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&bars[b])), "r"(b == 2 ? 2 : 1));
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -638,10 +641,15 @@ static size_t umma64_smem_bytes(int S, int OUT, bool table, int E) {
   return 1024 + T_END + fl * sizeof(float);
 }
 
+constexpr size_t kUmmaSmemLimit = 227 * 1024 - 512;   // 512 B of static __shared__
+
 template <int S, int A, bool IS_PI, int MODE>
-static int launch_umma64(const UmmaArgs& g, cudaStream_t st, const char* what) {
+static int launch_umma64(const UmmaArgs& g0, cudaStream_t st, const char* what) {
   constexpr int OUT = IS_PI ? A : 1;
-  const size_t smem = umma64_smem_bytes(S, OUT, MODE == kRowsTable, g.d.n_envs);
+  UmmaArgs g = g0;
+  size_t smem = umma64_smem_bytes(S, OUT, MODE == kRowsTable, g.d.n_envs);
+  g.stage_lamb = smem <= kUmmaSmemLimit;
+  if (!g.stage_lamb) smem = umma64_smem_bytes(S, OUT, MODE == kRowsTable, 0);   // large E: lambda stays in global memory
   auto kern = ppo_table_umma64_kernel<S, A, IS_PI, MODE>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return fail(RMAB_E_LAUNCH, "%s: cannot reserve %zu B of shared memory", what, smem);
@@ -649,9 +657,9 @@ static int launch_umma64(const UmmaArgs& g, cudaStream_t st, const char* what) {
   return check_launch(what);
 }
 
-// Does the tcgen05 kernel's shared-memory plan fit this shape?  (E bounds the staged lambda vector.)
+// Does the tcgen05 kernel's shared-memory plan fit this shape?  (Always: lambda is staged only when there is room.)
 bool ppo_table_umma64_fits(const RmabNetDesc* net) {
-  return umma64_smem_bytes(net->n_states, 2, true, net->n_envs) <= 227 * 1024 - 512;   // 512 B of static __shared__
+  return umma64_smem_bytes(net->n_states, 2, true, 0) <= kUmmaSmemLimit;
 }
 
 // Entry used by rmab_ppo_update_table (ppo_table.cu) for H = 64.
@@ -677,7 +685,7 @@ int ppo_table_umma64_run(const RmabNetDesc* net, const RmabHyper* hp, int T, flo
 // ---- per-sample rows, scalar state input (rmab_ppo_update / rmab_critic_extra_iter with hidden 64, one_hot = 0) ----
 bool ppo_sample_umma64_fits(const RmabNetDesc* net) {
   return !net->one_hot && net->hidden == H && net->n_actions >= 2 && net->n_actions <= 3 &&
-         umma64_smem_bytes(1, 3, false, net->n_envs) <= 227 * 1024 - 512;
+         umma64_smem_bytes(1, 3, false, 0) <= kUmmaSmemLimit;
 }
 
 // One policy pass (hp->pi_iters Adam steps) and / or one value pass over the [N,T,E] sample buffers.

@@ -99,7 +99,8 @@ def test_epoch_table_vs_oracle(K, domain, h, N, E, T):
 
 
 @pytest.mark.parametrize("S,h,N,T,E", [(2, 16, 4, 30, 8), (3, 64, 3, 10, 32), (3, 8, 3, 7, 5), (3, 32, 2, 12, 70),
-                                       (3, 64, 2, 6, 100), (2, 64, 2, 5, 200), (3, 64, 2, 4, 128), (3, 64, 2, 9, 1), (2, 64, 3, 7, 3)])
+                                       (3, 64, 2, 6, 100), (2, 64, 2, 5, 200), (3, 64, 2, 4, 128), (3, 64, 2, 9, 1), (2, 64, 3, 7, 3),
+                                       (2, 64, 1, 2, 6500)])   # lambda [E] no longer fits beside the tiles: read from global
 def test_ppo_update_table_equals_per_sample(K, S, h, N, T, E):
     """The statistics-based update against the oracle's per-sample torch-autograd update on the same batch."""
     rs = np.random.RandomState(S * 10 + h)
