@@ -3,7 +3,8 @@
 // Same algorithm as ppo_table_mma64.cu (loss statistics, 3xTF32 hi/lo split, fp32 accumulation); one CTA per arm.
 //
 // A CTA walks the arm's rows in tiles of 128 (TMEM lane = tile row).  16 warps: warp (q, cq) owns rows 32q..32q+31 (its
-// TMEM lane quarter) and the 16 hidden features 16cq..16cq+15.  Per tile, three GEMMs issued by one thread:
+// TMEM lane quarter) and the 16 hidden features 16cq..16cq+15.  Per tile, three GEMMs, each issued by one elected lane
+// (G2 by warp 0 after the tile's barrier, G1 of the next tile by warp 1 once G2 has completed, G3 in two halves by warps 2, 3):
 //   G1  z2   [128x64] = a1 . W2^T    A = a1 hi/lo in TMEM (written with tcgen05.st), B = W2   K-major in smem
 //   G2  d1'  [128x64] = d2 . W2      A = d2 hi/lo in TMEM,                           B = W2^T K-major in smem
 //   G3  dW2  [ 64x64] += d2^T . a1   A = d2, B = a1 tiles in smem, both MN-major (128-byte rows, 32-byte swizzle atoms:
@@ -14,6 +15,8 @@
 // Schedule: ONE block barrier per tile.  E2(t) computes d2 (FMA pipe) interleaved with layer 1 of tile t+1 (MUFU pipe), then
 //   | barrier, issue G2(t), G1(t+1), G3(t) |  E3(t) (row sums of d1, needs G2)  ->  E2(t+1) (needs G1)  ->  ...
 // so the tensor pipe works under E3 and E2; G3 is never waited for inside the pass.
+// Row modes (MODE): statistics rows (rmab_ppo_update_table), or one row per sample with the scalar state input for
+// rmab_ppo_update / rmab_critic_extra_iter (SIS, MA-RMABPPO agent nets) -- see kRowsTable / kRowsSample / kRowsSampleExtra.
 //
 // Reference behaviour: agent_oracle.py compute_loss_pi :285-322, compute_loss_v :325-339, update :399-436.
 #include "common.cuh"
