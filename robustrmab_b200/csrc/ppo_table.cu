@@ -495,6 +495,10 @@ int ppo_table_mma_run(const RmabNetDesc* net, const RmabHyper* hp, int T, float*
 int ppo_table_mma64_run(const RmabNetDesc* net, const RmabHyper* hp, int T, float* Wpi, float* Wv, float* adam_pi,
                         float* adam_v, const float* stats, const float* arm_stats, const float* lamb, float* loss_pi,
                         float* loss_v, cudaStream_t st);
+// tcgen05 / TMEM variant for H = 16 (ppo_table_umma16.cu)
+int ppo_table_umma16_run(const RmabNetDesc* net, const RmabHyper* hp, int T, float* Wpi, float* Wv, float* adam_pi,
+                         float* adam_v, const float* stats, const float* arm_stats, const float* lamb, float* loss_pi,
+                         float* loss_v, cudaStream_t st);
 // tcgen05 / TMEM variant for H = 64 (ppo_table_umma64.cu)
 bool ppo_table_umma64_fits(const RmabNetDesc* net);
 int ppo_table_umma64_run(const RmabNetDesc* net, const RmabHyper* hp, int T, float* Wpi, float* Wv, float* adam_pi,
@@ -526,6 +530,9 @@ extern "C" int rmab_ppo_update_table(const RmabNetDesc* net, const RmabHyper* hp
   // used when E is too large for its shared-memory plan); H = 8 (and RMAB_TABLE_FFMA=1, for A/B measurements): FFMA kernel
   static const bool force_ffma = getenv("RMAB_TABLE_FFMA") != nullptr;
   static const bool h64_mma_sync = getenv("RMAB_H64_MMA_SYNC") != nullptr;
+  static const bool h16_mma_sync = getenv("RMAB_H16_MMA_SYNC") != nullptr;
+  if (h == 16 && !force_ffma && !h16_mma_sync)
+    return ppo_table_umma16_run(net, hp, T, Wpi, Wv, adam_pi, adam_v, stats, arm_stats, lamb, loss_pi, loss_v, st);
   if ((h == 16 || h == 32) && !force_ffma)
     return ppo_table_mma_run(net, hp, T, Wpi, Wv, adam_pi, adam_v, stats, arm_stats, lamb, loss_pi, loss_v, st);
   if (h == 64 && !force_ffma && !h64_mma_sync && ppo_table_umma64_fits(net))

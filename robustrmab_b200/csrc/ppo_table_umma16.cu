@@ -1,0 +1,543 @@
+// Statistics-based PPO update for hidden width 16 on tcgen05 / TMEM -- the headline shape (BASELINE configs[1]: CE,
+// 4098 arms x 256 envs, hidden [16,16]).  Same algorithm and building blocks as ppo_table_umma64.cu (umma.cuh); what
+// changes is the plan, because a 16 x 16 layer leaves the tensor core idle and the CUDA-core work is everything:
+//   * one CTA = 4 warps = one 128-row tile at a time (thread = tile row = TMEM lane, all 16 features), FOUR CTAs per SM
+//     (44 KB of shared memory, 128 TMEM columns, 128 registers each) -- the other CTAs' work hides a CTA's barriers and its
+//     waits for the tensor pipe, so the schedule inside a CTA is simply E1 | G1 | E2 | G2, G3 | E3 per tile;
+//   * the a1 and d2 tiles G3 contracts over hold hi AND lo side by side in one 128-byte swizzled row (features 0..15 = hi,
+//     16..31 = lo), so ONE pass of 16 MMAs with M = 64, N = 32 produces all hi/lo cross products of d2^T a1 at once
+//     (rows 0..15 x cols 0..15 = hi.hi, rows 0..15 x cols 16..31 = hi.lo, rows 16..31 x cols 0..15 = lo.hi); the d2 tile is
+//     followed by the a1 tile in memory, which is what the M = 64 operand's second 32-feature block reads (ignored rows);
+//   * G1 / G2 are six MMAs each (M = 128, N = 16): A = hi / lo in TMEM, B = W2 / W2^T K-major 16 x 16 tiles in smem.
+// tools/umma_probe.cu modes 6 and 7 pin these two patterns against a CPU product on the device.
+//
+// Reference behaviour: agent_oracle.py compute_loss_pi :285-322, compute_loss_v :325-339, update :399-436.
+#include "common.cuh"
+#include "mlp.cuh"
+#include "umma.cuh"
+
+namespace rmab {
+
+namespace {
+
+namespace u = umma;
+
+constexpr int H16 = 16, HH16 = 256, TM16 = 128, NT16 = 128;
+constexpr int CTAS16 = 4;   // measured: 3 CTAs with the E3 row sums in registers (170 regs) is 5 % slower, occupancy wins
+// shared memory (bytes from a 1024-byte aligned base): swizzled [128 x (hi16 | lo16)] tiles, K-major 16 x 16 tiles
+constexpr uint32_t S_D2 = 0, S_A1 = 16384, S_W2H = 32768, S_W2L = 33792, S_WTH = 34816, S_WTL = 35840, S_END = 36864;
+// TMEM columns (128 allocated per CTA)
+constexpr uint32_t Q_D = 0, Q_OM1 = 16, Q_A1H = 32, Q_A1L = 48, Q_D2H = 64, Q_D2L = 80, Q_DW2 = 96;
+constexpr uint32_t DESC16_HI_K = (512u >> 4) | (1u << 14);                 // SBO = 512 (next 8 rows of a 16-column tile)
+constexpr uint32_t DESC16_HI_MN = (512u >> 4) | (1u << 14) | (1u << 29);   // SBO = 512 (next 4 rows), layout type 1
+
+__host__ __device__ __forceinline__ int kmaj16(int r, int f) { return (r >> 3) * 128 + (f >> 2) * 32 + (r & 7) * 4 + (f & 3); }
+__device__ __forceinline__ uint32_t lo_k16(uint32_t saddr) { return (saddr >> 4) | ((128u >> 4) << 16); }
+__device__ __forceinline__ uint32_t lo_mn16(uint32_t saddr) { return (saddr >> 4) | ((16384u >> 4) << 16); }
+
+struct U16Args {
+  RmabNetDesc d;
+  RmabHyper hp;
+  int T;
+  float* W; float* adam;
+  const float* lamb; const float* stats; const float* arm_stats;
+  float* loss_out;
+  int stage_lamb;
+};
+
+}  // namespace
+
+template <int S, bool IS_PI>
+__global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args g) {
+  constexpr int H = H16, HH = HH16, A = 2, OUT = IS_PI ? A : 1, IN = S + 1, SA = S * A, FW = 16;
+  constexpr int ROW0 = IS_PI ? 0 : 3 * SA, KST = 4 * SA + 3 * S;
+  constexpr int NQ = 2 + S + OUT;   // per-feature row sums: db2, dW1[:, lambda], dW1[:, s] x S, dW3 x OUT
+  extern __shared__ unsigned char smraw16[];
+  __shared__ __align__(8) uint64_t bars[3];
+  __shared__ uint32_t tmem_s;
+  __shared__ float red[64];
+  unsigned char* base = smraw16 + ((1024u - (u::smem_u32(smraw16) & 1023u)) & 1023u);
+  const uint32_t sbase = u::smem_u32(base);
+  const int E = g.d.n_envs, T = g.T;
+  const MlpLayout L(IN, H, OUT);
+  const int P = L.P, Ps = L.padded() - HH;   // w / G hold the packed layout WITHOUT the W2 block
+  float* w = reinterpret_cast<float*>(base + S_END);
+  float* G = w + Ps;
+  float* wb = G + Ps;                 // [S][H]  (W1[:, s] + b1) * kTanhScale
+  float* wl = wb + S * H;             // [H]     W1[:, lambda] * kTanhScale
+  float* b2s = wl + H;                // [H]     b2 * kTanhScale
+  float* redw = b2s + H;              // [4 warps][NQ][16]
+  float* scrA = redw + 4 * NQ * FW;   // [16][32]  dW2 readback: hi rows
+  float* scrB = scrA + H * 32;        // [16][16]  lo rows x hi cols
+  float* slam_s = scrB + HH;          // [E] when it fits
+  const float* slam = g.stage_lamb ? slam_s : g.lamb;
+  float* W2H = reinterpret_cast<float*>(base + S_W2H);
+  float* W2L = reinterpret_cast<float*>(base + S_W2L);
+  float* WTH = reinterpret_cast<float*>(base + S_WTH);
+  float* WTL = reinterpret_cast<float*>(base + S_WTL);
+
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, r = tid;
+  float* Wn = g.W + (int64_t)n * P;
+  float* An = g.adam + (int64_t)n * 2 * P;
+  for (int i = tid; i < P; i += NT16) {
+    const float x = Wn[i];
+    if (i < L.oW2) w[i] = x;
+    else if (i >= L.ob2) w[i - HH] = x;
+    else {
+      const int j = (i - L.oW2) >> 4, c = (i - L.oW2) & 15;
+      uint32_t hi, lo;
+      u::split_u(x, hi, lo);
+      W2H[kmaj16(j, c)] = __uint_as_float(hi); W2L[kmaj16(j, c)] = __uint_as_float(lo);
+      WTH[kmaj16(c, j)] = __uint_as_float(hi); WTL[kmaj16(c, j)] = __uint_as_float(lo);
+    }
+  }
+  if (g.stage_lamb)
+    for (int i = tid; i < E; i += NT16) slam_s[i] = g.lamb[i];
+  if (tid == 0) {
+    for (int b = 0; b < 3; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(u::smem_u32(&bars[b])));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;\n" ::"r"(u::smem_u32(&tmem_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  u::tc_fence_before();
+  __syncthreads();
+  u::tc_fence_after();
+  const uint32_t tmem = tmem_s;
+  const uint32_t tl = tmem + ((uint32_t)(32 * warp) << 16);   // this warp's lane quarter
+  const uint32_t bar1 = u::smem_u32(&bars[0]), bar2 = u::smem_u32(&bars[1]), bar3 = u::smem_u32(&bars[2]);
+  // this thread's row of the swizzled tiles: four 32-byte chunks (hi 0..7, hi 8..15, lo 0..7, lo 8..15)
+  const uint32_t rowb = (uint32_t)(r >> 2) * 512 + (uint32_t)(r & 3) * 128;
+  uint32_t off_c[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) off_c[c] = rowb + (uint32_t)((c ^ (r & 3)) * 32);
+
+  const float* st = g.stats + ((int64_t)n * KST + ROW0) * E;
+  const int M = S * E;
+  const int n_tiles = (M + TM16 - 1) / TM16;
+  const float invM = 1.f / (float)((int64_t)T * E);
+  const int iters = IS_PI ? g.hp.pi_iters : g.hp.v_iters;
+  const double lr = IS_PI ? g.hp.pi_lr : g.hp.vf_lr;
+  const int step0 = IS_PI ? g.hp.adam_step0_pi : g.hp.adam_step0_v;
+  const float clip_lo = (float)(1.0 - g.hp.clip_ratio), clip_hi = (float)(1.0 + g.hp.clip_ratio);
+  const float beta_ent = (float)g.hp.entropy_coeff;
+  const float lerp_w = (float)(1.0 - g.hp.beta1), beta2f = (float)g.hp.beta2, omb2 = (float)(1.0 - g.hp.beta2);
+  const float epsf = (float)g.hp.adam_eps;
+  double b1p = pow(g.hp.beta1, (double)step0), b2p = pow(g.hp.beta2, (double)step0);
+  uint32_t gt = 0;   // tiles issued so far: every barrier completes one phase per tile
+
+  auto store_row = [&](uint32_t tile, const uint32_t (&hi)[FW], const uint32_t (&lo)[FW]) {
+    *reinterpret_cast<uint4*>(base + tile + off_c[0]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + tile + off_c[0] + 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    *reinterpret_cast<uint4*>(base + tile + off_c[1]) = make_uint4(hi[8], hi[9], hi[10], hi[11]);
+    *reinterpret_cast<uint4*>(base + tile + off_c[1] + 16) = make_uint4(hi[12], hi[13], hi[14], hi[15]);
+    *reinterpret_cast<uint4*>(base + tile + off_c[2]) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(base + tile + off_c[2] + 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    *reinterpret_cast<uint4*>(base + tile + off_c[3]) = make_uint4(lo[8], lo[9], lo[10], lo[11]);
+    *reinterpret_cast<uint4*>(base + tile + off_c[3] + 16) = make_uint4(lo[12], lo[13], lo[14], lo[15]);
+  };
+
+  for (int it = 0; it < iters; ++it) {
+    for (int i = tid; i < S * H; i += NT16) {
+      const int s = i >> 4, k = i & 15;
+      wb[i] = u::kTanhScale * (w[L.oW1 + k * IN + s] + w[L.ob1 + k]);
+    }
+    if (tid < H) {
+      wl[tid] = u::kTanhScale * w[L.oW1 + tid * IN + IN - 1];
+      b2s[tid] = u::kTanhScale * w[L.ob2 - HH + tid];
+    }
+    {
+      const uint32_t z[FW] = {};
+      u::tmem_st16(tl + Q_DW2, z);   // G3 only ever accumulates
+      u::tmem_st16(tl + Q_DW2 + 16, z);
+    }
+    __syncthreads();
+
+    float s_b2[FW], s_w3[OUT][FW], s_w1r[S], s_b3[OUT], s_wlr = 0.f;
+#pragma unroll
+    for (int k = 0; k < FW; ++k) {
+      s_b2[k] = 0.f;
+#pragma unroll
+      for (int a = 0; a < OUT; ++a) s_w3[a][k] = 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < S; ++c) s_w1r[c] = 0.f;
+#pragma unroll
+    for (int a = 0; a < OUT; ++a) s_b3[a] = 0.f;
+    float loss_acc = 0.f;
+
+    for (int t = 0; t < n_tiles; ++t, ++gt) {
+      const int m = t * TM16 + r;
+      const bool valid = m < M;
+      const int mm = valid ? m : M - 1;
+      const int srow = (mm >= E) + (mm >= 2 * E), erow = mm - srow * E;   // S <= 3: no integer division
+      const float lam = slam[erow];
+      // statistics of this row (L2 resident), in flight during E1 and G1
+      const float* sp = st + erow;
+      const float wrow = sp[(3 * SA - ROW0 + srow) * E];   // CntS
+      float stA[IS_PI ? 6 : 1];
+      if (IS_PI) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const int c = srow * A + a;
+          stA[a] = sp[c * E]; stA[2 + a] = sp[(SA + c) * E]; stA[4 + a] = sp[(2 * SA + c) * E];
+        }
+      } else {
+        stA[0] = sp[(3 * SA + S - ROW0 + srow) * E];
+      }
+
+      // ---- E1: a1 = tanh(W1 x + b1); hi/lo -> TMEM (A of G1) and the smem tile (B of G3); 1 - a1^2 parked in TMEM ----
+      {
+        uint32_t hi[FW], lo[FW], om[FW];
+        const float keep = valid ? 1.f : 0.f;   // rows past the end contribute a1 = 0 (and so d2 = d1 = 0)
+        const bool last = t == n_tiles - 1;     // only the last tile can hold such rows
+#pragma unroll
+        for (int k4 = 0; k4 < FW / 4; ++k4) {
+          const float4 b = *reinterpret_cast<const float4*>(wb + srow * H + 4 * k4);
+          const float4 l = *reinterpret_cast<const float4*>(wl + 4 * k4);
+          float x[4] = {u::tanh_scaled_u(fmaf(l.x, lam, b.x)), u::tanh_scaled_u(fmaf(l.y, lam, b.y)),
+                        u::tanh_scaled_u(fmaf(l.z, lam, b.z)), u::tanh_scaled_u(fmaf(l.w, lam, b.w))};
+          if (last) { x[0] *= keep; x[1] *= keep; x[2] *= keep; x[3] *= keep; }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            u::split_u(x[j], hi[4 * k4 + j], lo[4 * k4 + j]);
+            om[4 * k4 + j] = __float_as_uint(fmaf(-x[j], x[j], 1.f));
+          }
+        }
+        u::tmem_st16(tl + Q_A1H, hi);
+        u::tmem_st16(tl + Q_A1L, lo);
+        u::tmem_st16(tl + Q_OM1, om);
+        if (gt > 0) u::mbar_wait(bar3, (gt - 1) & 1);   // the previous tile's G3 has finished reading the a1 / d2 tiles
+        store_row(S_A1, hi, lo);
+        u::tmem_wait_st();
+      }
+      u::fence_async_smem();
+      u::tc_fence_before();
+      __syncthreads();
+      if (warp == 0) {
+        u::tc_fence_after();
+        if (u::elect_one()) {   // G1: z2 = a1 . W2^T as lo.hi + hi.lo + hi.hi, two k-steps each
+          constexpr uint32_t idesc = u::make_idesc(128, 16, 0, 0);
+          const uint32_t wh = lo_k16(sbase + S_W2H), wlo = lo_k16(sbase + S_W2L);
+#pragma unroll
+          for (int term = 0; term < 3; ++term)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+              u::umma_ts(tmem + Q_D, tmem + (term == 0 ? Q_A1L : Q_A1H) + 8 * ks, (term == 1 ? wlo : wh) + 16 * ks, DESC16_HI_K, idesc,
+                         (term | ks) != 0);
+          u::umma_commit(bar1);
+        }
+        __syncwarp();
+      }
+
+      // ---- E2: a2 = tanh(z2 + b2); logits, loss terms, d2 ----
+      u::mbar_wait(bar1, gt & 1);
+      u::tc_fence_after();
+      float a2[FW];
+      {
+        uint32_t v[FW];
+        u::tmem_ld16(tl + Q_D, v);
+        u::tmem_wait_ld();
+#pragma unroll
+        for (int k4 = 0; k4 < FW / 4; ++k4) {
+          const float4 b = *reinterpret_cast<const float4*>(b2s + 4 * k4);
+          a2[4 * k4] = u::tanh_scaled_u(fmaf(__uint_as_float(v[4 * k4]), u::kTanhScale, b.x));
+          a2[4 * k4 + 1] = u::tanh_scaled_u(fmaf(__uint_as_float(v[4 * k4 + 1]), u::kTanhScale, b.y));
+          a2[4 * k4 + 2] = u::tanh_scaled_u(fmaf(__uint_as_float(v[4 * k4 + 2]), u::kTanhScale, b.z));
+          a2[4 * k4 + 3] = u::tanh_scaled_u(fmaf(__uint_as_float(v[4 * k4 + 3]), u::kTanhScale, b.w));
+        }
+      }
+      float gl[OUT];
+      {
+        float logit[OUT];
+#pragma unroll
+        for (int a = 0; a < OUT; ++a) {
+          const float4* w34 = reinterpret_cast<const float4*>(w + L.oW3 - HH + a * H);
+          float pl = w[L.ob3 - HH + a];
+#pragma unroll
+          for (int k4 = 0; k4 < FW / 4; ++k4) {
+            const float4 w3 = w34[k4];
+            pl = fmaf(w3.x, a2[4 * k4], pl); pl = fmaf(w3.y, a2[4 * k4 + 1], pl);
+            pl = fmaf(w3.z, a2[4 * k4 + 2], pl); pl = fmaf(w3.w, a2[4 * k4 + 3], pl);
+          }
+          logit[a] = pl;
+          gl[a] = 0.f;
+        }
+        if (IS_PI) {
+          const float mx = fmaxf(logit[0], logit[OUT - 1]);
+          const float e0 = __expf(logit[0] - mx), e1 = __expf(logit[OUT - 1] - mx);
+          const float sum = e0 + e1, lse = __logf(sum), inv = __fdividef(1.f, sum);
+          const float p[2] = {e0 * inv, e1 * inv};
+          const float lp[2] = {(logit[0] - mx) - lse, (logit[OUT - 1] - mx) - lse};
+          const float ent = -(p[0] * lp[0] + p[1] * lp[1]);
+          float ga[2], sumg = 0.f, lrow = 0.f;
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            const float Ap = stA[a], Am = stA[IS_PI ? 2 + a : 0];
+            const float ratio = __expf(lp[a] - stA[IS_PI ? 4 + a : 0]);
+            lrow -= fminf(ratio, clip_hi) * Ap + fmaxf(ratio, clip_lo) * Am;
+            ga[a] = -((ratio <= clip_hi ? ratio * Ap : 0.f) + (ratio >= clip_lo ? ratio * Am : 0.f));
+            sumg += ga[a];
+          }
+          if (valid) {
+            loss_acc += lrow - beta_ent * wrow * ent;
+#pragma unroll
+            for (int a = 0; a < 2; ++a) gl[a < OUT ? a : 0] = invM * (ga[a] - p[a] * sumg + beta_ent * wrow * p[a] * (lp[a] + ent));
+          }
+        } else {
+          const float diff = logit[0] - stA[0];
+          if (valid) {
+            loss_acc = fmaf(wrow * diff, diff, loss_acc);
+            gl[0] = invM * 2.f * wrow * diff;
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < OUT; ++a) s_b3[a] += gl[a];
+      }
+      {
+        uint32_t hi[FW], lo[FW];
+#pragma unroll
+        for (int k4 = 0; k4 < FW / 4; ++k4) {
+          float up[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int a = 0; a < OUT; ++a) {
+            const float4 w3 = *reinterpret_cast<const float4*>(w + L.oW3 - HH + a * H + 4 * k4);
+            up[0] = fmaf(gl[a], w3.x, up[0]); up[1] = fmaf(gl[a], w3.y, up[1]);
+            up[2] = fmaf(gl[a], w3.z, up[2]); up[3] = fmaf(gl[a], w3.w, up[3]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = 4 * k4 + j;
+            const float x = a2[k], d2 = up[j] * fmaf(-x, x, 1.f);
+            s_b2[k] += d2;
+#pragma unroll
+            for (int a = 0; a < OUT; ++a) s_w3[a][k] = fmaf(gl[a], x, s_w3[a][k]);
+            u::split_u(d2, hi[k], lo[k]);
+          }
+        }
+        u::tmem_st16(tl + Q_D2H, hi);
+        u::tmem_st16(tl + Q_D2L, lo);
+        store_row(S_D2, hi, lo);
+        u::tmem_wait_st();
+      }
+      u::fence_async_smem();
+      u::tc_fence_before();
+      __syncthreads();
+      if (warp == 0) {
+        u::tc_fence_after();
+        if (u::elect_one()) {
+          {   // G2: d1' = d2 . W2 (the accumulator of G1: E2 has consumed z2)
+            constexpr uint32_t idesc = u::make_idesc(128, 16, 0, 0);
+            const uint32_t wh = lo_k16(sbase + S_WTH), wlo = lo_k16(sbase + S_WTL);
+#pragma unroll
+            for (int term = 0; term < 3; ++term)
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks)
+                u::umma_ts(tmem + Q_D, tmem + (term == 0 ? Q_D2L : Q_D2H) + 8 * ks, (term == 1 ? wlo : wh) + 16 * ks, DESC16_HI_K, idesc,
+                           (term | ks) != 0);
+            u::umma_commit(bar2);
+          }
+          {   // G3: [d2 hi | d2 lo | (a1 tile)]^T . [a1 hi | a1 lo] over the tile's 128 rows, accumulated across the pass
+            constexpr uint32_t idesc3 = u::make_idesc(64, 32, 1, 1);
+            const uint32_t da = lo_mn16(sbase + S_D2), db = lo_mn16(sbase + S_A1);
+#pragma unroll
+            for (int ks = 0; ks < 16; ++ks) u::umma_ss(tmem + Q_DW2, da + 64 * ks, db + 64 * ks, DESC16_HI_MN, idesc3, 1u);
+            u::umma_commit(bar3);
+          }
+        }
+        __syncwarp();
+      }
+
+      // ---- E3: d1 = d1' (1 - a1^2); column sums for db1 / dW1 ----
+      u::mbar_wait(bar2, gt & 1);
+      u::tc_fence_after();
+      {
+        uint32_t v[FW], om[FW];
+        u::tmem_ld16(tl + Q_D, v);
+        u::tmem_ld16(tl + Q_OM1, om);
+        u::tmem_wait_ld();
+        float d1[FW], d1l[FW];
+#pragma unroll
+        for (int k = 0; k < FW; ++k) {
+          d1[k] = __uint_as_float(v[k]) * __uint_as_float(om[k]);
+          d1l[k] = d1[k] * lam;
+        }
+        s_wlr += u::colsum16(d1l, lane);
+        // db1 / dW1[:, s]: the tile's column sums go straight to one register per state (lane l holds feature l / 2)
+        const int m_lo = min(t * TM16 + 32 * warp, M - 1), m_hi = min(t * TM16 + 32 * warp + 31, M - 1);
+        const int s_lo = (m_lo >= E) + (m_lo >= 2 * E), s_hi = (m_hi >= E) + (m_hi >= 2 * E);
+        if (s_lo == s_hi) {   // warp-uniform: all 32 rows are in one state
+          const float x = u::colsum16(d1, lane);
+#pragma unroll
+          for (int c = 0; c < S; ++c) s_w1r[c] += (c == s_lo) ? x : 0.f;
+        } else {              // the warp's rows straddle a state boundary: masked sums for this tile
+#pragma unroll
+          for (int c = 0; c < S; ++c) {
+            float msk[FW];
+#pragma unroll
+            for (int k = 0; k < FW; ++k) msk[k] = (srow == c) ? d1[k] : 0.f;
+            s_w1r[c] += u::colsum16(msk, lane);
+          }
+        }
+      }
+    }
+
+    // ---- end of the pass over the rows: per-warp row sums -> smem, dW2 blocks from TMEM -> smem ----
+    {
+      float vals[NQ];
+      vals[0] = u::colsum16(s_b2, lane);
+      vals[1] = s_wlr;
+#pragma unroll
+      for (int c = 0; c < S; ++c) vals[2 + c] = s_w1r[c];
+#pragma unroll
+      for (int a = 0; a < OUT; ++a) vals[2 + S + a] = u::colsum16(s_w3[a], lane);
+      if ((lane & 1) == 0)
+#pragma unroll
+        for (int v = 0; v < NQ; ++v) redw[(warp * NQ + v) * FW + (lane >> 1)] = vals[v];
+    }
+    float b3tot[OUT];
+#pragma unroll
+    for (int a = 0; a < OUT; ++a) b3tot[a] = warp_sum(s_b3[a]);
+    const float loss_tot = g.loss_out ? block_sum(loss_acc, red) : 0.f;
+    if (lane == 0)
+#pragma unroll
+      for (int a = 0; a < OUT; ++a) red[40 + warp * OUT + a] = b3tot[a];
+    u::mbar_wait(bar3, (gt - 1) & 1);   // every G3 of this pass has landed in TMEM
+    u::tc_fence_after();
+    if (warp < 2) {   // M = 64 accumulator: row m sits on lane (m % 16) + 32 (m / 16): warp 0 = d2 hi rows, warp 1 = d2 lo rows
+      uint32_t v0[FW], v1[FW];
+      u::tmem_ld16(tl + Q_DW2, v0);        // columns 0..15  = a1 hi
+      u::tmem_ld16(tl + Q_DW2 + 16, v1);   // columns 16..31 = a1 lo
+      u::tmem_wait_ld();
+      if (lane < 16) {
+        if (warp == 0) {
+#pragma unroll
+          for (int k = 0; k < FW; ++k) { scrA[lane * 32 + k] = __uint_as_float(v0[k]); scrA[lane * 32 + 16 + k] = __uint_as_float(v1[k]); }
+        } else {
+#pragma unroll
+          for (int k = 0; k < FW; ++k) scrB[lane * 16 + k] = __uint_as_float(v0[k]);
+        }
+      }
+    }
+    u::tc_fence_before();
+    __syncthreads();
+    for (int i = tid; i < H * NQ; i += NT16) {
+      const int k = i / NQ, v = i - k * NQ;
+      float x = redw[(0 * NQ + v) * FW + k];
+#pragma unroll
+      for (int qq = 1; qq < 4; ++qq) x += redw[(qq * NQ + v) * FW + k];   // fixed order over the four row quarters
+      if (v == 0) G[L.ob2 - HH + k] = x;
+      else if (v == 1) G[L.oW1 + k * IN + IN - 1] = x;
+      else if (v < 2 + S) G[L.oW1 + k * IN + (v - 2)] = x;
+      else G[L.oW3 - HH + (v - 2 - S) * H + k] = x;
+    }
+    if (tid < OUT) {
+      float x = 0.f;
+      for (int qq = 0; qq < 4; ++qq) x += red[40 + qq * OUT + tid];
+      G[L.ob3 - HH + tid] = x;
+    }
+    if (g.loss_out && tid == 0) {
+      float extra = 0.f;
+      if (!IS_PI && g.arm_stats) extra = g.arm_stats[4 * (int64_t)n + 2];
+      g.loss_out[(int64_t)n * iters + it] = (loss_tot + extra) * invM;
+    }
+    __syncthreads();
+    if (tid < H) {   // db1 = sum over states of dW1[:, s]
+      float x = 0.f;
+#pragma unroll
+      for (int c = 0; c < S; ++c) x += G[L.oW1 + tid * IN + c];
+      G[L.ob1 + tid] = x;
+    }
+
+    // ---- Adam; moments live in global memory (one read-modify-write per iteration) ----
+    b1p *= g.hp.beta1;
+    b2p *= g.hp.beta2;
+    if (tid == 0) {
+      red[62] = (float)(lr / (1.0 - b1p));
+      red[63] = (float)sqrt(1.0 - b2p);
+    }
+    __syncthreads();
+    const float step_size = red[62], bc2s = red[63];
+    auto adam = [&](float x, float gi, int i) {
+      const float m0 = An[i], v0 = An[P + i];
+      const float mi = m0 + lerp_w * (gi - m0);
+      const float vi = v0 * beta2f + (omb2 * gi) * gi;
+      An[i] = mi;
+      An[P + i] = vi;
+      const float denom = sqrtf(vi) / bc2s + epsf;
+      return x - step_size * (mi / denom);
+    };
+#pragma unroll
+    for (int k = 0; k < HH / NT16; ++k) {   // W2 block in the order of the K-major tile
+      const int p = tid + k * NT16;
+      const int j = ((p >> 7) << 3) | ((p >> 2) & 7), c = (((p >> 5) & 3) << 2) | (p & 3);
+      const float gi = (scrA[j * 32 + c] + scrA[j * 32 + 16 + c]) + scrB[j * 16 + c];   // hi.hi + hi.lo + lo.hi
+      const float xn = adam(W2H[p] + W2L[p], gi, L.oW2 + j * H + c);                    // hi + lo = exact fp32 weight
+      uint32_t hi, lo;
+      u::split_u(xn, hi, lo);
+      W2H[p] = __uint_as_float(hi); W2L[p] = __uint_as_float(lo);
+      WTH[kmaj16(c, j)] = __uint_as_float(hi); WTL[kmaj16(c, j)] = __uint_as_float(lo);
+    }
+    for (int k = tid; k < P - HH; k += NT16) {   // everything else, packed order without the W2 block
+      const int i = k < L.oW2 ? k : k + HH;
+      w[k] = adam(w[k], G[k], i);
+    }
+    u::fence_async_smem();   // the new W2 tiles are read by the tensor core in the next pass
+    __syncthreads();
+  }
+  for (int i = tid; i < P; i += NT16) {
+    if (i < L.oW2) Wn[i] = w[i];
+    else if (i >= L.ob2) Wn[i] = w[i - HH];
+    else {
+      const int j = (i - L.oW2) >> 4, c = (i - L.oW2) & 15;
+      Wn[i] = W2H[kmaj16(j, c)] + W2L[kmaj16(j, c)];
+    }
+  }
+  u::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;\n" ::"r"(tmem) : "memory");
+}
+
+static size_t umma16_smem_bytes(int S, int OUT, int E) {
+  const MlpLayout L(S + 1, H16, OUT);
+  const int NQ = 2 + S + OUT;
+  const size_t fl = 2 * (size_t)(L.padded() - HH16) + S * H16 + 2 * H16 + 4 * NQ * 16 + H16 * 32 + HH16 + (((size_t)E + 3) & ~(size_t)3);
+  return 1024 + S_END + fl * sizeof(float);
+}
+
+template <int S, bool IS_PI>
+static int launch_umma16(const U16Args& g0, cudaStream_t st) {
+  constexpr int OUT = IS_PI ? 2 : 1;
+  U16Args g = g0;
+  size_t smem = umma16_smem_bytes(S, OUT, g.d.n_envs);
+  g.stage_lamb = smem <= (size_t)(226 / CTAS16) * 1024;   // CTAS16 CTAs per SM
+  if (!g.stage_lamb) smem = umma16_smem_bytes(S, OUT, 0);
+  auto kern = ppo_table_umma16_kernel<S, IS_PI>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return fail(RMAB_E_LAUNCH, "rmab_ppo_update_table: cannot reserve %zu B of shared memory", smem);
+  kern<<<g.d.n_arms, NT16, smem, st>>>(g);
+  return check_launch(IS_PI ? "rmab_ppo_update_table(pi, tcgen05 h16)" : "rmab_ppo_update_table(v, tcgen05 h16)");
+}
+
+// Entry used by rmab_ppo_update_table (ppo_table.cu) for H = 16.
+int ppo_table_umma16_run(const RmabNetDesc* net, const RmabHyper* hp, int T, float* Wpi, float* Wv, float* adam_pi,
+                         float* adam_v, const float* stats, const float* arm_stats, const float* lamb, float* loss_pi,
+                         float* loss_v, cudaStream_t st) {
+  U16Args g = {};
+  g.d = *net; g.hp = *hp; g.T = T; g.lamb = lamb; g.stats = stats; g.arm_stats = arm_stats;
+  U16Args gp = g, gv = g;
+  gp.W = Wpi; gp.adam = adam_pi; gp.loss_out = loss_pi;
+  gv.W = Wv; gv.adam = adam_v; gv.loss_out = loss_v;
+  int rc = RMAB_OK;
+  if (net->n_states == 2) {
+    if (hp->pi_iters > 0) rc = launch_umma16<2, true>(gp, st);
+    if (rc == RMAB_OK && hp->v_iters > 0) rc = launch_umma16<2, false>(gv, st);
+  } else {
+    if (hp->pi_iters > 0) rc = launch_umma16<3, true>(gp, st);
+    if (rc == RMAB_OK && hp->v_iters > 0) rc = launch_umma16<3, false>(gv, st);
+  }
+  return rc;
+}
+
+}  // namespace rmab

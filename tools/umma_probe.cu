@@ -7,6 +7,11 @@
 //   mode 4: as mode 0 with A read from TMEM (written with tcgen05.st, lane = row, column = k)
 //   mode 5: as mode 2 with both tiles in the 128B/32B-atom swizzled MN-major layout (layout type 1), the only MN-major
 //           layout tf32 operands have: addr(r, f) = (f/32)*BLK + (r/4)*512 + (r%4)*128 + (((f%32)/8) ^ (r%4))*32 + (f%8)*4
+//   mode 6: hidden-16 weight-gradient pattern: 128 x 32 tiles (one 128-byte row per tile row, features 0..15 = hi, 16..31 = lo),
+//           X tile followed by the Y tile; A = X with M = 64 (its second 32-feature block, one LBO further, is the Y tile),
+//           B = Y with N = 32: D[m][n] = sum_r X[r][m] Y[r][n] (m < 32), sum_r Y[r][m-32] Y[r][n] (m >= 32) -- all four
+//           hi/lo cross products of d2^T a1 in one pass of 16 MMAs
+//   mode 7: hidden-16 forward pattern: A [128 x 16] from TMEM, B [16 x 16] K-major with 512-byte row groups, N = 16
 // Tiles live in shared memory as 8-row x 16-byte core matrices: addr(r, f) = (r/8)*LDG + (f/4)*128 + (r%8)*16 + (f%4)*4.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -o umma_probe tools/umma_probe.cu ; run on a B200.
 #include <cstdio>
@@ -87,14 +92,28 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const float* __restrict__
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int rowsB = (mode == 2 || mode == 5) ? 128 : 64;
-  for (int i = tid; i < 128 * 64; i += 128) {
+  if (mode == 6) {   // packed 32-wide swizzled tiles: X at tA, Y right behind it (16 KB each)
+    for (int i = tid; i < 128 * 32; i += 128) {
+      const int r = i >> 5, f = i & 31;
+      const int o = ((r >> 2) * 512 + (r & 3) * 128 + (((f >> 3) ^ (r & 3)) * 32) + (f & 7) * 4) >> 2;
+      tA[o] = gA[r * 64 + f];
+      tA[4096 + o] = gB[r * 64 + f];
+    }
+  }
+  if (mode == 7) {   // B [16 n][16 k] K-major, 8-row groups 512 B apart
+    for (int i = tid; i < 16 * 16; i += 128) {
+      const int r = i >> 4, f = i & 15;
+      tB[(r >> 3) * 128 + (f >> 2) * 32 + (r & 7) * 4 + (f & 3)] = gB[r * 64 + f];
+    }
+  }
+  for (int i = tid; i < 128 * 64 && mode < 6; i += 128) {
     const int r = i >> 6, f = i & 63;
     float hi, lo;
     if (mode == 3) split(gA[i], hi, lo); else { hi = gA[i]; lo = 0.f; }
     const int o = (mode == 5) ? tile_off_mn(r, f) : tile_off(r, f);
     tA[o] = hi; tAl[o] = lo;
   }
-  for (int i = tid; i < rowsB * 64; i += 128) {
+  for (int i = tid; i < rowsB * 64 && mode < 6; i += 128) {
     const int r = i >> 6, f = i & 63;
     float hi, lo;
     if (mode == 3) split(gB[i], hi, lo); else { hi = gB[i]; lo = 0.f; }
@@ -109,9 +128,9 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const float* __restrict__
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;\n" ::"r"(smem_u32(&tmem_base_s)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
-  if (mode == 4) {
+  if (mode == 4 || mode == 7) {
     __syncthreads();  // tmem_base_s
-    for (int c0 = 0; c0 < 64; c0 += 16) {
+    for (int c0 = 0; c0 < (mode == 7 ? 16 : 64); c0 += 16) {
       uint32_t v[16];
       for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(gA[tid * 64 + c0 + j]);
       const uint32_t taddr = tmem_base_s + ((uint32_t)(warp * 32) << 16) + 64 + c0;
@@ -155,6 +174,13 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const float* __restrict__
     } else if (mode == 4) {
       const uint32_t idesc = make_idesc(128, 64, 0, 0);
       for (int ks = 0; ks < 8; ++ks) umma_tf32_ts(tmem, tmem + 64 + ks * 8, make_desc(b0 + ks * 256, K_LBO, K_SBO), idesc, ks > 0);
+    } else if (mode == 6) {
+      const uint32_t idesc = make_idesc(64, 32, 1, 1);
+      for (int ks = 0; ks < 16; ++ks)
+        umma_tf32(tmem, make_desc(a0 + ks * 1024, 16384, 512, 1), make_desc(a0 + 16384 + ks * 1024, 16384, 512, 1), idesc, ks > 0);
+    } else if (mode == 7) {
+      const uint32_t idesc = make_idesc(128, 16, 0, 0);
+      for (int ks = 0; ks < 2; ++ks) umma_tf32_ts(tmem, tmem + 64 + ks * 8, make_desc(b0 + ks * 256, 128, 512), idesc, ks > 0);
     } else {
       const uint32_t idesc = make_idesc(64, 64, 1, 1);
       const uint32_t lbo = (variant & 1) ? 512 : BLK, sbo = (variant & 1) ? BLK : 512;   // expected: LBO = next 32 features, SBO = next 4 rows
@@ -195,7 +221,7 @@ int main() {
   float *dA, *dB, *dD; int* dS;
   CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dD, D.size() * 4)); CK(cudaMalloc(&dS, 4));
   int fails = 0;
-  for (int mode = 0; mode < 6; ++mode) {
+  for (int mode = 0; mode < 8; ++mode) {
     for (int variant = 0; variant < ((mode == 1 || mode == 2 || mode == 5) ? 2 : 1); ++variant) {
       srand(1234 + mode);
       for (auto& x : A) x = (mode == 3) ? (rand() / (float)RAND_MAX * 2.f - 1.f) : q(rand() / (float)RAND_MAX * 4.f - 2.f);
@@ -208,14 +234,17 @@ int main() {
       int st; CK(cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost));
       CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
       double maxerr = 0, maxref = 0;
-      const int M = (mode == 2 || mode == 5) ? 64 : 128;
+      const int M = (mode == 2 || mode == 5 || mode == 6) ? 64 : 128;
+      const int NN = mode == 6 ? 32 : (mode == 7 ? 16 : 64);
       for (int m = 0; m < M; ++m)
-        for (int n = 0; n < 64; ++n) {
+        for (int n = 0; n < NN; ++n) {
           double ref = 0;
+          if (mode == 6) for (int r = 0; r < 128; ++r) ref += (double)(m < 32 ? A[r * 64 + m] : B[r * 64 + m - 32]) * B[r * 64 + n];
+          if (mode == 7) for (int k = 0; k < 16; ++k) ref += (double)A[m * 64 + k] * B[n * 64 + k];
           if (mode == 0 || mode == 3 || mode == 4) for (int k = 0; k < 64; ++k) ref += (double)A[m * 64 + k] * B[n * 64 + k];
           else if (mode == 1) for (int k = 0; k < 64; ++k) ref += (double)A[m * 64 + k] * B[k * 64 + n];
-          else for (int r = 0; r < 128; ++r) ref += (double)A[r * 64 + m] * B[r * 64 + n];
-          const int lane = (mode == 2 || mode == 5) ? ((m & 15) + 32 * (m >> 4)) : m;   // M = 64: 16 rows per 32-lane quarter
+          else if (mode == 2 || mode == 5) for (int r = 0; r < 128; ++r) ref += (double)A[r * 64 + m] * B[r * 64 + n];
+          const int lane = (mode == 2 || mode == 5 || mode == 6) ? ((m & 15) + 32 * (m >> 4)) : m;   // M = 64: 16 rows per 32-lane quarter
           const double got = D[lane * 64 + n];
           maxerr = fmax(maxerr, fabs(got - ref)); maxref = fmax(maxref, fabs(ref));
         }
