@@ -380,7 +380,7 @@ def run_ours(a):
     try:   # DRAM bytes per launch from the committed ncu capture of this same command (profiles/), default workload only
         tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
         if (a.arms, a.envs, a.horizon, a.hidden, a.domain) == (4098, 256, 100, 16, "counterexample"):
-            traffic = {"ppo_update": tj["ppo_table_mma_kernel_pi"] + tj["ppo_table_mma_kernel_v"],
+            traffic = {"ppo_update": tj["ppo_table_umma16_kernel_pi"] + tj["ppo_table_umma16_kernel_v"],
                        "rollout_gae_stats": tj["epoch_table_kernel"]}.get(dom_name)
     except (OSError, KeyError, ValueError):
         pass
@@ -398,9 +398,9 @@ def run_ours(a):
            "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
-                        "note": "ppo_update = the two Adam-loop kernels (policy + value) of one epoch; the statistics "
-                                "reformulation (DESIGN.md 3.1) keeps the batch out of HBM, so both kernels are instruction-"
-                                "issue bound (ncu: issue active 56-61 %, DRAM < 1 %) and frac is small by construction",
+                        "note": "ppo_update = the two Adam-loop kernels (policy + value, tcgen05 hidden-16 kernel) of one epoch; the "
+                                "statistics reformulation (DESIGN.md 3.1) keeps the batch out of HBM, so both kernels are instruction-"
+                                "issue bound (ncu: issue active 54 %, tensor pipe 15-18 %, DRAM < 1 %) and frac is small by construction",
                         "stages": stage_roofs},
            "stage_ms_per_step": stage_ms, "clocks": clk}
     if dom_name == "ppo_update" and dom_ms:

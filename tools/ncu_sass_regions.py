@@ -1,5 +1,5 @@
 """Per-region view of an `ncu --page source --csv` export (SASS level): instructions per warp per unit and sample share.
-usage: python tools/ncu_sass_regions.py src.csv <units (e.g. warps x tiles)> [chunk]"""
+usage: python tools/ncu_sass_regions.py src.csv <units (e.g. warps x tiles)> [chunk] [kernel-name substring]"""
 import csv, collections, sys
 rows = list(csv.reader(open(sys.argv[1])))
 units = float(sys.argv[2]); chunk = int(sys.argv[3]) if len(sys.argv) > 3 else 50
@@ -9,7 +9,8 @@ for r in rows:
     if r[0] == "Kernel Name": blocks.append((r[1], [])); continue
     if r[0] == "Address": hdr = r; continue
     blocks[-1][1].append(r)
-k, rs = blocks[0]
+want = sys.argv[4] if len(sys.argv) > 4 else None
+k, rs = next(b for b in blocks if b[1] and (want is None or want in b[0]))
 iS = hdr.index("# Samples"); iI = hdr.index("Instructions Executed")
 stall_cols = [i for i, h in enumerate(hdr) if h.startswith('stall_') and 'Not Issued' not in h]
 tot = sum(int(r[iS]) for r in rs)
