@@ -28,6 +28,7 @@ constexpr int CTAS16 = 4;   // measured: 3 CTAs with the E3 row sums in register
 constexpr uint32_t S_D2 = 0, S_A1 = 16384, S_W2H = 32768, S_W2L = 33792, S_WTH = 34816, S_WTL = 35840, S_END = 36864;
 // TMEM columns (128 allocated per CTA)
 constexpr uint32_t Q_D = 0, Q_OM1 = 16, Q_A1H = 32, Q_A1L = 48, Q_D2H = 64, Q_D2L = 80, Q_DW2 = 96;
+constexpr int kAdamTab = 128;
 constexpr uint32_t DESC16_HI_K = (512u >> 4) | (1u << 14);                 // SBO = 512 (next 8 rows of a 16-column tile)
 constexpr uint32_t DESC16_HI_MN = (512u >> 4) | (1u << 14) | (1u << 29);   // SBO = 512 (next 4 rows), layout type 1
 
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args 
   __shared__ __align__(8) uint64_t bars[3];
   __shared__ uint32_t tmem_s;
   __shared__ float red[64];
+  __shared__ float2 adam_tab[kAdamTab];   // (lr / (1 - beta1^t), sqrt(1 - beta2^t)) of every Adam step of this launch
   unsigned char* base = smraw16 + ((1024u - (u::smem_u32(smraw16) & 1023u)) & 1023u);
   const uint32_t sbase = u::smem_u32(base);
   const int E = g.d.n_envs, T = g.T;
@@ -125,6 +127,9 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args 
   const float lerp_w = (float)(1.0 - g.hp.beta1), beta2f = (float)g.hp.beta2, omb2 = (float)(1.0 - g.hp.beta2);
   const float epsf = (float)g.hp.adam_eps;
   double b1p = pow(g.hp.beta1, (double)step0), b2p = pow(g.hp.beta2, (double)step0);
+  for (int k = tid; k < min(iters, kAdamTab); k += NT16)   // the double-precision bias corrections once, in parallel
+    adam_tab[k] = make_float2((float)(lr / (1.0 - pow(g.hp.beta1, (double)(step0 + k + 1)))),
+                              (float)sqrt(1.0 - pow(g.hp.beta2, (double)(step0 + k + 1))));
   uint32_t gt = 0;   // tiles issued so far: every barrier completes one phase per tile
 
   auto store_row = [&](uint32_t tile, const uint32_t (&hi)[FW], const uint32_t (&lo)[FW]) {
@@ -443,22 +448,21 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args 
       g.loss_out[(int64_t)n * iters + it] = (loss_tot + extra) * invM;
     }
     __syncthreads();
-    if (tid < H) {   // db1 = sum over states of dW1[:, s]
-      float x = 0.f;
-#pragma unroll
-      for (int c = 0; c < S; ++c) x += G[L.oW1 + tid * IN + c];
-      G[L.ob1 + tid] = x;
-    }
 
     // ---- Adam; moments live in global memory (one read-modify-write per iteration) ----
-    b1p *= g.hp.beta1;
-    b2p *= g.hp.beta2;
-    if (tid == 0) {
-      red[62] = (float)(lr / (1.0 - b1p));
-      red[63] = (float)sqrt(1.0 - b2p);
+    float step_size, bc2s;
+    if (it < kAdamTab) {
+      step_size = adam_tab[it].x; bc2s = adam_tab[it].y;
+    } else {   // beyond the table: one thread computes, everybody waits
+      b1p = pow(g.hp.beta1, (double)(step0 + it + 1));
+      b2p = pow(g.hp.beta2, (double)(step0 + it + 1));
+      if (tid == 0) {
+        red[62] = (float)(lr / (1.0 - b1p));
+        red[63] = (float)sqrt(1.0 - b2p);
+      }
+      __syncthreads();
+      step_size = red[62]; bc2s = red[63];
     }
-    __syncthreads();
-    const float step_size = red[62], bc2s = red[63];
     auto adam = [&](float x, float gi, int i) {
       const float m0 = An[i], v0 = An[P + i];
       const float mi = m0 + lerp_w * (gi - m0);
@@ -481,7 +485,13 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args 
     }
     for (int k = tid; k < P - HH; k += NT16) {   // everything else, packed order without the W2 block
       const int i = k < L.oW2 ? k : k + HH;
-      w[k] = adam(w[k], G[k], i);
+      float gi = G[k];
+      if (k >= L.ob1 && k < L.ob1 + H) {          // db1 = sum over states of dW1[:, s]
+        gi = 0.f;
+#pragma unroll
+        for (int c = 0; c < S; ++c) gi += G[L.oW1 + (k - L.ob1) * IN + c];
+      }
+      w[k] = adam(w[k], gi, i);
     }
     u::fence_async_smem();   // the new W2 tiles are read by the tensor core in the next pass
     __syncthreads();
