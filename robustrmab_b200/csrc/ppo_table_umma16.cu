@@ -64,8 +64,7 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args 
   const MlpLayout L(IN, H, OUT);
   const int P = L.P, Ps = L.padded() - HH;   // w / G hold the packed layout WITHOUT the W2 block
   float* w = reinterpret_cast<float*>(base + S_END);
-  float* G = w + Ps;
-  float* wb = G + Ps;                 // [S][H]  (W1[:, s] + b1) * kTanhScale
+  float* wb = w + Ps;                 // [S][H]  (W1[:, s] + b1) * kTanhScale
   float* wl = wb + S * H;             // [H]     W1[:, lambda] * kTanhScale
   float* b2s = wl + H;                // [H]     b2 * kTanhScale
   float* redw = b2s + H;              // [4 warps][NQ][16]
@@ -427,27 +426,11 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args 
     }
     u::tc_fence_before();
     __syncthreads();
-    for (int i = tid; i < H * NQ; i += NT16) {
-      const int k = i / NQ, v = i - k * NQ;
-      float x = redw[(0 * NQ + v) * FW + k];
-#pragma unroll
-      for (int qq = 1; qq < 4; ++qq) x += redw[(qq * NQ + v) * FW + k];   // fixed order over the four row quarters
-      if (v == 0) G[L.ob2 - HH + k] = x;
-      else if (v == 1) G[L.oW1 + k * IN + IN - 1] = x;
-      else if (v < 2 + S) G[L.oW1 + k * IN + (v - 2)] = x;
-      else G[L.oW3 - HH + (v - 2 - S) * H + k] = x;
-    }
-    if (tid < OUT) {
-      float x = 0.f;
-      for (int qq = 0; qq < 4; ++qq) x += red[40 + qq * OUT + tid];
-      G[L.ob3 - HH + tid] = x;
-    }
     if (g.loss_out && tid == 0) {
       float extra = 0.f;
       if (!IS_PI && g.arm_stats) extra = g.arm_stats[4 * (int64_t)n + 2];
       g.loss_out[(int64_t)n * iters + it] = (loss_tot + extra) * invM;
     }
-    __syncthreads();
 
     // ---- Adam; moments live in global memory (one read-modify-write per iteration) ----
     float step_size, bc2s;
@@ -483,13 +466,29 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args 
       W2H[p] = __uint_as_float(hi); W2L[p] = __uint_as_float(lo);
       WTH[kmaj16(c, j)] = __uint_as_float(hi); WTL[kmaj16(c, j)] = __uint_as_float(lo);
     }
-    for (int k = tid; k < P - HH; k += NT16) {   // everything else, packed order without the W2 block
+    // everything else, packed order without the W2 block: [W1 | b1 | b2 | W3 | b3]; its gradient is the sum over the four
+    // row quarters (fixed order) of the per-warp row sums
+    auto sum4 = [&](int f, int v) {
+      return ((redw[(0 * NQ + v) * FW + f] + redw[(1 * NQ + v) * FW + f]) + redw[(2 * NQ + v) * FW + f]) + redw[(3 * NQ + v) * FW + f];
+    };
+    for (int k = tid; k < P - HH; k += NT16) {
       const int i = k < L.oW2 ? k : k + HH;
-      float gi = G[k];
-      if (k >= L.ob1 && k < L.ob1 + H) {          // db1 = sum over states of dW1[:, s]
+      float gi;
+      if (k < L.ob1) {                       // W1[f][c]: c < S state columns, c == S the lambda column
+        const int f = k / IN, c = k - f * IN;
+        gi = sum4(f, c == IN - 1 ? 1 : 2 + c);
+      } else if (k < L.oW2) {                // b1 = sum over states of dW1[:, s]
         gi = 0.f;
 #pragma unroll
-        for (int c = 0; c < S; ++c) gi += G[L.oW1 + (k - L.ob1) * IN + c];
+        for (int c = 0; c < S; ++c) gi += sum4(k - L.ob1, 2 + c);
+      } else if (k < L.oW3 - HH) {           // b2
+        gi = sum4(k - (L.ob2 - HH), 0);
+      } else if (k < L.ob3 - HH) {           // W3[a][f]
+        const int a = (k - (L.oW3 - HH)) >> 4, f = (k - (L.oW3 - HH)) & 15;
+        gi = sum4(f, 2 + S + a);
+      } else {                               // b3[a]
+        const int a = k - (L.ob3 - HH);
+        gi = ((red[40 + a] + red[40 + OUT + a]) + red[40 + 2 * OUT + a]) + red[40 + 3 * OUT + a];
       }
       w[k] = adam(w[k], gi, i);
     }
@@ -512,7 +511,7 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args 
 static size_t umma16_smem_bytes(int S, int OUT, int E) {
   const MlpLayout L(S + 1, H16, OUT);
   const int NQ = 2 + S + OUT;
-  const size_t fl = 2 * (size_t)(L.padded() - HH16) + S * H16 + 2 * H16 + 4 * NQ * 16 + H16 * 32 + HH16 + (((size_t)E + 3) & ~(size_t)3);
+  const size_t fl = (size_t)(L.padded() - HH16) + S * H16 + 2 * H16 + 4 * NQ * 16 + H16 * 32 + HH16 + (((size_t)E + 3) & ~(size_t)3);
   return 1024 + S_END + fl * sizeof(float);
 }
 
