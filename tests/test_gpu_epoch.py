@@ -187,6 +187,41 @@ def test_trainer_matches_cpu_epoch_loop(K, domain, h):
     np.testing.assert_allclose(K.n(tr.lam_params), lam_cpu, rtol=1e-3, atol=1e-5)
 
 
+def test_learned_policy_returns_statistically_indistinguishable(K):
+    """north_star's third parity criterion: after training, the device trainer's returns are statistically
+    indistinguishable from the CPU restatement's.  Three seeds x 24 epochs each; mean per-env return over the last six
+    epochs compared with the spread over envs and epochs (the two runs share the Philox convention but drift apart
+    after the first updates, so this is a comparison of learned policies, not of identical trajectories)."""
+    from robustrmab_b200.trainer import RMABPPOTrainer
+    N, E, T, h, epochs = 12, 32, 20, 16, 24
+    diffs, ses, gains = [], [], []
+    for seed in (1, 2, 3):
+        kw = dict(gamma=0.9, lam_other=0.97, clip_ratio=2.0, pi_lr=2e-3, vf_lr=2e-3, lm_lr=2e-3, train_pi_iters=10,
+                  train_v_iters=10, epochs=epochs, lamb_update_freq=4, final_train_lambdas=2, start_entropy_coeff=0.5,
+                  end_entropy_coeff=0.0, seed=seed)
+        tr = RMABPPOTrainer(0, N, E, T, hidden=h, B=N // 3, device=K.dev, **kw)
+        lam_flat = K.n(tr.lam_params)
+        lam = [lam_flat[:8 * N].reshape(8, N), lam_flat[8 * N:8 * N + 8], lam_flat[8 * N + 8:8 * N + 72].reshape(8, 8),
+               lam_flat[8 * N + 72:8 * N + 80], lam_flat[8 * N + 80:8 * N + 88].reshape(1, 8), lam_flat[8 * N + 88:]]
+        cpu = CpuRMABPPO(0, K.n(tr.Wpi), K.n(tr.Wv), lam, K.n(tr.nature), K.n(tr.ranges), K.n(tr.R), K.n(tr.C), E, T, h,
+                         N // 3, **kw)
+        rg, rc = [], []
+        for ep in range(epochs):
+            rg.append(K.n(tr.epoch()["EpActualRet"]))
+            rc.append(cpu.epoch()["rew_sum"])
+        rg, rc = np.array(rg), np.array(rc)                      # [epochs, E]
+        tail_g, tail_c = rg[-6:], rc[-6:]
+        diffs.append(tail_g.mean() - tail_c.mean())
+        ses.append(np.sqrt(tail_g.var() / tail_g.size + tail_c.var() / tail_c.size))
+        gains.append((tail_g.mean() - rg[:3].mean(), tail_c.mean() - rc[:3].mean()))
+    diffs, ses = np.array(diffs), np.array(ses)
+    assert (np.abs(diffs) < 3.0 * ses).all(), (diffs, ses)      # every seed within three standard errors
+    assert abs(diffs.mean()) < 3.0 * np.sqrt((ses ** 2).sum()) / len(ses), (diffs, ses)
+    # and both actually learned the same amount (return change from the first to the last epochs)
+    for gg, gc in gains:
+        assert abs(gg - gc) < 3.0 * ses.max() * np.sqrt(2), gains
+
+
 @pytest.mark.parametrize("name,domain", [("ce", 0), ("armman", 1)])
 def test_trainer_matches_reference_best_response(K, golden, name, domain):
     """Device trainer (E = 1) against the values logged by the UNMODIFIED reference AgentOracle.best_response run
