@@ -5,6 +5,16 @@
 
 namespace rmab {
 
+// tanh(x) = 1 - 2 / (2^(2 log2(e) x) + 1): FMUL, MUFU.EX2, FADD, MUFU.RCP, FFMA.  Absolute error < 2e-7 (the level of fp32
+// rounding of the pre-activation itself); saturates correctly (ex2 -> inf gives 1, ex2 -> 0 gives -1).  The same formula as
+// in the update kernels, so rollout and update evaluate the nets identically.
+__device__ __forceinline__ float tanh_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+  return fmaf(-2.f, r, 1.f);
+}
+
 constexpr int kMaxA = 4;   // actor outputs supported (reference domains: 2 or 3)
 constexpr int kMaxIn = 8;  // input features supported by the thread-per-sample kernels
 
@@ -59,7 +69,7 @@ __device__ __forceinline__ void mlp_layer1(const float* __restrict__ w, const Sm
       const float* row = w + L.oW1 + j * in;
       float z = fmaf(row[in - 1], lam, row[s]) + w[L.ob1 + j];
       if (add) z += add[j * add_stride];
-      a1[j] = tanhf(z);
+      a1[j] = tanh_fast(z);
     }
   } else {
     const float x0 = __fdiv_rn((float)s, state_norm);
@@ -68,7 +78,7 @@ __device__ __forceinline__ void mlp_layer1(const float* __restrict__ w, const Sm
       const float* row = w + L.oW1 + j * in;
       float z = fmaf(row[1], lam, fmaf(row[0], x0, w[L.ob1 + j]));
       if (add) z += add[j * add_stride];
-      a1[j] = tanhf(z);
+      a1[j] = tanh_fast(z);
     }
   }
 }
@@ -92,7 +102,7 @@ __device__ __forceinline__ void mlp_tail(const float* __restrict__ w, const Smem
       z = fmaf(q.z, a1[4 * k4 + 2], z);
       z = fmaf(q.w, a1[4 * k4 + 3], z);
     }
-    const float a2 = tanhf(z);
+    const float a2 = tanh_fast(z);
 #pragma unroll
     for (int o = 0; o < kMaxA; ++o)
       if (o < n_out) acc[o] = fmaf(w[L.oW3 + o * H + j], a2, acc[o]);

@@ -33,13 +33,7 @@ struct TblCfg {
   static constexpr int NB2 = H / NJB;             // db2 features accumulated per thread (j = jb + NJB * i)
 };
 
-__device__ __forceinline__ float tanh_fast(float x) {
-  // 1 - 2 / (exp(2x) + 1) with two MUFU ops; absolute error < 2e-7 (what propagates through the next layer)
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
-  return fmaf(-2.f, r, 1.f);
-}
+// tanh_fast: mlp.cuh
 
 struct TblArgs {
   RmabNetDesc d;
