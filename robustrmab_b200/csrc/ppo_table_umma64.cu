@@ -48,6 +48,7 @@ struct UmmaArgs {
 // MODE 1: one row per sample (t, env) of the [N,T,E] buffers, scalar state input s / state_norm (the SIS domain).
 // MODE 2: MODE 1 for the MA agent critics: the caller's dense-GEMM term is added to the first layer, dLoss/dz1 is written.
 constexpr int kRowsTable = 0, kRowsSample = 1, kRowsSampleExtra = 2;
+constexpr int kAdamTab64 = 128;
 
 }  // namespace
 
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
   __shared__ __align__(8) uint64_t bars[3];
   __shared__ uint32_t tmem_s;
   __shared__ float red[64];
+  __shared__ float2 adam_tab[kAdamTab64];   // (lr / (1 - beta1^t), sqrt(1 - beta2^t)) of every Adam step of this launch
   unsigned char* base = smraw + ((1024u - (smem_u32(smraw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(base);
   const int E = g.d.n_envs, T = g.T;
@@ -138,6 +140,9 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
   const float lerp_w = (float)(1.0 - g.hp.beta1), beta2f = (float)g.hp.beta2, omb2 = (float)(1.0 - g.hp.beta2);
   const float epsf = (float)g.hp.adam_eps;
   double b1p = pow(g.hp.beta1, (double)step0), b2p = pow(g.hp.beta2, (double)step0);
+  for (int k = tid; k < min(iters, kAdamTab64); k += NTHR)   // the double-precision bias corrections once, in parallel
+    adam_tab[k] = make_float2((float)(lr / (1.0 - pow(g.hp.beta1, (double)(step0 + k + 1)))),
+                              (float)sqrt(1.0 - pow(g.hp.beta2, (double)(step0 + k + 1))));
   uint32_t gt = 0;   // tiles issued so far: every barrier completes one phase per tile
 
   for (int it = 0; it < iters; ++it) {
@@ -570,23 +575,21 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
       g.loss_out[(int64_t)n * iters + it] = (loss_tot + extra) * invM;
     }
     __syncthreads();
-    if (TABLE)
-      for (int k = tid; k < H; k += NTHR) {   // db1 = sum over states of dW1[:, s]
-        float x = 0.f;
-#pragma unroll
-        for (int c = 0; c < S; ++c) x += G[L.oW1 + k * IN + c];
-        G[L.ob1 + k] = x;
-      }
 
     // ---- Adam; moments live in global memory (one read-modify-write per iteration) ----
-    b1p *= g.hp.beta1;
-    b2p *= g.hp.beta2;
-    if (tid == 0) {
-      red[62] = (float)(lr / (1.0 - b1p));
-      red[63] = (float)sqrt(1.0 - b2p);
+    float step_size, bc2s;
+    if (it < kAdamTab64) {
+      step_size = adam_tab[it].x; bc2s = adam_tab[it].y;
+    } else {   // beyond the table: one thread computes, everybody waits
+      b1p = pow(g.hp.beta1, (double)(step0 + it + 1));
+      b2p = pow(g.hp.beta2, (double)(step0 + it + 1));
+      if (tid == 0) {
+        red[62] = (float)(lr / (1.0 - b1p));
+        red[63] = (float)sqrt(1.0 - b2p);
+      }
+      __syncthreads();
+      step_size = red[62]; bc2s = red[63];
     }
-    __syncthreads();
-    const float step_size = red[62], bc2s = red[63];
     auto adam = [&](float x, float gi, float m0, float v0, int i) {
       const float mi = m0 + lerp_w * (gi - m0);
       const float vi = v0 * beta2f + (omb2 * gi) * gi;
@@ -619,7 +622,13 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
     }
     for (int k = tid; k < P - HH; k += NTHR) {   // everything else, packed order without the W2 block
       const int i = k < L.oW2 ? k : k + HH;
-      w[k] = adam(w[k], G[k], An[i], An[P + i], i);
+      float gi = G[k];
+      if (TABLE && k >= L.ob1 && k < L.oW2) {      // db1 = sum over states of dW1[:, s]
+        gi = 0.f;
+#pragma unroll
+        for (int c = 0; c < S; ++c) gi += G[L.oW1 + (k - L.ob1) * IN + c];
+      }
+      w[k] = adam(w[k], gi, An[i], An[P + i], i);
     }
     fence_async_smem();   // the new W2 tiles are read by the tensor core in the next pass
     __syncthreads();
