@@ -248,6 +248,11 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
         if (elect_one()) issue_g1();
         __syncwarp();
       }
+      const bool last_tile = tt + 1 == n_tiles;
+      if (last_tile && (warp == 2 || warp == 3)) {   // no G1 follows the last tile: its G3 runs under E3 and the reductions
+        if (elect_one()) issue_g3_half(warp == 2 ? 0 : 8);
+        __syncwarp();
+      }
       uint32_t v[FW], om[FW];
       tmem_ld16(tl + C_D1P + f0, v);
       tmem_ld16(tl + C_OM1 + f0, om);   // 1 - a1^2, parked in TMEM by E2 of the same tile
@@ -287,7 +292,7 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
         for (int k = 0; k < FW; ++k) d1l[k] = d1[k] * rw.x0;
         s_w1r[0] += colsum16(d1l, lane);                      // dW1[:, 0]
       }
-      if (warp == 2 || warp == 3) {   // G3(tt) behind G1(tt + 1): never waited for before the next tile's d2 is ready
+      if (!last_tile && (warp == 2 || warp == 3)) {   // G3(tt) behind G1(tt + 1): never waited for before the next tile's d2 is ready
         if (elect_one()) issue_g3_half(warp == 2 ? 0 : 8);
         __syncwarp();
       }
