@@ -280,10 +280,44 @@ def gen_vi():
     np.savez_compressed(os.path.join(OUT, "vi.npz"), **out)
 
 
+def gen_baselines():
+    """Nature baseline policies (robust_rmab/baselines/nature_baselines_*.py): their answers at every constant state
+    vector and at a mixed one, for ranges of each domain's shape -- what baselines.nature_param_table must reproduce."""
+    from robust_rmab.baselines import nature_baselines_armman as nb_a
+    from robust_rmab.baselines import nature_baselines_counterexample as nb_c
+    from robust_rmab.baselines import nature_baselines_sis as nb_s
+    rs = np.random.RandomState(31)
+    out = {}
+    N, S, A = 7, 3, 2
+    shapes = dict(ce=(N, 2), armman=(N, S, A, 2), sis=(N, 4, 2))
+    mods = dict(ce=nb_c, armman=nb_a, sis=nb_s)
+    for dom, shp in shapes.items():
+        ranges = np.sort(rs.rand(*shp), axis=-1)
+        out[f"{dom}_ranges"] = ranges
+        pert = rs.rand(*shp[:-1])
+        out[f"{dom}_pert"] = pert
+        m = mods[dom]
+        pols = dict(pess=m.PessimisticNaturePolicy(ranges, 0), opt=m.OptimisticNaturePolicy(ranges, 1),
+                    mid=m.MiddleNaturePolicy(ranges, 2), midp=m.MiddleNaturePolicy(ranges, 3, perturbations=pert,
+                                                                                   perturbation_size=0.2),
+                    samp=m.SampledRandomNaturePolicy(ranges, 4))
+        pols["samp"].sample_param_setting(5)
+        n_s = S if dom == "armman" else 2
+        mixed = np.arange(N) % n_s
+        for k, pol in pols.items():
+            with ref_shims.quiet():
+                rows = np.stack([np.asarray(pol.get_nature_action(np.full(N, s_, dtype=int)), dtype=np.float64)
+                                 for s_ in range(n_s)])
+                out[f"{dom}_{k}_const"] = rows
+                out[f"{dom}_{k}_mixed"] = np.asarray(pol.get_nature_action(mixed), dtype=np.float64)
+            out[f"{dom}_{k}_repr"] = np.array(repr(pol))
+    np.savez_compressed(os.path.join(OUT, "baselines.npz"), **out)
+
+
 def main(which=None):
     ref_shims.import_reference()
     os.makedirs(OUT, exist_ok=True)
-    gens = dict(env=gen_env, ac=gen_ac, buffer=gen_buffer, select=gen_select, vi=gen_vi)
+    gens = dict(env=gen_env, ac=gen_ac, buffer=gen_buffer, select=gen_select, vi=gen_vi, baselines=gen_baselines)
     try:
         from .gen_golden_train import gen_train, gen_ma, gen_ma_train
         gens.update(train=gen_train, ma=gen_ma, ma_train=gen_ma_train)

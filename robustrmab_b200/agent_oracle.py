@@ -17,12 +17,33 @@ import numpy as np
 import torch
 
 from . import _lib, ops
+from .baselines import nature_param_table
 from .core import MLPActorCriticRMAB
 from .environments import ARMMANRobustEnv, CounterExampleRobustEnv, SISRobustEnv
 from .evaluate import simulate_reward as _simulate_reward
 from .trainer import RMABPPOTrainer
 
 _F32 = torch.float32
+
+
+def lambda_pretrain(lam_params, s0, n_total, arm0, B, gamma, lr, n, allreduce=None):
+    """`init_lambda_trains` SGD steps (agent_oracle.py:465-477, nature_oracle.py:605-617) on
+    loss = lambda_net(o) * (B/(1-gamma) - 2B/(1-gamma)), o = the first observation, unnormalised."""
+    E = s0.shape[1]
+    coef = torch.full((E,), -float(B) / (1.0 - float(gamma)), dtype=_F32, device=s0.device)
+    for _ in range(int(n)):
+        _, h1 = ops.lambda_forward(lam_params, s0, n_total, arm0, 1.0, want_h1=True, want_lamb=False)
+        if allreduce is not None:
+            allreduce(h1)
+        ops.lambda_sgd(lam_params, s0, n_total, arm0, 1.0, h1, coef, lr)
+
+
+def check_episode_length(max_ep_len, steps_per_epoch):
+    """The reference cuts a path (finish_path + env.reset) whenever ep_len == max_ep_len (:541-568).  The device loops run
+    one path per epoch, which is what every shipped config does (max_ep_len defaults to 1000 > steps_per_epoch)."""
+    if int(max_ep_len) < int(steps_per_epoch):
+        raise NotImplementedError(f"max_ep_len={max_ep_len} < steps_per_epoch={steps_per_epoch}: mid-epoch path cuts are "
+                                  "not implemented on the device loops")
 
 
 class StepwiseRMABPPO:
@@ -53,6 +74,11 @@ class StepwiseRMABPPO:
         env.seed(seed)
         self.s = env.reset_device()
 
+    def init_lambda_trains(self, n):
+        """agent_oracle.py:465-477: n SGD steps on return_large_lambda_loss = lambda(o) (B/(1-gamma) - 2B/(1-gamma)) at the
+        first observation (raw, rmabppo_core.py:188-195)."""
+        lambda_pretrain(self.lam_params, self.s.contiguous(), self.N, 0, float(self.ac.B), self.gamma, self.lm_lr, n)
+
     def _entropy(self, ep):
         head = float(np.linspace(self.ent0, self.ent1, self.epochs)[min(ep, self.epochs - 1)])
         if (self.epochs - ep) > self.final:
@@ -63,13 +89,19 @@ class StepwiseRMABPPO:
         if hasattr(nature_pol, "get_nature_action_device"):
             raw = nature_pol.get_nature_action_device(s)                       # [E,D] raw, bounded by the policy's env
             return nature_pol.bound_nature_device(raw, s), True
-        return torch.as_tensor(np.asarray(nature_pol.param_setting, dtype=np.float32), device=self.dev), False
+        tab = nature_param_table(nature_pol, self.env)
+        if tab is None:
+            raise NotImplementedError(f"{nature_pol!r}: neither a device policy (get_nature_action_device) nor a "
+                                      "deterministic per-arm parameter table")
+        return torch.as_tensor(tab, device=self.dev), False
 
     def epoch(self, nature_pol):
         env, ac, T, N, E = self.env, self.ac, self.T, self.N, self.E
         ep = self.epoch_idx
         s0 = self.s.contiguous()
-        lamb, h1 = ops.lambda_forward(self.lam_params, s0, N, 0, self.obs_scale, want_h1=True)
+        # the rollout's lambda is predicted from the RAW observation (agent_oracle.py:497), while compute_loss_lambda
+        # (:360-376) and get_lambda (rmabppo_core.py:281-287) divide by state_norm first -- kept as the reference has it
+        lamb, h1 = ops.lambda_forward(self.lam_params, s0, N, 0, 1.0, want_h1=True)
         self.s_traj[:, 0] = s0
         ret = torch.zeros((E,), dtype=_F32, device=self.dev)
         for t in range(T):
@@ -97,6 +129,8 @@ class StepwiseRMABPPO:
         if ep % self.freq == 0 and ep > 0 and (self.epochs - ep) > self.final:
             cd = ops.cost_togo(self.a, self.C, self.gamma)
             coef = (float(ac.B) / (1.0 - self.gamma) - cd[0]).contiguous()
+            if self.obs_scale != 1.0:
+                _, h1 = ops.lambda_forward(self.lam_params, s0, N, 0, self.obs_scale, want_h1=True, want_lamb=False)
             ops.lambda_sgd(self.lam_params, s0, N, 0, self.obs_scale, h1, coef, self.lm_lr)
         self.epoch_idx += 1
         self.s = env.reset_device()
@@ -151,6 +185,7 @@ class AgentOracle:
                               target_kl=0.01, logger_kwargs=dict(), save_freq=10, lamb_update_freq=10,
                               init_lambda_trains=0, final_train_lambdas=0):
         env = self.env
+        check_episode_length(max_ep_len, steps_per_epoch)
         hidden = list(ac_kwargs.get("hidden_sizes", (64, 64)))
         ac = MLPActorCriticRMAB(env.observation_space, env.action_space, hidden_sizes=hidden, N=env.N, C=env.C, B=env.B,
                                 strat_ind=self.strat_ind, one_hot_encode=self.one_hot_encode,
@@ -160,7 +195,8 @@ class AgentOracle:
         nature_eq[nature_eq < 0] = 0
         nature_eq = nature_eq / nature_eq.sum()
         nature_pol = np.random.choice(nature_strats, p=nature_eq)                      # :489
-        fused = self.data in ("counterexample", "armman") and all(hasattr(p, "param_setting") for p in nature_strats) \
+        tables = {id(p): nature_param_table(p, env) for p in nature_strats}
+        fused = self.data in ("counterexample", "armman") and all(t is not None for t in tables.values()) \
             and self.one_hot_encode
         hist = []
         if fused:
@@ -169,15 +205,16 @@ class AgentOracle:
                                 train_pi_iters=train_pi_iters, train_v_iters=train_v_iters, epochs=epochs,
                                 lamb_update_freq=lamb_update_freq, final_train_lambdas=final_train_lambdas,
                                 start_entropy_coeff=start_entropy_coeff, end_entropy_coeff=end_entropy_coeff, seed=seed,
-                                ranges=np.asarray(env.sampled_parameter_ranges), nature=np.asarray(nature_pol.param_setting),
+                                ranges=np.asarray(env.sampled_parameter_ranges), nature=tables[id(nature_pol)],
                                 device=self.device)
             tr.Wpi.copy_(ac.Wpi)                                # the nets the reference would have built (torch RNG)
             tr.Wv.copy_(ac.Wv)
             tr.lam_params.copy_(ac.lambda_net.packed().to(tr.dev))
+            lambda_pretrain(tr.lam_params, tr._s0(), tr.N_total, tr.arm0, tr.B, gamma, lm_lr, init_lambda_trains)
             for epoch in range(epochs):
                 if epoch % lamb_update_freq == 0 and epoch > 0:                         # :501-503
                     nature_pol = np.random.choice(nature_strats, p=nature_eq)
-                    tr.nature.copy_(torch.as_tensor(np.asarray(nature_pol.param_setting, dtype=np.float32)))
+                    tr.nature.copy_(torch.as_tensor(tables[id(nature_pol)]))
                 hist.append({k: v.detach().cpu().numpy() for k, v in tr.epoch().items()})
             ac.Wpi.copy_(tr.Wpi)
             ac.Wv.copy_(tr.Wv)
@@ -190,6 +227,7 @@ class AgentOracle:
             sw = StepwiseRMABPPO(env, ac, steps_per_epoch, gamma, lam_OTHER, clip_ratio, pi_lr, vf_lr, lm_lr, train_pi_iters,
                                  train_v_iters, epochs, lamb_update_freq, final_train_lambdas, start_entropy_coeff,
                                  end_entropy_coeff, seed)
+            sw.init_lambda_trains(init_lambda_trains)
             for epoch in range(epochs):
                 if epoch % lamb_update_freq == 0 and epoch > 0:
                     nature_pol = np.random.choice(nature_strats, p=nature_eq)
@@ -202,14 +240,14 @@ class AgentOracle:
         """agent_oracle.py:599-652 with the `epochs` rollouts as env replicas of one batched rollout."""
         env = self.env_fn(n_envs=epochs)
         env.sampled_parameter_ranges = self.sampled_nature_parameter_ranges
-        if hasattr(nature_pol, "param_setting"):
-            nature = torch.as_tensor(np.asarray(nature_pol.param_setting, dtype=np.float32), device=env.device)
+        tab = nature_param_table(nature_pol, env)
+        if tab is not None:
+            nature = torch.as_tensor(tab, device=env.device)
         else:
             def nature(s, pol=nature_pol):
                 nb = pol.bound_nature_device(pol.get_nature_action_device(s), s)          # [E,D]
                 N, E = s.shape
                 return nb.t().reshape((N, -1, E)).contiguous() if nb.shape[1] != N else nb.t().contiguous()
-        if hasattr(agent_pol, "n_envs"):
-            agent_pol.n_envs = epochs
+        # the caller's strategy object is left untouched: act_test_device takes E from the state tensor
         return _simulate_reward(agent_pol, env, nature, steps_per_epoch=steps_per_epoch, epochs=epochs, gamma=gamma,
                                 seed=seed)

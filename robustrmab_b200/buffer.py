@@ -57,8 +57,10 @@ class RMABPPO_Buffer:
 
     def finish_path(self, last_vals=0, last_costs=0):
         """GAE-lambda advantages, rewards-to-go, q and the arm-summed discounted cost-to-go of the path
-        [path_start_idx, ptr) (agent_oracle.py:90-139).  lambda is constant over a path in the reference
-        (:497: one prediction per epoch), so the per-env lambda of the path's first step is used."""
+        [path_start_idx, ptr) (agent_oracle.py:90-139).  The reference charges each step its own stored lambda
+        (:115-120).  Its training loop predicts lambda once per epoch (:497), so a path normally has one lambda per
+        env and the kernel applies it; a caller that stored per-step lambdas gets them folded into the reward
+        (r_t - lambda_t c_t in fp32, as numpy does there) before the same scan."""
         a, b = self.path_start_idx, self.ptr
         if b == a:
             return
@@ -68,7 +70,11 @@ class RMABPPO_Buffer:
             lv = self._row(last_vals).contiguous()
         sl = lambda t: t[:, a:b].contiguous()
         lamb = self.lamb_buf[a].contiguous()
-        adv, ret, q, _ = ops.gae_explicit(sl(self.rew_buf), sl(self.cost_buf), sl(self.val_buf), lv, lamb, self.gamma,
+        rew, cost = sl(self.rew_buf), sl(self.cost_buf)
+        if b - a > 1 and not bool((self.lamb_buf[a:b] == self.lamb_buf[a]).all()):
+            rew = (rew - self.lamb_buf[a:b][None] * cost).contiguous()      # per-step lambdas (:115-120)
+            cost, lamb = torch.zeros_like(cost), torch.zeros_like(lamb)
+        adv, ret, q, _ = ops.gae_explicit(rew, cost, sl(self.val_buf), lv, lamb, self.gamma,
                                           self.lam_OTHER, normalize=False, want_q=True)
         self.adv_buf[:, a:b], self.ret_buf[:, a:b], self.q_buf[:, a:b] = adv, ret, q
         # cost-to-go of the arm-summed cost (:117, :139); costs are C[a] with small integer action indices

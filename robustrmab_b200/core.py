@@ -242,7 +242,18 @@ class MLPActorCriticRMAB(nn.Module):
         return (a[:, 0] if E == 1 else a).cpu().numpy().astype(int)
 
     def act_test_deterministic(self, obs):
-        return self.act_test(obs)
+        """rmabppo_core.py:289-334 (binary actions only): action 1 for the top floor(B / C[1]) arms by p(a = 1), with NO
+        positivity filter -- unlike the multi-action sweep behind `act_test`, an arm with p1 == 0 is still selected when
+        fewer than k arms have p1 > 0."""
+        if self.act_dim != 2:
+            raise NotImplementedError("act_test_deterministic is only implemented for binary actions (rmabppo_core.py:288)")
+        E = self.n_envs
+        s = self._obs_dev(np.asarray(obs).reshape(-1) if E == 1 else obs, E)
+        lamb = self.get_lambda_device(s)
+        _, _, _, p1, _ = self.step_device(s, lamb)
+        self._steps -= 1
+        a = ops.budget_select_binary(p1, float(self.C[1]), float(self.B), positive_only=False)
+        return (a[:, 0] if E == 1 else a).cpu().numpy().astype(int)
 
     def act_test_deterministic_multiaction(self, obs):
         return self.act_test(obs)

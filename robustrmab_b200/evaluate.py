@@ -36,17 +36,4 @@ def simulate_reward(agent_pol, env, nature, steps_per_epoch=100, epochs=100, gam
     return float(ret.mean().item())
 
 
-class PessimisticAgentPolicy:
-    """baselines/agent_baselines.py: never acts."""
-
-    def __init__(self, N, ind=0):
-        self.N, self.ind, self.name = N, ind, "PessimisticAgentPolicy"
-
-    def __repr__(self):
-        return "%s_%i" % (self.name, self.ind)
-
-    def act_test(self, obs):
-        return np.zeros(self.N, dtype=int)
-
-    def act_test_device(self, s):
-        return torch.zeros_like(s)
+from .baselines import PessimisticAgentPolicy  # noqa: E402,F401  (kept importable from here)

@@ -136,13 +136,21 @@ class MARolloutTrainer:
         torch.distributed.all_gather_into_tensor(out, pad, group=self.pg)
         return out[:self.N_total]
 
-    def _lambda(self, s0):
+    def _lambda(self, s0, scale=1.0):
+        """lambda [E] and the (all-reduced) first-layer sums.  The rollout predicts lambda from the RAW observation
+        (nature_oracle.py:664); compute_loss_lambda (:447-459) divides by state_norm first -- `scale` says which."""
         if self.world == 1:
-            return ops.lambda_forward(self.lam_params, s0, self.N_total, 0, self.obs_scale, want_h1=True)
-        _, h1 = ops.lambda_forward(self.lam_params, s0, self.N_total, self.arm0, self.obs_scale, want_h1=True, want_lamb=False)
+            return ops.lambda_forward(self.lam_params, s0, self.N_total, 0, scale, want_h1=True)
+        _, h1 = ops.lambda_forward(self.lam_params, s0, self.N_total, self.arm0, scale, want_h1=True, want_lamb=False)
         self._allreduce(h1)
-        lamb, _ = ops.lambda_forward(self.lam_params, s0, self.N_total, self.arm0, self.obs_scale, h1_in=h1)
+        lamb, _ = ops.lambda_forward(self.lam_params, s0, self.N_total, self.arm0, scale, h1_in=h1)
         return lamb, h1
+
+    def init_lambda_trains(self, n):
+        """nature_oracle.py:605-617."""
+        from .agent_oracle import lambda_pretrain
+        lambda_pretrain(self.lam_params, self.s.contiguous(), self.N_total, self.arm0, float(self.ac.B), self.gamma,
+                        self.lm_lr, n, allreduce=self._allreduce if self.world > 1 else None)
 
     # ---------------------------------------------------------------------------------------------
     def rollout(self, agent_pol):
@@ -250,6 +258,8 @@ class MARolloutTrainer:
                 cd0 = ops.cost_togo(a, self.C, self.gamma)[0].contiguous()
                 self._allreduce(cd0)
                 coef = (float(ac.B) / (1.0 - self.gamma) - cd0).contiguous()
+                if self.obs_scale != 1.0:
+                    _, h1 = self._lambda(s0, self.obs_scale)
                 ops.lambda_sgd(self.lam_params, s0, self.N_total, self.arm0, self.obs_scale, h1, coef, self.lm_lr)
             s_all = self.s_full_traj if sharded else self.s_traj
             a_all = self.a_full if sharded else a
@@ -342,6 +352,8 @@ class NatureOracle:
                               start_entropy_coeff=0.0, end_entropy_coeff=0.0, target_kl=0.01, logger_kwargs=dict(),
                               save_freq=10, lamb_update_freq=10, init_lambda_trains=0, final_train_lambdas=0):
         env = self.env
+        from .agent_oracle import check_episode_length
+        check_episode_length(max_ep_len, steps_per_epoch)
         shard = None
         if self.world > 1:   # arm-sharded ranks must draw the same nets and pick the same agent strategy
             from .mpi_tools import arm_shard
@@ -358,12 +370,18 @@ class NatureOracle:
         agent_eq[agent_eq < 0] = 0
         agent_eq = agent_eq / agent_eq.sum()
         agent_pol = np.random.choice(agent_strats, p=agent_eq)                   # :651
-        if hasattr(agent_pol, "n_envs"):
-            agent_pol.n_envs = self.n_envs
         tr = MARolloutTrainer(env, ac, steps_per_epoch, gamma, lam_OTHER, clip_ratio, pi_lr_agent, pi_lr_nature,
                               vf_lr_agent, vf_lr_nature, lm_lr, train_pi_iters, train_v_iters, epochs, lamb_update_freq,
                               final_train_lambdas, start_entropy_coeff, end_entropy_coeff, seed, rank=self.rank,
                               world_size=self.world, process_group=self.pg)
-        self.history = [{k: v.detach().cpu().numpy() for k, v in tr.epoch(agent_pol).items()} for _ in range(epochs)]
+        tr.init_lambda_trains(init_lambda_trains)
+        self.history, self.agent_pol_history = [], []
+        for epoch in range(epochs):
+            # the agent strategy is re-drawn from the mixed equilibrium every lamb_update_freq epochs (:669-670); under
+            # world > 1 np.random was seeded identically on every rank above, so all ranks draw the same strategy
+            if epoch % lamb_update_freq == 0 and epoch > 0:
+                agent_pol = np.random.choice(agent_strats, p=agent_eq)
+            self.agent_pol_history.append(agent_pol)
+            self.history.append({k: v.detach().cpu().numpy() for k, v in tr.epoch(agent_pol).items()})
         tr.export_lambda()
         return ac

@@ -144,10 +144,10 @@ class RMABPPOTrainer:
     # ------------------------------------------------------------------------------------------
     @staticmethod
     def default_ranges(domain, N, rs):
-        """sampled_parameter_ranges: sorted U(0,1) pair scaled into PARAMETER_RANGES
-        (bandit_env_robust.py:468-481, :790-818)."""
+        """sampled_parameter_ranges.  Counterexample: PARAMETER_RANGES itself, no sub-sampling
+        (bandit_env_robust.py:790-824); ARMMAN: a sorted U(0,1) pair scaled into PARAMETER_RANGES (:468-481)."""
         if domain == _lib.DOMAIN_CE:
-            base = np.array([[0.0, 1.0], [0.05, 0.9], [0.1, 0.95]])[np.arange(N) % 3]
+            return np.array([[0.0, 1.0], [0.05, 0.9], [0.1, 0.95]])[np.arange(N) % 3]
         else:
             rA = [[[0.0, 1.0], [0.0, 1.0]], [[0.5, 1.0], [0.5, 1.0]], [[0.35, 0.85], [0.35, 0.85]]]
             rB = [[[0.0, 1.0], [0.0, 1.0]], [[0.35, 0.85], [0.15, 0.65]], [[0.35, 0.85], [0.35, 0.85]]]

@@ -365,20 +365,25 @@ def test_checkpoint_roundtrip_and_resume(torch_mod, tmp_path):
     kw = dict(hidden=16, B=4, train_pi_iters=2, train_v_iters=2, epochs=6, seed=2)
     tr = RMABPPOTrainer("armman", 12, 8, 6, **kw)
     tr.epoch(); tr.epoch()
+    # `ac` only supplies the constructor arguments: its (stale, freshly drawn) nets must NOT reach the file
     ac = MLPActorCriticRMAB(np.arange(3), np.arange(2), hidden_sizes=[16, 16], C=np.array([0, 1]), N=12, B=4, n_envs=8)
-    ac.Wpi.copy_(tr.Wpi); ac.Wv.copy_(tr.Wv)
-    flat, o = tr.lam_params.cpu(), 0
-    with torch.no_grad():
-        for p in ac.lambda_net.parameters():
-            p.copy_(flat[o:o + p.numel()].reshape(p.shape)); o += p.numel()
     f = str(tmp_path / "model.npz")
     checkpoint.save(f, ac, trainer=tr)
     ac2, extra = checkpoint.load(f, n_envs=8)
+    assert torch.equal(ac2.Wpi, tr.Wpi) and torch.equal(ac2.Wv, tr.Wv)
+    assert torch.equal(ac2.lambda_net.packed().to(tr.dev), tr.lam_params)
+    ac.Wpi.copy_(tr.Wpi); ac.Wv.copy_(tr.Wv)
+    with torch.no_grad():
+        for p, q in zip(ac.lambda_net.parameters(), ac2.lambda_net.parameters()):
+            p.copy_(q)
     obs = np.random.RandomState(0).randint(0, 3, (12, 8))
     assert np.array_equal(ac.act_test(obs), ac2.act_test(obs)) and repr(ac2) == repr(ac)
     tr2 = RMABPPOTrainer("armman", 12, 8, 6, **kw)
     checkpoint.restore_trainer(tr2, ac2, extra)
-    tr2.s_traj[:, 0] = tr.s_traj[:, 0]
+    assert torch.equal(tr2.s_traj[:, 0], tr.s_traj[:, 0])          # regenerated from the restored epoch counter
+    tr3 = RMABPPOTrainer("armman", 24, 8, 6, rank=1, world_size=2, **kw)
+    with pytest.raises(ValueError):
+        checkpoint.restore_trainer(tr3, ac2, extra)                 # a different arm shard is refused
     a, b = tr.epoch(), tr2.epoch()
     assert torch.equal(a["EpActualRet"], b["EpActualRet"]) and torch.equal(tr.Wpi, tr2.Wpi) and torch.equal(tr.Wv, tr2.Wv)
 
@@ -438,3 +443,35 @@ def test_value_iteration_dropin(torch_mod, golden):
         ValueIteration(np.array([[[0.9, 0.1], [0.2, 0.8]], [[0.5, 0.5], [0.3, 0.7]]]), np.ones((2, 2)), 0.9)
     with pytest.raises(ValueError):         # k = 0 -> math.log(0)
         ValueIteration(np.array([[[0.5, 0.5], [0.5, 0.5]]] * 2), np.array([[1.0, 1.0], [2.0, 2.0]]), 0.9)
+
+
+def test_double_oracle_tiny(torch_mod):
+    """BASELINE configs[4]'s driver on the drop-ins (double_oracle.py:51-278): strategy sets, payoff matrix and the
+    minimax-regret equilibrium of the restricted game after every iteration, counterexample domain."""
+    torch = torch_mod
+    from robustrmab_b200.double_oracle import DoubleOracle
+    from robustrmab_b200 import nfg_solver as nfg
+    N, B, T = 6, 2.0, 8
+    common = dict(steps_per_epoch=T, epochs=3, gamma=0.9, clip_ratio=2.0, lm_lr=2e-3, train_pi_iters=2, train_v_iters=2,
+                  lamb_update_freq=2, final_train_lambdas=1, ac_kwargs=dict(hidden_sizes=[16, 16]))
+    agent_kwargs = dict(common, pi_lr=2e-3, vf_lr=2e-3, start_entropy_coeff=0.5, end_entropy_coeff=0.0)
+    nature_kwargs = dict(common, pi_lr_agent=2e-3, pi_lr_nature=2e-3, vf_lr_agent=2e-3, vf_lr_nature=2e-3)
+    np.random.seed(0)
+    torch.manual_seed(0)
+    do = DoubleOracle("counterexample", N, B, T, max_epochs_double_oracle=1, S=2, A=2, seed=0, n_simu_epochs=6, gamma=0.9,
+                      agent_kwargs=agent_kwargs, nature_kwargs=nature_kwargs, n_envs=4)
+    assert np.asarray(do.payoffs).shape == (1, 1)                       # Pessimist agent vs Pessimist nature (:124-139)
+    agent_eq, nature_eq = do.run()
+    P = np.asarray(do.payoffs)
+    assert P.shape == (3, 3) == (len(do.agent_strategies), len(do.nature_strategies)) and np.isfinite(P).all()
+    assert [repr(s) for s in do.agent_strategies] == ["Pessimist_Agent_0", "RMABPPO_1", "RMABPPO_2"]
+    assert [repr(s) for s in do.nature_strategies] == ["Pessimist_Nature_c_0", "MA-RMABPPO_0", "MA-RMABPPO_1"]
+    assert abs(agent_eq.sum() - 1) < 1e-9 and abs(nature_eq.sum() - 1) < 1e-9
+    reg = P - P.max(axis=0)
+    v = nfg.get_payoff(reg, agent_eq, nature_eq)
+    assert (reg @ nature_eq).max() <= v + 1e-7 and (agent_eq @ reg).min() >= v - 1e-7
+    # a payoff entry is reproducible: same seed, same batched rollout
+    again = do.agent_oracle.simulate_reward(do.agent_strategies[1], do.nature_strategies[2], seed=0, steps_per_epoch=T,
+                                            epochs=6, gamma=0.9)
+    assert again == P[1, 2]
+    assert do.compute_payoff_regret(np.array([1.0, 0.0, 0.0])) >= 0

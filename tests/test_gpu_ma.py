@@ -269,3 +269,32 @@ def test_ma_device_loop_matches_reference_nature_oracle(K, golden):
     tr.export_lambda()
     for i, p in enumerate(ac.lambda_net.parameters()):
         np.testing.assert_allclose(p.detach().numpy(), g[f"lam1_{i}"], rtol=1e-4, atol=1e-6)
+
+
+def test_nature_oracle_resamples_agent_strategy(K):
+    """nature_oracle.py:651, :669-670: the agent strategy nature trains against is drawn from the mixed equilibrium at the
+    start AND re-drawn every lamb_update_freq epochs -- with a mixed agent_eq nature must meet both strategies."""
+    torch = K.torch
+    from robustrmab_b200.baselines import PessimisticAgentPolicy
+    from robustrmab_b200.core import MLPActorCriticRMAB
+    from robustrmab_b200.nature_oracle import NatureOracle
+    N, E, T, epochs = 6, 4, 5, 8
+    kw = dict(steps_per_epoch=T, epochs=epochs, gamma=0.9, clip_ratio=2.0, pi_lr_agent=2e-3, pi_lr_nature=2e-3,
+              vf_lr_agent=2e-3, vf_lr_nature=2e-3, lm_lr=2e-3, train_pi_iters=1, train_v_iters=1, lamb_update_freq=1,
+              final_train_lambdas=0, ac_kwargs=dict(hidden_sizes=[16, 16]))
+    tmp = NatureOracle("counterexample", N, 2, 2, 2.0, 3, 1, nature_kwargs=kw, n_envs=E)
+    orc = NatureOracle("counterexample", N, 2, 2, 2.0, 3, 1, nature_kwargs=kw, n_envs=E,
+                       sampled_nature_parameter_ranges=tmp.env.sample_parameter_ranges())
+    pess = PessimisticAgentPolicy(N)
+    ac = MLPActorCriticRMAB(np.arange(2), np.arange(2), hidden_sizes=[16, 16], C=np.array([0, 1]), N=N, B=2.0, n_envs=1)
+    strats, eq = [pess, ac], [0.5, 0.5]
+    np.random.seed(123)
+    orc.best_response(strats, eq, 0)
+    np.random.seed(123)
+    want = [np.random.choice(strats, p=np.array(eq))]
+    for epoch in range(1, epochs):
+        want.append(np.random.choice(strats, p=np.array(eq)))
+    assert [id(p) for p in orc.agent_pol_history] == [id(p) for p in want]
+    assert {id(p) for p in orc.agent_pol_history} == {id(pess), id(ac)}
+    assert ac.n_envs == 1                                   # the caller's strategy object is not mutated
+    assert all(np.isfinite(h["EpLambAdjRetNature"]).all() for h in orc.history)
