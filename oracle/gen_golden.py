@@ -319,8 +319,8 @@ def main(which=None):
     os.makedirs(OUT, exist_ok=True)
     gens = dict(env=gen_env, ac=gen_ac, buffer=gen_buffer, select=gen_select, vi=gen_vi, baselines=gen_baselines)
     try:
-        from .gen_golden_train import gen_train, gen_ma, gen_ma_train
-        gens.update(train=gen_train, ma=gen_ma, ma_train=gen_ma_train)
+        from .gen_golden_train import gen_train, gen_ma, gen_ma_train, gen_train_sis, gen_ma_train_sis
+        gens.update(train=gen_train, ma=gen_ma, ma_train=gen_ma_train, train_sis=gen_train_sis, ma_train_sis=gen_ma_train_sis)
     except ImportError:
         pass
     for k, f in gens.items():

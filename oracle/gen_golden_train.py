@@ -55,18 +55,25 @@ def _recorder_class(core):
     return globals()["Recorder"]
 
 
-def _run(data, N, B, T, epochs, hidden, seed, kw):
+def _run(data, N, B, T, epochs, hidden, seed, kw, pop=0):
     import torch
     from robust_rmab.algos.rmabppo import agent_oracle as ao
     from robust_rmab.algos.rmabppo import rmabppo_core as core
+    A, extra = 2, {}
     if data == "counterexample":
         from robust_rmab.environments.bandit_env_robust import CounterExampleRobustEnv as Env
         from robust_rmab.baselines.nature_baselines_counterexample import SampledRandomNaturePolicy
         S = 2
-    else:
+    elif data == "armman":
         from robust_rmab.environments.bandit_env_robust import ARMMANRobustEnv as Env
         from robust_rmab.baselines.nature_baselines_armman import SampledRandomNaturePolicy
         S = 3
+    else:   # SIS: S = pop + 1 states, 3 actions, scalar state input s / state_norm (agent_oracle.py:775-785)
+        from robust_rmab.environments.bandit_env_robust import SISRobustEnv
+        from robust_rmab.baselines.nature_baselines_sis import SampledRandomNaturePolicy
+        Env = lambda N_, B_, seed_: SISRobustEnv(N_, B_, pop, seed_)
+        S, A = pop + 1, 3
+        extra = dict(pop_size=pop, one_hot_encode=False, non_ohe_obs_dim=1, state_norm=pop)
     rec = _REC
     rec.clear()
     Recorder = _recorder_class(core)
@@ -77,8 +84,8 @@ def _run(data, N, B, T, epochs, hidden, seed, kw):
         ranges = env0.sample_parameter_ranges().astype(F32).astype(np.float64)
         agent_kwargs = dict(steps_per_epoch=T, epochs=epochs, ac_kwargs=dict(hidden_sizes=[hidden, hidden]),
                             actor_critic=Recorder, **kw)
-        orc = ao.AgentOracle(data, N, S, 2, B, seed, 1, agent_kwargs=agent_kwargs, home_dir=home, exp_name="golden",
-                             sampled_nature_parameter_ranges=ranges, robust_keyword="sample_random")
+        orc = ao.AgentOracle(data, N, S, A, B, seed, 1, agent_kwargs=agent_kwargs, home_dir=home, exp_name="golden",
+                             sampled_nature_parameter_ranges=ranges, robust_keyword="sample_random", **extra)
         step_src = ref_shims.UniformSource(seed, philox.STREAM_ENV, N)
         reset_src = ref_shims.UniformSource(seed, philox.STREAM_RESET, N)
         orc.env.random_stream = ref_shims.InjectedStream(step_src, reset_src, S)
@@ -95,7 +102,7 @@ def _run(data, N, B, T, epochs, hidden, seed, kw):
                 prog = os.path.join(dp, "progress.txt")
         rows = [l.rstrip("\n").split("\t") for l in open(prog)]
         cols = {c: np.array([float(r[i]) for r in rows[1:]]) for i, c in enumerate(rows[0])}
-        out = dict(meta=np.array([N, S, T, epochs, hidden, seed]), B=np.array(B), ranges=ranges,
+        out = dict(meta=np.array([N, S, T, epochs, hidden, seed]), B=np.array(B), ranges=ranges, pop=np.array(pop),
                    nature=nature.param_setting, Wpi0=rec["Wpi0"], Wv0=rec["Wv0"],
                    Wpi1=np.stack([nets.pack_torch_mlp(ac.pi_list[i].logits_net) for i in range(N)]),
                    Wv1=np.stack([nets.pack_torch_mlp(ac.v_list[i].v_net) for i in range(N)]),
@@ -122,6 +129,16 @@ def gen_train():
         r = _run(data, N, B, T, epochs, hidden, 3, KW)
         out.update({f"{name}_{k}": v for k, v in r.items()})
     np.savez_compressed(os.path.join(OUT, "train.npz"), **out)
+
+
+def gen_train_sis():
+    """AgentOracle.best_response(data='sis') -- S = pop + 1, A = 3, C = [0,1,2], non-one-hot scalar inputs -- at hidden 16
+    and 64 (the widths of the per-sample update kernels): tests/golden/train_sis.npz."""
+    out = {}
+    for name, N, B, T, epochs, hidden, pop in [("h16", 5, 3.0, 8, 5, 16, 10), ("h64", 4, 2.0, 7, 4, 64, 20)]:
+        r = _run("sis", N, B, T, epochs, hidden, 5, KW, pop=pop)
+        out.update({f"{name}_{k}": v for k, v in r.items()})
+    np.savez_compressed(os.path.join(OUT, "train_sis.npz"), **out)
 
 
 def gen_ma():
@@ -267,7 +284,14 @@ def _pack_ma_critics(ac, in_dim):
     return np.stack(packed).astype(F32), np.stack(w1n).astype(F32)
 
 
-def gen_ma_train(epochs=5, out_name="ma_train.npz", final_train_lambdas=1):
+def gen_ma_train_sis():
+    """NatureOracle.best_response on SISRobustEnv (BASELINE configs[3]'s domain: S = pop + 1, A = 3, D = 4N nature
+    parameters, scalar state inputs) at hidden 64: tests/golden/ma_train_sis.npz."""
+    gen_ma_train(epochs=5, out_name="ma_train_sis.npz", data="sis", N=6, pop=10, h=64, T=6, B=3.0, seed=6)
+
+
+def gen_ma_train(epochs=5, out_name="ma_train.npz", final_train_lambdas=1, data="counterexample", N=6, pop=0, h=16, T=7,
+                 B=2.0, seed=4):
     """The UNMODIFIED reference NatureOracle.best_response (nature_oracle.py:252-806) against a Pessimist agent on a
     tiny counterexample problem with every random draw injected from the Philox convention of the CUDA path."""
     import contextlib
@@ -276,15 +300,17 @@ def gen_ma_train(epochs=5, out_name="ma_train.npz", final_train_lambdas=1):
     from robust_rmab.algos.ma_rmabppo import ma_rmabppo_core as core
     from robust_rmab.algos.ma_rmabppo import nature_oracle as no
     from robust_rmab.baselines.agent_baselines import PessimisticAgentPolicy
-    from robust_rmab.environments.bandit_env_robust import CounterExampleRobustEnv
+    from robust_rmab.environments.bandit_env_robust import CounterExampleRobustEnv, SISRobustEnv
     from . import ma as oma
-    N, S, B, T, h, seed = 6, 2, 2.0, 7, 16, 4
+    sis = data == "sis"
+    S, A = (pop + 1, 3) if sis else (2, 2)
+    extra = dict(pop_size=pop, one_hot_encode=False, non_ohe_obs_dim=1, state_norm=pop, nature_state_norm=1) if sis else {}
     kw = dict(gamma=0.9, clip_ratio=2.0, pi_lr_agent=2e-3, pi_lr_nature=2e-3, vf_lr_agent=2e-3, vf_lr_nature=2e-3, lm_lr=2e-3,
               train_pi_iters=3, train_v_iters=3, lam_OTHER=0.97, start_entropy_coeff=0.5, end_entropy_coeff=0.0,
               lamb_update_freq=2, final_train_lambdas=final_train_lambdas)
-    env0 = CounterExampleRobustEnv(N, B, seed)
+    env0 = SISRobustEnv(N, B, pop, seed) if sis else CounterExampleRobustEnv(N, B, seed)
     ranges = env0.sample_parameter_ranges().astype(F32).astype(np.float64)
-    D = N
+    D = env0.action_dim_nature
     sweep = {"k": 0}
 
     @contextlib.contextmanager
@@ -307,8 +333,8 @@ def gen_ma_train(epochs=5, out_name="ma_train.npz", final_train_lambdas=1):
         _MA_REC.clear()
         Rec = _ma_recorder_class(core)
         nature_kwargs = dict(steps_per_epoch=T, epochs=epochs, ac_kwargs=dict(hidden_sizes=[h, h]), ma_actor_critic=Rec, **kw)
-        orc = no.NatureOracle("counterexample", N, S, 2, B, seed, 1, nature_kwargs=nature_kwargs, home_dir=home,
-                              exp_name="golden_ma", sampled_nature_parameter_ranges=ranges)
+        orc = no.NatureOracle(data, N, S, A, B, seed, 1, nature_kwargs=nature_kwargs, home_dir=home,
+                              exp_name="golden_ma", sampled_nature_parameter_ranges=ranges, **extra)
         orc.env.random_stream = _MAEnvStream(seed, N, S)
         torch.manual_seed(seed)
         np.random.seed(seed)
@@ -321,14 +347,14 @@ def gen_ma_train(epochs=5, out_name="ma_train.npz", final_train_lambdas=1):
         rows = [l.rstrip("\n").split("\t") for l in open(prog)]
         cols = {c: np.array([float(r[i]) for r in rows[1:]]) for i, c in enumerate(rows[0])}
         lin = lambda seq: [m for m in seq if isinstance(m, torch.nn.Linear)]
-        out = dict(meta=np.array([N, S, T, epochs, h, seed, D]), B=np.array(B), ranges=ranges,
+        out = dict(meta=np.array([N, S, T, epochs, h, seed, D]), B=np.array(B), ranges=ranges, pop=np.array(pop),
                    Wpi0=_MA_REC["Wpi0"], Wv0=_MA_REC["Wv0"], W1n0=_MA_REC["W1n0"], log_std0=_MA_REC["log_std0"],
                    Wpi1=np.stack([nets.pack_torch_mlp(ac.pi_list_agent[i].logits_net) for i in range(N)]),
                    log_std1=ac.pi_nature.log_std.detach().numpy().copy(),
                    Lamb=cols["Lamb"], EpActualRetAgent=cols["AverageEpActualRetAgent"],
                    EpLambAdjRetNature=cols["AverageEpLambAdjRetNature"], VVals_agent=cols["AverageVVals_agent"],
                    VVals_nature=cols["AverageVVals_nature"])
-        out["Wv1"], out["W1n1"] = _pack_ma_critics(ac, S + 1)
+        out["Wv1"], out["W1n1"] = _pack_ma_critics(ac, ac.obs_dim + 1)
         for tag, lst in (("lam0", _MA_REC["lam0"]), ("mu0", _MA_REC["mu0"]), ("vn0", _MA_REC["vn0"])):
             for i, p in enumerate(lst):
                 out[f"{tag}_{i}"] = p

@@ -34,9 +34,13 @@ def _dense(sizes):
 class CpuMARMABPPO:
     def __init__(self, domain, Wpi, Wv, W1n, lam_params, mu_net, log_std, v_nature, ranges, R, C, n_envs, T, hidden, B,
                  gamma, lam_other, clip_ratio, pi_lr_agent, pi_lr_nature, vf_lr_agent, vf_lr_nature, lm_lr, pi_iters,
-                 v_iters, epochs, lamb_update_freq, final_train_lambdas, ent0, ent1, seed, pop=None):
+                 v_iters, epochs, lamb_update_freq, final_train_lambdas, ent0, ent1, seed, pop=None, one_hot=True,
+                 state_norm=1.0, nature_state_norm=1.0):
         self.domain, self.pop = domain, pop
         self.S = {oenv.DOMAIN_CE: 2, oenv.DOMAIN_ARMMAN: 3}.get(domain, (pop or 0) + 1)
+        self.A = len(C)
+        self.one_hot, self.state_norm, self.nsn = bool(one_hot), float(state_norm if state_norm else 1.0), float(nature_state_norm)
+        self.in_dim = (self.S if self.one_hot else 1) + 1
         self.N, self.E, self.T, self.h = Wpi.shape[0], n_envs, T, hidden
         self.D = W1n.shape[2]
         self.opt = oppo.ArmOptim(Wpi, Wv, pi_lr_agent, vf_lr_agent)
@@ -54,8 +58,10 @@ class CpuMARMABPPO:
         self.seed, self.epoch_idx, self.t_global = seed, 0, 0
         self.s = oenv.reset_states(seed, 0, self.S, self.E, self.N)
 
-    def _lambda(self, s):
-        x = torch.as_tensor(s.T.astype(F32))
+    def _lambda(self, s, scale=1.0):
+        """Raw observation for the rollout's prediction (nature_oracle.py:664); obs / state_norm inside
+        compute_loss_lambda for non-one-hot nets (:447-459)."""
+        x = torch.as_tensor(s.T.astype(F32)) * F32(scale)
         p = self.lam_params
         return (torch.tanh(torch.tanh(x @ p[0].T + p[1]) @ p[2].T + p[3]) @ p[4].T + p[5])[:, 0]
 
@@ -87,6 +93,7 @@ class CpuMARMABPPO:
     def epoch(self, act_test):
         """act_test(s [N,E]) -> actions [N,E] of the sampled agent strategy."""
         N, E, T, S, D, h = self.N, self.E, self.T, self.S, self.D, self.h
+        A, oh, sn = self.A, self.one_hot, self.state_norm
         ep = self.epoch_idx
         s0 = self.s.copy()
         with torch.no_grad():
@@ -100,14 +107,16 @@ class CpuMARMABPPO:
 
         def step(s, t, sample=True):
             with torch.no_grad():
-                mu = self.mu_net(torch.as_tensor(s.T.astype(F32))).numpy()
+                # ma_rmabppo_core.py:276-289: obs / state_norm (non-one-hot only), then / nature_state_norm for the actor
+                obs_ac = torch.as_tensor(s.T.astype(F32)) / F32(1.0 if oh else sn)
+                mu = self.mu_net(obs_ac / F32(self.nsn)).numpy()
                 eps = oma.normal_eps(self.seed, t, E, D)
                 an, lpn = oma.gaussian_sample(mu, self.log_std.detach().numpy(), eps)
                 nb = self._bound(an, s)
                 ua = philox.uniform_grid(self.seed, philox.STREAM_ACT, t, E, N)
-                aa, _, lp, p1, _ = nets.ac_step(Wpi, Wv, s, lamb, ua, S, 2, h)
-                v = oma.agent_critic_extra(Wv, W1n, s, lamb, nb, S, h)
-                x = torch.as_tensor(np.concatenate([s.T.astype(F32), aa.T.astype(F32)], axis=1))
+                aa, _, lp, p1, _ = nets.ac_step(Wpi, Wv, s, lamb, ua, S, A, h, oh, sn)
+                v = oma.agent_critic_extra(Wv, W1n, s, lamb, nb, S, h, oh, sn)
+                x = torch.cat([obs_ac, torch.as_tensor(aa.T.astype(F32))], dim=1)              # :322-323
                 vn = self.v_nature(x)[:, 0].numpy()
             return aa, v, lp, an, nb, lpn, vn
 
@@ -135,14 +144,15 @@ class CpuMARMABPPO:
         adv_n = ((adv_n - m) / sd).astype(F32)
         # ---- agent pi ----
         ent = oppo.entropy_coeff_for(ep, self.epochs, self.ent0, self.ent1, self.freq, self.final)
-        oppo.update(self.opt, s_traj[:, :T], a, adv, logp, ret, lamb, S, 2, h, self.clip, ent, self.pi_iters, 0)
+        oppo.update(self.opt, s_traj[:, :T], a, adv, logp, ret, lamb, S, A, h, self.clip, ent, self.pi_iters, 0,
+                    one_hot=oh, state_norm=sn)
         # ---- agent critics over [x_i, bounded nature vector] ----
-        x = np.stack([nets.features(s_traj[:, t], lamb, S, True) for t in range(T)], axis=1).reshape(N, T * E, S + 1)
+        x = np.stack([nets.features(s_traj[:, t], lamb, S, oh, sn) for t in range(T)], axis=1).reshape(N, T * E, self.in_dim)
         xt, rt = torch.as_tensor(x), torch.as_tensor(ret.reshape(N, T * E))
         natM = torch.as_tensor(nat_b.reshape(T * E, D))
         for _ in range(self.v_iters):
             self.opt_v.zero_grad()
-            W1, b1, W2, b2, W3, b3 = oppo._unpack_t(self.opt.Wv, S + 1, h, 1)
+            W1, b1, W2, b2, W3, b3 = oppo._unpack_t(self.opt.Wv, self.in_dim, h, 1)
             z1 = torch.bmm(xt, W1.transpose(1, 2)) + b1[:, None, :] + torch.matmul(natM, self.W1n.transpose(1, 2))
             a2 = torch.tanh(torch.bmm(torch.tanh(z1), W2.transpose(1, 2)) + b2[:, None, :])
             v = (torch.bmm(a2, W3.transpose(1, 2)) + b3[:, None, :])[..., 0]
@@ -154,11 +164,15 @@ class CpuMARMABPPO:
                 for p in self.lam_params:
                     p.grad = None
                 coef = torch.as_tensor((self.B / (1.0 - self.gamma) - cdcost[0]).astype(F32))
-                (self._lambda(s0) * coef).mean().backward()
+                (self._lambda(s0, 1.0 if oh else 1.0 / sn) * coef).mean().backward()
                 with torch.no_grad():
                     for p in self.lam_params:
                         p -= self.lm_lr * p.grad
+            # compute_loss_pi_nature / compute_loss_v_nature divide the RAW buffer observations by nature_state_norm when
+            # the nets are not one-hot, and by nothing otherwise (:359-364, :421-428) -- unlike the rollout's step()
             obs = torch.as_tensor(np.ascontiguousarray(s_traj[:, :T].transpose(1, 2, 0)).reshape(T * E, N).astype(F32))
+            if not oh:
+                obs = obs / F32(self.nsn)
             act = torch.as_tensor(a_nat.reshape(T * E, D))
             advn, lpo, retn = torch.as_tensor(adv_n.reshape(-1)), torch.as_tensor(logp_nat.reshape(-1)), torch.as_tensor(ret_n.reshape(-1))
             for _ in range(self.pi_iters):

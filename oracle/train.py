@@ -27,10 +27,12 @@ class CpuRMABPPO:
     def __init__(self, domain, Wpi, Wv, lam_params, nature, ranges, R, C, n_envs, steps_per_epoch, hidden, B,
                  gamma=0.9, lam_other=0.97, clip_ratio=2.0, pi_lr=2e-3, vf_lr=2e-3, lm_lr=2e-3, train_pi_iters=20,
                  train_v_iters=20, epochs=20, lamb_update_freq=4, final_train_lambdas=2, start_entropy_coeff=0.5,
-                 end_entropy_coeff=0.0, seed=0, arm0=0):
-        self.domain = domain
-        self.S = 2 if domain == oenv.DOMAIN_CE else 3
-        self.A = 2
+                 end_entropy_coeff=0.0, seed=0, arm0=0, pop=None, one_hot=True, state_norm=1.0):
+        self.domain, self.pop = domain, pop
+        self.S = {oenv.DOMAIN_CE: 2, oenv.DOMAIN_ARMMAN: 3}.get(domain, (pop or 0) + 1)
+        self.A = len(C)
+        self.one_hot, self.state_norm = bool(one_hot), float(state_norm if state_norm else 1.0)
+        self.in_dim = (self.S if self.one_hot else 1) + 1
         self.N, self.E, self.T, self.h = Wpi.shape[0], n_envs, steps_per_epoch, hidden
         self.opt = oppo.ArmOptim(Wpi, Wv, pi_lr, vf_lr)
         self.lam_params = [torch.nn.Parameter(torch.as_tensor(np.array(p, F32))) for p in lam_params]
@@ -43,8 +45,10 @@ class CpuRMABPPO:
         self.epoch_idx, self.t_global = 0, 0
         self.s = oenv.reset_states(seed, 0, self.S, self.E, self.N, arm0)
 
-    def _lambda(self, s):
-        x = torch.as_tensor(s.T.astype(F32))
+    def _lambda(self, s, scale=1.0):
+        """lambda_net on the observation times `scale`: 1 for the rollout's prediction (raw obs, agent_oracle.py:497),
+        1/state_norm inside compute_loss_lambda when the nets are not one-hot (:364-367)."""
+        x = torch.as_tensor(s.T.astype(F32)) * F32(scale)
         p = self.lam_params
         return (torch.tanh(torch.tanh(x @ p[0].T + p[1]) @ p[2].T + p[3]) @ p[4].T + p[5])[:, 0]
 
@@ -60,26 +64,31 @@ class CpuRMABPPO:
         logp = np.zeros((N, T, E), F32)
         val = np.zeros((N, T, E), F32)
         s_traj[:, 0] = s0
-        step = oenv.ce_step if self.domain == oenv.DOMAIN_CE else oenv.armman_step
+        if self.domain == oenv.DOMAIN_SIS:
+            step = lambda s_, a_, nat, rg, R_, u_: oenv.sis_step(self.pop, s_, a_, nat, R_, u_)
+        else:
+            step = oenv.ce_step if self.domain == oenv.DOMAIN_CE else oenv.armman_step
         for t in range(T):
             ua = philox.uniform_grid(self.seed, philox.STREAM_ACT, self.t_global + t, E, N, self.arm0)
             ue = philox.uniform_grid(self.seed, philox.STREAM_ENV, self.t_global + t, E, N, self.arm0)
-            a[:, t], val[:, t], logp[:, t], _, _ = nets.ac_step(Wpi, Wv, s_traj[:, t], lamb, ua, S, self.A, self.h)
+            a[:, t], val[:, t], logp[:, t], _, _ = nets.ac_step(Wpi, Wv, s_traj[:, t], lamb, ua, S, self.A, self.h,
+                                                                self.one_hot, self.state_norm)
             s_traj[:, t + 1], _ = step(s_traj[:, t], a[:, t], self.nature, self.ranges, self.R, ue)
-        x = nets.features(s_traj[:, T], lamb, S, True)
-        last_val = nets.mlp_forward(Wv, x, S + 1, self.h, 1)[..., 0].astype(F32)
+        x = nets.features(s_traj[:, T], lamb, S, self.one_hot, self.state_norm)
+        last_val = nets.mlp_forward(Wv, x, self.in_dim, self.h, 1)[..., 0].astype(F32)
         rew = np.stack([np.take_along_axis(self.R, s_traj[:, t + 1].astype(np.int64), axis=1) for t in range(T)], 1)
         cost = self.C[a]
         adv, ret, _, cdcost = obuf.finish_path(rew, cost, val, last_val, lamb, self.gamma, self.lam_other)
         adv_n = obuf.normalize_adv(adv)
         ent = oppo.entropy_coeff_for(ep, self.epochs, self.ent0, self.ent1, self.freq, self.final)
         lp, lv = oppo.update(self.opt, s_traj[:, :T], a, adv_n, logp, ret, lamb, S, self.A, self.h, self.clip, ent,
-                             self.pi_iters, self.v_iters)
+                             self.pi_iters, self.v_iters, one_hot=self.one_hot, state_norm=self.state_norm)
         if oppo.lambda_update_due(ep, self.epochs, self.freq, self.final):
             for p in self.lam_params:
                 p.grad = None
             coef = torch.as_tensor((self.B / (1.0 - self.gamma) - cdcost[0]).astype(F32))
-            (self._lambda(s0) * coef).mean().backward()           # compute_loss_lambda (:360-376), mean over replicas
+            scale = 1.0 if self.one_hot else 1.0 / self.state_norm
+            (self._lambda(s0, scale) * coef).mean().backward()    # compute_loss_lambda (:360-376), mean over replicas
             with torch.no_grad():
                 for p in self.lam_params:
                     p -= self.lm_lr * p.grad

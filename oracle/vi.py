@@ -193,3 +193,117 @@ def hawkins_action_knapsack(T, R, C, B, state, lam, gamma, eps=1e-10):
     V, _, _, _ = batched_vi(T, R, C, np.array([lam]), gamma, eps, stop="abs")
     Q = q_values(T, R, C, V, np.array([lam]), gamma)[:, 0]                       # [N,S,A]
     return knapsack_multichoice(Q[np.arange(N), state], C, B)
+
+
+def whittle_lp_highs(T, R, C, B, start_state, a_index, gamma, lambda_lim=None, index_range=None):
+    """lp_methods.lp_to_compute_index (:111-212) restated for scipy's HiGHS (Gurobi is absent; small N only, test
+    infrastructure).  The reference builds ONE model over all arms, but no constraint couples two arms, so it is
+    solved here arm by arm.  Per arm p: variables (index_p, L_p[S]), all with Gurobi's default lower bound 0
+    (index_p <= lambda_lim);
+        minimise  L_p[start_p]  (+ index_p B/(1-gamma) for ONE arm only: the objective at :163 reads
+                  `index_variables[i]` with `i` left over from the loop at :144-146, i.e. arm S-1)
+        s.t.      L_p[s] >= R_p[s] - index_p C[a] + gamma T_p[s,a].L_p                      for all s, a   (:166-170)
+                  Q(start_p, a_index) == Q(start_p, a_index - 1),  Q(s,a) = R[s] - index C[a] + gamma T[s,a].L  (:176-181)
+    Returns (L_vals [N,S], index [N]); NaN where the LP is infeasible (Gurobi would raise on `.x`).
+    index_range: optional [N,2] array that receives the smallest and largest index on the LP's optimal face."""
+    from scipy.optimize import linprog
+    T = np.asarray(T, np.float64)
+    R = np.asarray(R, np.float64)
+    C = np.asarray(C, np.float64)
+    N, S, A, _ = T.shape
+    L_vals, index = np.full((N, S), np.nan), np.full(N, np.nan)
+    for p in range(N):
+        s0 = int(start_state[p])
+        c = np.zeros(1 + S)
+        c[1 + s0] = 1.0
+        if p == S - 1:
+            c[0] = B / (1 - gamma)
+        A_ub, b_ub = [], []
+        for s in range(S):
+            for a in range(A):
+                row = np.zeros(1 + S)
+                row[0] = -C[a]
+                row[1:] = gamma * T[p, s, a]
+                row[1 + s] -= 1.0
+                A_ub.append(row)
+                b_ub.append(-R[p, s])
+        eq = np.zeros(1 + S)
+        eq[0] = -(C[a_index] - C[a_index - 1])
+        eq[1:] = gamma * (T[p, s0, a_index] - T[p, s0, a_index - 1])
+        bounds = [(0, lambda_lim)] + [(0, None)] * S
+        res = linprog(c, A_ub=np.array(A_ub), b_ub=np.array(b_ub), A_eq=eq[None], b_eq=[0.0], bounds=bounds, method="highs")
+        if res.status == 0:
+            index[p], L_vals[p] = res.x[0], res.x[1:]
+            if index_range is not None:
+                # the optimal FACE: the LP is often degenerate (a continuum of indices attains the optimum, e.g. every
+                # index above the indifference point when the start state's value no longer depends on it), and which
+                # vertex a solver returns is then its own business -- so also report the smallest / largest optimal index
+                cap = np.concatenate([c, [res.fun + 1e-9 * max(1.0, abs(res.fun))]])
+                for k, sign in enumerate((1.0, -1.0)):
+                    obj = np.zeros(1 + S)
+                    obj[0] = sign
+                    r2 = linprog(obj, A_ub=np.array(A_ub + [cap[:-1]]), b_ub=np.array(b_ub + [cap[-1]]), A_eq=eq[None],
+                                 b_eq=[0.0], bounds=bounds, method="highs")
+                    index_range[p, k] = r2.x[0] if r2.status == 0 else np.nan
+    return L_vals, index
+
+
+def whittle_pin_instances(seed, N=10):
+    """Small instances for pinning the Whittle index to the LP restatement: counterexample, ARMMAN and dense random MDPs.
+    Yields (name, T [N,S,2,S], R [N,S], C, lambda_lim)."""
+    from . import envs as oenv
+    rs = np.random.RandomState(seed)
+    C = np.array([0.0, 1.0])
+    rgc = oenv.ce_param_ranges(N)
+    p = rgc[:, 0] + rs.rand(N) * (rgc[:, 1] - rgc[:, 0])
+    T = np.zeros((N, 2, 2, 2))
+    T[:, 0] = 0.5
+    T[:, 1, 0, 0] = 1.0
+    T[:, 1, 1, 1], T[:, 1, 1, 0] = p, 1 - p
+    yield "ce", T, np.tile([0.0, 1.0], (N, 1)), C, 10.0
+    pa = oenv.sample_sub_ranges(oenv.armman_param_ranges(N), rs).mean(-1)
+    T = np.zeros((N, 3, 2, 3))
+    for s in range(3):
+        for a in range(2):
+            T[:, s, a] = oenv.armman_probs(np.full(N, s), np.full(N, a), pa[:, s, a]).astype(np.float64)
+    yield "armman", T, np.tile([1.0, 0.5, 0.0], (N, 1)), C, 10.0
+    S = 4
+    R = np.sort(rs.rand(N, S), axis=1)
+    yield "random", rs.dirichlet(np.ones(S), size=(N, S, 2)), R, C, float(R.max() / 0.1)
+
+
+def whittle_lp_pin(index, T, R, C, gamma, lambda_lim, B=3.0, tol=1e-6):
+    """Compare indifference-point indices `index [N,S]` (bisection on Q(s,1;l) = Q(s,0;l) under the optimal value
+    function) with the reference's index LP (whittle_lp_highs, lp_methods.py:111-212) for start state s on every arm.
+
+    The two definitions coincide where the LP's minimal solution is the Bellman solution; the LP is a relaxation of it
+    (L only has to DOMINATE the Bellman backup, so it may buy a lower L[start] with an inflated L elsewhere) and is
+    frequently degenerate, so an entry counts as
+      'agree'      index == the smallest index on the LP's optimal face;
+      'lp_relaxed' the LP optimum is strictly below V^index(start): the LP left the Bellman solution (or the true
+                   indifference point is <= 0 and the index variable's lower bound 0 forces that);
+      'nonpositive' acting is not preferred even at lambda = 0 (indifference point <= 0): the bisection returns its lower
+                   end 0, while the LP (index >= 0 and the equality enforced) has no Bellman solution and inflates L;
+      'quirk'      arm S-1, whose index carries the stray B/(1-gamma) objective term (lp_methods.py:163);
+      'mismatch'   anything else -- must not happen.
+    Returns a dict of counts and the list of mismatches."""
+    N, S = index.shape
+    out = dict(agree=0, lp_relaxed=0, nonpositive=0, quirk=0, mismatch=0)
+    bad = []
+    for s in range(S):
+        rng_ = np.zeros((N, 2))
+        L, _ = whittle_lp_highs(T, R, C, B, np.full(N, s), 1, gamma, lambda_lim, index_range=rng_)
+        Vw, _, _, _ = batched_vi(T, R, C, index[:, s:s + 1], gamma, 1e-13, stop="abs")      # per-arm lambda = its index
+        for p in range(N):
+            if p == S - 1:
+                out["quirk"] += 1
+            elif abs(rng_[p, 0] - index[p, s]) <= tol:
+                out["agree"] += 1
+            elif L[p, s] < Vw[p, 0, s] - 1e-9:
+                out["lp_relaxed"] += 1
+            elif index[p, s] <= tol:
+                out["nonpositive"] += 1
+            else:
+                out["mismatch"] += 1
+                bad.append((s, p, float(index[p, s]), rng_[p].tolist(), float(L[p, s]), float(Vw[p, 0, s])))
+    return out, bad

@@ -37,6 +37,7 @@ class HawkinsAgentPolicy:
         self._R = torch.as_tensor(self.R, dtype=_F64, device=self.device).contiguous()
         self._C = torch.as_tensor(self.C, dtype=_F64, device=self.device).contiguous()
         self.lambda_lim = float(self.R.max() / (self.C[self.C > 0].min() * (1 - self.gamma)))   # agent_baselines.py:61
+        self.max_ws_bytes = 1 << 30            # value-function scratch per refinement chunk
 
     def __repr__(self):
         return "%s_%s" % (self.name, self.ind)
@@ -49,23 +50,42 @@ class HawkinsAgentPolicy:
         obj = vs.sum(dim=0).t() + lambdas[None, :] * (self.B / (1.0 - self.gamma))   # [E,L]
         return obj, V, Q
 
+    def _objective_per_env(self, s, grids):
+        """obj[e, k] = sum_i V_i(s_i(e); grids[e, k]) + grids[e, k] B / (1 - gamma): every env has its OWN probes.  One
+        batched VI per chunk of envs over the chunk's flattened grids (the kernel shares a probe list between arms, so
+        env e's probes are also solved for the other envs' states and discarded: the cost of batching E refinements)."""
+        N, E = s.shape
+        P = grids.shape[1]
+        S = self._T.shape[1]
+        per_env = N * P * S * 8 * 2                                   # V (fp64) + the gathered copy
+        chunk = max(1, min(E, int(self.max_ws_bytes // max(per_env, 1))))
+        obj = torch.empty((E, P), dtype=_F64, device=self.device)
+        for e0 in range(0, E, chunk):
+            e1 = min(E, e0 + chunk)
+            lam = grids[e0:e1].reshape(-1).contiguous()
+            V, _, _, _, _ = ops.vi_batched(self._T, self._R, self._C, lam, self.gamma, self.eps, stop="abs")
+            V = V.view(N, e1 - e0, P, S)
+            idx = s[:, e0:e1].long()[:, :, None, None].expand(-1, -1, P, 1)
+            obj[e0:e1] = torch.gather(V, 3, idx)[..., 0].sum(dim=0) + grids[e0:e1] * (self.B / (1.0 - self.gamma))
+        return obj
+
     def hawkins_lambda_device(self, s):
-        """lambda* per env `[E]` (grid + refinement; refinement re-grids around each env's minimiser)."""
+        """lambda* per env `[E]`: a shared grid of n_probes over [0, lambda_lim], then n_refine rounds that re-grid
+        around EACH env's own minimiser (obj is convex piecewise linear in lambda, so the minimiser stays bracketed).
+        Final resolution: lambda_lim * (2 / (n_probes - 1)) ** n_refine / (n_probes - 1) for every env."""
         E = s.shape[1]
-        lo = torch.zeros(E, dtype=_F64, device=self.device)
-        hi = torch.full((E,), self.lambda_lim, dtype=_F64, device=self.device)
-        best = None
-        for rd in range(1 + self.n_refine):
-            if rd == 0 or E == 1:
-                grid = lo[0] + (hi[0] - lo[0]) * torch.linspace(0, 1, self.n_probes, dtype=_F64, device=self.device)
-                obj, _, _ = self.objective(s, grid.contiguous())
-                k = obj.argmin(dim=1)
-                best = grid[k]
-                step = (hi[0] - lo[0]) / (self.n_probes - 1)
-                lo = torch.clamp(best - step, min=0.0)
-                hi = torch.clamp(best + step, max=self.lambda_lim)
-            else:
-                break   # per-env refinement needs one VI batch per env; the shared grid is the E > 1 resolution
+        unit = torch.linspace(0, 1, self.n_probes, dtype=_F64, device=self.device)
+        grid = (self.lambda_lim * unit).contiguous()
+        obj, _, _ = self.objective(s, grid)
+        best = grid[obj.argmin(dim=1)]                                                # [E]
+        step = self.lambda_lim / (self.n_probes - 1)
+        for _ in range(self.n_refine):
+            lo = torch.clamp(best - step, min=0.0)
+            hi = torch.clamp(best + step, max=self.lambda_lim)
+            grids = (lo[:, None] + (hi - lo)[:, None] * unit[None, :]).contiguous()   # [E,P]
+            obj = self._objective_per_env(s, grids)
+            best = torch.gather(grids, 1, obj.argmin(dim=1, keepdim=True))[:, 0]
+            step = 2.0 * step / (self.n_probes - 1)
         return best
 
     def act_test_device(self, s):

@@ -264,8 +264,13 @@ class MARolloutTrainer:
             s_all = self.s_full_traj if sharded else self.s_traj
             a_all = self.a_full if sharded else a
             NT = self.N_total
-            obs = s_all[:, :T].permute(1, 2, 0).reshape(T * E, NT).to(_F32) * self.obs_scale
-            obs_n = obs / float(ac.nature_state_norm)
+            # compute_loss_pi_nature / compute_loss_v_nature (:359-364, :421-428) divide the RAW buffer observations by
+            # nature_state_norm when the nets are not one-hot and by nothing otherwise -- NOT by state_norm as step() does
+            # (ma_rmabppo_core.py:276-289); kept as the reference has it
+            obs = s_all[:, :T].permute(1, 2, 0).reshape(T * E, NT).to(_F32)
+            if not ac.one_hot_encode:
+                obs = obs / float(ac.nature_state_norm)
+            obs_n = obs
             act = self.a_nat.reshape(T * E, D)
             advn, lpo, retn = adv_n.reshape(-1), self.logp_nat.reshape(-1), ret_n.reshape(-1)
             for _ in range(self.pi_iters):

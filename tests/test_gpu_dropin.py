@@ -251,6 +251,39 @@ def test_hawkins_policy_against_highs_lp(torch_mod):
         assert a.sum() == B and np.array_equal(a, ovi.hawkins_action_binary(T, R, C, B, state, lam, gamma))
 
 
+def test_hawkins_policy_batched_envs_against_highs_lp(torch_mod):
+    """E > 1: every env's lambda* is refined around ITS OWN minimiser (one batched VI over the envs' grids per round) and
+    must reach the HiGHS optimum of the reference LP (lp_methods.py:11-105) for that env's state vector, as E = 1 does."""
+    torch = torch_mod
+    from oracle import vi as ovi
+    from robustrmab_b200.hawkins import HawkinsAgentPolicy
+    rs = np.random.RandomState(8)
+    N, B, gamma, E = 9, 3.0, 0.9, 5
+    rg = oenv.sample_sub_ranges(oenv.armman_param_ranges(N), rs)
+    p = rg.mean(-1)
+    T = np.zeros((N, 3, 2, 3))
+    for s in range(3):
+        for a in range(2):
+            T[:, s, a] = oenv.armman_probs(np.full(N, s), np.full(N, a), p[:, s, a]).astype(np.float64)
+    R = oenv.rewards_table(1, N, 3).astype(np.float64)
+    C = np.array([0.0, 1.0])
+    pol = HawkinsAgentPolicy(N, T, R, C, B, gamma, 0, n_probes=64, n_refine=4)
+    pol.max_ws_bytes = N * 64 * 3 * 8 * 2 * 2                       # forces the env-chunked path (2 envs per chunk)
+    states = rs.randint(0, 3, (N, E))
+    s_dev = torch.as_tensor(states.astype(np.uint8), device=pol.device)
+    lam = pol.hawkins_lambda_device(s_dev).cpu().numpy()
+    acts = pol.act_test(states)
+    assert acts.shape == (N, E)
+    for e in range(E):
+        _, lam_lp, obj_lp = ovi.hawkins_lp_highs(T, R, C, B, states[:, e], gamma, pol.lambda_lim)
+        obj, _, _ = pol.objective(s_dev[:, e:e + 1].contiguous(), torch.tensor([lam[e], lam_lp], dtype=torch.float64,
+                                                                                device=pol.device))
+        assert obj[0, 0].item() <= obj_lp + 1e-3 and abs(obj[0, 1].item() - obj_lp) < 1e-4 * max(1.0, abs(obj_lp))
+        one = float(pol.act_test(states[:, e], just_hawkins_lambda=True)[0])
+        assert abs(one - lam[e]) < 1e-9                              # the batched refinement = the single-env one
+        assert acts[:, e].sum() == B and np.array_equal(acts[:, e], ovi.hawkins_action_binary(T, R, C, B, states[:, e], lam[e], gamma))
+
+
 @pytest.mark.parametrize("N,A,E,B", [(7, 3, 5, 6), (40, 3, 9, 16), (300, 3, 4, 120), (12, 2, 3, 5), (5, 3, 2, 11)])
 def test_knapsack_multichoice_kernel(torch_mod, N, A, E, B):
     """rmab_knapsack_multichoice against the oracle's DP (same recurrence and tie rule: bit-exact actions), the ILP of
@@ -411,6 +444,82 @@ def test_agent_oracle_sis_stepwise(torch_mod):
     assert a.shape == (N, E) and a.max() <= 2 and (np.array([0, 1, 2])[a].sum(0) <= B).all()
     val = orc.simulate_reward(ac, nature, seed=3, steps_per_epoch=8, epochs=8, gamma=0.9)
     assert np.isfinite(val)
+
+
+def _sis_stepwise(torch, g, name, E):
+    """StepwiseRMABPPO on the problem of tests/golden/train_sis.npz[name] with E env replicas."""
+    from robustrmab_b200.agent_oracle import StepwiseRMABPPO
+    from robustrmab_b200.core import MLPActorCriticRMAB
+    from robustrmab_b200.environments import SISRobustEnv
+    N, S, T, epochs, hidden, seed = [int(x) for x in g[name + "_meta"]]
+    pop = int(g[name + "_pop"])
+    kw = dict(zip([str(k) for k in g[name + "_hyper_names"]], [float(v) for v in g[name + "_hyper_values"]]))
+    env = SISRobustEnv(N, float(g[name + "_B"]), pop, seed, n_envs=E)
+    env.sampled_parameter_ranges = g[name + "_ranges"]
+    ac = MLPActorCriticRMAB(env.observation_space, env.action_space, hidden_sizes=[hidden, hidden], C=env.C, N=N, B=env.B,
+                            one_hot_encode=False, non_ohe_obs_dim=1, state_norm=pop, n_envs=E)
+    ac.Wpi.copy_(torch.as_tensor(g[name + "_Wpi0"])); ac.Wv.copy_(torch.as_tensor(g[name + "_Wv0"]))
+    with torch.no_grad():
+        for i, p in enumerate(ac.lambda_net.parameters()):
+            p.copy_(torch.as_tensor(g[f"{name}_lam0_{i}"]))
+    sw = StepwiseRMABPPO(env, ac, T, kw["gamma"], kw["lam_OTHER"], kw["clip_ratio"], kw["pi_lr"], kw["vf_lr"], kw["lm_lr"],
+                         int(kw["train_pi_iters"]), int(kw["train_v_iters"]), epochs, int(kw["lamb_update_freq"]),
+                         int(kw["final_train_lambdas"]), kw["start_entropy_coeff"], kw["end_entropy_coeff"], seed)
+
+    class Nature:
+        param_setting = g[name + "_nature"]
+    return sw, ac, Nature(), epochs
+
+
+@pytest.mark.parametrize("name", ["h16", "h64"])
+def test_stepwise_sis_matches_reference_best_response(torch_mod, golden, name):
+    """The stepwise device loop on SIS (S = pop + 1, A = 3, C = [0,1,2], scalar input s / state_norm; hidden 16 = FFMA
+    per-sample update, hidden 64 = tcgen05 per-sample rows) against the values logged by the UNMODIFIED reference
+    AgentOracle.best_response(data='sis') run with every draw injected (tests/golden/train_sis.npz), E = 1.
+    Contract: identical trajectories (returns) while the nets agree, lambda 1e-4 relative, nets 3e-3 absolute after
+    epochs x 10 Adam steps of lr 2e-3 (one Adam step of slack, see tests/test_gpu_ma.py)."""
+    torch = torch_mod
+    g = golden("train_sis")
+    sw, ac, nature, epochs = _sis_stepwise(torch, g, name, 1)
+    ret, lamb, vv = [], [], []
+    for _ in range(epochs):
+        st = sw.epoch(nature)
+        ret.append(float(st["EpActualRet"][0])); lamb.append(float(st["Lamb"][0])); vv.append(float(st["VVals"][0]))
+    np.testing.assert_allclose(ret[:2], g[name + "_AverageEpActualRet"][:2], rtol=1e-6)
+    np.testing.assert_allclose(lamb, g[name + "_AverageLamb"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(vv[:2], g[name + "_AverageVVals"][:2], rtol=1e-3, atol=1e-4)
+    if np.allclose(ret, g[name + "_AverageEpActualRet"], rtol=1e-6):     # identical trajectories throughout
+        np.testing.assert_allclose(ac.Wpi.cpu().numpy(), g[name + "_Wpi1"], atol=3e-3)
+        np.testing.assert_allclose(ac.Wv.cpu().numpy(), g[name + "_Wv1"], atol=3e-3)
+        sw.export_lambda()
+        for i, p in enumerate(ac.lambda_net.parameters()):
+            np.testing.assert_allclose(p.detach().numpy(), g[f"{name}_lam1_{i}"], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["h16", "h64"])
+def test_stepwise_sis_matches_oracle_batched(torch_mod, golden, name):
+    """The same loop with E = 6 env replicas against oracle/train.py (pinned to the reference on SIS by
+    test_epoch_loop_sis_matches_reference_best_response): first-epoch states / actions bit for bit, buffers 1e-4."""
+    torch = torch_mod
+    from oracle.golden_setup import sis_rmabppo_oracle
+    g = golden("train_sis")
+    E = 6
+    sw, ac, nature, epochs = _sis_stepwise(torch, g, name, E)
+    cpu, _ = sis_rmabppo_oracle(g, name, n_envs=E)
+    for ep in range(3):
+        st = sw.epoch(nature)
+        w = cpu.epoch()
+        np.testing.assert_allclose(st["Lamb"].cpu().numpy(), w["lamb"], rtol=1e-4, atol=1e-5)
+        if ep == 0:
+            assert np.array_equal(sw.a.cpu().numpy(), w["a"])
+            assert np.array_equal(sw.s_traj.cpu().numpy()[:, 1:], w["s_traj"][:, 1:])
+            np.testing.assert_allclose(sw.val.cpu().numpy(), w["val"], rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(sw.logp.cpu().numpy(), w["logp"], rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(st["EpActualRet"].cpu().numpy(), w["rew_sum"], rtol=1e-6)
+        else:
+            assert (sw.a.cpu().numpy() == w["a"]).mean() > 0.9
+    np.testing.assert_allclose(ac.Wpi.cpu().numpy(), cpu.opt.Wpi.detach().numpy(), atol=3e-3)
+    np.testing.assert_allclose(ac.Wv.cpu().numpy(), cpu.opt.Wv.detach().numpy(), atol=3e-3)
 
 
 def test_value_iteration_dropin(torch_mod, golden):

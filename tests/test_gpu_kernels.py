@@ -480,6 +480,24 @@ def test_whittle_bisect(K, golden, dom):
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_whittle_bisect_pinned_to_index_lp(K, seed):
+    """rmab_whittle_bisect against a HiGHS restatement of the reference's index LP (lp_methods.py:111-212,
+    oracle/vi.py::whittle_lp_highs; Gurobi itself is absent), N = 10 arms per domain.  Where the LP's optimum is the
+    Bellman solution the indices agree to 1e-6 (the whole counterexample domain); every other entry is one of the
+    documented ways that LP leaves the Bellman solution (oracle/vi.py::whittle_lp_pin) -- never an unexplained one."""
+    tot = {}
+    for name, T, R, C, lim in ovi.whittle_pin_instances(seed):
+        idx = K.n(K.ops.whittle_bisect(K.t(T, np.float64), K.t(R, np.float64), K.t(C, np.float64), 0.9, 1e-10, 0.0, lim, 40))
+        cnt, bad = ovi.whittle_lp_pin(idx, T, R, C, 0.9, lim)
+        assert cnt["mismatch"] == 0, (name, bad)
+        if name == "ce":
+            assert cnt["agree"] == idx.size - cnt["quirk"]
+        for k, v in cnt.items():
+            tot[k] = tot.get(k, 0) + v
+    assert tot["agree"] >= 0.75 * (sum(tot.values()) - tot["quirk"])
+
+
 def test_vi_per_arm_lambdas_and_scale(K):
     rs = np.random.RandomState(4)
     N, L = 2000, 16

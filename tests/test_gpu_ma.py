@@ -298,3 +298,175 @@ def test_nature_oracle_resamples_agent_strategy(K):
     assert {id(p) for p in orc.agent_pol_history} == {id(pess), id(ac)}
     assert ac.n_envs == 1                                   # the caller's strategy object is not mutated
     assert all(np.isfinite(h["EpLambAdjRetNature"]).all() for h in orc.history)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# SIS (BASELINE configs[3]'s domain: S = pop + 1, A = 3, C = [0,1,2], D = 4N nature parameters, scalar state inputs)
+# Tolerances: the integer path (states, actions) is compared bit for bit on the first epoch, i.e. while both sides hold
+# identical nets; per-step float outputs of that epoch are held to 1e-4 relative (fp32 nets evaluated with different
+# summation orders: tensor-core 3xTF32 / fused FMA here, numpy / torch CPU in the oracle; north_star's 1e-5 applies to
+# returns, advantages, losses and indices, which test_gpu_kernels / test_gpu_epoch hold at 1e-5 on fixed inputs).  Nets
+# AFTER several Adam steps are compared at 3e-3 absolute: Adam divides by sqrt(v) + 1e-8, so a gradient entry near zero
+# turns an fp32 rounding difference into a full +-lr step (lr = 2e-3 here) -- the bound is one such step plus drift, and
+# it is what the reference-golden tests below also use.
+def _sis_problem(K, N, E, pop, h, seed, B):
+    from robustrmab_b200.environments import SISRobustEnv
+    from robustrmab_b200.ma_core import RMABLambdaNatureOracle
+    env = SISRobustEnv(N, B, pop, seed, n_envs=E)
+    env.sampled_parameter_ranges = env.sample_parameter_ranges()
+    K.torch.manual_seed(seed)
+    ac = RMABLambdaNatureOracle(env.observation_space, env.action_space, env.sampled_parameter_ranges,
+                                env.action_dim_nature, env, hidden_sizes=[h, h], C=env.C, N=N, B=B, n_envs=E,
+                                one_hot_encode=False, non_ohe_obs_dim=1, state_norm=pop, nature_state_norm=1)
+    return env, ac
+
+
+@pytest.mark.parametrize("pop,h", [(10, 16), (20, 64), (10, 64)])
+def test_ma_epoch_loop_sis_matches_oracle(K, pop, h):
+    """Device MA-RMABPPO loop on SIS against oracle/ma_train.py (itself pinned to the unmodified reference on SIS by
+    tests/golden/ma_train_sis.npz), E = 4 envs, incl. the lambda step and the nature PPO updates of epoch 2."""
+    import copy
+    from oracle.ma_train import CpuMARMABPPO
+    from robustrmab_b200.baselines import PessimisticAgentPolicy
+    from robustrmab_b200.nature_oracle import MARolloutTrainer
+    N, E, T, B, epochs = 6, 4, 6, 3.0, 4
+    S = pop + 1
+    env, ac = _sis_problem(K, N, E, pop, h, 13, B)
+    hyp = dict(gamma=0.9, lam_other=0.97, clip_ratio=2.0, pi_lr_agent=2e-3, pi_lr_nature=2e-3, vf_lr_agent=2e-3,
+               vf_lr_nature=2e-3, lm_lr=2e-3, pi_iters=3, v_iters=3, epochs=epochs, lamb_update_freq=2,
+               final_train_lambdas=1, ent0=0.5, ent1=0.0, seed=13)
+    lam = [p.detach().numpy().copy() for p in ac.lambda_net.parameters()]
+    cpu = CpuMARMABPPO(oenv.DOMAIN_SIS, K.n(ac.Wpi), K.n(ac.Wv), K.n(ac.W1n), lam, copy.deepcopy(ac.pi_nature.mu_net).cpu(),
+                       K.n(ac.pi_nature.log_std), copy.deepcopy(ac.v_nature.v_net).cpu(), env.sampled_parameter_ranges,
+                       oenv.rewards_table(2, N, S), np.array([0, 1, 2], F32), E, T, h, B, hyp["gamma"], hyp["lam_other"],
+                       hyp["clip_ratio"], hyp["pi_lr_agent"], hyp["pi_lr_nature"], hyp["vf_lr_agent"], hyp["vf_lr_nature"],
+                       hyp["lm_lr"], hyp["pi_iters"], hyp["v_iters"], epochs, hyp["lamb_update_freq"],
+                       hyp["final_train_lambdas"], hyp["ent0"], hyp["ent1"], hyp["seed"], pop=pop, one_hot=False,
+                       state_norm=pop, nature_state_norm=1.0)
+    tr = MARolloutTrainer(env, ac, T, hyp["gamma"], hyp["lam_other"], hyp["clip_ratio"], hyp["pi_lr_agent"],
+                          hyp["pi_lr_nature"], hyp["vf_lr_agent"], hyp["vf_lr_nature"], hyp["lm_lr"], hyp["pi_iters"],
+                          hyp["v_iters"], epochs, hyp["lamb_update_freq"], hyp["final_train_lambdas"], hyp["ent0"],
+                          hyp["ent1"], hyp["seed"])
+    pess = PessimisticAgentPolicy(N)
+    for ep in range(3):
+        st = tr.epoch(pess)
+        w = cpu.epoch(lambda s: np.zeros_like(s))
+        np.testing.assert_allclose(K.n(st["Lamb"]), w["lamb"], rtol=1e-4, atol=1e-5)
+        if ep == 0:
+            assert np.array_equal(K.n(tr.a), w["a"]) and np.array_equal(K.n(tr.s_traj), w["s_traj"])
+            np.testing.assert_allclose(K.n(tr.a_nat), w["a_nat"], rtol=1e-4, atol=2e-5)
+            np.testing.assert_allclose(K.n(tr.rew_nat), w["rew_nat"], rtol=1e-4, atol=1e-4)
+            np.testing.assert_allclose(K.n(tr.val), w["val"], rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(K.n(tr.val_nat), w["val_nat"], rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(K.n(st["EpActualRetAgent"]), w["ret_agent"], rtol=1e-6)
+        else:
+            assert (K.n(tr.a) == w["a"]).mean() > 0.9, ep
+    np.testing.assert_allclose(K.n(ac.Wpi), cpu.opt.Wpi.detach().numpy(), atol=3e-3)
+    np.testing.assert_allclose(K.n(ac.Wv), cpu.opt.Wv.detach().numpy(), atol=3e-3)
+    np.testing.assert_allclose(K.n(ac.W1n), cpu.W1n.detach().numpy(), atol=3e-3)
+    np.testing.assert_allclose(K.n(ac.pi_nature.log_std), cpu.log_std.detach().numpy(), atol=3e-3)
+    for p, q in zip(ac.pi_nature.mu_net.parameters(), cpu.mu_net.parameters()):
+        np.testing.assert_allclose(K.n(p), q.detach().numpy(), atol=5e-3)
+    for p, q in zip(ac.v_nature.v_net.parameters(), cpu.v_nature.parameters()):
+        np.testing.assert_allclose(K.n(p), q.detach().numpy(), atol=5e-3)
+
+
+def test_ma_device_loop_sis_matches_reference_nature_oracle(K, golden):
+    """Device MA-RMABPPO loop on SIS (hidden 64, E = 1) against the values logged by the UNMODIFIED reference
+    NatureOracle.best_response on SISRobustEnv with every draw injected (tests/golden/ma_train_sis.npz)."""
+    torch = K.torch
+    from robustrmab_b200.baselines import PessimisticAgentPolicy
+    from robustrmab_b200.environments import SISRobustEnv
+    from robustrmab_b200.ma_core import RMABLambdaNatureOracle
+    from robustrmab_b200.nature_oracle import MARolloutTrainer
+    g = golden("ma_train_sis")
+    N, S, T, epochs, h, seed, D = [int(x) for x in g["meta"]]
+    pop = int(g["pop"])
+    kw = dict(zip([str(k) for k in g["hyper_names"]], [float(v) for v in g["hyper_values"]]))
+    env = SISRobustEnv(N, float(g["B"]), pop, seed)
+    env.sampled_parameter_ranges = g["ranges"]
+    ac = RMABLambdaNatureOracle(env.observation_space, env.action_space, env.sampled_parameter_ranges, D, env,
+                                hidden_sizes=[h, h], C=env.C, N=N, B=env.B, one_hot_encode=False, non_ohe_obs_dim=1,
+                                state_norm=pop, nature_state_norm=1)
+    ac.Wpi.copy_(K.t(g["Wpi0"])); ac.Wv.copy_(K.t(g["Wv0"])); ac.W1n.copy_(K.t(g["W1n0"]))
+    with torch.no_grad():
+        for tag, seq in (("mu0", ac.pi_nature.mu_net), ("vn0", ac.v_nature.v_net)):
+            for j, m in enumerate([m for m in seq if isinstance(m, torch.nn.Linear)]):
+                m.weight.copy_(K.t(g[f"{tag}_{2 * j}"])); m.bias.copy_(K.t(g[f"{tag}_{2 * j + 1}"]))
+        ac.pi_nature.log_std.copy_(K.t(g["log_std0"]))
+        for i, p in enumerate(ac.lambda_net.parameters()):
+            p.copy_(torch.as_tensor(g[f"lam0_{i}"]))
+    tr = MARolloutTrainer(env, ac, T, kw["gamma"], kw["lam_OTHER"], kw["clip_ratio"], kw["pi_lr_agent"], kw["pi_lr_nature"],
+                          kw["vf_lr_agent"], kw["vf_lr_nature"], kw["lm_lr"], int(kw["train_pi_iters"]),
+                          int(kw["train_v_iters"]), epochs, int(kw["lamb_update_freq"]), int(kw["final_train_lambdas"]),
+                          kw["start_entropy_coeff"], kw["end_entropy_coeff"], seed)
+    pess = PessimisticAgentPolicy(N)
+    lamb, ret, rn, vv, vn = [], [], [], [], []
+    for _ in range(epochs):
+        st = tr.epoch(pess)
+        lamb.append(float(st["Lamb"][0])); ret.append(float(st["EpActualRetAgent"][0]))
+        rn.append(float(st["EpLambAdjRetNature"][0])); vv.append(float(st["VVals_agent"][0])); vn.append(float(st["VVals_nature"][0]))
+    # the first two epochs run on (nearly) the reference's nets: same trajectories; later ones may flip single draws
+    np.testing.assert_allclose(ret[:2], g["EpActualRetAgent"][:2], rtol=1e-6)
+    np.testing.assert_allclose(lamb, g["Lamb"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(rn[:2], g["EpLambAdjRetNature"][:2], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(vv[:2], g["VVals_agent"][:2], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(vn[:2], g["VVals_nature"][:2], rtol=1e-3, atol=1e-4)
+    if np.allclose(ret, g["EpActualRetAgent"], rtol=1e-6):        # identical trajectories throughout: nets comparable
+        np.testing.assert_allclose(K.n(ac.Wpi), g["Wpi1"], atol=3e-3)
+        np.testing.assert_allclose(K.n(ac.Wv), g["Wv1"], atol=3e-3)
+        np.testing.assert_allclose(K.n(ac.W1n), g["W1n1"], atol=3e-3)
+        tr.export_lambda()
+        for i, p in enumerate(ac.lambda_net.parameters()):
+            np.testing.assert_allclose(p.detach().numpy(), g[f"lam1_{i}"], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("N,T,E,S", [(3, 6, 8, 11), (2, 20, 40, 51)])
+def test_critic_extra_iter_h64_vs_autograd_oracle(K, N, T, E, S):
+    """rmab_critic_extra_iter at hidden 64 in its tcgen05 (sample-major) mode DIRECTLY against torch autograd on the
+    reference's critic (compute_loss_v_agent, nature_oracle.py:388-416, as restated in oracle/ma_train.py): loss before
+    the step, dLoss/dz1, and the packed critic after three Adam steps.  Contract: loss 1e-5 relative (north_star);
+    dz1 (of the THIRD step, i.e. after two Adam steps on either side) 1e-3 relative + 1e-8 -- entries are O(1e-6), the
+    mean over T*E samples; weights 2e-4 absolute after 3 Adam steps of lr 2e-3."""
+    import torch
+    from oracle import ppo as oppo
+    rs = np.random.RandomState(N * 10 + E)
+    h, in_dim = 64, 2
+    Wv0 = onets.init_linear_default(rs, N, in_dim, h, 1)
+    s = rs.randint(0, S, size=(N, T + 1, E)).astype(np.uint8)
+    ret = (rs.randn(N, T, E) * 2).astype(F32)
+    lamb = rs.uniform(0, 2, size=E).astype(F32)
+    z1 = (rs.randn(T * E, N, h) * 0.3).astype(F32)                               # sample-major extra pre-activation
+    net = K.ops.net_desc(N, E, S, 3, h, False, float(S - 1))
+    # ---- oracle: autograd + torch Adam on the same loss ----
+    W = torch.nn.Parameter(torch.as_tensor(Wv0.copy()))
+    opt = torch.optim.Adam([W], lr=2e-3)
+    x = np.stack([onets.features(s[:, t], lamb, S, False, float(S - 1)) for t in range(T)], axis=1).reshape(N, T * E, in_dim)
+    xt, rt = torch.as_tensor(x), torch.as_tensor(ret.reshape(N, T * E))
+    zt = torch.as_tensor(z1.transpose(1, 0, 2).copy()).requires_grad_(True)       # [N, T*E, h]
+    want_loss, want_dz = [], None
+    for it in range(3):
+        opt.zero_grad()
+        zt.grad = None
+        W1, b1, W2, b2, W3, b3 = oppo._unpack_t(W, in_dim, h, 1)
+        pre = torch.bmm(xt, W1.transpose(1, 2)) + b1[:, None, :] + zt
+        a2 = torch.tanh(torch.bmm(torch.tanh(pre), W2.transpose(1, 2)) + b2[:, None, :])
+        v = (torch.bmm(a2, W3.transpose(1, 2)) + b3[:, None, :])[..., 0]
+        loss = ((v - rt) ** 2).mean(dim=1)
+        loss.sum().backward()
+        want_loss.append(loss.detach().numpy().copy())
+        want_dz = zt.grad.detach().numpy().copy()
+        opt.step()
+    # ---- device ----
+    Wv = K.t(Wv0.copy())
+    adam = K.torch.zeros((N, 2, Wv0.shape[1]), device=K.dev)
+    got_loss = []
+    for it in range(3):
+        hp = K.ops.hyper(0.2, 0.0, 2e-3, 2e-3, 0, 1, 0, it)
+        dz, loss = K.ops.critic_extra_iter(net, hp, Wv, adam, K.t(s), K.t(ret), K.t(lamb), K.t(z1), want_loss=True,
+                                           sample_major=True)
+        got_loss.append(K.n(loss)[:, 0])
+    np.testing.assert_allclose(np.array(got_loss)[0], want_loss[0], rtol=1e-5)
+    np.testing.assert_allclose(np.array(got_loss), np.array(want_loss), rtol=1e-4)     # after 1-2 Adam steps
+    np.testing.assert_allclose(K.n(dz).transpose(1, 0, 2), want_dz, rtol=1e-3, atol=1e-8)
+    np.testing.assert_allclose(K.n(Wv), W.detach().numpy(), rtol=0, atol=2e-4)

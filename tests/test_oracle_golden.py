@@ -3,6 +3,7 @@
 import numpy as np
 import pytest
 
+from oracle.golden_setup import ma_train_setup, sis_ma_oracle, sis_rmabppo_oracle
 from oracle import buffer as obuf
 from oracle import envs as oenv
 from oracle import nets as onets
@@ -221,6 +222,25 @@ def test_epoch_loop_matches_reference_best_response(golden, name, domain):
         np.testing.assert_allclose(p.detach().numpy(), g[f"{name}_lam1_{i}"], rtol=1e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize("name", ["h16", "h64"])
+def test_epoch_loop_sis_matches_reference_best_response(golden, name):
+    """oracle/train.py on the SIS domain (S = pop + 1, A = 3, C = [0,1,2], scalar state input s / state_norm) against the
+    unmodified reference AgentOracle.best_response(data='sis') with every draw injected (gen_train_sis)."""
+    g = golden("train_sis")
+    cpu, epochs = sis_rmabppo_oracle(g, name)
+    lamb, ret, vv = [], [], []
+    for _ in range(epochs):
+        w = cpu.epoch()
+        lamb.append(w["lamb"][0]); ret.append(w["rew_sum"][0]); vv.append(w["val"].mean())
+    np.testing.assert_allclose(ret, g[name + "_AverageEpActualRet"], rtol=1e-6)   # same trajectories (R = linspace: fp32 sums)
+    np.testing.assert_allclose(lamb, g[name + "_AverageLamb"], rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(vv, g[name + "_AverageVVals"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(cpu.opt.Wpi.detach().numpy(), g[name + "_Wpi1"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(cpu.opt.Wv.detach().numpy(), g[name + "_Wv1"], rtol=0, atol=2e-5)
+    for i, p in enumerate(cpu.lam_params):
+        np.testing.assert_allclose(p.detach().numpy(), g[f"{name}_lam1_{i}"], rtol=1e-5, atol=1e-7)
+
+
 @pytest.mark.parametrize("name,domain", [("ce", 0), ("armman", 1)])
 def test_ma_step_matches_reference(golden, name, domain):
     """oracle/ma.py against RMABLambdaNatureOracle.step of the unmodified reference (injected Normal / Categorical draws)."""
@@ -254,28 +274,12 @@ def test_ma_step_matches_reference(golden, name, domain):
         np.testing.assert_allclose(vn, g[name + "_out_vn"][k], rtol=1e-5, atol=1e-6)
 
 
-def _ma_train_setup(g):
-    import torch
-    N, S, T, epochs, h, seed, D = [int(x) for x in g["meta"]]
-    kw = dict(zip([str(k) for k in g["hyper_names"]], [float(v) for v in g["hyper_values"]]))
-
-    def dense(prefix, sizes):
-        layers = []
-        for j in range(len(sizes) - 1):
-            lin = torch.nn.Linear(sizes[j], sizes[j + 1])
-            with torch.no_grad():
-                lin.weight.copy_(torch.as_tensor(g[f"{prefix}_{2 * j}"])); lin.bias.copy_(torch.as_tensor(g[f"{prefix}_{2 * j + 1}"]))
-            layers += [lin, torch.nn.Tanh() if j < len(sizes) - 2 else torch.nn.Identity()]
-        return torch.nn.Sequential(*layers)
-    return N, S, T, epochs, h, seed, D, kw, dense
-
-
 def test_ma_epoch_loop_matches_reference_nature_oracle(golden):
     """oracle/ma_train.py against the UNMODIFIED reference NatureOracle.best_response (vs a Pessimist agent) run with
     every draw injected (oracle/gen_golden_train.py::gen_ma_train): logged per-epoch values and the final nets."""
     from oracle.ma_train import CpuMARMABPPO
     g = golden("ma_train")
-    N, S, T, epochs, h, seed, D, kw, dense = _ma_train_setup(g)
+    N, S, T, epochs, h, seed, D, kw, dense = ma_train_setup(g)
     cpu = CpuMARMABPPO(0, g["Wpi0"], g["Wv0"], g["W1n0"], [g[f"lam0_{i}"] for i in range(6)], dense("mu0", [N, h, h, D]),
                        g["log_std0"], dense("vn0", [2 * N, h, h, 1]), g["ranges"], oenv.rewards_table(0, N, S),
                        np.array([0, 1], F32), 1, T, h, float(g["B"]), kw["gamma"], kw["lam_OTHER"], kw["clip_ratio"],
@@ -302,3 +306,49 @@ def test_ma_epoch_loop_matches_reference_nature_oracle(golden):
         np.testing.assert_allclose(p.detach().numpy(), g[f"vn1_{i}"], atol=2e-5)
     for i, p in enumerate(cpu.lam_params):
         np.testing.assert_allclose(p.detach().numpy(), g[f"lam1_{i}"], rtol=1e-5, atol=1e-7)
+
+
+def test_ma_epoch_loop_sis_matches_reference_nature_oracle(golden):
+    """BASELINE configs[3]'s domain: oracle/ma_train.py on SIS (S = pop + 1, A = 3, D = 4N, hidden 64, scalar inputs)
+    against the UNMODIFIED reference NatureOracle.best_response with every draw injected (gen_ma_train_sis)."""
+    g = golden("ma_train_sis")
+    cpu, epochs = sis_ma_oracle(g)
+    lamb, ret, rn, vv, vn = [], [], [], [], []
+    for _ in range(epochs):
+        w = cpu.epoch(lambda s: np.zeros_like(s))
+        lamb.append(w["lamb"][0]); ret.append(w["ret_agent"][0]); rn.append(w["rew_nat"].sum())
+        vv.append(w["val"].mean()); vn.append(w["val_nat"].mean())
+    np.testing.assert_allclose(ret, g["EpActualRetAgent"], rtol=1e-6)             # same trajectories
+    np.testing.assert_allclose(lamb, g["Lamb"], rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(rn, g["EpLambAdjRetNature"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(vv, g["VVals_agent"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(vn, g["VVals_nature"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(cpu.opt.Wpi.detach().numpy(), g["Wpi1"], atol=2e-5)
+    np.testing.assert_allclose(cpu.opt.Wv.detach().numpy(), g["Wv1"], atol=2e-5)
+    np.testing.assert_allclose(cpu.W1n.detach().numpy(), g["W1n1"], atol=2e-5)
+    np.testing.assert_allclose(cpu.log_std.detach().numpy(), g["log_std1"], atol=2e-5)
+    for i, p in enumerate(cpu.mu_net.parameters()):
+        np.testing.assert_allclose(p.detach().numpy(), g[f"mu1_{i}"], atol=2e-5)
+    for i, p in enumerate(cpu.v_nature.parameters()):
+        np.testing.assert_allclose(p.detach().numpy(), g[f"vn1_{i}"], atol=2e-5)
+    for i, p in enumerate(cpu.lam_params):
+        np.testing.assert_allclose(p.detach().numpy(), g[f"lam1_{i}"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("seed", [0])
+def test_whittle_bisect_pinned_to_index_lp(seed):
+    """The indifference-point index (oracle bisection) against a HiGHS restatement of the reference's index LP
+    (lp_methods.py:111-212, oracle/vi.py::whittle_lp_highs; Gurobi itself is absent).  Wherever the LP's optimum is the
+    Bellman solution the two agree to 1e-6 (all of the counterexample domain); every other entry is one of the
+    documented ways the LP leaves the Bellman solution -- never an unexplained difference."""
+    from oracle import vi as ovi
+    tot = {}
+    for name, T, R, C, lim in ovi.whittle_pin_instances(seed):
+        idx = ovi.whittle_bisect(T, R, C, 0.9, 1e-10, 0.0, lim, 36, stop="abs")
+        cnt, bad = ovi.whittle_lp_pin(idx, T, R, C, 0.9, lim)
+        assert cnt["mismatch"] == 0, (name, bad)
+        if name == "ce":
+            assert cnt["agree"] == idx.size - cnt["quirk"]
+        for k, v in cnt.items():
+            tot[k] = tot.get(k, 0) + v
+    assert tot["agree"] >= 0.75 * (sum(tot.values()) - tot["quirk"])
