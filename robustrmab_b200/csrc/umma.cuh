@@ -135,6 +135,60 @@ __device__ __forceinline__ void split_u(float x, uint32_t& hi, uint32_t& lo) {
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100a): one issue slot for two IEEE-rn fp32 operations.  The
+// update kernels are bound by instruction issue, not by the FMA pipe, so the per-feature elementwise work runs on
+// feature PAIRS held in aligned 64-bit registers; results are bit-identical to the scalar fmaf / * / + forms.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 pack2u(uint32_t a, uint32_t b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ void unpack2u(f32x2 v, uint32_t& a, uint32_t& b) { asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 dup2(float a) { return pack2(a, a); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// tanh of a pair given y = x * 2 / ln 2:  t = 1 - 2 / (2^y + 1)  and  -t = 2 / (2^y + 1) - 1  (both exact mirror images)
+__device__ __forceinline__ void tanh2_scaled(f32x2 y, f32x2& t, f32x2& nt) {
+  float y0, y1, e0, e1, r0, r1;
+  unpack2(y, y0, y1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(y0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(y1));
+  float d0, d1;
+  unpack2(add2(pack2(e0, e1), dup2(1.f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+  const f32x2 r = pack2(r0, r1);
+  t = fma2(r, dup2(-2.f), dup2(1.f));
+  nt = fma2(r, dup2(2.f), dup2(-1.f));
+}
+// 3xTF32 split of a pair: hi = the tf32-representable head, lo = x - hi (exact)
+__device__ __forceinline__ void split2(f32x2 x, f32x2& hi, f32x2& lo) {
+  uint32_t a, b;
+  unpack2u(x, a, b);
+  hi = pack2u(a & 0xffffe000u, b & 0xffffe000u);
+  lo = fma2(hi, dup2(-1.f), x);
+}
+
 // Column sums over the 32 lanes of 16 per-lane values: lane l returns the sum of column l >> 1 (both lanes of a pair).
 __device__ __forceinline__ float colsum16(const float (&v)[16], int lane) {
   float a[8], b[4], c[2];

@@ -385,8 +385,8 @@ def test_agent_oracle_dropin_and_stepwise_equals_fused(torch_mod, data):
     for ep in range(epochs):
         agree = (rets[ep] == orc.history[ep]["EpActualRet"]).mean()
         assert agree == 1.0 if ep == 0 else agree > 0.7, (ep, agree)         # epoch 0: identical trajectories
-    np.testing.assert_allclose(ac2.Wpi.cpu().numpy(), ac.Wpi.cpu().numpy(), atol=3e-3)
-    np.testing.assert_allclose(ac2.Wv.cpu().numpy(), ac.Wv.cpu().numpy(), atol=3e-3)
+    np.testing.assert_allclose(ac2.Wpi.cpu().numpy(), ac.Wpi.cpu().numpy(), atol=0.0001)
+    np.testing.assert_allclose(ac2.Wv.cpu().numpy(), ac.Wv.cpu().numpy(), atol=0.0001)
 
 
 def test_checkpoint_roundtrip_and_resume(torch_mod, tmp_path):
@@ -476,8 +476,8 @@ def test_stepwise_sis_matches_reference_best_response(torch_mod, golden, name):
     """The stepwise device loop on SIS (S = pop + 1, A = 3, C = [0,1,2], scalar input s / state_norm; hidden 16 = FFMA
     per-sample update, hidden 64 = tcgen05 per-sample rows) against the values logged by the UNMODIFIED reference
     AgentOracle.best_response(data='sis') run with every draw injected (tests/golden/train_sis.npz), E = 1.
-    Contract: identical trajectories (returns) while the nets agree, lambda 1e-4 relative, nets 3e-3 absolute after
-    epochs x 10 Adam steps of lr 2e-3 (one Adam step of slack, see tests/test_gpu_ma.py)."""
+    Contract: identical trajectories (returns) while the nets agree, lambda 1e-5 relative, nets 1e-4 absolute after
+    epochs x 10 Adam steps of lr 2e-3 (measured headroom: profiles/r2_tolerance_headroom.json)."""
     torch = torch_mod
     g = golden("train_sis")
     sw, ac, nature, epochs = _sis_stepwise(torch, g, name, 1)
@@ -485,15 +485,23 @@ def test_stepwise_sis_matches_reference_best_response(torch_mod, golden, name):
     for _ in range(epochs):
         st = sw.epoch(nature)
         ret.append(float(st["EpActualRet"][0])); lamb.append(float(st["Lamb"][0])); vv.append(float(st["VVals"][0]))
-    np.testing.assert_allclose(ret[:2], g[name + "_AverageEpActualRet"][:2], rtol=1e-6)
-    np.testing.assert_allclose(lamb, g[name + "_AverageLamb"], rtol=1e-4, atol=2e-6)
-    np.testing.assert_allclose(vv[:2], g[name + "_AverageVVals"][:2], rtol=1e-3, atol=1e-4)
-    if np.allclose(ret, g[name + "_AverageEpActualRet"], rtol=1e-6):     # identical trajectories throughout
-        np.testing.assert_allclose(ac.Wpi.cpu().numpy(), g[name + "_Wpi1"], atol=3e-3)
-        np.testing.assert_allclose(ac.Wv.cpu().numpy(), g[name + "_Wv1"], atol=3e-3)
+    # With ONE env and a handful of arms a single draw that lands on the other side of a cdf edge (nets equal to ~1e-6
+    # after an Adam step) changes the whole remaining trajectory, so values are compared over the leading epochs whose
+    # trajectories are identical to the reference's -- at least the first two (hidden 16: all of them).
+    want = g[name + "_AverageEpActualRet"]
+    same = 0
+    while same < epochs and abs(ret[same] - want[same]) <= 1e-6 * max(1.0, abs(want[same])):
+        same += 1
+    assert same >= 2 and (name != "h16" or same == epochs), (same, ret, want)
+    k = min(same + 1, epochs)                                    # lambda of epoch `same` still comes from an identical history
+    np.testing.assert_allclose(lamb[:k], g[name + "_AverageLamb"][:k], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(vv[:same], g[name + "_AverageVVals"][:same], rtol=1e-4, atol=1e-5)
+    if same == epochs:
+        np.testing.assert_allclose(ac.Wpi.cpu().numpy(), g[name + "_Wpi1"], atol=1e-4)
+        np.testing.assert_allclose(ac.Wv.cpu().numpy(), g[name + "_Wv1"], atol=1e-4)
         sw.export_lambda()
         for i, p in enumerate(ac.lambda_net.parameters()):
-            np.testing.assert_allclose(p.detach().numpy(), g[f"{name}_lam1_{i}"], rtol=1e-4, atol=1e-6)
+            np.testing.assert_allclose(p.detach().numpy(), g[f"{name}_lam1_{i}"], rtol=1e-5, atol=1e-7)
 
 
 @pytest.mark.parametrize("name", ["h16", "h64"])
@@ -509,17 +517,17 @@ def test_stepwise_sis_matches_oracle_batched(torch_mod, golden, name):
     for ep in range(3):
         st = sw.epoch(nature)
         w = cpu.epoch()
-        np.testing.assert_allclose(st["Lamb"].cpu().numpy(), w["lamb"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(st["Lamb"].cpu().numpy(), w["lamb"], rtol=1e-05, atol=1e-06)
         if ep == 0:
             assert np.array_equal(sw.a.cpu().numpy(), w["a"])
             assert np.array_equal(sw.s_traj.cpu().numpy()[:, 1:], w["s_traj"][:, 1:])
-            np.testing.assert_allclose(sw.val.cpu().numpy(), w["val"], rtol=1e-4, atol=1e-5)
-            np.testing.assert_allclose(sw.logp.cpu().numpy(), w["logp"], rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(sw.val.cpu().numpy(), w["val"], rtol=1e-05, atol=1e-06)
+            np.testing.assert_allclose(sw.logp.cpu().numpy(), w["logp"], rtol=1e-05, atol=1e-06)
             np.testing.assert_allclose(st["EpActualRet"].cpu().numpy(), w["rew_sum"], rtol=1e-6)
         else:
             assert (sw.a.cpu().numpy() == w["a"]).mean() > 0.9
-    np.testing.assert_allclose(ac.Wpi.cpu().numpy(), cpu.opt.Wpi.detach().numpy(), atol=3e-3)
-    np.testing.assert_allclose(ac.Wv.cpu().numpy(), cpu.opt.Wv.detach().numpy(), atol=3e-3)
+    np.testing.assert_allclose(ac.Wpi.cpu().numpy(), cpu.opt.Wpi.detach().numpy(), atol=0.0003)
+    np.testing.assert_allclose(ac.Wv.cpu().numpy(), cpu.opt.Wv.detach().numpy(), atol=0.0001)
 
 
 def test_value_iteration_dropin(torch_mod, golden):

@@ -222,7 +222,7 @@ def test_lambda_net(K, N, E, S):
     half = N // 2
     _, h1a = K.ops.lambda_forward(flat, K.t(s[:half]), N, arm0=0, obs_scale=scale, want_h1=True, want_lamb=False)
     _, h1b = K.ops.lambda_forward(flat, K.t(s[half:]), N, arm0=half, obs_scale=scale, want_h1=True, want_lamb=False)
-    np.testing.assert_allclose(K.n(h1a + h1b), K.n(h1), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(K.n(h1a + h1b), K.n(h1), rtol=1e-05, atol=1e-06)
     lamb2, _ = K.ops.lambda_forward(flat, K.t(s[:half]), N, arm0=0, obs_scale=scale, h1_in=(h1a + h1b).contiguous())
     np.testing.assert_allclose(K.n(lamb2), want, rtol=2e-5, atol=2e-6)
     # SGD step on mean_e lamb_e * coef_e  (compute_loss_lambda, agent_oracle.py:360-376)
@@ -236,7 +236,7 @@ def test_lambda_net(K, N, E, S):
     want_grad = np.concatenate([p.grad.numpy().reshape(-1) for p in tp])
     newp = flat.clone()
     grad = K.ops.lambda_sgd(newp, K.t(s), N, 0, scale, h1, K.t(coef), lr, want_grad=True)
-    np.testing.assert_allclose(K.n(grad), want_grad, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(K.n(grad), want_grad, rtol=1e-05, atol=1e-07)
     np.testing.assert_allclose(K.n(newp), want_new, rtol=1e-5, atol=1e-6)
 
 
@@ -301,7 +301,7 @@ def test_gae_golden(K, golden, name):
     adv_n, _, _, _ = K.ops.gae_explicit(K.t(tr(g[name + "_rew"])), K.t(tr(g[name + "_cost"])),
                                         K.t(tr(g[name + "_val"])), K.t(np.asarray(g[name + "_last"], F32)[:, None]),
                                         K.t(lamb), gamma, lam, normalize=True)
-    np.testing.assert_allclose(K.n(adv_n)[:, :, 0].T, g[name + "_get_adv"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(K.n(adv_n)[:, :, 0].T, g[name + "_get_adv"], rtol=1e-05, atol=1e-06)
 
 
 @pytest.mark.parametrize("domain,N,T,E", [(0, 7, 20, 33), (1, 5, 100, 256), (1, 3, 1, 4), (0, 2, 10, 1024)])
@@ -328,12 +328,12 @@ def test_gae_oracle(K, domain, N, T, E):
     assert np.array_equal(K.n(adv2), wadv) and np.array_equal(K.n(ret2), wret)
     mean = wadv.reshape(N, -1).astype(np.float64).mean(1)
     std = wadv.reshape(N, -1).astype(np.float64).std(1)
-    np.testing.assert_allclose(K.n(stats)[:, 0], mean, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(K.n(stats)[:, 0], mean, rtol=1e-05, atol=1e-06)
     np.testing.assert_allclose(K.n(stats)[:, 1], std, rtol=1e-5)
     if T * E > 1:
         adv_n, _, _, _ = K.ops.gae(K.t(s_traj), K.t(a), K.t(val), K.t(last), K.t(lamb), K.t(Cc), K.t(R), 0.9, 0.97,
                                    normalize=True)
-        np.testing.assert_allclose(K.n(adv_n), obuf.normalize_adv(wadv), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(K.n(adv_n), obuf.normalize_adv(wadv), rtol=1e-05, atol=1e-06)
     cd = K.ops.cost_togo(K.t(a), K.t(Cc), 0.9)
     assert np.array_equal(K.n(cd), wcd)
 
@@ -373,16 +373,16 @@ def test_ppo_update(K, S, A, h, one_hot, N, T, E):
     # of two correct implementations drift apart by rounding)
     np.testing.assert_allclose(K.n(lp)[:, 0], wlp[0], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(K.n(lv)[:, 0], wlv[0], rtol=1e-5, atol=1e-6)
-    np.testing.assert_allclose(K.n(lp).T, wlp, rtol=2e-4, atol=2e-5)
-    np.testing.assert_allclose(K.n(lv).T, wlv, rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(K.n(lp).T, wlp, rtol=2e-05, atol=2e-06)
+    np.testing.assert_allclose(K.n(lv).T, wlv, rtol=2e-05, atol=2e-06)
     np.testing.assert_allclose(K.n(dWpi), opt.Wpi.detach().numpy(), rtol=0, atol=2e-4)
-    np.testing.assert_allclose(K.n(dWv), opt.Wv.detach().numpy(), rtol=0, atol=2e-4)
+    np.testing.assert_allclose(K.n(dWv), opt.Wv.detach().numpy(), rtol=0, atol=2e-05)
     # a second call continues the same Adam state (optimisers persist across epochs, agent_oracle.py:383-388)
     wlp2, _ = oppo.update(opt, s, a, adv, logp_old, ret, lamb, S, A, h, clip, 0.0, 3, 0, one_hot, norm)
     hp2 = K.ops.hyper(clip, 0.0, lr, lr, 3, 0, step0_pi=pi_iters, step0_v=v_iters)
     lp2, _ = K.ops.ppo_update(net, hp2, dWpi, dWv, adam_pi, adam_v, K.t(s), K.t(a), K.t(adv), K.t(logp_old), K.t(ret),
                               K.t(lamb), want_loss=True)
-    np.testing.assert_allclose(K.n(lp2).T, wlp2, rtol=5e-4, atol=5e-5)
+    np.testing.assert_allclose(K.n(lp2).T, wlp2, rtol=5e-05, atol=5e-06)
 
 
 # ------------------------------------------------------------------------------------ selection

@@ -38,13 +38,13 @@ def test_gaussian_sample(K, E, D):
     a, lp = K.ops.gaussian_sample(K.t(mu), K.t(log_std), eps=K.t(eps))
     wa, wlp = oma.gaussian_sample(mu, log_std, eps)
     np.testing.assert_allclose(K.n(a), wa, rtol=1e-6, atol=1e-6)
-    np.testing.assert_allclose(K.n(lp), wlp, rtol=2e-5, atol=1e-4)
+    np.testing.assert_allclose(K.n(lp), wlp, rtol=2e-05, atol=1e-05)
     # Philox path: same normals as the oracle's Box-Muller on the NATURE stream
     a2, lp2 = K.ops.gaussian_sample(K.t(mu), K.t(log_std), r=K.ops.rng(99, K.lib.STREAM_NATURE, 5, env0=2))
     weps = oma.normal_eps(99, 5, E, D, env0=2)
     wa2, wlp2 = oma.gaussian_sample(mu, log_std, weps)
-    np.testing.assert_allclose(K.n(a2), wa2, rtol=1e-4, atol=2e-5)      # sincos / log ulps between libm and CUDA
-    np.testing.assert_allclose(K.n(lp2), wlp2, rtol=1e-4, atol=1e-2 * max(1, D / 1000))
+    np.testing.assert_allclose(K.n(a2), wa2, rtol=1e-05, atol=2e-06)      # sincos / log ulps between libm and CUDA
+    np.testing.assert_allclose(K.n(lp2), wlp2, rtol=1e-05, atol=5e-4 * max(1, D / 1000))
     if E * D > 10000:
         z = (K.n(a2) - mu) / np.exp(log_std)
         assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
@@ -76,8 +76,8 @@ def test_ma_step_dropin_matches_reference(K, golden, name, domain):
         np.testing.assert_allclose(K.n(d["a_nature"])[0], g[name + "_out_an"][k], rtol=1e-5, atol=2e-6)
         np.testing.assert_allclose(K.n(d["a_nature_bounded"])[0], g[name + "_out_anb"][k], rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(K.n(d["logp_nature"])[0], g[name + "_out_lpn"][k], rtol=2e-5)
-        np.testing.assert_allclose(K.n(d["v_nature"])[0], g[name + "_out_vn"][k], rtol=1e-4, atol=2e-6)
-        np.testing.assert_allclose(K.n(d["v_agent"])[:, 0], g[name + "_out_v"][k], rtol=1e-4, atol=5e-6)
+        np.testing.assert_allclose(K.n(d["v_nature"])[0], g[name + "_out_vn"][k], rtol=1e-05, atol=2e-07)
+        np.testing.assert_allclose(K.n(d["v_agent"])[:, 0], g[name + "_out_v"][k], rtol=1e-05, atol=5e-07)
         np.testing.assert_allclose(K.n(d["logp_agent"])[:, 0], g[name + "_out_logp"][k], rtol=1e-5, atol=2e-6)
         np.testing.assert_allclose(K.n(d["p1"])[:, 0], g[name + "_out_p1"][k], rtol=1e-5, atol=1e-7)
     out = ac.step(g[name + "_obs"][0].astype(np.float32), 0.5)      # the reference's 9-tuple and shapes
@@ -100,7 +100,7 @@ def test_agent_critic_extra_batched(K):
     net = K.ops.net_desc(N, E, S, 2, h, n_extra=D)
     a, v, logp, p1, _ = K.ops.ac_step(net, K.t(Wpi), K.t(Wv), K.t(s), K.t(lamb), u=K.t(u), extra=extra)
     want = oma.agent_critic_extra(Wv, W1n, s, lamb, nat, S, h)
-    np.testing.assert_allclose(K.n(v), want, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(K.n(v), want, rtol=1e-05, atol=1e-06)
     with pytest.raises(K.lib.RmabError):
         K.ops.ac_step(net, K.t(Wpi), K.t(Wv), K.t(s), K.t(lamb), u=K.t(u))      # n_extra > 0 without the addend
 
@@ -135,7 +135,7 @@ def test_critic_extra_iter_tcgen05_vs_per_sample_kernel(K, N, T, E, S):
     (l0, d0, w0), (l1, d1, w1) = outs
     np.testing.assert_allclose(l1, l0, rtol=2e-5, atol=1e-6)
     np.testing.assert_allclose(d1, d0, rtol=1e-3, atol=2e-8)
-    np.testing.assert_allclose(w1, w0, rtol=0, atol=1e-4)
+    np.testing.assert_allclose(w1, w0, rtol=0, atol=1e-05)
 
 
 @pytest.mark.parametrize("domain,pop", [(0, None), (1, None), (2, 10), (2, 50)])
@@ -199,23 +199,23 @@ def test_ma_epoch_loop_matches_oracle(K, data, domain):
     for ep in range(3):                                   # epoch 2 runs the lambda step and the nature PPO updates
         st = tr.epoch(pess)
         w = cpu.epoch(lambda s: np.zeros_like(s))
-        np.testing.assert_allclose(K.n(st["Lamb"]), w["lamb"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(K.n(st["Lamb"]), w["lamb"], rtol=1e-05, atol=1e-06)
         agree = (K.n(tr.a) == w["a"]).mean()
         if ep == 0:
             assert agree == 1.0 and np.array_equal(K.n(tr.s_traj), w["s_traj"])
-            np.testing.assert_allclose(K.n(tr.a_nat), w["a_nat"], rtol=1e-4, atol=2e-5)
-            np.testing.assert_allclose(K.n(tr.rew_nat), w["rew_nat"], rtol=1e-4, atol=1e-4)
-            np.testing.assert_allclose(K.n(tr.val), w["val"], rtol=1e-4, atol=1e-5)
-            np.testing.assert_allclose(K.n(tr.val_nat), w["val_nat"], rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(K.n(tr.a_nat), w["a_nat"], rtol=1e-05, atol=2e-06)
+            np.testing.assert_allclose(K.n(tr.rew_nat), w["rew_nat"], rtol=1e-05, atol=1e-05)
+            np.testing.assert_allclose(K.n(tr.val), w["val"], rtol=1e-05, atol=1e-06)
+            np.testing.assert_allclose(K.n(tr.val_nat), w["val_nat"], rtol=1e-05, atol=1e-06)
             assert np.array_equal(K.n(st["EpActualRetAgent"]), w["ret_agent"])
         else:
             assert agree > 0.95, (ep, agree)
-    np.testing.assert_allclose(K.n(ac.Wpi), cpu.opt.Wpi.detach().numpy(), atol=3e-3)
-    np.testing.assert_allclose(K.n(ac.Wv), cpu.opt.Wv.detach().numpy(), atol=3e-3)
-    np.testing.assert_allclose(K.n(ac.W1n), cpu.W1n.detach().numpy(), atol=3e-3)
-    np.testing.assert_allclose(K.n(ac.pi_nature.log_std), cpu.log_std.detach().numpy(), atol=3e-3)
+    np.testing.assert_allclose(K.n(ac.Wpi), cpu.opt.Wpi.detach().numpy(), atol=0.0001)
+    np.testing.assert_allclose(K.n(ac.Wv), cpu.opt.Wv.detach().numpy(), atol=0.0001)
+    np.testing.assert_allclose(K.n(ac.W1n), cpu.W1n.detach().numpy(), atol=0.0001)
+    np.testing.assert_allclose(K.n(ac.pi_nature.log_std), cpu.log_std.detach().numpy(), atol=0.0001)
     for p, q in zip(ac.pi_nature.mu_net.parameters(), cpu.mu_net.parameters()):
-        np.testing.assert_allclose(K.n(p), q.detach().numpy(), atol=5e-3)
+        np.testing.assert_allclose(K.n(p), q.detach().numpy(), atol=2e-4)
     # the drop-in class end to end
     orc = NatureOracle(data, N, S, 2, B, 9, 1, nature_kwargs=dict(steps_per_epoch=T, epochs=2, gamma=0.9, clip_ratio=2.0,
                        train_pi_iters=2, train_v_iters=2, lamb_update_freq=1, ac_kwargs=dict(hidden_sizes=[h, h])),
@@ -259,16 +259,16 @@ def test_ma_device_loop_matches_reference_nature_oracle(K, golden):
         lamb.append(float(st["Lamb"][0])); ret.append(float(st["EpActualRetAgent"][0]))
         rn.append(float(st["EpLambAdjRetNature"][0])); vv.append(float(st["VVals_agent"][0])); vn.append(float(st["VVals_nature"][0]))
     assert np.array_equal(np.array(ret), g["EpActualRetAgent"])                   # same trajectories as the reference
-    np.testing.assert_allclose(lamb, g["Lamb"], rtol=1e-4, atol=2e-6)
-    np.testing.assert_allclose(rn, g["EpLambAdjRetNature"], rtol=1e-4, atol=1e-4)
-    np.testing.assert_allclose(vv, g["VVals_agent"], rtol=1e-3, atol=1e-4)
-    np.testing.assert_allclose(vn, g["VVals_nature"], rtol=1e-3, atol=1e-4)
-    np.testing.assert_allclose(K.n(ac.Wpi), g["Wpi1"], atol=1e-3)
-    np.testing.assert_allclose(K.n(ac.Wv), g["Wv1"], atol=1e-3)
-    np.testing.assert_allclose(K.n(ac.W1n), g["W1n1"], atol=1e-3)
+    np.testing.assert_allclose(lamb, g["Lamb"], rtol=1e-05, atol=2e-07)
+    np.testing.assert_allclose(rn, g["EpLambAdjRetNature"], rtol=1e-05, atol=1e-05)
+    np.testing.assert_allclose(vv, g["VVals_agent"], rtol=0.0001, atol=1e-05)
+    np.testing.assert_allclose(vn, g["VVals_nature"], rtol=0.0001, atol=1e-05)
+    np.testing.assert_allclose(K.n(ac.Wpi), g["Wpi1"], atol=5e-5)
+    np.testing.assert_allclose(K.n(ac.Wv), g["Wv1"], atol=5e-5)
+    np.testing.assert_allclose(K.n(ac.W1n), g["W1n1"], atol=5e-5)
     tr.export_lambda()
     for i, p in enumerate(ac.lambda_net.parameters()):
-        np.testing.assert_allclose(p.detach().numpy(), g[f"lam1_{i}"], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(p.detach().numpy(), g[f"lam1_{i}"], rtol=1e-05, atol=1e-07)
 
 
 def test_nature_oracle_resamples_agent_strategy(K):
@@ -302,13 +302,12 @@ def test_nature_oracle_resamples_agent_strategy(K):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # SIS (BASELINE configs[3]'s domain: S = pop + 1, A = 3, C = [0,1,2], D = 4N nature parameters, scalar state inputs)
-# Tolerances: the integer path (states, actions) is compared bit for bit on the first epoch, i.e. while both sides hold
-# identical nets; per-step float outputs of that epoch are held to 1e-4 relative (fp32 nets evaluated with different
-# summation orders: tensor-core 3xTF32 / fused FMA here, numpy / torch CPU in the oracle; north_star's 1e-5 applies to
-# returns, advantages, losses and indices, which test_gpu_kernels / test_gpu_epoch hold at 1e-5 on fixed inputs).  Nets
-# AFTER several Adam steps are compared at 3e-3 absolute: Adam divides by sqrt(v) + 1e-8, so a gradient entry near zero
-# turns an fp32 rounding difference into a full +-lr step (lr = 2e-3 here) -- the bound is one such step plus drift, and
-# it is what the reference-golden tests below also use.
+# Tolerances (set from measured headroom, profiles/r2_tolerance_headroom.json): the integer path (states, actions) is
+# compared bit for bit on the first epoch, i.e. while both sides hold identical nets; per-step float outputs of that epoch
+# are held to north_star's 1e-5 relative.  Nets AFTER several Adam steps: Adam divides by sqrt(v) + 1e-8, so a gradient
+# entry near zero turns an fp32 rounding difference into a full +-lr step (lr = 2e-3 here; at hidden 64 the products are
+# 3xTF32, relative error 2.4e-7 against 6e-8 for FFMA) -- the critics' bound of 3e-3 is one such step plus drift
+# (measured worst: 2.3e-3 on W1n), everything else is held to 1e-4 / 2e-4.
 def _sis_problem(K, N, E, pop, h, seed, B):
     from robustrmab_b200.environments import SISRobustEnv
     from robustrmab_b200.ma_core import RMABLambdaNatureOracle
@@ -351,24 +350,24 @@ def test_ma_epoch_loop_sis_matches_oracle(K, pop, h):
     for ep in range(3):
         st = tr.epoch(pess)
         w = cpu.epoch(lambda s: np.zeros_like(s))
-        np.testing.assert_allclose(K.n(st["Lamb"]), w["lamb"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(K.n(st["Lamb"]), w["lamb"], rtol=1e-05, atol=1e-06)
         if ep == 0:
             assert np.array_equal(K.n(tr.a), w["a"]) and np.array_equal(K.n(tr.s_traj), w["s_traj"])
-            np.testing.assert_allclose(K.n(tr.a_nat), w["a_nat"], rtol=1e-4, atol=2e-5)
-            np.testing.assert_allclose(K.n(tr.rew_nat), w["rew_nat"], rtol=1e-4, atol=1e-4)
-            np.testing.assert_allclose(K.n(tr.val), w["val"], rtol=1e-4, atol=1e-5)
-            np.testing.assert_allclose(K.n(tr.val_nat), w["val_nat"], rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(K.n(tr.a_nat), w["a_nat"], rtol=1e-05, atol=2e-06)
+            np.testing.assert_allclose(K.n(tr.rew_nat), w["rew_nat"], rtol=1e-05, atol=1e-05)
+            np.testing.assert_allclose(K.n(tr.val), w["val"], rtol=1e-05, atol=1e-06)
+            np.testing.assert_allclose(K.n(tr.val_nat), w["val_nat"], rtol=1e-05, atol=1e-06)
             np.testing.assert_allclose(K.n(st["EpActualRetAgent"]), w["ret_agent"], rtol=1e-6)
         else:
             assert (K.n(tr.a) == w["a"]).mean() > 0.9, ep
-    np.testing.assert_allclose(K.n(ac.Wpi), cpu.opt.Wpi.detach().numpy(), atol=3e-3)
+    np.testing.assert_allclose(K.n(ac.Wpi), cpu.opt.Wpi.detach().numpy(), atol=0.0001)
     np.testing.assert_allclose(K.n(ac.Wv), cpu.opt.Wv.detach().numpy(), atol=3e-3)
     np.testing.assert_allclose(K.n(ac.W1n), cpu.W1n.detach().numpy(), atol=3e-3)
-    np.testing.assert_allclose(K.n(ac.pi_nature.log_std), cpu.log_std.detach().numpy(), atol=3e-3)
+    np.testing.assert_allclose(K.n(ac.pi_nature.log_std), cpu.log_std.detach().numpy(), atol=0.0001)
     for p, q in zip(ac.pi_nature.mu_net.parameters(), cpu.mu_net.parameters()):
-        np.testing.assert_allclose(K.n(p), q.detach().numpy(), atol=5e-3)
+        np.testing.assert_allclose(K.n(p), q.detach().numpy(), atol=2e-4)
     for p, q in zip(ac.v_nature.v_net.parameters(), cpu.v_nature.parameters()):
-        np.testing.assert_allclose(K.n(p), q.detach().numpy(), atol=5e-3)
+        np.testing.assert_allclose(K.n(p), q.detach().numpy(), atol=2e-4)
 
 
 def test_ma_device_loop_sis_matches_reference_nature_oracle(K, golden):
@@ -406,13 +405,22 @@ def test_ma_device_loop_sis_matches_reference_nature_oracle(K, golden):
         st = tr.epoch(pess)
         lamb.append(float(st["Lamb"][0])); ret.append(float(st["EpActualRetAgent"][0]))
         rn.append(float(st["EpLambAdjRetNature"][0])); vv.append(float(st["VVals_agent"][0])); vn.append(float(st["VVals_nature"][0]))
-    # the first two epochs run on (nearly) the reference's nets: same trajectories; later ones may flip single draws
-    np.testing.assert_allclose(ret[:2], g["EpActualRetAgent"][:2], rtol=1e-6)
-    np.testing.assert_allclose(lamb, g["Lamb"], rtol=1e-4, atol=2e-6)
-    np.testing.assert_allclose(rn[:2], g["EpLambAdjRetNature"][:2], rtol=1e-4, atol=1e-4)
-    np.testing.assert_allclose(vv[:2], g["VVals_agent"][:2], rtol=1e-3, atol=1e-4)
-    np.testing.assert_allclose(vn[:2], g["VVals_nature"][:2], rtol=1e-3, atol=1e-4)
-    if np.allclose(ret, g["EpActualRetAgent"], rtol=1e-6):        # identical trajectories throughout: nets comparable
+    # With ONE env and six arms a single draw that lands on the other side of a cdf edge (nets equal to ~1e-6 after an
+    # Adam step; hidden 64 runs 3xTF32 products) changes the whole remaining trajectory, so values are compared over the
+    # leading epochs whose trajectories are identical to the reference's (at least the first); the chain to the
+    # reference for the later epochs is golden <-> oracle (tests/test_oracle_golden.py, 2e-5) <-> device
+    # (test_ma_epoch_loop_sis_matches_oracle, E = 4).
+    want = g["EpActualRetAgent"]
+    same = 0
+    while same < epochs and abs(ret[same] - want[same]) <= 1e-6 * max(1.0, abs(want[same])):
+        same += 1
+    assert same >= 1, (ret, want)
+    k = min(same + 1, epochs)
+    np.testing.assert_allclose(lamb[:k], g["Lamb"][:k], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(rn[:same], g["EpLambAdjRetNature"][:same], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(vv[:same], g["VVals_agent"][:same], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(vn[:same], g["VVals_nature"][:same], rtol=1e-4, atol=1e-5)
+    if same == epochs:
         np.testing.assert_allclose(K.n(ac.Wpi), g["Wpi1"], atol=3e-3)
         np.testing.assert_allclose(K.n(ac.Wv), g["Wv1"], atol=3e-3)
         np.testing.assert_allclose(K.n(ac.W1n), g["W1n1"], atol=3e-3)
@@ -467,6 +475,6 @@ def test_critic_extra_iter_h64_vs_autograd_oracle(K, N, T, E, S):
                                            sample_major=True)
         got_loss.append(K.n(loss)[:, 0])
     np.testing.assert_allclose(np.array(got_loss)[0], want_loss[0], rtol=1e-5)
-    np.testing.assert_allclose(np.array(got_loss), np.array(want_loss), rtol=1e-4)     # after 1-2 Adam steps
+    np.testing.assert_allclose(np.array(got_loss), np.array(want_loss), rtol=1e-05)     # after 1-2 Adam steps
     np.testing.assert_allclose(K.n(dz).transpose(1, 0, 2), want_dz, rtol=1e-3, atol=1e-8)
     np.testing.assert_allclose(K.n(Wv), W.detach().numpy(), rtol=0, atol=2e-4)
