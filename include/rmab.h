@@ -244,7 +244,10 @@ size_t rmab_epoch_ws_bytes(int N, int E);
  * start state on input) and a [N,T,E] are written; stats [N,K,E]; arm_stats [N,4] = (adv mean, adv std,
  * sum (ret - mean_ret[s,e])^2, 0) (may be NULL); env_sums [2,E] = per-env sum over arms and steps of the
  * reward, and of the discounted cost-to-go at t = 0 (cdcost_buf[0], :117/:139) (may be NULL; needs ws of
- * rmab_epoch_ws_bytes); adv (normalised), ret [N,T,E] and last_val [N,E] are written when non-NULL. */
+ * rmab_epoch_ws_bytes); adv (normalised), ret [N,T,E] and last_val [N,E] are written when non-NULL.
+ * a == NULL: the trajectory is not materialised -- it lives in shared memory as bit planes for the kernel's own two
+ * backward passes -- and s_traj is then just the start states [N,E] (read only).  Needs (T/32 + 1) * (S == 2 ? 2 : 3)
+ * * E * 4 bytes of shared memory beside the staged nets (fails with RMAB_E_BADARG otherwise). */
 int rmab_epoch_table(int domain, const RmabNetDesc* net, int T, const float* Wpi, const float* Wv,
                      const float* lamb, const float* nature, const float* ranges, const float* R, const float* C,
                      double gamma, double lam, uint64_t seed, uint32_t t_act0, uint32_t t_env0, uint32_t env0,

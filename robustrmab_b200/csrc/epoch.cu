@@ -16,6 +16,7 @@
 // One CTA walks arms blockIdx.x, blockIdx.x + gridDim.x, ...; one thread per env.  HBM traffic per arm-step:
 // the trajectory write (s' 1 B + a 1 B) and its two L2-resident re-reads by the same thread; the statistics
 // are (4*S*A + 3*S) floats per (arm, env), i.e. < 1 B per arm-step at T = 100.
+#include <stdlib.h>
 #include "common.cuh"
 #include "mlp.cuh"
 
@@ -61,10 +62,16 @@ struct EpochArgs {
   float* adv; float* ret; float* last_val;
 };
 
-template <int H, int DOMAIN>
+// ONCHIP: the trajectory of every (arm, env) chain stays in shared memory as bit planes -- one 32-bit word per 32 time
+// steps for the action bit and for each state bit (S = 2: one plane, S = 3: two), words of env e at [word][plane][e] so
+// that a warp's accesses are consecutive -- instead of the [N,T+1,E] / [N,T,E] byte arrays in HBM that only this kernel
+// re-reads (two backward passes).  The byte arrays are still written when the caller passes `a` (MA-RMABPPO, tests,
+// keep_buffers); with a == NULL nothing but the statistics leaves the SM.
+template <int H, int DOMAIN, bool ONCHIP>
 __global__ void __launch_bounds__(256, 2) epoch_table_kernel(EpochArgs g) {
   constexpr int S = DOMAIN == RMAB_DOMAIN_CE ? 2 : 3;
   constexpr int A = 2;
+  constexpr int PL = S == 2 ? 2 : 3;   // bit planes per 32 steps: action, state bit 0 (, state bit 1)
   using SR = StatRows<S, A>;
   extern __shared__ __align__(16) float smem[];
   __shared__ double dred[3][8];
@@ -74,6 +81,8 @@ __global__ void __launch_bounds__(256, 2) epoch_table_kernel(EpochArgs g) {
   const MlpLayout Gp(S + 1, H, A), Gv(S + 1, H, 1);
   float* sp = smem;
   float* sv = smem + Lp.size;
+  uint32_t* bits = reinterpret_cast<uint32_t*>(smem + Lp.size + Lv.size);   // [n_words][PL][E]
+  const int64_t wstride = (int64_t)PL * E;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const double gamma = g.gamma, gl = g.gl;
   const float C0 = __ldg(g.C), C1 = __ldg(g.C + 1);
@@ -98,7 +107,7 @@ __global__ void __launch_bounds__(256, 2) epoch_table_kernel(EpochArgs g) {
         pn1[si] = fminf(fmaxf(__ldg(g.nature + c0 + 1), __ldg(g.ranges + 2 * c0 + 2)), __ldg(g.ranges + 2 * c0 + 3));
       }
     }
-    const int64_t traj0 = (int64_t)n * (T + 1) * E;
+    const int64_t traj0 = (int64_t)n * (g.a ? (int64_t)(T + 1) * E : (int64_t)E);   // a == NULL: s_traj is the [N,E] start states
     const int64_t step0 = (int64_t)n * T * E;
     const uint32_t gn = g.arm0 + (uint32_t)n;
 
@@ -122,20 +131,40 @@ __global__ void __launch_bounds__(256, 2) epoch_table_kernel(EpochArgs g) {
         st[(int64_t)(SR::kV + si) * E] = vout[0];
       }
       uint8_t* tr = g.s_traj + traj0 + e;
-      uint8_t* ac = g.a + step0 + e;
+      uint8_t* ac = g.a ? g.a + step0 + e : nullptr;
       int si = tr[0];
       si = si < S ? si : S - 1;
       const uint32_t ge = g.env0 + (uint32_t)e;
       uint4 blk = make_uint4(0u, 0u, 0u, 0u);
+      // bit t of the state planes = s_t (t = 0..T), bit t of the action plane = a_t (t = 0..T-1)
+      uint32_t aw = 0u, sw0 = (uint32_t)(si & 1), sw1 = (uint32_t)(si >> 1);
+      uint32_t* bw = bits + e;
       for (int t = 0; t < T; ++t) {
         const uint32_t tt = g.t_act0 + (uint32_t)t;
         if (t == 0 || (tt & 1u) == 0u) blk = philox_step_block(g.k0, g.k1, tt, ge, gn);  // one Philox block per two steps
         float pr[2] = {pick_f<S>(p0t, si), pick_f<S>(p1t, si)};
         const int act = categorical<2>(pr, u24(step_word(blk, tt, true)));
-        ac[(int64_t)t * E] = (uint8_t)act;
+        if (!ONCHIP || ac) ac[(int64_t)t * E] = (uint8_t)act;
         const float p = act ? pick_f<S>(pn1, si) : pick_f<S>(pn0, si);
         si = table_next<DOMAIN>(si, act, p, u24(step_word(blk, tt, false)));
-        tr[(int64_t)(t + 1) * E] = (uint8_t)si;
+        if (!ONCHIP || ac) tr[(int64_t)(t + 1) * E] = (uint8_t)si;
+        if (ONCHIP) {
+          aw |= (uint32_t)act << (t & 31);
+          const int b = (t + 1) & 31;
+          if (b == 0) {   // the word holding s_{t-31..t} and a_{t-31..t} is complete
+            uint32_t* wp = bw + (int64_t)(t >> 5) * wstride;
+            wp[0] = aw; wp[E] = sw0;
+            if (PL == 3) wp[2 * E] = sw1;
+            aw = sw0 = sw1 = 0u;
+          }
+          sw0 |= (uint32_t)(si & 1) << b;
+          sw1 |= (uint32_t)(si >> 1) << b;
+        }
+      }
+      if (ONCHIP) {       // the last (partial) word: s_T sits at bit T & 31
+        uint32_t* wp = bw + (int64_t)(T >> 5) * wstride;
+        wp[0] = aw; wp[E] = sw0;
+        if (PL == 3) wp[2 * E] = sw1;
       }
       // backward scan 1: only the advantage moments are needed here, so the recurrence runs in fp32 (relative error
       // ~1e-7 per step, damped by gamma*lam); pass 2 below redoes it in fp64 for the values that are kept
@@ -144,9 +173,21 @@ __global__ void __launch_bounds__(256, 2) epoch_table_kernel(EpochArgs g) {
       const float gam_f = (float)gamma, gl_f = (float)gl;
       float next_v = lvf, adv_acc = 0.f;
       int sn = si;
+      uint32_t ca = aw, cs0 = sw0, cs1 = sw1;   // the last word is still in registers
       for (int t = T - 1; t >= 0; --t) {
-        const int a_t = ac[(int64_t)t * E];
-        const int s_t = tr[(int64_t)t * E];
+        int a_t, s_t;
+        if (ONCHIP) {
+          if ((t & 31) == 31) {
+            const uint32_t* wp = bw + (int64_t)(t >> 5) * wstride;
+            ca = wp[0]; cs0 = wp[E];
+            if (PL == 3) cs1 = wp[2 * E];
+          }
+          a_t = (int)((ca >> (t & 31)) & 1u);
+          s_t = (int)((cs0 >> (t & 31)) & 1u) | (PL == 3 ? (int)(((cs1 >> (t & 31)) & 1u) << 1) : 0);
+        } else {
+          a_t = ac[(int64_t)t * E];
+          s_t = tr[(int64_t)t * E];
+        }
         const float v = pick_f<S>(vt, s_t);
         const float rt = fmaf(-lam, a_t ? C1 : C0, pick_f<S>(Rn, sn));
         const float delta = fmaf(gam_f, next_v, rt) - v;
@@ -188,9 +229,19 @@ __global__ void __launch_bounds__(256, 2) epoch_table_kernel(EpochArgs g) {
 #pragma unroll
       for (int si = 0; si < S; ++si) vt[si] = st[(int64_t)(SR::kV + si) * E];
       const uint8_t* tr = g.s_traj + traj0 + e;
-      const uint8_t* ac = g.a + step0 + e;
+      const uint8_t* ac = g.a ? g.a + step0 + e : nullptr;
       const double lm = (double)g.lamb[e];
-      int sn = tr[(int64_t)T * E];
+      const uint32_t* bw = bits + e;
+      uint32_t ca = 0u, cs0 = 0u, cs1 = 0u;
+      int sn;
+      if (ONCHIP) {
+        const uint32_t* wp = bw + (int64_t)(T >> 5) * wstride;
+        ca = wp[0]; cs0 = wp[E];
+        if (PL == 3) cs1 = wp[2 * E];
+        sn = (int)((cs0 >> (T & 31)) & 1u) | (PL == 3 ? (int)(((cs1 >> (T & 31)) & 1u) << 1) : 0);
+      } else {
+        sn = tr[(int64_t)T * E];
+      }
       const double lv = (double)pick_f<S>(vt, sn);
       double next_v = lv, adv_acc = 0.0, ret_acc = lv, dcost = 0.0, rsum = 0.0;
       float Ap[S * A], Am[S * A];
@@ -201,8 +252,19 @@ __global__ void __launch_bounds__(256, 2) epoch_table_kernel(EpochArgs g) {
 #pragma unroll
       for (int s = 0; s < S; ++s) { Sr[s] = 0.0; Sr2[s] = 0.0; }
       for (int t = T - 1; t >= 0; --t) {
-        const int a_t = ac[(int64_t)t * E];
-        const int s_t = tr[(int64_t)t * E];
+        int a_t, s_t;
+        if (ONCHIP) {
+          if ((t & 31) == 31) {
+            const uint32_t* wp = bw + (int64_t)(t >> 5) * wstride;
+            ca = wp[0]; cs0 = wp[E];
+            if (PL == 3) cs1 = wp[2 * E];
+          }
+          a_t = (int)((ca >> (t & 31)) & 1u);
+          s_t = (int)((cs0 >> (t & 31)) & 1u) | (PL == 3 ? (int)(((cs1 >> (t & 31)) & 1u) << 1) : 0);
+        } else {
+          a_t = ac[(int64_t)t * E];
+          s_t = tr[(int64_t)t * E];
+        }
         const double r = (double)pick_f<S>(Rn, sn), c = (double)(a_t ? C1 : C0), v = (double)pick_f<S>(vt, s_t);
         const double rt = __dsub_rn(r, __dmul_rn(lm, c));
         const double qv = __dadd_rn(rt, __dmul_rn(gamma, next_v));
@@ -325,7 +387,7 @@ extern "C" int rmab_epoch_table(int domain, const RmabNetDesc* net, int T, const
   RMAB_REQUIRE(T > 0 && net->n_envs > 0 && net->n_arms >= 0, RMAB_E_SHAPE, "rmab_epoch_table: bad T/E/N");
   RMAB_REQUIRE(t_act0 == t_env0, RMAB_E_BADARG, "rmab_epoch_table: the action and transition draws of a step share one "
                "Philox block, so t_act0 must equal t_env0");
-  RMAB_REQUIRE(Wpi && Wv && lamb && nature && ranges && R && C && s_traj && a && stats, RMAB_E_BADARG,
+  RMAB_REQUIRE(Wpi && Wv && lamb && nature && ranges && R && C && s_traj && stats, RMAB_E_BADARG,
                "rmab_epoch_table: null pointer");
   RMAB_REQUIRE(!env_sums || (ws && ws_bytes >= rmab_epoch_ws_bytes(net->n_arms, net->n_envs)), RMAB_E_BADARG,
                "rmab_epoch_table: env_sums needs a workspace of rmab_epoch_ws_bytes()");
@@ -337,16 +399,25 @@ extern "C" int rmab_epoch_table(int domain, const RmabNetDesc* net, int T, const
   g.t_act0 = t_act0; g.t_env0 = t_env0; g.env0 = env0; g.arm0 = arm0;
   g.s_traj = s_traj; g.a = a; g.stats = stats; g.arm_stats = arm_stats; g.env_part = env_sums ? (double*)ws : nullptr;
   g.adv = adv; g.ret = ret; g.last_val = last_val;
-  const size_t smem = sizeof(float) * (SmemNet(S + 1, h, 2).size + SmemNet(S + 1, h, 1).size);
+  size_t smem = sizeof(float) * (SmemNet(S + 1, h, 2).size + SmemNet(S + 1, h, 1).size);
+  // on-chip trajectory: (T / 32 + 1) words x (1 action + 1 or 2 state) planes x E envs; two CTAs per SM must still fit
+  const size_t bit_bytes = (size_t)(T / 32 + 1) * (S == 2 ? 2 : 3) * (size_t)net->n_envs * sizeof(uint32_t);
+  static const bool force_hbm = getenv("RMAB_EPOCH_HBM_TRAJ") != nullptr;   // A/B switch: round-1 behaviour
+  const bool onchip = !force_hbm && smem + bit_bytes <= 100 * 1024;
+  RMAB_REQUIRE(a || onchip, RMAB_E_BADARG, "rmab_epoch_table: a == NULL needs the on-chip trajectory (T = %d, E = %d is too "
+               "large for shared memory)", T, net->n_envs);
+  if (onchip) smem += bit_bytes;
   const int grid = epoch_grid(net->n_arms);
   int threads = ((net->n_envs + 31) / 32) * 32;
   threads = threads > 256 ? 256 : threads;
   cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH(H, D)                                                                                           \
+#define LAUNCH2(H, D, O)                                                                                       \
   {                                                                                                            \
-    RMAB_REQUIRE(set_smem_attr(epoch_table_kernel<H, D>, smem) == 0, RMAB_E_LAUNCH, "rmab_epoch_table: smem %zu B", smem); \
-    epoch_table_kernel<H, D><<<grid, threads, smem, st>>>(g);                                                  \
+    RMAB_REQUIRE(set_smem_attr(epoch_table_kernel<H, D, O>, smem) == 0, RMAB_E_LAUNCH, "rmab_epoch_table: smem %zu B", smem); \
+    epoch_table_kernel<H, D, O><<<grid, threads, smem, st>>>(g);                                               \
   }
+#define LAUNCH(H, D) \
+  if (onchip) LAUNCH2(H, D, true) else LAUNCH2(H, D, false)
 #define LAUNCH_H(D)               \
   switch (h) {                    \
     case 8: LAUNCH(8, D) break;   \
@@ -357,6 +428,7 @@ extern "C" int rmab_epoch_table(int domain, const RmabNetDesc* net, int T, const
   if (domain == RMAB_DOMAIN_CE) { LAUNCH_H(RMAB_DOMAIN_CE) } else { LAUNCH_H(RMAB_DOMAIN_ARMMAN) }
 #undef LAUNCH_H
 #undef LAUNCH
+#undef LAUNCH2
   int rc = check_launch("rmab_epoch_table");
   if (rc || !env_sums) return rc;
   const int64_t ke = 2 * (int64_t)net->n_envs;

@@ -125,7 +125,9 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
 
   const float* st = TABLE ? g.stats + ((int64_t)n * KST + ROW0) * E : nullptr;
   const int M = TABLE ? S * E : T * E;
-  const uint32_t e_magic = (uint32_t)(0x100000000ull / (uint32_t)E);   // floor(2^32 / E): m / E with one correction step
+  // floor(2^32 / E): m / E with one correction step.  E = 1 (the reference's own shape) would overflow the 32-bit magic to
+  // 0 and leave env indices >= 1 -- lambda was then read past its single entry; 2^32 - 1 gives m - 1 there, corrected to m.
+  const uint32_t e_magic = E > 1 ? (uint32_t)(0x100000000ull / (uint32_t)E) : 0xFFFFFFFFu;
   const int64_t smp_base = (int64_t)n * T * E, st_base = (int64_t)n * g.s_rows * E;
   const int64_t z_stride = (int64_t)g.d.n_arms * H;                    // sample-major [T*E, N, h]
   const int s_max = g.d.n_states - 1;
@@ -225,18 +227,34 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
       umma_commit(bar1);
     };
 
-    // G3 half (k-steps ks0 .. ks0+7 of this tile's 16): dW2 += d2^T . a1; DW2 is zeroed at the start of the pass
-    auto issue_g3_half = [&](int ks0) {
+    // G3 half (k-steps 8 half .. 8 half + 7 of this tile's 16): dW2 += d2^T . a1; DW2 is zeroed at the start of the pass.
+    // Two warps issue one half each (issue spread), both accumulating into the same TMEM columns -- so the halves are
+    // ORDERED: warp 3 issues only after warp 2 has (named barrier 5 + the tcgen05 thread-sync fences), which fixes the
+    // order of the fp32 sum.  Round 1 let them race: the sum, and with it every later trajectory, varied from run to run
+    // in the last bits (tools/determinism_probe.py).
+    auto issue_g3_half = [&](int half) {
       constexpr uint32_t idesc3 = make_idesc(64, 64, 1, 1);
       const uint32_t dh = desc_lo_mn(sbase + T_D2H), dl = desc_lo_mn(sbase + T_D2L);
       const uint32_t ah = desc_lo_mn(sbase + T_A1H), al = desc_lo_mn(sbase + T_A1L);
-#pragma unroll
-      for (int term = 0; term < 3; ++term) {
-        const uint32_t at = term == 0 ? dl : dh, bt = term == 1 ? al : ah;
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) umma_ss(tmem + C_DW2, at + 64 * (ks0 + ks), bt + 64 * (ks0 + ks), DESC_HI_MN, idesc3, 1u);
+      if (half == 1) {
+        asm volatile("bar.sync 5, 64;\n" ::: "memory");
+        tc_fence_after();
       }
-      umma_commit(bar3);
+      if (elect_one()) {
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+          const uint32_t at = term == 0 ? dl : dh, bt = term == 1 ? al : ah;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_ss(tmem + C_DW2, at + 64 * (8 * half + ks), bt + 64 * (8 * half + ks), DESC_HI_MN, idesc3, 1u);
+        }
+        umma_commit(bar3);
+      }
+      __syncwarp();
+      if (half == 0) {
+        tc_fence_before();
+        asm volatile("bar.arrive 5, 64;\n" ::: "memory");
+      }
     };
     // E3 of tile tt (its G2 has been issued): d1 = d1' (1 - a1^2); column sums for db1 / dW1.
     auto backward_rowsums = [&](int tt) {
@@ -249,10 +267,8 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
         __syncwarp();
       }
       const bool last_tile = tt + 1 == n_tiles;
-      if (last_tile && (warp == 2 || warp == 3)) {   // no G1 follows the last tile: its G3 runs under E3 and the reductions
-        if (elect_one()) issue_g3_half(warp == 2 ? 0 : 8);
-        __syncwarp();
-      }
+      if (last_tile && (warp == 2 || warp == 3))     // no G1 follows the last tile: its G3 runs under E3 and the reductions
+        issue_g3_half(warp == 2 ? 0 : 1);
       uint32_t v[FW], om[FW];
       tmem_ld16(tl + C_D1P + f0, v);
       tmem_ld16(tl + C_OM1 + f0, om);   // 1 - a1^2, parked in TMEM by E2 of the same tile
@@ -292,10 +308,8 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
         for (int k = 0; k < FW; ++k) d1l[k] = d1[k] * rw.x0;
         s_w1r[0] += colsum16(d1l, lane);                      // dW1[:, 0]
       }
-      if (!last_tile && (warp == 2 || warp == 3)) {   // G3(tt) behind G1(tt + 1): never waited for before the next tile's d2 is ready
-        if (elect_one()) issue_g3_half(warp == 2 ? 0 : 8);
-        __syncwarp();
-      }
+      if (!last_tile && (warp == 2 || warp == 3))     // G3(tt) behind G1(tt + 1): never waited for before the next tile's d2 is ready
+        issue_g3_half(warp == 2 ? 0 : 1);
     };
     {
       Row rw;

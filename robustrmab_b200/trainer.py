@@ -68,7 +68,9 @@ class RMABPPOTrainer:
                  clip_ratio=2.0, pi_lr=2e-3, vf_lr=2e-3, lm_lr=2e-3, train_pi_iters=20, train_v_iters=20,
                  epochs=20, lamb_update_freq=4, final_train_lambdas=2, start_entropy_coeff=0.5,
                  end_entropy_coeff=0.0, seed=0, ranges=None, nature=None, device="cuda", rank=0, world_size=1,
-                 process_group=None):
+                 process_group=None, keep_trajectory=False):
+        """keep_trajectory: also materialise the [N,T+1,E] / [N,T,E] state / action byte arrays in HBM (`s_traj`, `a`);
+        by default the fused epoch keeps the trajectory on chip and only the loss statistics leave the SM."""
         self.domain = DOMAINS[domain] if isinstance(domain, str) else int(domain)
         if self.domain not in _DOMAIN_S:
             raise ValueError("RMABPPOTrainer covers the table domains; SIS goes through ops.env_step_sis")
@@ -114,8 +116,10 @@ class RMABPPOTrainer:
         Rrow = [0.0, 1.0] if self.domain == _lib.DOMAIN_CE else [1.0, 0.5, 0.0]
         self.R = torch.tensor(Rrow, dtype=f32).repeat(N, 1).contiguous().to(dev)
         self.C = torch.tensor([0.0, 1.0], dtype=f32, device=dev)
-        self.s_traj = torch.empty((N, T + 1, E), dtype=u8, device=dev)
-        self.a = torch.empty((N, T, E), dtype=u8, device=dev)
+        self.keep_trajectory = bool(keep_trajectory)
+        # row 0 = the epoch's start states; rows 1..T (and `a`) exist only when the trajectory is kept in HBM
+        self.s_traj = torch.empty((N, T + 1 if self.keep_trajectory else 1, E), dtype=u8, device=dev)
+        self.a = torch.empty((N, T, E), dtype=u8, device=dev) if self.keep_trajectory else None
         self.last_val = torch.empty((N, E), dtype=f32, device=dev)
         self.stats = torch.empty((N, ops.stat_rows(self.domain), E), dtype=f32, device=dev)
         self.arm_stats = torch.empty((N, 4), dtype=f32, device=dev)
@@ -242,7 +246,8 @@ class RMABPPOTrainer:
 
     def buffer_bytes(self):
         N, T, E = self.N, self.T, self.E
-        return N * (T + 1) * E + N * T * E + self.stats.numel() * 4
+        traj = N * (T + 1) * E + N * T * E if self.keep_trajectory else N * E
+        return traj + self.stats.numel() * 4 + (self.Wpi.numel() + self.Wv.numel()) * 4 * 3
 
     def algorithmic_bytes(self):
         """Algorithmic HBM bytes per launch of each stage: SURVEY.md section 8d per-unit figures x N*T*E
@@ -274,12 +279,15 @@ class RMABPPOTrainer:
         N, E, T, S, A = self.N, self.E, self.T, self.S, self.A
         with self._stage("lambda"):
             lamb, h1, s0 = self.compute_lambda()
+        if keep_buffers and not self.keep_trajectory:
+            raise ValueError("keep_buffers needs a trainer built with keep_trajectory=True")
         if keep_buffers and self.adv is None:
             self.adv = torch.empty((N, T, E), dtype=torch.float32, device=self.dev)
             self.ret = torch.empty((N, T, E), dtype=torch.float32, device=self.dev)
         with self._stage("rollout_gae_stats"):
             ops.epoch_table(self.domain, self.net, T, self.Wpi, self.Wv, lamb, self.nature, self.ranges, self.R, self.C,
-                            self.gamma, self.lam_other, self.seed, self.t_global, self.t_global, self.s_traj, self.a,
+                            self.gamma, self.lam_other, self.seed, self.t_global, self.t_global,
+                            self.s_traj if self.keep_trajectory else self.s_traj[:, 0], self.a,
                             stats=self.stats, arm_stats=self.arm_stats, env_sums=self.env_sums, ws=self.ws,
                             adv=self.adv if keep_buffers else None, ret=self.ret if keep_buffers else None,
                             last_val=self.last_val, env0=0, arm0=self.arm0)

@@ -48,7 +48,12 @@ def _problem(domain, N, E, h, seed):
 
 
 @pytest.mark.parametrize("domain,h,N,E,T", [(0, 16, 9, 40, 25), (1, 64, 5, 128, 10), (1, 8, 700, 3, 6),
-                                            (0, 32, 4, 300, 12)])
+                                            (0, 32, 4, 300, 12),
+                                            # on-chip trajectory words: T = 32 / 33 / 64 / 100 cross 32-step word boundaries
+                                            (0, 16, 3, 33, 32), (1, 16, 3, 33, 33), (1, 8, 2, 70, 64), (0, 16, 2, 256, 100),
+                                            (1, 16, 2, 64, 131),
+                                            # too long for shared memory: the trajectory is re-read from HBM
+                                            (1, 8, 2, 300, 3000)])
 def test_epoch_table_vs_oracle(K, domain, h, N, E, T):
     S, ranges, nature, Wpi, Wv, lam, R, C = _problem(domain, N, E, h, 11 + h)
     cpu = CpuRMABPPO(domain, Wpi, Wv, lam, nature, ranges, R, C, E, T, h, N // 3, train_pi_iters=0, train_v_iters=0,
@@ -96,6 +101,28 @@ def test_epoch_table_vs_oracle(K, domain, h, N, E, T):
     es = K.n(env_sums)
     assert np.array_equal(es[0], w["rew_sum"])                     # rewards are multiples of 0.5: exact
     np.testing.assert_allclose(es[1], w["cdcost"][0], rtol=1e-6)
+
+
+@pytest.mark.parametrize("domain,h,N,E,T", [(0, 16, 7, 256, 100), (1, 64, 3, 1024, 10), (1, 16, 5, 77, 95), (0, 8, 4, 33, 1)])
+def test_epoch_table_onchip_trajectory_equals_materialised(K, domain, h, N, E, T):
+    """a == NULL (trajectory only in shared-memory bit planes, s_traj = the [N,E] start states) gives bit-identical
+    statistics, per-arm moments and per-env sums to the launch that also writes the byte trajectory to HBM."""
+    torch = K.torch
+    S, ranges, nature, Wpi, Wv, lam, R, C = _problem(domain, N, E, h, 3 + h)
+    rs = np.random.RandomState(T)
+    s0 = rs.randint(0, S, (N, E)).astype(np.uint8)
+    lamb = rs.uniform(0, 2, E).astype(F32)
+    net = K.ops.net_desc(N, E, S, 2, h)
+    s_traj = torch.zeros((N, T + 1, E), dtype=torch.uint8, device=K.dev)
+    s_traj[:, 0] = K.t(s0)
+    a = torch.empty((N, T, E), dtype=torch.uint8, device=K.dev)
+    args = (domain, net, T, K.t(Wpi), K.t(Wv), K.t(lamb), K.t(nature), K.t(ranges), K.t(R), K.t(C), 0.9, 0.97, 5, 8, 8)
+    last1 = torch.empty((N, E), dtype=torch.float32, device=K.dev)
+    last2 = torch.empty((N, E), dtype=torch.float32, device=K.dev)
+    st1, as1, es1 = K.ops.epoch_table(*args, s_traj, a, last_val=last1, arm0=2)
+    st2, as2, es2 = K.ops.epoch_table(*args, K.t(s0), None, last_val=last2, arm0=2)
+    assert torch.equal(st1, st2) and torch.equal(as1, as2) and torch.equal(es1, es2) and torch.equal(last1, last2)
+    assert int(s_traj.max()) < S and int(a.max()) <= 1
 
 
 @pytest.mark.parametrize("S,h,N,T,E", [(2, 16, 4, 30, 8), (3, 64, 3, 10, 32), (3, 8, 3, 7, 5), (3, 32, 2, 12, 70),
@@ -161,7 +188,7 @@ def test_trainer_matches_cpu_epoch_loop(K, domain, h):
     kw = dict(gamma=0.9, lam_other=0.97, clip_ratio=2.0, pi_lr=2e-3, vf_lr=2e-3, lm_lr=2e-3, train_pi_iters=5,
               train_v_iters=5, epochs=6, lamb_update_freq=2, final_train_lambdas=1, start_entropy_coeff=0.5,
               end_entropy_coeff=0.0, seed=5)
-    tr = RMABPPOTrainer(domain, N, E, T, hidden=h, B=N // 3, device=K.dev, **kw)
+    tr = RMABPPOTrainer(domain, N, E, T, hidden=h, B=N // 3, device=K.dev, keep_trajectory=True, **kw)
     S = tr.S
     lam_flat = K.n(tr.lam_params)
     lam = [lam_flat[:8 * N].reshape(8, N), lam_flat[8 * N:8 * N + 8], lam_flat[8 * N + 8:8 * N + 72].reshape(8, 8),
@@ -261,7 +288,7 @@ def test_full_size_config3_armman_properties(K):
     from robustrmab_b200.trainer import RMABPPOTrainer
     N, E, T = 100000, 1024, 10
     tr = RMABPPOTrainer("armman", N, E, T, hidden=64, B=0.2 * N, train_pi_iters=1, train_v_iters=1, epochs=4, seed=1,
-                        device=K.dev)
+                        device=K.dev, keep_trajectory=True)
     w0 = tr.Wpi[:64].clone()
     st = tr.epoch(keep_buffers=False)
     torch.cuda.synchronize()

@@ -22,8 +22,8 @@ ok = True
 for domain, hidden, N, E, T in (("counterexample", 16, 3000, 64, 25), ("armman", 64, 1001, 96, 10)):
     kw = dict(hidden=hidden, B=N // 3, train_pi_iters=4, train_v_iters=4, epochs=8, lamb_update_freq=2, final_train_lambdas=1,
               seed=11, device=dev)
-    sh = RMABPPOTrainer(domain, N, E, T, rank=rank, world_size=world, **kw)
-    full = RMABPPOTrainer(domain, N, E, T, **kw)
+    sh = RMABPPOTrainer(domain, N, E, T, rank=rank, world_size=world, keep_trajectory=True, **kw)
+    full = RMABPPOTrainer(domain, N, E, T, keep_trajectory=True, **kw)
     sl = slice(sh.arm0, sh.arm0 + sh.N)
     assert torch.equal(sh.Wpi, full.Wpi[sl]) and torch.equal(sh.nature, full.nature[sl]), "initial shard differs"
     for ep in range(4):
