@@ -52,7 +52,7 @@ def measure_tf32_gemm(dev, n=8192, reps=5):
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arms", type=int, default=4098)
@@ -64,12 +64,18 @@ def parse():
     ap.add_argument("--v-iters", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-whittle", action="store_true")
-    ap.add_argument("--no-armman", action="store_true", help="skip the secondary ARMMAN hidden-64 block (N = 1 only)")
+    ap.add_argument("--no-armman", action="store_true", help="skip the configs[2] block (ARMMAN 100k x 1024, hidden 64)")
+    ap.add_argument("--no-ma", action="store_true", help="skip the configs[3] block (MA-RMABPPO on SIS)")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel HBM lines (env step, GAE, budget select)")
+    ap.add_argument("--quick", action="store_true", help="headline only: no secondary blocks, no CPU legs")
     ap.add_argument("--vi-arms", type=int, default=99999)
     ap.add_argument("--vi-probes", type=int, default=64)
     ap.add_argument("--cpu-arms", type=int, default=192)
     ap.add_argument("--cpu-envs", type=int, default=16)
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.quick:
+        a.no_cpu_baseline = a.no_whittle = a.no_armman = a.no_ma = a.no_kernels = True
+    return a
 
 
 def workload_name(a, n_ranks):
@@ -154,99 +160,13 @@ def run_reference(a):
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": len(rates), "warmup": a.warmup,
            "ms_per_step": 1e3 * sum(step_times) / len(step_times), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-           "config": {"workload": workload_name(a, 1), "sample": sample},
+           "config": {"workload": f"RMABPPO {a.domain} domain, {cores} host processes x (N={a.cpu_arms} arms x {a.cpu_envs} envs), "
+                                  f"T={a.horizon}, hidden [{a.hidden},{a.hidden}], {a.pi_iters}+{a.v_iters} iters -- the CPU-sized sample of: "
+                                  + workload_name(a, 1), "sample": sample},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
-
-
-# ------------------------------------------------------------------------------------------ Whittle / VI
-def armman_bench(dev, peaks):
-    """One GPU's shard of BASELINE configs[2] (ARMMAN, 100k arms x 1024 envs over 8 GPUs = 12 500 arms per GPU, T = 10,
-    hidden [64,64], 20+20 Adam steps): the shape whose update runs on tcgen05 (ppo_table_umma64.cu).  Secondary block of
-    the default bench line: throughput, stage times and the update kernels' tensor roofline."""
-    import torch
-    from robustrmab_b200.trainer import RMABPPOTrainer
-    N, E, T, h, iters = 12500, 1024, 10, 64, 20
-    tr = RMABPPOTrainer("armman", N, E, T, hidden=h, train_pi_iters=iters, train_v_iters=iters, epochs=20, seed=0, device=dev)
-    tr.prewarm()
-    for _ in range(3):
-        tr.epoch()
-    torch.cuda.synchronize()
-    tr.timers = {}
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    steps = 2
-    e0.record()
-    for _ in range(steps):
-        tr.epoch()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    stage_ms = tr.stage_times()
-    upd = stage_ms.get("ppo_update", 0.0)
-    rows = ((3 * E + 127) // 128) * 128
-    flops = float(N) * 2 * iters * rows * 3 * 3 * 2 * h * h          # 3 GEMMs x 3 tf32 products per row and Adam step
-    tf32_peak = peaks.get("bf16_tflops_sustained", 2250.0 * 0.6) / 2
-    ach = flops / (upd * 1e-3) / 1e12 if upd else 0.0
-    del tr
-    torch.cuda.empty_cache()
-    return {"metric": METRIC, "unit": UNIT, "value": N * E * T / (ms * 1e-3), "ms_per_step": ms, "stage_ms_per_step": stage_ms,
-            "dtype": "f32 (3xTF32 tcgen05 GEMMs, fp32 accumulation in TMEM)",
-            "config": {"workload": f"RMABPPO armman domain, N={N} arms/GPU x {E} envs, T={T}, hidden [{h},{h}], {iters}+{iters} iters"},
-            "roofline": {"bound": "tensor", "kernel": "ppo_table_umma64_kernel (pi + v)", "achieved": ach, "peak": tf32_peak,
-                         "unit": "TFLOP/s", "frac": ach / tf32_peak if tf32_peak else None, "fp32_equivalent_TFLOPs": ach / 3,
-                         "peak_source": "measured bf16 sustained / 2 (tf32)" if "bf16_tflops_sustained" in peaks else "fallback"}}
-
-
-def whittle_bench(a, dev, want_cpu):
-    """BASELINE configs[4]: batched value iteration over N arms x L lambda-probes (mdptoolbox ValueIteration per
-    probe, simulator.py:504-521) and the Whittle index by bisection (lp_methods.py:181), counterexample domain.
-    Returns the secondary metric block (Whittle-index arms/sec)."""
-    import numpy as np
-    import torch
-    from robustrmab_b200 import ops
-    from oracle import envs as oenv, vi as ovi
-    N, L = a.vi_arms, a.vi_probes
-    rs = np.random.RandomState(0)
-    rg = oenv.ce_param_ranges(N)
-    p = rg.mean(-1)
-    T = np.zeros((N, 2, 2, 2))
-    T[:, 0] = 0.5
-    T[:, 1, 0, 0] = 1.0
-    T[:, 1, 1, 1], T[:, 1, 1, 0] = p, 1 - p
-    R = np.tile(np.array([0.0, 1.0]), (N, 1))
-    C = np.array([0.0, 1.0])
-    gamma, eps, rounds = 0.9, 1e-1, 20
-    lam_lim = R.max() / (C[C > 0].min() * (1 - gamma))              # agent_baselines.py:61
-    lambdas = np.linspace(0, lam_lim, L)
-    dT, dR, dC, dL = (torch.as_tensor(x, device=dev) for x in (T, R, C, lambdas))
-
-    def timed(fn, reps=5):
-        fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps
-    ms_vi = timed(lambda: ops.vi_batched(dT, dR, dC, dL, gamma, eps))
-    ms_wh = timed(lambda: ops.whittle_bisect(dT, dR, dC, gamma, eps, 0.0, lam_lim, rounds))
-    out = {"metric": "Whittle-index arms/sec", "unit": "arms/s", "value": N / (ms_wh * 1e-3),
-           "vi_probe_solves_per_s": N * L / (ms_vi * 1e-3), "ms_vi_batched": ms_vi, "ms_whittle_bisect": ms_wh,
-           "dtype": "f64",
-           "config": {"workload": f"counterexample domain, N={N} arms x {L} lambda-probes, gamma={gamma}, eps={eps} "
-                                  f"(simulator.py:595 default), Whittle index by {rounds}-round bisection per (arm, state)"}}
-    if want_cpu:
-        n_cpu = 400
-        t0 = time.perf_counter()
-        ovi.batched_vi(T[:n_cpu], R[:n_cpu], C, lambdas, gamma, eps)
-        dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": n_cpu * L / dt, "unit": "probe solves/s", "cores": 1, "kind": "port",
-                               "sample": f"{n_cpu} arms x {L} probes (oracle port of mdptoolbox ValueIteration, {dt:.1f} s)"}
-    return out
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -370,82 +290,84 @@ def run_ours(a):
     h2d = s0_host.numel() + nat_host.numel() * 4
     d2h = sum(v.numel() * v.element_size() for v in res.values())
 
+    # ---- secondary blocks that every rank takes part in (sharded by arm under torchrun) ----
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_blocks as bb
+    S_dom = tr.S
+    Ppi, Pv, buf_mib = tr.Ppi, tr.Pv, tr.buffer_bytes() / 2 ** 20
+    alg_bytes = tr.algorithmic_bytes()
+    del tr
+    torch.cuda.empty_cache()
+    blocks = {}
+    if not a.no_armman and a.hidden != 64:
+        blocks["armman_full"] = bb.guarded(bb.armman_block, dev, peaks, rank, world)
+    if not a.no_ma:
+        blocks["ma_sis"] = bb.guarded(bb.ma_sis_block, dev, peaks, rank, world)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    dom_name, dom_ms, dom_bytes = tr.dominant_kernel(stage_ms)
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms else 0.0
+
+    # ---- the dominant kernel against its binding roof ----
+    dom_name = max(stage_ms, key=stage_ms.get) if stage_ms else "none"
+    dom_ms = stage_ms.get(dom_name, 0.0)
+    tf32_peak = peaks.get("bf16_tflops_sustained", 2250.0 * 0.6) / 2
+    tf32_src = "measured bf16 sustained / 2 (tf32)" if "bf16_tflops_sustained" in peaks else "fallback 0.6 x 2250 / 2"
     traffic = None
     try:   # DRAM bytes per launch from the committed ncu capture of this same command (profiles/), default workload only
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         if (a.arms, a.envs, a.horizon, a.hidden, a.domain) == (4098, 256, 100, 16, "counterexample"):
-            traffic = {"ppo_update": tj["ppo_table_umma16_kernel_pi"] + tj["ppo_table_umma16_kernel_v"],
-                       "rollout_gae_stats": tj["epoch_table_kernel"]}.get(dom_name)
+            traffic = {"ppo_update": tj["ppo_update"], "rollout_gae_stats": tj["rollout_gae_stats"]}.get(dom_name)
     except (OSError, KeyError, ValueError):
         pass
-    stage_roofs = {k: {"achieved_GBps": tr.algorithmic_bytes()[k] / (stage_ms[k] * 1e-3) / 1e9,
-                       "frac": tr.algorithmic_bytes()[k] / (stage_ms[k] * 1e-3) / 1e9 / hbm_peak}
-                   for k in tr.algorithmic_bytes() if stage_ms.get(k)}
+    hbm_stage = {k: {"achieved_GBps": alg_bytes[k] / (stage_ms[k] * 1e-3) / 1e9,
+                     "frac": alg_bytes[k] / (stage_ms[k] * 1e-3) / 1e9 / hbm_peak,
+                     "algorithmic_bytes_per_launch": alg_bytes[k]} for k in alg_bytes if stage_ms.get(k)}
+    if dom_name == "ppo_update":
+        # The update's binding roof is the tensor / issue side (K5 is compute-bound; the statistics reformulation of
+        # DESIGN.md 3.1 keeps the batch out of HBM).  achieved = EXECUTED tensor-core flops: 3 GEMMs x 3 split products of
+        # [rows, h] x [h, h] per arm and Adam step, rows = S*E padded to the 128-row tile; peak = tf32 dense.
+        h = a.hidden
+        rows = ((S_dom * E + 127) // 128) * 128
+        flops = float(N) * (a.pi_iters + a.v_iters) * rows * 3 * 3 * 2 * h * h
+        ach = flops / (dom_ms * 1e-3) / 1e12
+        per_sample = 6.0 * (a.pi_iters * Ppi + a.v_iters * Pv) * N * T * E
+        roof = {"bound": "tensor", "kernel": f"ppo_update = ppo_table_umma{h}_kernel (pi + v launches of one epoch)",
+                "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": traffic,
+                "peak_source": tf32_src, "executed_tf32_flops_per_launch": flops, "ms_per_launch": dom_ms,
+                "fp32_equivalent_TFLOPs": ach / 3, "rows_per_arm": S_dom * E, "samples_per_arm": T * E,
+                "algorithmic_per_sample_TFLOPs": per_sample / (dom_ms * 1e-3) / 1e12,
+                "note": "tensor-core flops actually executed (the statistics reformulation runs S*E rows per arm instead of T*E "
+                        "samples); the CUDA-core work around the small GEMMs (tanh, splits, row sums, Adam) issue-bounds the kernel -- "
+                        "see profiles/ for issue-active and tensor-pipe activity",
+                "hbm_view": hbm_stage}
+        if h == 64:
+            tf32_measured = measure_tf32_gemm(dev)
+            roof.update({"cublas_tf32_8192_TFLOPs": tf32_measured, "frac_of_cublas_tf32": ach / tf32_measured if tf32_measured else None})
+    else:
+        b_dom = alg_bytes.get(dom_name, 0)
+        ach = b_dom / (dom_ms * 1e-3) / 1e9 if dom_ms else 0.0
+        roof = {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": b_dom, "ms_per_launch": dom_ms,
+                "hbm_view": hbm_stage}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": workload_name(a, world), "l2": "per-step working set (trajectory + advantage "
-                      f"buffers, {tr.buffer_bytes() / 2**20:.0f} MiB/GPU) exceeds the 126 MB L2; no explicit flush",
+           "config": {"workload": workload_name(a, world), "l2": "per-step working set (statistics + packed nets + Adam "
+                      f"moments, {buf_mib:.0f} MiB/GPU) exceeds the 126 MB L2; no explicit flush",
                       "parallelism": f"arm-sharded x{world}"},
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-           "gpu_launches": int(launches),
-           "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                        "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
-                        "note": "ppo_update = the two Adam-loop kernels (policy + value, tcgen05 hidden-16 kernel) of one epoch; the "
-                                "statistics reformulation (DESIGN.md 3.1) keeps the batch out of HBM, so both kernels are instruction-"
-                                "issue bound (ncu: issue active 54 %, tensor pipe 15-18 %, DRAM < 1 %) and frac is small by construction",
-                        "stages": stage_roofs},
-           "stage_ms_per_step": stage_ms, "clocks": clk}
-    if dom_name == "ppo_update" and dom_ms:
-        # the flop side of the same kernel, for context: SURVEY 8(d) counts the update at 6 (K_pi P_pi + K_v P_v) flops per
-        # arm-step (one forward + backward per sample and Adam step); the statistics reformulation executes those on
-        # S*E rows instead of T*E samples, i.e. T/S times fewer, as 3xTF32 tensor-core products
-        S_dom = 2 if a.domain == "counterexample" else 3
-        per_sample = 6.0 * (a.pi_iters * tr.Ppi + a.v_iters * tr.Pv)
-        alg = per_sample * N * T * E
-        h = a.hidden
-        tf32_exec = float(N) * (a.pi_iters + a.v_iters) * S_dom * E * 3 * 3 * 2 * h * h
-        out["roofline"]["flops_view"] = {
-            "algorithmic_TFLOPs": alg / (dom_ms * 1e-3) / 1e12, "executed_tf32_TFLOPs": tf32_exec / (dom_ms * 1e-3) / 1e12,
-            "rows_per_arm": S_dom * E, "samples_per_arm": T * E,
-            "note": "algorithmic = per-sample autograd flops of the reference update; executed = tensor-core products of the "
-                    "3 h x h GEMMs per row and Adam step (the rest of the kernel is CUDA-core work)"}
-    if a.hidden == 64 and dom_name == "ppo_update":
-        # hidden 64: the update runs its three 64 x 64 GEMMs per row on tcgen05 as 3 tf32 products each (3xTF32), so the
-        # dominant kernel is reported against the tensor roofline.  peak = tf32 dense = half the measured bf16 rate.
-        S_dom = 2 if a.domain == "counterexample" else 3
-        rows = ((S_dom * E + 127) // 128) * 128
-        flops = float(a.arms) * (a.pi_iters + a.v_iters) * rows * 3 * 3 * 2 * 64 * 64
-        tf32_peak = peaks.get("bf16_tflops_sustained", 2250.0 * 0.6) / 2
-        tf32_measured = measure_tf32_gemm(dev)   # cuBLAS TF32 8192^3, same recipe as MEASURED_PEAKS' bf16 line (reported beside)
-        ach = flops / (dom_ms * 1e-3) / 1e12
-        out["roofline"] = {"bound": "tensor", "kernel": "ppo_table_umma64_kernel (pi + v)", "achieved": ach, "peak": tf32_peak,
-                           "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None,
-                           "peak_source": "measured bf16 sustained / 2 (tf32)" if "bf16_tflops_sustained" in peaks else "fallback",
-                           "tf32_flops_per_launch": flops, "fp32_equivalent_TFLOPs": ach / 3, "ms_per_launch": dom_ms,
-                           "cublas_tf32_8192_TFLOPs": tf32_measured, "frac_of_cublas_tf32": ach / tf32_measured if tf32_measured else None,
-                           "note": "executed tf32 MMA flops (3 GEMMs x 3 split products per row and Adam step) over the two "
-                                   "update kernels' time; the CUDA-core work between the GEMMs (tanh, softmax terms, row sums) "
-                                   "bounds the kernel, see DESIGN.md 3.2", "stages": stage_roofs}
+           "gpu_launches": int(launches), "roofline": roof, "stage_ms_per_step": stage_ms, "clocks": clk}
     if not a.no_cpu_baseline:
-        t0 = time.perf_counter()
         rate, tmax, _ = cpu_port_rate(a, 1, 1)
         out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
                                "sample": f"1 epoch of N={a.cpu_arms} arms x {a.cpu_envs} envs x T={a.horizon} "
                                          f"(oracle port, 1 thread, {tmax:.1f} s)"}
+    out.update(blocks)
     if not a.no_whittle:
-        out["whittle"] = whittle_bench(a, dev, not a.no_cpu_baseline)
-    if not a.no_armman and world == 1 and a.hidden != 64:
-        del tr
-        torch.cuda.empty_cache()
-        out["armman_h64"] = armman_bench(dev, peaks)
+        out["whittle"] = bb.guarded(bb.whittle_block, dev, hbm_peak, peak_src, not a.no_cpu_baseline, a.vi_arms, a.vi_probes)
+    if not a.no_kernels:
+        out["kernels"] = bb.guarded(bb.kernel_lines, dev, hbm_peak, peak_src)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
