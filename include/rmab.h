@@ -261,6 +261,24 @@ int rmab_ppo_update_table(const RmabNetDesc* net, const RmabHyper* hp, int T, fl
                           float* adam_pi, float* adam_v, const float* stats, const float* arm_stats,
                           const float* lamb, float* loss_pi, float* loss_v, rmab_stream_t stream);
 
+/* ---- dense products of the MA-RMABPPO agent critics' nature block ------------------------ */
+
+/* Every agent critic reads the whole bounded nature vector (ma_rmabppo_core.py:203), so the first layers of all N
+ * critics over the D nature inputs are ONE dense product per batch, z1 = nat . W1n^T (nature_oracle.py:388-416), and
+ * its weight gradient is dW1n = dz1^T . nat (:505-513).  These entry points evaluate such products with fp32 accuracy
+ * on the fp16 tensor-core path (csrc/gemm3h.cu): rmab_split16_* write x = rs * (hi + lo) with per-row power-of-two
+ * scales (hi, lo fp16, 22 significant bits), rmab_gemm3h computes
+ *     C[m, n] = rsA[m] * rsB[n] * sum_k (Ah Bh + Al Bh + Ah Bl)[m, n]       (fp32 accumulation)
+ * for K-major operands Ah, Al [M, ldk] and Bh, Bl [N, ldk] (fp16, ldk % 8 == 0, 16-byte aligned), C [M, N] fp32 with
+ * row stride ldc.  n_fast = 1 walks consecutive tiles along N (A block reused), 0 along M (B block reused).
+ * rmab_split16_rows: X [R, K] (row stride ldx) -> Xh, Xl [R, ldk], rs [R].
+ * rmab_split16_cols: X [Rk, Cn] -> the TRANSPOSED split Xh, Xl [Cn, ldk] (k = row of X), rs [Cn]; amax_ws: Cn words. */
+int rmab_split16_rows(int R, int K, const float* X, int64_t ldx, int ldk, void* Xh, void* Xl, float* rs, rmab_stream_t stream);
+int rmab_split16_cols(int Rk, int Cn, const float* X, int64_t ldx, int ldk, void* Xh, void* Xl, float* rs, uint32_t* amax_ws,
+                      rmab_stream_t stream);
+int rmab_gemm3h(int M, int N, int K, int ldk, const void* Ah, const void* Al, const float* rsA, const void* Bh, const void* Bl,
+                const float* rsB, float* C, int64_t ldc, int n_fast, rmab_stream_t stream);
+
 /* ---- budget-constrained selection -------------------------------------------------------- */
 
 size_t rmab_select_ws_bytes(int E, int N, int A);
@@ -274,6 +292,18 @@ size_t rmab_select_ws_bytes(int E, int N, int A);
  *                      arms act if fewer than k have p1 > 0. */
 int rmab_budget_select_binary(int E, int N, const float* p1, float cost1, float B, int positive_only, uint8_t* actions,
                               void* ws, size_t ws_bytes, rmab_stream_t stream);
+
+/* The phases of the large-problem path of rmab_budget_select_binary, exposed so that ARM-SHARDED ranks can select a
+ * global top-k: per pass (0..3, 8 key bits each, from the top) every rank computes its per-env digit
+ * histogram hist [ceil(E/32)][256][32] uint32 (lane = env within the group), the caller all-reduces it, and the scan
+ * fixes the next 8 bits of every env's threshold key.  rmab_select_mark then writes the actions; above_ranks [E] =
+ * number of keys equal to the threshold held by ranks that own HIGHER arm indices (NULL on one rank), so that ties
+ * go to the higher global arm index as np.argsort does in the reference.  ws: rmab_select_ws_bytes(E, N, 2) bytes;
+ * its first 3*32*ceil(E/32) words are prefix | remain | eqtot per env.  hist == NULL uses the workspace's own array. */
+int rmab_select_hist(int E, int N, const float* p1, int pass, void* ws, size_t ws_bytes, uint32_t* hist, rmab_stream_t stream);
+int rmab_select_scan(int E, int N, int pass, int k, const uint32_t* hist, void* ws, size_t ws_bytes, rmab_stream_t stream);
+int rmab_select_mark(int E, int N, const float* p1, const uint32_t* above_ranks, int positive_only, uint8_t* actions,
+                     void* ws, size_t ws_bytes, rmab_stream_t stream);
 
 /* act_test_deterministic_multiaction (rmabppo_core.py:338-445), one CTA per env, stepwise argmax
  * formulation (oracle/select.py::greedy_multiaction_stepwise).  probs [N,A,E], C [A] strictly

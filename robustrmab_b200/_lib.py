@@ -74,8 +74,14 @@ SIGNATURES = {
                          C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P, C.c_size_t, _P, _P, _P, _P],
     "rmab_ppo_update_table": [C.POINTER(RmabNetDesc), C.POINTER(RmabHyper), _I, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                               _P],
+    "rmab_split16_rows": [_I, _I, _P, C.c_int64, _I, _P, _P, _P, _P],
+    "rmab_split16_cols": [_I, _I, _P, C.c_int64, _I, _P, _P, _P, _P, _P],
+    "rmab_gemm3h": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, C.c_int64, _I, _P],
     "rmab_select_ws_bytes": [_I, _I, _I],
     "rmab_budget_select_binary": [_I, _I, _P, _F, _F, _I, _P, _P, C.c_size_t, _P],
+    "rmab_select_hist": [_I, _I, _P, _I, _P, C.c_size_t, _P, _P],
+    "rmab_select_scan": [_I, _I, _I, _I, _P, _P, C.c_size_t, _P],
+    "rmab_select_mark": [_I, _I, _P, _P, _I, _P, _P, C.c_size_t, _P],
     "rmab_budget_select_multi": [_I, _I, _I, _P, _P, _F, _P, _P, C.c_size_t, _P],
     "rmab_knapsack_ws_bytes": [_I, _I, _I],
     "rmab_knapsack_multichoice": [_I, _I, _I, _P, _P, _I, _P, _P, _P, C.c_size_t, _P],

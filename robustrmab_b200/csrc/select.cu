@@ -89,6 +89,166 @@ __global__ void __launch_bounds__(kSelEnvs* kSelWarps) select_binary_kernel(int 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Large problems (act_test over 10^5 arms x 10^3 envs): the same 4 x 8-bit radix select spread over the whole GPU.
+// Grid = env groups (32 envs, lane = env) x arm chunks; every pass streams p1 once, coalesced, into a per-CTA shared
+// histogram [digit][lane] (bank = lane: conflict-free), written out as a partial; a reduce kernel sums the partials of
+// an env group, a scan kernel walks the 256 digits per env.  The reduce output is the array ranks all-reduce when the
+// arms are sharded.  Marking is one more pass: key > tau -> 1, key == tau -> 1 for the `remain` highest
+// arm indices (decided without ordering unless an env really has a tie at the boundary).
+// ws (u32 words): prefix[E] remain[E] eqtot[E] | tot[G][256][32] | part[G*Cn][256][32].
+constexpr int kSelThreads = 256;
+constexpr int kSelTargetCtas = 4 * kNumSMs;
+
+struct SelPlan {
+  int G, Cn, chunk;
+  size_t tot_off, part_off, words;
+};
+
+static SelPlan select_plan(int E, int N) {
+  SelPlan p;
+  p.G = (E + 31) / 32;
+  int cn = kSelTargetCtas / p.G;
+  const int max_cn = (N + 255) / 256;
+  cn = cn < 1 ? 1 : cn;
+  p.Cn = cn > max_cn ? (max_cn < 1 ? 1 : max_cn) : cn;
+  p.chunk = (N + p.Cn - 1) / p.Cn;
+  p.tot_off = 3 * (size_t)p.G * 32;
+  p.part_off = p.tot_off + (size_t)p.G * 8192;
+  p.words = p.part_off + (size_t)p.G * p.Cn * 8192;
+  return p;
+}
+
+__global__ void __launch_bounds__(kSelThreads) select_hist_kernel(int E, int N, const float* __restrict__ p1, int chunk, int pass,
+                                                                  const uint32_t* __restrict__ prefix, uint32_t* __restrict__ part) {
+  __shared__ uint32_t hist[256][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int g = blockIdx.x, c = blockIdx.y;
+  const int e = g * 32 + lane;
+  const bool live = e < E;
+  for (int i = threadIdx.x; i < 8192; i += kSelThreads) (&hist[0][0])[i] = 0u;
+  __syncthreads();
+  const int n0 = min(N, c * chunk), n1 = min(N, n0 + chunk);
+  const int shift = 24 - 8 * pass;
+  const uint32_t himask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+  const uint32_t pf = (live && pass > 0) ? prefix[e] : 0u;
+  if (live) {
+    const float* col = p1 + e;
+    int n = n0 + w;
+    for (; n + 3 * 8 < n1; n += 4 * 8) {   // four independent loads in flight per thread
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = __ldg(col + (int64_t)(n + 8 * j) * E);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t key = sortable(v[j]);
+        if ((key & himask) == pf) atomicAdd(&hist[(key >> shift) & 255u][lane], 1u);
+      }
+    }
+    for (; n < n1; n += 8) {
+      const uint32_t key = sortable(__ldg(col + (int64_t)n * E));
+      if ((key & himask) == pf) atomicAdd(&hist[(key >> shift) & 255u][lane], 1u);
+    }
+  }
+  __syncthreads();
+  uint32_t* out = part + ((size_t)g * gridDim.y + c) * 8192;
+  for (int i = threadIdx.x; i < 8192; i += kSelThreads) out[i] = (&hist[0][0])[i];
+}
+
+__global__ void __launch_bounds__(kSelThreads) select_reduce_kernel(int Cn, const uint32_t* __restrict__ part,
+                                                                    uint32_t* __restrict__ tot) {
+  const int g = blockIdx.x;
+  const int i = blockIdx.y * kSelThreads + threadIdx.x;   // 0 .. 8191
+  uint32_t s = 0u;
+  for (int c = 0; c < Cn; ++c) s += part[((size_t)g * Cn + c) * 8192 + i];
+  tot[(size_t)g * 8192 + i] = s;
+}
+
+// one warp per env group: lane = env walks the digits from the top
+__global__ void __launch_bounds__(32) select_scan_kernel(int E, int pass, uint32_t k, const uint32_t* __restrict__ tot,
+                                                         uint32_t* __restrict__ prefix, uint32_t* __restrict__ remain,
+                                                         uint32_t* __restrict__ eqtot) {
+  const int g = blockIdx.x, lane = threadIdx.x, e = g * 32 + lane;
+  if (e >= E) return;
+  const uint32_t* h = tot + (size_t)g * 8192 + lane;
+  const uint32_t need = pass == 0 ? k : remain[e];
+  const uint32_t pf = pass == 0 ? 0u : prefix[e];
+  uint32_t run = 0u, cnt = 0u;
+  int dsel = 0;
+  for (int dgt = 255; dgt >= 0; --dgt) {
+    cnt = h[dgt * 32];
+    if (run + cnt >= need) { dsel = dgt; break; }
+    run += cnt;
+  }
+  prefix[e] = pf | ((uint32_t)dsel << (24 - 8 * pass));
+  remain[e] = need - run;
+  if (pass == 3) eqtot[e] = cnt;
+}
+
+__global__ void __launch_bounds__(kSelThreads) select_mark_kernel(int E, int N, const float* __restrict__ p1, int chunk,
+                                                                  const uint32_t* __restrict__ prefix,
+                                                                  const uint32_t* __restrict__ remain,
+                                                                  const uint32_t* __restrict__ eqtot,
+                                                                  const uint32_t* __restrict__ part,
+                                                                  const uint32_t* __restrict__ above_ranks, int positive_only,
+                                                                  uint8_t* __restrict__ actions) {
+  __shared__ uint32_t eqcnt[kSelThreads / 32][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int g = blockIdx.x, c = blockIdx.y, Cn = gridDim.y;
+  const int e = g * 32 + lane;
+  const bool live = e < E;
+  const int n0 = min(N, c * chunk), n1 = min(N, n0 + chunk);
+  const uint32_t tau = live ? prefix[e] : 0u, r = live ? remain[e] : 0u;
+  const bool tie = live && eqtot[e] > r;
+  if (!__syncthreads_or(tie ? 1 : 0)) {
+    // every key equal to the threshold is taken: no ordering needed
+    if (live) {
+      const float* col = p1 + e;
+      uint8_t* ac = actions + e;
+      int n = n0 + w;
+      for (; n + 3 * 8 < n1; n += 4 * 8) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = __ldg(col + (int64_t)(n + 8 * j) * E);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint8_t a = sortable(v[j]) >= tau ? 1 : 0;
+          if (positive_only && !(v[j] > 0.f)) a = 0;
+          ac[(int64_t)(n + 8 * j) * E] = a;
+        }
+      }
+      for (; n < n1; n += 8) {
+        const float pv = __ldg(col + (int64_t)n * E);
+        uint8_t a = sortable(pv) >= tau ? 1 : 0;
+        if (positive_only && !(pv > 0.f)) a = 0;
+        ac[(int64_t)n * E] = a;
+      }
+    }
+    return;
+  }
+  // ordered path: equal keys are taken from the highest (global) arm index down
+  const int sub = (n1 - n0 + (kSelThreads / 32) - 1) / (kSelThreads / 32);
+  const int s0 = min(n1, n0 + w * sub), s1 = min(n1, s0 + sub);
+  uint32_t eq = 0u;
+  if (live)
+    for (int n = s0; n < s1; ++n) eq += (sortable(p1[(int64_t)n * E + e]) == tau) ? 1u : 0u;
+  eqcnt[w][lane] = eq;
+  __syncthreads();
+  if (!live) return;
+  uint32_t above = above_ranks ? above_ranks[e] : 0u;
+  for (int cc = c + 1; cc < Cn; ++cc) above += part[((size_t)g * Cn + cc) * 8192 + (tau & 255u) * 32 + lane];
+  for (int ww = w + 1; ww < kSelThreads / 32; ++ww) above += eqcnt[ww][lane];
+  for (int n = s1 - 1; n >= s0; --n) {
+    const float pv = p1[(int64_t)n * E + e];
+    const uint32_t key = sortable(pv);
+    uint8_t a = 0;
+    if (key > tau) a = 1;
+    else if (key == tau) { a = (above < r) ? 1 : 0; ++above; }
+    if (positive_only && !(pv > 0.f)) a = 0;
+    actions[(int64_t)n * E + e] = a;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 constexpr int kMultiThreads = 256;
 constexpr int kMultiMaxA = 8;
 
@@ -265,16 +425,13 @@ __global__ void __launch_bounds__(kKnapThreads) knapsack_mc_kernel(int E, int N,
 }
 
 extern "C" size_t rmab_select_ws_bytes(int E, int N, int A) {
-  (void)E; (void)N; (void)A;
-  return 16;  // both kernels keep their working set in shared memory; a token workspace keeps the ABI stable
+  (void)A;
+  if (E <= 0 || N <= 0) return 16;
+  return select_plan(E, N).words * sizeof(uint32_t);
 }
 
-extern "C" int rmab_budget_select_binary(int E, int N, const float* p1, float cost1, float B, int positive_only,
-                                         uint8_t* actions, void* ws, size_t ws_bytes, rmab_stream_t stream) {
-  (void)ws; (void)ws_bytes;
-  RMAB_REQUIRE(E > 0 && N >= 0 && p1 && actions, RMAB_E_BADARG, "rmab_budget_select_binary: bad argument");
-  if (N == 0) return RMAB_OK;
-  // number of ones exactly as the while-loop of rmabppo_core.py:320-331 counts them
+// number of ones exactly as the while-loop of rmabppo_core.py:320-331 counts them
+static int select_count(int N, float cost1, float B) {
   int k = 0;
   double spent = 0.0;
   while (spent < (double)B && k < N) {
@@ -282,9 +439,67 @@ extern "C" int rmab_budget_select_binary(int E, int N, const float* p1, float co
     spent += (double)cost1;
     ++k;
   }
-  select_binary_kernel<<<(E + kSelEnvs - 1) / kSelEnvs, kSelEnvs * kSelWarps, 0, (cudaStream_t)stream>>>(
-      E, N, p1, k, positive_only, actions);
-  return check_launch("rmab_budget_select_binary");
+  return k;
+}
+
+extern "C" int rmab_select_hist(int E, int N, const float* p1, int pass, void* ws, size_t ws_bytes, uint32_t* hist,
+                                rmab_stream_t stream) {
+  RMAB_REQUIRE(E > 0 && N > 0 && p1 && ws && pass >= 0 && pass < 4, RMAB_E_BADARG, "rmab_select_hist: bad argument");
+  const SelPlan p = select_plan(E, N);
+  RMAB_REQUIRE(ws_bytes >= p.words * sizeof(uint32_t), RMAB_E_BADARG, "rmab_select_hist: workspace of %zu B needed",
+               p.words * sizeof(uint32_t));
+  uint32_t* w = static_cast<uint32_t*>(ws);
+  cudaStream_t st = (cudaStream_t)stream;
+  select_hist_kernel<<<dim3(p.G, p.Cn), kSelThreads, 0, st>>>(E, N, p1, p.chunk, pass, w, w + p.part_off);
+  select_reduce_kernel<<<dim3(p.G, 8192 / kSelThreads), kSelThreads, 0, st>>>(p.Cn, w + p.part_off, hist ? hist : w + p.tot_off);
+  return check_launch("rmab_select_hist");
+}
+
+extern "C" int rmab_select_scan(int E, int N, int pass, int k, const uint32_t* hist, void* ws, size_t ws_bytes,
+                                rmab_stream_t stream) {
+  RMAB_REQUIRE(E > 0 && N > 0 && ws && pass >= 0 && pass < 4 && k > 0, RMAB_E_BADARG, "rmab_select_scan: bad argument");
+  const SelPlan p = select_plan(E, N);
+  RMAB_REQUIRE(ws_bytes >= p.words * sizeof(uint32_t), RMAB_E_BADARG, "rmab_select_scan: workspace too small");
+  uint32_t* w = static_cast<uint32_t*>(ws);
+  const size_t GE = (size_t)p.G * 32;
+  select_scan_kernel<<<p.G, 32, 0, (cudaStream_t)stream>>>(E, pass, (uint32_t)k, hist ? hist : w + p.tot_off, w, w + GE,
+                                                           w + 2 * GE);
+  return check_launch("rmab_select_scan");
+}
+
+extern "C" int rmab_select_mark(int E, int N, const float* p1, const uint32_t* above_ranks, int positive_only,
+                                uint8_t* actions, void* ws, size_t ws_bytes, rmab_stream_t stream) {
+  RMAB_REQUIRE(E > 0 && N > 0 && p1 && ws && actions, RMAB_E_BADARG, "rmab_select_mark: bad argument");
+  const SelPlan p = select_plan(E, N);
+  RMAB_REQUIRE(ws_bytes >= p.words * sizeof(uint32_t), RMAB_E_BADARG, "rmab_select_mark: workspace too small");
+  uint32_t* w = static_cast<uint32_t*>(ws);
+  const size_t GE = (size_t)p.G * 32;
+  select_mark_kernel<<<dim3(p.G, p.Cn), kSelThreads, 0, (cudaStream_t)stream>>>(E, N, p1, p.chunk, w, w + GE, w + 2 * GE,
+                                                                                w + p.part_off, above_ranks, positive_only,
+                                                                                actions);
+  return check_launch("rmab_select_mark");
+}
+
+extern "C" int rmab_budget_select_binary(int E, int N, const float* p1, float cost1, float B, int positive_only,
+                                         uint8_t* actions, void* ws, size_t ws_bytes, rmab_stream_t stream) {
+  RMAB_REQUIRE(E > 0 && N >= 0 && p1 && actions, RMAB_E_BADARG, "rmab_budget_select_binary: bad argument");
+  if (N == 0) return RMAB_OK;
+  const int k = select_count(N, cost1, B);
+  // the one-CTA-per-32-envs kernel wins while the whole problem is a few waves of it; beyond that (or whenever the caller
+  // provides the workspace and the problem is large) the multi-CTA radix select streams p1 at HBM speed
+  const bool big = ws && ws_bytes >= rmab_select_ws_bytes(E, N, 2) && (int64_t)N * E >= (1 << 21) && k > 0 && k < N;
+  if (!big) {
+    select_binary_kernel<<<(E + kSelEnvs - 1) / kSelEnvs, kSelEnvs * kSelWarps, 0, (cudaStream_t)stream>>>(
+        E, N, p1, k, positive_only, actions);
+    return check_launch("rmab_budget_select_binary");
+  }
+  for (int pass = 0; pass < 4; ++pass) {
+    int rc = rmab_select_hist(E, N, p1, pass, ws, ws_bytes, nullptr, stream);
+    if (rc != RMAB_OK) return rc;
+    rc = rmab_select_scan(E, N, pass, k, nullptr, ws, ws_bytes, stream);
+    if (rc != RMAB_OK) return rc;
+  }
+  return rmab_select_mark(E, N, p1, nullptr, positive_only, actions, ws, ws_bytes, stream);
 }
 
 extern "C" int rmab_budget_select_multi(int E, int N, int A, const float* probs, const float* C, float B,

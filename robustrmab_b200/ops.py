@@ -208,6 +208,56 @@ def matmul_3xtf32(a, b):
     return out
 
 
+# The package's own dense product for the same job (csrc/gemm3h.cu): x = rs * (hi + lo) with fp16 hi / lo and a per-row
+# power-of-two scale, three kind::f16 tcgen05 products per k-block with fp32 accumulation in TMEM, operands fed by TMA.
+f16 = torch.float16
+
+
+def _ldk(K):
+    return (int(K) + 7) // 8 * 8
+
+
+def split16_rows(x):
+    """x `[R,K]` fp32 (row stride may exceed K) -> (hi, lo `[R,ldk]` fp16, rs `[R]`): the K-major operand form of gemm3h."""
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == f32 and x.is_cuda, "split16_rows: [R,K] fp32 CUDA rows"
+    R, K = x.shape
+    ldk = _ldk(K)
+    hi = torch.empty((R, ldk), dtype=f16, device=x.device)
+    lo = torch.empty((R, ldk), dtype=f16, device=x.device)
+    rs = torch.empty((R,), dtype=f32, device=x.device)
+    check(lib().rmab_split16_rows(R, K, C.c_void_p(x.data_ptr()), x.stride(0), ldk, _p(hi, f16), _p(lo, f16), _p(rs, f32),
+                                  _stream()))
+    return hi, lo, rs
+
+
+def split16_cols(x):
+    """x `[Rk,Cn]` fp32 -> the split of x^T: (hi, lo `[Cn,ldk]` fp16 with k = the row index of x, rs `[Cn]`)."""
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == f32 and x.is_cuda, "split16_cols: [Rk,Cn] fp32 CUDA rows"
+    Rk, Cn = x.shape
+    ldk = _ldk(Rk)
+    hi = torch.empty((Cn, ldk), dtype=f16, device=x.device)
+    lo = torch.empty((Cn, ldk), dtype=f16, device=x.device)
+    rs = torch.empty((Cn,), dtype=f32, device=x.device)
+    amax = torch.empty((Cn,), dtype=i32, device=x.device)
+    check(lib().rmab_split16_cols(Rk, Cn, C.c_void_p(x.data_ptr()), x.stride(0), ldk, _p(hi, f16), _p(lo, f16), _p(rs, f32),
+                                  _p(amax, i32), _stream()))
+    return hi, lo, rs
+
+
+def gemm3h(a, b, K, out=None, n_fast=True):
+    """a = (Ah, Al, rsA) `[M,ldk]`, b = (Bh, Bl, rsB) `[N,ldk]` from split16_* -> a . b^T `[M,N]` fp32."""
+    Ah, Al, rsA = a
+    Bh, Bl, rsB = b
+    M, ldk = Ah.shape
+    N = Bh.shape[0]
+    assert Bh.shape[1] == ldk and ldk >= K, "gemm3h: operands must share the padded K"
+    out = torch.empty((M, N), dtype=f32, device=Ah.device) if out is None else out
+    assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype == f32
+    check(lib().rmab_gemm3h(M, N, int(K), ldk, _p(Ah, f16), _p(Al, f16), _p(rsA, f32), _p(Bh, f16), _p(Bl, f16), _p(rsB, f32),
+                            C.c_void_p(out.data_ptr()), out.stride(0), int(bool(n_fast)), _stream()))
+    return out
+
+
 def adam_step(p, grad, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
     check(lib().rmab_adam_step(p.numel(), _p(p, f32, "p"), _p(grad, f32, "grad"), _p(m, f32, "m"), _p(v, f32, "v"),
                                float(lr), float(beta1), float(beta2), float(eps), int(step), _stream()))
@@ -314,11 +364,81 @@ def ppo_update_table(net, hp, T, Wpi, Wv, adam_pi, adam_v, stats, arm_stats, lam
 
 
 # ------------------------------------------------------------------------------------------ selection
+_SELECT_WS = {}
+
+
+def _select_ws(E, N, dev):
+    need = int(lib().rmab_select_ws_bytes(E, N, 2))
+    ws = _SELECT_WS.get((dev, need))
+    if ws is None:
+        ws = _SELECT_WS[(dev, need)] = torch.empty((need + 3) // 4, dtype=i32, device=dev)
+    return ws, need
+
+
 def budget_select_binary(p1, cost1, B, positive_only=False):
     N, E = p1.shape
     out = torch.empty((N, E), dtype=u8, device=p1.device)
+    ws, need = _select_ws(E, N, p1.device) if N * E >= (1 << 21) else (None, 0)
     check(lib().rmab_budget_select_binary(E, N, _p(p1, f32, "p1"), float(cost1), float(B), int(bool(positive_only)),
-                                          _p(out, u8), None, 0, _stream()))
+                                          _p(out, u8), _p(ws, i32), need, _stream()))
+    return out
+
+
+def select_count(N, cost1, B):
+    """Number of ones the while-loop of rmabppo_core.py:320-331 hands out."""
+    k, spent = 0, 0.0
+    while spent < float(B) and k < N:
+        if spent + float(cost1) > float(B):
+            break
+        spent += float(cost1)
+        k += 1
+    return k
+
+
+def budget_select_binary_sharded(p1, cost1, B, n_total, rank, world, group=None, positive_only=False):
+    """Global top-k over arms that are sharded across ranks (contiguous arm ranges in rank order): p1 `[N_local,E]` of
+    this rank -> its rows of the actions.  Per 8-bit radix pass one all-reduce of the per-env digit histograms
+    `[ceil(E/32), 256, 32]`, then one all-gather of the per-env boundary-tie counts so that ties go to the
+    higher GLOBAL arm index."""
+    import torch.distributed as dist
+    N, E = p1.shape
+    dev = p1.device
+    out = torch.empty((N, E), dtype=u8, device=dev)
+    k = select_count(n_total, cost1, B)
+    if k <= 0 or k >= n_total:
+        out.fill_(1 if k >= n_total else 0)
+        if positive_only and k >= n_total:
+            out.copy_((p1 > 0).to(u8))
+        return out
+    G = (E + 31) // 32
+    Nw = max(N, 1)
+    ws, need = _select_ws(E, Nw, dev)
+    hist = torch.zeros((G, 256, 32), dtype=i32, device=dev)
+    local3 = None
+    for ps in range(4):
+        if N > 0:
+            check(lib().rmab_select_hist(E, N, _p(p1, f32, "p1"), ps, _p(ws, i32), need, _p(hist, i32), _stream()))
+        else:
+            hist.zero_()
+        if ps == 3:
+            local3 = hist.clone()
+        if world > 1:
+            dist.all_reduce(hist, group=group)
+        check(lib().rmab_select_scan(E, Nw, ps, k, _p(hist, i32), _p(ws, i32), need, _stream()))
+    # keys equal to the threshold on ranks holding higher arm indices
+    tau = ws[:G * 32]
+    lane = torch.arange(32, device=dev).repeat(G)
+    grp = torch.arange(G, device=dev).repeat_interleave(32)
+    eq_local = local3[grp, (tau & 255).long(), lane].contiguous()            # [G*32]
+    above = torch.zeros_like(eq_local)
+    if world > 1:
+        allc = torch.empty((world, G * 32), dtype=i32, device=dev)
+        dist.all_gather_into_tensor(allc, eq_local, group=group)
+        if rank + 1 < world:
+            above = allc[rank + 1:].sum(dim=0).to(i32).contiguous()
+    if N > 0:
+        check(lib().rmab_select_mark(E, N, _p(p1, f32, "p1"), _p(above, i32), int(bool(positive_only)), _p(out, u8),
+                                     _p(ws, i32), need, _stream()))
     return out
 
 

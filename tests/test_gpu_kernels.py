@@ -414,6 +414,80 @@ def test_select_binary_oracle(K, N, E):
     assert (got.sum(0) == min(3, N)).all()
 
 
+@pytest.mark.parametrize("N,E,pos", [(70001, 37, False), (3000, 700, False), (20000, 129, True)])
+def test_select_binary_large_path(K, N, E, pos):
+    """The multi-CTA radix select (N*E >= 2^21: env groups x arm chunks, global histograms) against np.argsort per env,
+    with heavy ties, an all-equal env, zeros (positive_only) and negative keys."""
+    rs = np.random.RandomState(N + E)
+    p1 = rs.rand(N, E).astype(F32)
+    p1[:, 0] = np.round(p1[:, 0] * 8) / 8
+    p1[:, 1] = 0.5
+    p1[:, 2] -= 0.5                                            # negative keys (top-B by index, simulator.py:309-325)
+    if pos:
+        p1[rs.rand(N, E) < 0.5] = 0.0
+    for B in (1, N // 5, N - 1):
+        got = K.n(K.ops.budget_select_binary(K.t(p1), 1.0, float(B), positive_only=pos))
+        for e in list(range(4)) + [E - 1, E // 2]:
+            assert np.array_equal(got[:, e], osel.topk_binary(p1[:, e], [0, 1], B, positive_only=pos)), (B, e)
+        if not pos:
+            assert (got.sum(0) == B).all()
+
+
+@pytest.mark.parametrize("splits", [(0.5,), (0.1, 0.45, 0.45), (0.0, 1.0)])
+def test_select_binary_sharded_phases(K, splits):
+    """Arm-sharded global top-k: the per-pass histogram / scan / mark phases driven for several arm shards on
+    one GPU, the all-reduce and all-gather between them emulated by sums -- equal to the unsharded selection bit for bit,
+    boundary ties included."""
+    import ctypes as C
+    import torch
+    ops, lib = K.ops, K.ops.lib()
+    N, E, B = 9000, 70, 2100
+    rs = np.random.RandomState(5)
+    p1 = rs.rand(N, E).astype(F32)
+    p1[:, 0] = np.round(p1[:, 0] * 4) / 4                      # boundary ties that straddle shards
+    p1[:, 1] = 0.25
+    want = np.stack([osel.topk_binary(p1[:, e], [0, 1], B) for e in range(E)], axis=1)
+    cuts = [0] + [int(round(N * sum(splits[:i + 1]))) for i in range(len(splits))]
+    if cuts[-1] != N:
+        cuts.append(N)
+    shards = [K.t(np.ascontiguousarray(p1[a:b])) for a, b in zip(cuts[:-1], cuts[1:])]
+    G = (E + 31) // 32
+    P = lambda t: C.c_void_p(t.data_ptr())
+    wss = []
+    for sh in shards:
+        need = int(lib.rmab_select_ws_bytes(E, max(sh.shape[0], 1), 2))
+        wss.append((torch.zeros((need + 3) // 4, dtype=torch.int32, device="cuda"), need))
+    k = ops.select_count(N, 1.0, B)
+    local3 = None
+    for ps in range(4):
+        hists = []
+        for sh, (ws, need) in zip(shards, wss):
+            h = torch.zeros((G, 256, 32), dtype=torch.int32, device="cuda")
+            if sh.shape[0]:
+                ops.check(lib.rmab_select_hist(E, sh.shape[0], P(sh), ps, P(ws), need, P(h), None))
+            hists.append(h)
+        tot = torch.stack(hists).sum(0).to(torch.int32).contiguous()     # the all-reduce
+        if ps == 3:
+            local3 = hists
+        for sh, (ws, need) in zip(shards, wss):
+            ops.check(lib.rmab_select_scan(E, max(sh.shape[0], 1), ps, k, P(tot), P(ws), need, None))
+    lane = torch.arange(32, device="cuda").repeat(G)
+    grp = torch.arange(G, device="cuda").repeat_interleave(32)
+    tau = wss[0][0][:G * 32]
+    eq = [h[grp, (tau & 255).long(), lane] for h in local3]              # the all-gather
+    outs = []
+    for r, (sh, (ws, need)) in enumerate(zip(shards, wss)):
+        above = torch.stack(eq[r + 1:]).sum(0).to(torch.int32).contiguous() if r + 1 < len(shards) else torch.zeros_like(eq[0])
+        out = torch.zeros((sh.shape[0], E), dtype=torch.uint8, device="cuda")
+        if sh.shape[0]:
+            ops.check(lib.rmab_select_mark(E, sh.shape[0], P(sh), P(above), 0, P(out), P(ws), need, None))
+        outs.append(out)
+    got = K.n(torch.cat(outs))
+    assert np.array_equal(got, want)
+    # and the one-call wrapper on a single rank
+    assert np.array_equal(K.n(ops.budget_select_binary_sharded(K.t(p1), 1.0, float(B), N, 0, 1)), want)
+
+
 def test_select_multi_property(K):
     rs = np.random.RandomState(8)
     for trial in range(12):

@@ -478,3 +478,32 @@ def test_critic_extra_iter_h64_vs_autograd_oracle(K, N, T, E, S):
     np.testing.assert_allclose(np.array(got_loss), np.array(want_loss), rtol=1e-05)     # after 1-2 Adam steps
     np.testing.assert_allclose(K.n(dz).transpose(1, 0, 2), want_dz, rtol=1e-3, atol=1e-8)
     np.testing.assert_allclose(K.n(Wv), W.detach().numpy(), rtol=0, atol=2e-4)
+
+
+@pytest.mark.parametrize("M,N,Kd", [(256, 256, 64), (300, 520, 200), (128, 1000, 72), (1000, 130, 1032), (5120, 1024, 2048)])
+def test_gemm3h_matches_fp64_product(K, M, N, Kd):
+    """The package's dense product for the agent critics' nature block (csrc/gemm3h.cu: fp16 hi/lo split with per-row
+    power-of-two scales, tcgen05 kind::f16 x 3, TMA-fed CTA pairs) against the fp64 product of the same fp32 inputs.
+    Tolerance: the scheme keeps 22 significant bits per operand and accumulates in fp32, so the error is bounded by a few
+    2^-22 of sum_k |a||b|; rows with very different magnitudes and an all-zero row exercise the per-row scales."""
+    import torch
+    ops = K.ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + Kd)
+    a = torch.randn((M, Kd), device="cuda", generator=g) * torch.logspace(-6, 3, M, device="cuda")[:, None]
+    b = torch.randn((N, Kd), device="cuda", generator=g) * torch.logspace(2, -8, N, device="cuda")[:, None]
+    a[M // 2] = 0.0
+    want = a.double() @ b.double().t()
+    bound = a.double().abs() @ b.double().abs().t()
+    for n_fast in (True, False):
+        got = ops.gemm3h(ops.split16_rows(a), ops.split16_rows(b), Kd, n_fast=n_fast)
+        err = ((got.double() - want).abs() / (bound + 1e-300)).max().item()
+        assert err < 2e-6, (n_fast, err)
+    # the transposed split: (a^T)^T . b^T from a^T stored [K, M]
+    at = a.t().contiguous()
+    got = ops.gemm3h(ops.split16_cols(at), ops.split16_rows(b), Kd)
+    err = ((got.double() - want).abs() / (bound + 1e-300)).max().item()
+    assert err < 2e-6, err
+    # an output view with a row stride (ldc > N)
+    big = torch.zeros((M, N + 8), device="cuda")
+    ops.gemm3h(ops.split16_rows(a), ops.split16_rows(b), Kd, out=big[:, :N])
+    assert torch.equal(big[:, :N], ops.gemm3h(ops.split16_rows(a), ops.split16_rows(b), Kd)) and float(big[:, N:].abs().max()) == 0.0
