@@ -6,9 +6,9 @@ a_nature, v_nature, logp_nature, q_nature=0, p1_agent), `get_nature_action(obs)`
 `bound_nature_actions`, `pi_nature` / `v_nature` / `lambda_net` as torch modules, `__repr__ == "MA-RMABPPO_%i"`.
 Device mapping: the per-arm agent actors / critics are packed `[N,P]` tensors evaluated by rmab_ac_step; the agent
 critics' first-layer block over the nature inputs is a `[N,h,D]` tensor applied to all arms and envs as ONE dense
-GEMM (a plain library GEMM) whose result the kernel adds to the first-layer pre-activation; the Gaussian nature
-actor's sample / log-prob is rmab_gaussian_sample; the dense nature nets (N -> h -> h -> D) are torch modules.
-The MA update (agent critics with nature inputs, nature PPO) is not yet on the device path.
+product (rmab_gemm3h: the package's TMA-fed tcgen05 kernel) whose result the kernel adds to the first-layer
+pre-activation; the Gaussian nature actor's sample / log-prob is rmab_gaussian_sample; the dense nature nets
+(N -> h -> h -> D) are torch modules.  The MA update lives in nature_oracle.MARolloutTrainer.
 """
 import math
 
@@ -135,7 +135,7 @@ class RMABLambdaNatureOracle(nn.Module):
     # -- step --------------------------------------------------------------------------------------
     def step_device(self, s, lamb, eps=None, u=None, w1n_split=None, s_full=None):
         """s `[N,E]` u8, lamb `[E]`.  Returns dict of device tensors: a_agent, v_agent, logp_agent, p1 `[N,E]`;
-        a_nature, a_nature_bounded `[E,D]`; logp_nature, v_nature `[E]`.  `w1n_split` = ops.split_tf32(W1n.reshape(-1, D))
+        a_nature, a_nature_bounded `[E,D]`; logp_nature, v_nature `[E]`.  `w1n_split` = ops.split16_rows(W1n.reshape(-1, D))
         when the caller keeps it across steps (W1n is constant during a rollout).  Arm-sharded: s holds the local arms,
         `s_full` `[N_total,E]` all of them (input of the nature nets); v_nature needs every arm's action and is left to
         the caller (None)."""
@@ -149,8 +149,12 @@ class RMABLambdaNatureOracle(nn.Module):
                                                   r=None if eps is not None else r_n, eps=eps)
             nat_b = self.bound_nature_device(a_nat, s_all)
             # first-layer nature term of every agent critic as one dense GEMM: [N*h, D] x [D, E] -> [N, h, E]
-            w1 = w1n_split if w1n_split is not None else self.W1n.reshape(-1, self.act_dim_nature)
-            extra = ops.matmul_3xtf32(w1, nat_b.t()).reshape(self.n_local, -1, E).contiguous()
+            D = self.act_dim_nature
+            if w1n_split is not None and len(w1n_split) == 2:        # tf32 (hi, lo) pair: the library-GEMM A/B arm
+                extra = ops.matmul_3xtf32(w1n_split, nat_b.t()).reshape(self.n_local, -1, E).contiguous()
+            else:
+                w1 = w1n_split if w1n_split is not None else ops.split16_rows(self.W1n.reshape(-1, D))
+                extra = ops.gemm3h(w1, ops.split16_rows(nat_b), D, n_fast=True).reshape(self.n_local, -1, E)
             r_a = ops.rng(self._seed, _lib.STREAM_ACT, self._steps, arm0=self.arm0)
             a, v, logp, p1, _ = ops.ac_step(self._net(E, True), self.Wpi, self.Wv, s, lamb,
                                             r=None if u is not None else r_a, u=u, extra=extra)

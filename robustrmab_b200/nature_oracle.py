@@ -10,10 +10,13 @@ the scalar stream), `get` (:168-193: per-arm and nature advantage normalisation)
   agent policies   train_pi_iters Adam steps (rmab_ppo_update, policy loss only)
   agent critics    train_v_iters Adam steps; every iteration = dense GEMM (nature block of the first layer), one
                    rmab_critic_extra_iter launch (everything else + Adam of the packed block), dense GEMM for the nature
-                   block's gradient, rmab_adam_step
+                   block's gradient, rmab_adam_step; the dense products are the package's TMA-fed tcgen05 kernel
+                   (rmab_gemm3h, csrc/gemm3h.cu)
   every lamb_update_freq epochs: lambda-net SGD step (rmab_lambda_sgd), nature policy and nature critic
                    train_pi_iters / train_v_iters Adam steps (dense N -> h -> h -> D nets: torch modules, library GEMMs).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -63,6 +66,8 @@ class MARolloutTrainer:
     all-gather per epoch, input of the nature critic), the lambda-net's first-layer partial sums and the discounted
     cost at t = 0 as in the RMABPPO trainer."""
     profile = False
+    # A/B switch: RMAB_MA_LIBRARY_GEMM=1 evaluates the nature-block products as three library TF32 GEMMs (round 1)
+    library_gemm = os.environ.get("RMAB_MA_LIBRARY_GEMM", "0") == "1"
 
     def __init__(self, env, ac, T, gamma, lam_other, clip_ratio, pi_lr_agent, pi_lr_nature, vf_lr_agent, vf_lr_nature,
                  lm_lr, pi_iters, v_iters, epochs, lamb_update_freq, final_train_lambdas, ent0, ent1, seed,
@@ -159,7 +164,8 @@ class MARolloutTrainer:
         s0 = self.s.contiguous()
         lamb, h1 = self._lambda(s0)
         self.s_traj[:, 0] = s0
-        w1n_split = ops.split_tf32(ac.W1n.reshape(-1, self.D))                 # constant over the rollout
+        # W1n is constant over the rollout: split it once (fp16 hi/lo rows for gemm3h, or tf32 hi/lo for the library arm)
+        w1n_split = ops.split_tf32(ac.W1n.reshape(-1, self.D)) if self.library_gemm else ops.split16_rows(ac.W1n.reshape(-1, self.D))
         sl = slice(self.arm0, self.arm0 + N)
         ret_local = torch.zeros((E,), dtype=_F32, device=self.dev)
         for t in range(T + 1):                                                  # step T = the bootstrap ac.step (:754)
@@ -230,26 +236,41 @@ class MARolloutTrainer:
         self.steps_pi += self.pi_iters
         # ---- agent critics over [x_i, bounded nature vector] (:505-513) ----
         st.mark("agent_critics")
-        natM = ops.split_tf32(self.nat_b.reshape(T * E, D))                      # sample m = t*E + e; (hi, lo) for 3xTF32
         net = ac._net(E, False)
         h = ac.hidden_sizes[0]
+        M = T * E
+        nat2d = self.nat_b.reshape(M, D)
+        if self.library_gemm:
+            natM = ops.split_tf32(nat2d)                                         # sample m = t*E + e; (hi, lo) for 3xTF32
+        else:
+            # operands of the package's own product (csrc/gemm3h.cu), constant over the iterations: nature rows [M, D]
+            # for z1 = nat . W1n^T and the transposed split [D, M] for dW1n = dz1^T . nat
+            nat_rows, nat_cols = ops.split16_rows(nat2d), ops.split16_cols(nat2d)
         for _ in range(self.v_iters):
-            # nature block of all N first layers as ONE dense GEMM: [T*E, D] x [D, N*h] -> sample-major [T*E, N, h]
+            # nature block of all N first layers as ONE dense product: [T*E, D] x [D, N*h] -> sample-major [T*E, N, h]
             st.mark("critics.z1_gemm")
-            w1h, w1l = ops.split_tf32(ac.W1n.reshape(N * h, D))
-            z1 = ops.matmul_3xtf32(natM, (w1h.t(), w1l.t())).reshape(T * E, N, h)
-            del w1h, w1l
+            if self.library_gemm:
+                w1h, w1l = ops.split_tf32(ac.W1n.reshape(N * h, D))
+                z1 = ops.matmul_3xtf32(natM, (w1h.t(), w1l.t())).reshape(M, N, h)
+                del w1h, w1l
+            else:
+                z1 = ops.gemm3h(nat_rows, ops.split16_rows(ac.W1n.reshape(N * h, D)), D, n_fast=False).reshape(M, N, h)
             st.mark("critics.kernel")
             hpv = ops.hyper(self.clip, 0.0, self.pi_lr_agent, self.vf_lr_agent, 0, 1, self.steps_pi, self.steps_v)
             dz1, _ = ops.critic_extra_iter(net, hpv, ac.Wv, self.adam_v, self.s_traj, ret, lamb, z1, sample_major=True)
             del z1
             st.mark("critics.grad_gemm")
-            dh, dl = ops.split_tf32(dz1.reshape(T * E, N * h))
-            gW1n = ops.matmul_3xtf32((dh.t(), dl.t()), natM).reshape(N, h, D)    # dW1_nature = dz1^T . nature, one GEMM
-            del dh, dl, dz1
+            if self.library_gemm:
+                dh, dl = ops.split_tf32(dz1.reshape(M, N * h))
+                gW1n = ops.matmul_3xtf32((dh.t(), dl.t()), natM).reshape(N, h, D)    # dW1_nature = dz1^T . nature, one GEMM
+                del dh, dl, dz1
+            else:
+                gW1n = ops.gemm3h(ops.split16_cols(dz1.reshape(M, N * h)), nat_cols, M, n_fast=True).reshape(N, h, D)
+                del dz1
             st.mark("critics.adam")
             self.steps_v += 1
             ops.adam_step(ac.W1n, gW1n, self.m_w1n, self.v_w1n, self.vf_lr_agent, self.steps_v)
+            del gW1n
         # ---- lambda net and the nature nets, every lamb_update_freq epochs (:516-576) ----
         st.mark("lambda_and_nature_nets")
         if ep % self.freq == 0 and ep > 0:

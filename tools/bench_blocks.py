@@ -209,7 +209,7 @@ def ma_sis_block(dev, peaks, rank=0, world=1, N=2048, E=256, T=20, pop=50, h=64,
     bf16_peak = peaks.get("bf16_tflops_sustained", 2250.0 * 0.6)
     ach = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms else 0.0
     mem = torch.cuda.max_memory_allocated() / 2 ** 30
-    info = getattr(tr, "gemm_info", "library 3xTF32")
+    info = "library 3xTF32" if tr.library_gemm else "rmab_gemm3h: tcgen05 kind::f16 x 3, TMA, CTA pairs"
     del tr, ac, env
     torch.cuda.empty_cache()
     return {"metric": "MA-RMABPPO arm-steps/sec (rollout incl. 50 counterfactual steps + update)", "unit": UNIT,
