@@ -279,6 +279,44 @@ int rmab_split16_cols(int Rk, int Cn, const float* X, int64_t ldx, int ldk, void
 int rmab_gemm3h(int M, int N, int K, int ldk, const void* Ah, const void* Al, const float* rsA, const void* Bh, const void* Bl,
                 const float* rsB, float* C, int64_t ldc, int n_fast, rmab_stream_t stream);
 
+/* ---- the dense nature nets of MA-RMABPPO ------------------------------------------------- */
+
+/* Gaussian nature actor N -> h -> h -> D (ma_rmabppo_core.py:84-113) and nature critic 2N -> h -> h -> 1 (:116-123) as
+ * tiled fp32 kernels (csrc/nature.cu); losses and updates follow nature_oracle.py:359-386, :421-428, :558-576.
+ * Packed parameters: [W1T (Nin x H) | b1 | W2 (H x H, [out][in]) | b2 | W3 (OUT x H) | b3 | log_std]; W1 is TRANSPOSED so
+ * that an arm's rows are contiguous.  Layer 1 reads the u8 trajectories directly: x [n][t][e] with arm stride `stride`
+ * (elements), sample m = t * E + e, value sc * x; the optional second source (the agent actions of the critic) has its own
+ * weight block.  Arm-sharded use: pass the rank's arms and weight rows; l1_fwd / logp / out_bwd.da2 are
+ * then partial sums the caller all-reduces.  All reductions are two-stage in a fixed order (deterministic).
+ * ws: rmab_nat_ws_bytes(M, H, n_loc, Dl) bytes.  H in {8, 16, 32, 64}. */
+size_t rmab_nat_ws_bytes(int M, int H, int n_loc, int Dl);
+/* z1 [M,H] = sum_n sc0 x0[n,m] W0[n,:] (+ x1[n,m] W1[n,:]) */
+int rmab_nat_l1_fwd(int M, int E, int H, int n_loc, const uint8_t* x0, int64_t stride0, float sc0, const float* W0,
+                    const uint8_t* x1, int64_t stride1, const float* W1, float* z1, void* ws, size_t ws_bytes, rmab_stream_t stream);
+/* a1 = tanh(z1 + b1), a2 = tanh(W2 a1 + b2) */
+int rmab_nat_mid_fwd(int M, int H, const float* z1, const float* b1, const float* W2, const float* b2, float* a1, float* a2,
+                     rmab_stream_t stream);
+/* mu [M, Dl] (row stride ld_mu) = a2 W3^T + b3 */
+int rmab_nat_mu(int M, int H, int Dl, const float* a2, const float* W3, const float* b3, float* mu, int64_t ld_mu, rmab_stream_t stream);
+/* logp [M] = sum_d Normal(mu_d, exp(log_std_d)).log_prob(act[m, d]) over the Dl given rows */
+int rmab_nat_logp(int M, int H, int Dl, const float* a2, const float* W3, const float* b3, const float* log_std, const float* act,
+                  int64_t ld_act, float* logp, void* ws, size_t ws_bytes, rmab_stream_t stream);
+/* g [M] = d/dlogp of -mean(min(ratio adv, clip(ratio) adv)), ratio = exp(logp - logp_old) */
+int rmab_nat_pi_coef(int M, const float* logp, const float* logp_old, const float* adv, float clip_ratio, float* g, rmab_stream_t stream);
+/* backward of the actor's output layer given g: dW3 [Dl,H], db3 [Dl], dlog_std [Dl], da2 [M,H] */
+int rmab_nat_out_bwd(int M, int H, int Dl, const float* a2, const float* W3, const float* b3, const float* log_std, const float* act,
+                     int64_t ld_act, const float* g, float* dW3, float* db3, float* dlog_std, float* da2, void* ws, size_t ws_bytes,
+                     rmab_stream_t stream);
+/* d2 = da2 (1 - a2^2), d1 = (W2^T d2)(1 - a1^2); dW2 = d2^T a1, db2 = sum d2, db1 = sum d1 */
+int rmab_nat_mid_bwd(int M, int H, const float* da2, const float* a1, const float* a2, const float* W2, float* d1, float* d2,
+                     float* dW2, float* db2, float* db1, void* ws, size_t ws_bytes, rmab_stream_t stream);
+/* dW0 [n_loc,H] = sum_m sc0 x0[n,m] d1[m,:] (and dW1 for the second source) */
+int rmab_nat_l1_bwd(int M, int E, int H, int n_loc, const uint8_t* x0, int64_t stride0, float sc0, const uint8_t* x1, int64_t stride1,
+                    const float* d1, float* dW0, float* dW1, void* ws, size_t ws_bytes, rmab_stream_t stream);
+/* critic output: v [M] = a2 W3 + b3; with ret: backward of mean((v - ret)^2): da2 [M,H], dW3 [H], db3 [1] */
+int rmab_nat_v_out(int M, int H, const float* a2, const float* W3, const float* b3, const float* ret, float* v, float* da2,
+                   float* dW3, float* db3, void* ws, size_t ws_bytes, rmab_stream_t stream);
+
 /* ---- budget-constrained selection -------------------------------------------------------- */
 
 size_t rmab_select_ws_bytes(int E, int N, int A);

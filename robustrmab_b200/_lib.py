@@ -74,6 +74,16 @@ SIGNATURES = {
                          C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P, C.c_size_t, _P, _P, _P, _P],
     "rmab_ppo_update_table": [C.POINTER(RmabNetDesc), C.POINTER(RmabHyper), _I, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                               _P],
+    "rmab_nat_ws_bytes": [_I, _I, _I, _I],
+    "rmab_nat_l1_fwd": [_I, _I, _I, _I, _P, C.c_int64, _F, _P, _P, C.c_int64, _P, _P, _P, C.c_size_t, _P],
+    "rmab_nat_mid_fwd": [_I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "rmab_nat_mu": [_I, _I, _I, _P, _P, _P, _P, C.c_int64, _P],
+    "rmab_nat_logp": [_I, _I, _I, _P, _P, _P, _P, _P, C.c_int64, _P, _P, C.c_size_t, _P],
+    "rmab_nat_pi_coef": [_I, _P, _P, _P, _F, _P, _P],
+    "rmab_nat_out_bwd": [_I, _I, _I, _P, _P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, C.c_size_t, _P],
+    "rmab_nat_mid_bwd": [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P],
+    "rmab_nat_l1_bwd": [_I, _I, _I, _I, _P, C.c_int64, _F, _P, C.c_int64, _P, _P, _P, _P, C.c_size_t, _P],
+    "rmab_nat_v_out": [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P],
     "rmab_split16_rows": [_I, _I, _P, C.c_int64, _I, _P, _P, _P, _P],
     "rmab_split16_cols": [_I, _I, _P, C.c_int64, _I, _P, _P, _P, _P, _P],
     "rmab_gemm3h": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, C.c_int64, _I, _P],
@@ -89,7 +99,7 @@ SIGNATURES = {
     "rmab_vi_general": [_I, _I, _I, _P, _P, _D, _D, _I, _P, _P, _P, _P, _P],
     "rmab_whittle_bisect": [_I, _I, _I, _P, _P, _P, _D, _D, _I, _D, _D, _I, _P, _P],
 }
-_RESTYPES = {"rmab_last_error": C.c_char_p, "rmab_launch_count": C.c_uint64, "rmab_select_ws_bytes": C.c_size_t, "rmab_knapsack_ws_bytes": C.c_size_t,
+_RESTYPES = {"rmab_last_error": C.c_char_p, "rmab_launch_count": C.c_uint64, "rmab_select_ws_bytes": C.c_size_t, "rmab_nat_ws_bytes": C.c_size_t, "rmab_knapsack_ws_bytes": C.c_size_t,
              "rmab_epoch_ws_bytes": C.c_size_t, "rmab_lambda_ws_bytes": C.c_size_t}
 
 _lib = None

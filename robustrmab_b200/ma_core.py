@@ -8,7 +8,8 @@ Device mapping: the per-arm agent actors / critics are packed `[N,P]` tensors ev
 critics' first-layer block over the nature inputs is a `[N,h,D]` tensor applied to all arms and envs as ONE dense
 product (rmab_gemm3h: the package's TMA-fed tcgen05 kernel) whose result the kernel adds to the first-layer
 pre-activation; the Gaussian nature actor's sample / log-prob is rmab_gaussian_sample; the dense nature nets
-(N -> h -> h -> D) are torch modules.  The MA update lives in nature_oracle.MARolloutTrainer.
+(N -> h -> h -> D, 2N -> h -> h -> 1) are evaluated and trained by the rmab_nat_* kernels on a packed copy of the
+torch modules the drop-in exposes (nature_nets.py).  The MA update lives in nature_oracle.MARolloutTrainer.
 """
 import math
 
@@ -120,8 +121,7 @@ class RMABLambdaNatureOracle(nn.Module):
         return ops.bound_nature(a_nature.contiguous(), lo.contiguous(), hi.contiguous())
 
     def get_nature_action_device(self, s):
-        with torch.no_grad():
-            return self.pi_nature.mu_net(self._nature_obs(s))
+        return self.nature_nets().actor_mu(s.contiguous(), self.nature_scales()[0])
 
     def get_nature_action(self, obs):
         s = torch.as_tensor(np.asarray(obs).reshape(self.N, -1).astype(np.uint8), device=self.device_)
@@ -133,22 +133,35 @@ class RMABLambdaNatureOracle(nn.Module):
         return torch.cat([s.t().to(_F32) / (1.0 if self.one_hot_encode else float(self.state_norm)), a.t().to(_F32)], dim=1)
 
     # -- step --------------------------------------------------------------------------------------
-    def step_device(self, s, lamb, eps=None, u=None, w1n_split=None, s_full=None):
+    def nature_nets(self):
+        """The dense nature nets in packed device form (nature_nets.NatureNets), freshly packed from the torch modules."""
+        from .nature_nets import NatureNets
+        return NatureNets(self, self.arm0, self.n_local)
+
+    def nature_scales(self):
+        """(actor input scale in step(), critic obs scale in step()): obs (/state_norm if not one-hot) / nature_state_norm
+        (:283-289) and obs (/state_norm if not one-hot) (:318-325)."""
+        c = 1.0 if self.one_hot_encode else 1.0 / float(self.state_norm)
+        return c / float(self.nature_state_norm), c
+
+    def step_device(self, s, lamb, eps=None, u=None, w1n_split=None, s_full=None, nat_nets=None, want_v_nature=True):
         """s `[N,E]` u8, lamb `[E]`.  Returns dict of device tensors: a_agent, v_agent, logp_agent, p1 `[N,E]`;
         a_nature, a_nature_bounded `[E,D]`; logp_nature, v_nature `[E]`.  `w1n_split` = ops.split16_rows(W1n.reshape(-1, D))
-        when the caller keeps it across steps (W1n is constant during a rollout).  Arm-sharded: s holds the local arms,
-        `s_full` `[N_total,E]` all of them (input of the nature nets); v_nature needs every arm's action and is left to
-        the caller (None)."""
+        when the caller keeps it across steps (W1n is constant during a rollout); `nat_nets` likewise the packed nature
+        nets.  Arm-sharded: s holds the local arms, `s_full` `[N_total,E]` all of them (input of the nature actor);
+        v_nature needs every arm's action and is left to the caller (None), as it is with want_v_nature = False."""
         E = s.shape[1]
         sharded = s_full is not None
         s_all = s_full if sharded else s
+        nets = nat_nets if nat_nets is not None else self.nature_nets()
+        sc_a, sc_c = self.nature_scales()
         with torch.no_grad():
-            mu = self.pi_nature.mu_net(self._nature_obs(s_all)).contiguous()
+            mu = nets.actor_mu(s_all.contiguous(), sc_a)
             r_n = ops.rng(self._seed, _lib.STREAM_NATURE, self._steps)
-            a_nat, logp_nat = ops.gaussian_sample(mu, self.pi_nature.log_std.detach().contiguous(),
-                                                  r=None if eps is not None else r_n, eps=eps)
+            log_std = nets.actor.ls(nets.actor.p)
+            a_nat, logp_nat = ops.gaussian_sample(mu, log_std, r=None if eps is not None else r_n, eps=eps)
             nat_b = self.bound_nature_device(a_nat, s_all)
-            # first-layer nature term of every agent critic as one dense GEMM: [N*h, D] x [D, E] -> [N, h, E]
+            # first-layer nature term of every agent critic as one dense product: [N*h, D] x [D, E] -> [N, h, E]
             D = self.act_dim_nature
             if w1n_split is not None and len(w1n_split) == 2:        # tf32 (hi, lo) pair: the library-GEMM A/B arm
                 extra = ops.matmul_3xtf32(w1n_split, nat_b.t()).reshape(self.n_local, -1, E).contiguous()
@@ -158,7 +171,9 @@ class RMABLambdaNatureOracle(nn.Module):
             r_a = ops.rng(self._seed, _lib.STREAM_ACT, self._steps, arm0=self.arm0)
             a, v, logp, p1, _ = ops.ac_step(self._net(E, True), self.Wpi, self.Wv, s, lamb,
                                             r=None if u is not None else r_a, u=u, extra=extra)
-            v_nat = None if sharded else self.v_nature(self.nature_critic_input(s, a))
+            v_nat = None
+            if want_v_nature and not sharded:
+                v_nat = nets.critic_values(s.view(-1, 1, E), a.view(-1, 1, E), sc_c, 1, E)
         self._steps += 1
         return dict(a_agent=a, v_agent=v, logp_agent=logp, p1=p1, a_nature=a_nat, a_nature_bounded=nat_b,
                     logp_nature=logp_nat, v_nature=v_nat)

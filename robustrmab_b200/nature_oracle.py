@@ -13,7 +13,8 @@ the scalar stream), `get` (:168-193: per-arm and nature advantage normalisation)
                    block's gradient, rmab_adam_step; the dense products are the package's TMA-fed tcgen05 kernel
                    (rmab_gemm3h, csrc/gemm3h.cu)
   every lamb_update_freq epochs: lambda-net SGD step (rmab_lambda_sgd), nature policy and nature critic
-                   train_pi_iters / train_v_iters Adam steps (dense N -> h -> h -> D nets: torch modules, library GEMMs).
+                   train_pi_iters / train_v_iters Adam steps (dense N -> h -> h -> D nets: rmab_nat_* kernels on packed
+                   parameters, nature_nets.py; layer 1 and the actor's output rows are sharded by arm).
 """
 import os
 
@@ -61,10 +62,11 @@ class MARolloutTrainer:
     Arm-sharded over `world_size` ranks when `ac` was built with `arm_shard`: every rank keeps all E envs
     of its arm range -- env transitions, per-arm agent actors / critics (and the nature block W1n of its critics), the
     50 counterfactual steps, GAE and the agent updates are local.  Exchanged over NCCL: the state vector (all-gather of
-    `[N,E]` u8, once per step: it is the input of the dense nature nets, which every rank evaluates and trains
-    identically), per-step reward / cost partial sums (`[T,3,E]`, one all-reduce per epoch), the agent actions (one
-    all-gather per epoch, input of the nature critic), the lambda-net's first-layer partial sums and the discounted
-    cost at t = 0 as in the RMABPPO trainer."""
+    `[N,E]` u8, once per step: input of the nature actor's forward, which every rank evaluates identically, and of the
+    agent strategy), per-step reward / cost partial sums (`[T,3,E]`, one all-reduce per epoch), the nature critic's
+    layer-1 partial sums (`[(T+1)E, h]`, once per epoch), the lambda-net's first-layer partial sums and the discounted
+    cost at t = 0 as in the RMABPPO trainer.  The nature nets are TRAINED sharded: per Adam step three small
+    all-reduces (`[TE,h]`, `[TE]`, `[TE,h]`; critic: one), and one exchange of the updated slices per update."""
     profile = False
     # A/B switch: RMAB_MA_LIBRARY_GEMM=1 evaluates the nature-block products as three library TF32 GEMMs (round 1)
     library_gemm = os.environ.get("RMAB_MA_LIBRARY_GEMM", "0") == "1"
@@ -84,8 +86,6 @@ class MARolloutTrainer:
             assert N < ac.N or self.world == 1, "build the actor-critic with arm_shard=mpi_tools.arm_shard(N, rank, world)"
             self.env = env.shard(ac.arm0, ac.arm0 + N)   # the rank's arms; `env` itself keeps the global ranges for ac
             self.per = (self.N_total + self.world - 1) // self.world
-            self.gather_buf = torch.zeros((self.world, self.per, E), dtype=torch.uint8, device=dev)
-            self.s_full_traj = torch.empty((self.N_total, T + 1, E), dtype=torch.uint8, device=dev)
         else:
             self.env = env
         env = self.env
@@ -106,8 +106,8 @@ class MARolloutTrainer:
         self.adam_v = torch.zeros((N, 2, ac.Wv.shape[1]), dtype=_F32, device=dev)
         self.m_w1n, self.v_w1n = torch.zeros_like(ac.W1n), torch.zeros_like(ac.W1n)
         self.steps_pi = self.steps_v = 0
-        self.opt_pi_nat = torch.optim.Adam(ac.pi_nature.parameters(), lr=pi_lr_nature)
-        self.opt_v_nat = torch.optim.Adam(ac.v_nature.parameters(), lr=vf_lr_nature)
+        self.pi_lr_nature, self.vf_lr_nature = float(pi_lr_nature), float(vf_lr_nature)
+        self.nets = ac.nature_nets()       # packed nature actor / critic + their Adam state (nature_nets.py)
         self.R = torch.as_tensor(np.asarray(env.R), dtype=_F32, device=dev).contiguous()
         self.C = torch.as_tensor(np.asarray(env.C), dtype=_F32, device=dev).contiguous()
         self.lam_params = ac.lambda_net.packed().to(dev)
@@ -171,9 +171,7 @@ class MARolloutTrainer:
         for t in range(T + 1):                                                  # step T = the bootstrap ac.step (:754)
             s = self.s_traj[:, t].contiguous()
             s_full = self._gather_arms(s) if sharded else None
-            d = ac.step_device(s, lamb, w1n_split=w1n_split, s_full=s_full)
-            if sharded:
-                self.s_full_traj[:, t] = s_full
+            d = ac.step_device(s, lamb, w1n_split=w1n_split, s_full=s_full, nat_nets=self.nets, want_v_nature=False)
             if t == T:
                 ac._steps -= 1
                 break
@@ -196,21 +194,16 @@ class MARolloutTrainer:
             self.logp[:, t], self.val[:, t], self.s_traj[:, t + 1] = d["logp_agent"], d["v_agent"], s_next
             self.a_nat[t], self.nat_b[t] = d["a_nature"], d["a_nature_bounded"]
             self.logp_nat[t] = d["logp_nature"]
-            if not sharded:
-                self.val_nat[t] = d["v_nature"]
-        last_v_nature = d["v_nature"]
         if sharded:
-            # nature critic over [obs, a_agent] of ALL arms (:318-325): one batch over the gathered trajectories
             self._allreduce(self.part)
             self._allreduce(ret_local)
-            self.a_full = self._gather_arms(self.a)
-            a_full = torch.cat([self.a_full, self._gather_arms(d["a_agent"])[:, None]], dim=1)   # + the bootstrap step's actions
-            with torch.no_grad():
-                x = torch.cat([self.s_full_traj.permute(1, 2, 0).reshape((T + 1) * E, self.N_total).to(_F32) * self.obs_scale,
-                               a_full.permute(1, 2, 0).reshape((T + 1) * E, self.N_total).to(_F32)], dim=1)
-                vn = ac.v_nature(x).reshape(T + 1, E)
-            self.val_nat.copy_(vn[:T])
-            last_v_nature = vn[T].contiguous()
+        # nature critic over [obs, a_agent] of ALL arms and all T + 1 steps (:318-325) in one batch: every rank's layer-1
+        # partial over its own arms, one all-reduce of [(T+1) E, h]
+        a_ext = torch.cat([self.a, d["a_agent"][:, None]], dim=1).contiguous()
+        vn = self.nets.critic_values(self.s_traj, a_ext, ac.nature_scales()[1], T + 1, E,
+                                     allreduce=self._allreduce if sharded else None).view(T + 1, E)
+        self.val_nat.copy_(vn[:T])
+        last_v_nature = vn[T].contiguous()
         torch.sub(self.part[:, 0] - self.part[:, 1], lamb * self.part[:, 2], out=self.rew_nat)   # lamb_adjusted_r_nature (:707-719)
         return lamb, h1, s0, d["v_agent"], last_v_nature, ret_local
 
@@ -282,36 +275,20 @@ class MARolloutTrainer:
                 if self.obs_scale != 1.0:
                     _, h1 = self._lambda(s0, self.obs_scale)
                 ops.lambda_sgd(self.lam_params, s0, self.N_total, self.arm0, self.obs_scale, h1, coef, self.lm_lr)
-            s_all = self.s_full_traj if sharded else self.s_traj
-            a_all = self.a_full if sharded else a
-            NT = self.N_total
             # compute_loss_pi_nature / compute_loss_v_nature (:359-364, :421-428) divide the RAW buffer observations by
             # nature_state_norm when the nets are not one-hot and by nothing otherwise -- NOT by state_norm as step() does
             # (ma_rmabppo_core.py:276-289); kept as the reference has it
-            obs = s_all[:, :T].permute(1, 2, 0).reshape(T * E, NT).to(_F32)
-            if not ac.one_hot_encode:
-                obs = obs / float(ac.nature_state_norm)
-            obs_n = obs
+            sc = 1.0 if ac.one_hot_encode else 1.0 / float(ac.nature_state_norm)
+            ar = self._allreduce if sharded else None
             act = self.a_nat.reshape(T * E, D)
-            advn, lpo, retn = adv_n.reshape(-1), self.logp_nat.reshape(-1), ret_n.reshape(-1)
-            for _ in range(self.pi_iters):
-                self.opt_pi_nat.zero_grad()
-                mu = ac.pi_nature.mu_net(obs_n)
-                pi = torch.distributions.Normal(mu, torch.exp(ac.pi_nature.log_std))
-                logp = pi.log_prob(act).sum(axis=-1)
-                ratio = torch.exp(logp - lpo)
-                clip_adv = torch.clamp(ratio, 1 - self.clip, 1 + self.clip) * advn
-                loss = -(torch.min(ratio * advn, clip_adv)).mean() - 0.0 * pi.entropy().mean()   # entropy_coeff = 0 (:544)
-                loss.backward()
-                self.opt_pi_nat.step()
-            x = torch.cat([obs, a_all.permute(1, 2, 0).reshape(T * E, NT).to(_F32)], dim=1)
+            advn, lpo, retn = adv_n.reshape(-1).contiguous(), self.logp_nat.reshape(-1), ret_n.reshape(-1).contiguous()
+            for _ in range(self.pi_iters):      # entropy_coeff = 0 for nature (:544)
+                self.nets.actor_step(self.s_traj, T, E, sc, act, lpo, advn, self.clip, self.pi_lr_nature, allreduce=ar)
             for _ in range(self.v_iters):
-                self.opt_v_nat.zero_grad()
-                ((ac.v_nature(x) - retn) ** 2).mean().backward()
-                self.opt_v_nat.step()
-            if sharded:   # every rank ran the same steps on the same data; rank 0's copy is the reference
-                for p_ in list(ac.pi_nature.parameters()) + list(ac.v_nature.parameters()):
-                    torch.distributed.broadcast(p_.data, src=0, group=self.pg)
+                self.nets.critic_step(self.s_traj, a, T, E, sc, retn, self.vf_lr_nature, allreduce=ar)
+            if sharded:
+                self.nets.exchange_shards(self._allreduce)
+            self.nets.unpack()                  # the drop-in's torch modules follow the packed parameters
         st.mark(None)
         self.epoch_idx += 1
 

@@ -505,3 +505,79 @@ def whittle_bisect(T, R, Cc, gamma, eps, lam_lo, lam_hi, n_rounds, stop="full"):
                                     float(eps), _lib.STOP_FAST if stop == "fast" else _lib.STOP_FULL, float(lam_lo),
                                     float(lam_hi), int(n_rounds), _p(idx, f64), _stream()))
     return idx
+
+
+# ------------------------------------------------------------------------ dense nature nets (MA-RMABPPO)
+def nat_ws(M, H, n_loc, Dl, dev):
+    need = int(lib().rmab_nat_ws_bytes(int(M), int(H), int(n_loc), int(Dl)))
+    return torch.empty((need + 3) // 4, dtype=f32, device=dev), need
+
+
+def _pv(t):
+    """Raw pointer of a (possibly offset) contiguous CUDA view."""
+    if t is None:
+        return None
+    if not t.is_cuda or not t.is_contiguous():
+        raise ValueError("robustrmab_b200: contiguous CUDA view expected (no CPU fallback)")
+    return C.c_void_p(t.data_ptr())
+
+
+def nat_l1_fwd(M, E, H, x0, sc0, W0, z1, ws, x1=None, W1=None):
+    """x0 / x1: u8 `[n_loc, rows, E]` (or `[n_loc, E]`) whose first M / E rows are the samples; W0 / W1 `[n_loc, H]`."""
+    n_loc = x0.shape[0]
+    st0 = x0.stride(0)
+    st1 = x1.stride(0) if x1 is not None else 0
+    check(lib().rmab_nat_l1_fwd(M, E, H, n_loc, _pv(x0) if n_loc else None, st0, float(sc0), _pv(W0) if n_loc else None,
+                                _pv(x1) if (x1 is not None and n_loc) else None, st1, _pv(W1) if (W1 is not None and n_loc) else None,
+                                _p(z1, f32), _p(ws[0], f32), ws[1], _stream()))
+    return z1
+
+
+def nat_mid_fwd(M, H, z1, b1, W2, b2, a1, a2):
+    check(lib().rmab_nat_mid_fwd(M, H, _p(z1, f32), _pv(b1), _pv(W2), _pv(b2), _p(a1, f32), _p(a2, f32), _stream()))
+
+
+def nat_mu(M, H, Dl, a2, W3, b3, mu):
+    check(lib().rmab_nat_mu(M, H, Dl, _p(a2, f32), _pv(W3), _pv(b3), _pv(mu), mu.stride(0), _stream()))
+    return mu
+
+
+def nat_logp(M, H, Dl, a2, W3, b3, log_std, act, logp, ws):
+    """act: `[M, >= Dl]` view whose column 0 is this rank's first output row (row stride = act.stride(0))."""
+    check(lib().rmab_nat_logp(M, H, Dl, _p(a2, f32), _pv(W3) if Dl else None, _pv(b3) if Dl else None,
+                              _pv(log_std) if Dl else None, C.c_void_p(act.data_ptr()) if Dl else None, act.stride(0),
+                              _p(logp, f32), _p(ws[0], f32), ws[1], _stream()))
+    return logp
+
+
+def nat_pi_coef(M, logp, logp_old, adv, clip_ratio, g):
+    check(lib().rmab_nat_pi_coef(M, _p(logp, f32), _p(logp_old, f32), _p(adv, f32), float(clip_ratio), _p(g, f32), _stream()))
+    return g
+
+
+def nat_out_bwd(M, H, Dl, a2, W3, b3, log_std, act, g, dW3, db3, dls, da2, ws):
+    check(lib().rmab_nat_out_bwd(M, H, Dl, _p(a2, f32), _pv(W3) if Dl else None, _pv(b3) if Dl else None,
+                                 _pv(log_std) if Dl else None, C.c_void_p(act.data_ptr()) if Dl else None, act.stride(0),
+                                 _p(g, f32), _pv(dW3) if Dl else None, _pv(db3) if Dl else None, _pv(dls) if Dl else None,
+                                 _p(da2, f32), _p(ws[0], f32), ws[1], _stream()))
+
+
+def nat_mid_bwd(M, H, da2, a1, a2, W2, d1, d2, dW2, db2, db1, ws):
+    check(lib().rmab_nat_mid_bwd(M, H, _p(da2, f32), _p(a1, f32), _p(a2, f32), _pv(W2), _p(d1, f32), _p(d2, f32), _pv(dW2),
+                                 _pv(db2), _pv(db1), _p(ws[0], f32), ws[1], _stream()))
+
+
+def nat_l1_bwd(M, E, H, x0, sc0, d1, dW0, ws, x1=None, dW1=None):
+    n_loc = x0.shape[0]
+    if n_loc == 0:
+        return
+    check(lib().rmab_nat_l1_bwd(M, E, H, n_loc, _pv(x0), x0.stride(0), float(sc0), _pv(x1) if x1 is not None else None,
+                                x1.stride(0) if x1 is not None else 0, _p(d1, f32), _pv(dW0), _pv(dW1) if dW1 is not None else None,
+                                _p(ws[0], f32), ws[1], _stream()))
+
+
+def nat_v_out(M, H, a2, W3, b3, v=None, ret=None, da2=None, dW3=None, db3=None, ws=None):
+    check(lib().rmab_nat_v_out(M, H, _p(a2, f32), _pv(W3), _pv(b3), _p(ret, f32) if ret is not None else None,
+                               _p(v, f32) if v is not None else None, _p(da2, f32) if da2 is not None else None, _pv(dW3), _pv(db3),
+                               _p(ws[0], f32) if ws is not None else None, ws[1] if ws is not None else 0, _stream()))
+    return v
