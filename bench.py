@@ -299,10 +299,10 @@ def run_ours(a):
     del tr
     torch.cuda.empty_cache()
     blocks = {}
+    if not a.no_ma:        # first: its rollout is launch-latency sensitive and measured slower right after the seconds-long ARMMAN epochs
+        blocks["ma_sis"] = bb.guarded(bb.ma_sis_block, dev, peaks, rank, world)
     if not a.no_armman and a.hidden != 64:
         blocks["armman_full"] = bb.guarded(bb.armman_block, dev, peaks, rank, world)
-    if not a.no_ma:
-        blocks["ma_sis"] = bb.guarded(bb.ma_sis_block, dev, peaks, rank, world)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

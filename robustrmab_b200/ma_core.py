@@ -110,15 +110,18 @@ class RMABLambdaNatureOracle(nn.Module):
         """tanh-bound raw nature actions `[E,D]` into the env's sampled ranges for states s `[N,E]`; returns `[E,D]`."""
         rg = self.env._ranges()
         E = a_nature.shape[0]
-        if rg.dim() == 2:                                   # counterexample: [N,2]
-            lo, hi = rg[:, 0].expand(E, -1), rg[:, 1].expand(E, -1)
-        elif rg.dim() == 4:                                 # ARMMAN: [N,S,A,2] looked up at the arm's state
+        if rg.dim() == 4:                                   # ARMMAN: [N,S,A,2] looked up at the arm's state
             sel = rg[torch.arange(self.N, device=rg.device)[:, None], s.long()]      # [N,E,A,2]
-            lo = sel[..., 0].permute(1, 0, 2).reshape(E, -1)
-            hi = sel[..., 1].permute(1, 0, 2).reshape(E, -1)
-        else:                                               # SIS: [N,4,2]
-            lo, hi = rg[..., 0].reshape(1, -1).expand(E, -1), rg[..., 1].reshape(1, -1).expand(E, -1)
-        return ops.bound_nature(a_nature.contiguous(), lo.contiguous(), hi.contiguous())
+            lo = sel[..., 0].permute(1, 0, 2).reshape(E, -1).contiguous()
+            hi = sel[..., 1].permute(1, 0, 2).reshape(E, -1).contiguous()
+        else:                                               # counterexample [N,2], SIS [N,4,2]: state-independent bounds
+            key = (E, rg.data_ptr(), rg._version)
+            if getattr(self, "_bounds_key", None) != key:
+                self._bounds = (rg[..., 0].reshape(1, -1).expand(E, -1).contiguous(),
+                                rg[..., 1].reshape(1, -1).expand(E, -1).contiguous())
+                self._bounds_key = key
+            lo, hi = self._bounds
+        return ops.bound_nature(a_nature.contiguous(), lo, hi)
 
     def get_nature_action_device(self, s):
         return self.nature_nets().actor_mu(s.contiguous(), self.nature_scales()[0])

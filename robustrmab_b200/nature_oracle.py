@@ -107,6 +107,7 @@ class MARolloutTrainer:
         self.m_w1n, self.v_w1n = torch.zeros_like(ac.W1n), torch.zeros_like(ac.W1n)
         self.steps_pi = self.steps_v = 0
         self.pi_lr_nature, self.vf_lr_nature = float(pi_lr_nature), float(vf_lr_nature)
+        self._gpad = self._gout = None
         self.nets = ac.nature_nets()       # packed nature actor / critic + their Adam state (nature_nets.py)
         self.R = torch.as_tensor(np.asarray(env.R), dtype=_F32, device=dev).contiguous()
         self.C = torch.as_tensor(np.asarray(env.C), dtype=_F32, device=dev).contiguous()
@@ -131,15 +132,17 @@ class MARolloutTrainer:
         return t
 
     def _gather_arms(self, x):
-        """Local `[N_local, ...]` u8 rows of every rank -> `[N_total, ...]` in global arm order (ragged last shard padded)."""
+        """Local `[N_local, E]` u8 rows of every rank -> `[N_total, E]` in global arm order (ragged last shard padded).
+        The buffers are allocated once: a fresh tensor per step would keep the caching allocator busy behind NCCL."""
         if self.world == 1:
             return x
-        tail = tuple(x.shape[1:])
-        pad = torch.zeros((self.per,) + tail, dtype=x.dtype, device=x.device)
-        pad[:x.shape[0]] = x
-        out = torch.empty((self.world * self.per,) + tail, dtype=x.dtype, device=x.device)
-        torch.distributed.all_gather_into_tensor(out, pad, group=self.pg)
-        return out[:self.N_total]
+        if self._gpad is None or self._gpad.shape[1:] != x.shape[1:]:
+            tail = tuple(x.shape[1:])
+            self._gpad = torch.zeros((self.per,) + tail, dtype=x.dtype, device=x.device)
+            self._gout = torch.empty((self.world * self.per,) + tail, dtype=x.dtype, device=x.device)
+        self._gpad[:x.shape[0]] = x
+        torch.distributed.all_gather_into_tensor(self._gout, self._gpad, group=self.pg)
+        return self._gout[:self.N_total]
 
     def _lambda(self, s0, scale=1.0):
         """lambda [E] and the (all-reduced) first-layer sums.  The rollout predicts lambda from the RAW observation

@@ -158,7 +158,7 @@ def armman_block(dev, peaks, rank=0, world=1, n_total=100_000, E=1024, T=10, h=6
 
 
 # ------------------------------------------------------------------------------------------ configs[3]
-def ma_sis_block(dev, peaks, rank=0, world=1, N=2048, E=256, T=20, pop=50, h=64, pi_iters=4, v_iters=4, steps=2, warm=1):
+def ma_sis_block(dev, peaks, rank=0, world=1, N=2048, E=256, T=20, pop=50, h=64, pi_iters=4, v_iters=4, steps=3, warm=2):
     """BASELINE configs[3]: SIS epidemic domain (S = 51, A = 3, C = [0,1,2]) with the MA-RMABPPO nature oracle against
     the Pessimist agent strategy; N = 2048 arms (D = 4N nature parameters), E = 256, T = 20, hidden [64,64], 50
     counterfactual env steps per step, nature nets updated every epoch.  Arm-sharded under torchrun (strong scaling)."""
@@ -223,9 +223,11 @@ def ma_sis_block(dev, peaks, rank=0, world=1, N=2048, E=256, T=20, pop=50, h=64,
             "roofline": {"bound": "tensor", "kernel": f"agent-critic nature-block GEMMs ({info}), rank 0", "achieved": ach,
                          "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak if bf16_peak else None, "traffic": None,
                          "fp32_equivalent_flops_per_step": gemm_flops, "ms_per_step": gemm_ms,
+                         "executed_f16_TFLOPs": 3 * ach,
                          "note": "achieved = fp32-equivalent flops (2 M N K per product) of the 2 x v_iters dense products over "
-                                 "their time; each is evaluated as 3 half-precision tensor-core products with fp32 accumulation, "
-                                 "so 1/3 of the 16-bit peak is the ceiling of this figure",
+                                 "their stage time (the fp16 hi/lo split kernels of W1n and dz1 included); each product is evaluated "
+                                 "as 3 fp16 tensor-core products with fp32 accumulation, so 1/3 of the 16-bit peak is the ceiling "
+                                 "of `achieved` and executed_f16_TFLOPs / peak is the tensor-pipe view",
                          "peak_source": "measured bf16 sustained" if "bf16_tflops_sustained" in peaks else "fallback"}}
 
 

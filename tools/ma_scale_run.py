@@ -57,7 +57,7 @@ def timed(fn):
     return out, float(ms.item())
 
 
-for ep in range(3):
+for ep in range(int(os.environ.get("MA_EPOCHS", "3"))):
     (lamb, h1, s0, lv, lvn, ret), ms_roll = timed(lambda: tr.rollout(pess))
     _, ms_upd = timed(lambda: tr.update(lamb, h1, s0, lv, lvn))
     tr.s = tr.env.reset_device()
