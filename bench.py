@@ -133,6 +133,15 @@ def cpu_port_rate(a, cores, epochs=1):
     return rate, max(times), wall
 
 
+def recorded_reference_classes():
+    """The UNMODIFIED reference classes timed in the build container (tools/time_reference_here.py -> profiles/): the
+    reference is pure Python that `pip install --target` cannot package (empty wheel), so it cannot run on the GPU box."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_reference_classes_cpu.json")))
+    except (OSError, ValueError):
+        return None
+
+
 def run_reference(a):
     """--impl reference: the reference algorithm on the host cores.  The reference is pure Python and cannot
     travel to the GPU box (nor be compiled), so this times its CPU restatement (oracle/, pinned to the
@@ -163,7 +172,8 @@ def run_reference(a):
            "config": {"workload": f"RMABPPO {a.domain} domain, {cores} host processes x (N={a.cpu_arms} arms x {a.cpu_envs} envs), "
                                   f"T={a.horizon}, hidden [{a.hidden},{a.hidden}], {a.pi_iters}+{a.v_iters} iters -- the CPU-sized sample of: "
                                   + workload_name(a, 1), "sample": sample},
-           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                            "reference_classes_recorded": recorded_reference_classes()},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
@@ -362,7 +372,8 @@ def run_ours(a):
         rate, tmax, _ = cpu_port_rate(a, 1, 1)
         out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
                                "sample": f"1 epoch of N={a.cpu_arms} arms x {a.cpu_envs} envs x T={a.horizon} "
-                                         f"(oracle port, 1 thread, {tmax:.1f} s)"}
+                                         f"(oracle port, 1 thread, {tmax:.1f} s)",
+                               "reference_classes_recorded": recorded_reference_classes()}
     out.update(blocks)
     if not a.no_whittle:
         out["whittle"] = bb.guarded(bb.whittle_block, dev, hbm_peak, peak_src, not a.no_cpu_baseline, a.vi_arms, a.vi_probes)
