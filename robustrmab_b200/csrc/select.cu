@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(kSelThreads) select_mark_kernel(int E, int N, 
                                                                   const uint32_t* __restrict__ eqtot,
                                                                   const uint32_t* __restrict__ part,
                                                                   const uint32_t* __restrict__ above_ranks, int positive_only,
-                                                                  uint8_t* __restrict__ actions) {
+                                                                  int only_ties, uint8_t* __restrict__ actions) {
   __shared__ uint32_t eqcnt[kSelThreads / 32][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int g = blockIdx.x, c = blockIdx.y, Cn = gridDim.y;
@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(kSelThreads) select_mark_kernel(int E, int N, 
   const bool tie = live && eqtot[e] > r;
   if (!__syncthreads_or(tie ? 1 : 0)) {
     // every key equal to the threshold is taken: no ordering needed
+    if (only_ties) return;   // select_mark4_kernel has written this env group
     if (live) {
       const float* col = p1 + e;
       uint8_t* ac = actions + e;
@@ -245,6 +246,52 @@ __global__ void __launch_bounds__(kSelThreads) select_mark_kernel(int E, int N, 
     else if (key == tau) { a = (above < r) ? 1 : 0; ++above; }
     if (positive_only && !(pv > 0.f)) a = 0;
     actions[(int64_t)n * E + e] = a;
+  }
+}
+
+// Marking, vectorised: lane = 4 consecutive envs (float4 load, uchar4 store), used when E % 4 == 0.  Env groups of 32 that
+// have a tie at the threshold are skipped here and written by select_mark_kernel (launched right after with only_ties = 1).
+__global__ void __launch_bounds__(kSelThreads) select_mark4_kernel(int E, int N, const float* __restrict__ p1, int chunk,
+                                                                   const uint32_t* __restrict__ prefix,
+                                                                   const uint32_t* __restrict__ remain,
+                                                                   const uint32_t* __restrict__ eqtot, int positive_only,
+                                                                   uint8_t* __restrict__ actions) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int e0 = (blockIdx.x * 32 + lane) * 4;
+  const bool live = e0 < E;
+  const int c = blockIdx.y;
+  const int n0 = min(N, c * chunk), n1 = min(N, n0 + chunk);
+  uint32_t tau[4] = {0u, 0u, 0u, 0u};
+  bool tie = false;
+  if (live) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      tau[j] = prefix[e0 + j];
+      tie |= eqtot[e0 + j] > remain[e0 + j];
+    }
+  }
+  // the scalar kernel's env groups are 32 wide = 8 lanes here
+  const uint32_t tb = __ballot_sync(0xffffffffu, tie);
+  const bool skip = !live || ((tb >> (lane & ~7)) & 0xFFu) != 0u;
+  if (skip) return;
+  const float* col = p1 + e0;
+  uint8_t* ac = actions + e0;
+  for (int n = n0 + w; n < n1; n += 2 * (kSelThreads / 32)) {
+    const int nb = n + kSelThreads / 32;
+    const float4 v0 = *reinterpret_cast<const float4*>(col + (int64_t)n * E);
+    float4 v1 = v0;
+    if (nb < n1) v1 = *reinterpret_cast<const float4*>(col + (int64_t)nb * E);
+    const float a0[4] = {v0.x, v0.y, v0.z, v0.w}, a1[4] = {v1.x, v1.y, v1.z, v1.w};
+    uchar4 o0, o1;
+    uint8_t* q0 = reinterpret_cast<uint8_t*>(&o0);
+    uint8_t* q1 = reinterpret_cast<uint8_t*>(&o1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      q0[j] = (sortable(a0[j]) >= tau[j] && (!positive_only || a0[j] > 0.f)) ? 1 : 0;
+      q1[j] = (sortable(a1[j]) >= tau[j] && (!positive_only || a1[j] > 0.f)) ? 1 : 0;
+    }
+    *reinterpret_cast<uchar4*>(ac + (int64_t)n * E) = o0;
+    if (nb < n1) *reinterpret_cast<uchar4*>(ac + (int64_t)nb * E) = o1;
   }
 }
 
@@ -474,9 +521,20 @@ extern "C" int rmab_select_mark(int E, int N, const float* p1, const uint32_t* a
   RMAB_REQUIRE(ws_bytes >= p.words * sizeof(uint32_t), RMAB_E_BADARG, "rmab_select_mark: workspace too small");
   uint32_t* w = static_cast<uint32_t*>(ws);
   const size_t GE = (size_t)p.G * 32;
-  select_mark_kernel<<<dim3(p.G, p.Cn), kSelThreads, 0, (cudaStream_t)stream>>>(E, N, p1, p.chunk, w, w + GE, w + 2 * GE,
-                                                                                w + p.part_off, above_ranks, positive_only,
-                                                                                actions);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (E % 4) == 0 && ((uintptr_t)p1 % 16) == 0 && ((uintptr_t)actions % 4) == 0;
+  if (vec) {
+    // its env groups are 128 wide: own arm chunking so that the grid still fills the GPU
+    const int g4 = (E / 4 + 31) / 32;
+    int cn4 = (2 * kSelTargetCtas) / g4;
+    const int max_cn4 = (N + 63) / 64;
+    cn4 = cn4 < 1 ? 1 : (cn4 > max_cn4 ? max_cn4 : cn4);
+    const int chunk4 = (N + cn4 - 1) / cn4;
+    select_mark4_kernel<<<dim3(g4, cn4), kSelThreads, 0, st>>>(E, N, p1, chunk4, w, w + GE, w + 2 * GE, positive_only, actions);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  select_mark_kernel<<<dim3(p.G, p.Cn), kSelThreads, 0, st>>>(E, N, p1, p.chunk, w, w + GE, w + 2 * GE, w + p.part_off,
+                                                              above_ranks, positive_only, vec ? 1 : 0, actions);
   return check_launch("rmab_select_mark");
 }
 
