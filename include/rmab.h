@@ -51,6 +51,8 @@ typedef struct RmabRng {
   uint32_t t;      /* time counter */
   uint32_t env0;   /* global index of the first env in the call */
   uint32_t arm0;   /* global index of the first arm in the call */
+  const uint32_t* t_base; /* optional DEVICE word added to t when the kernel runs (NULL = 0): lets a captured CUDA graph be
+                             replayed with advancing counters */
 } RmabRng;
 
 /* Shape of the N per-arm actor / critic nets (rmabppo_core.py:131-174). Two hidden layers of equal

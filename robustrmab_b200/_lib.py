@@ -23,7 +23,7 @@ class RmabError(RuntimeError):
 
 class RmabRng(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("stream", C.c_uint32), ("t", C.c_uint32),
-                ("env0", C.c_uint32), ("arm0", C.c_uint32)]
+                ("env0", C.c_uint32), ("arm0", C.c_uint32), ("t_base", C.c_void_p)]
 
 
 class RmabNetDesc(C.Structure):

@@ -24,7 +24,10 @@ constexpr int kNumSMs = 148;  // B200
 // ---- Philox4x32-10 (Salmon et al. SC'11; same constants as cuRAND / Random123) -----------------
 struct Rng {
   uint32_t k0, k1, stream, t, env0, arm0;
+  const uint32_t* t_base;   // optional device word added to t (graph replay with advancing counters)
 };
+
+__device__ __forceinline__ uint32_t rng_t(const Rng& g) { return g.t + (g.t_base ? __ldg(g.t_base) : 0u); }
 
 __host__ inline Rng make_rng(const RmabRng* r) {
   Rng g;
@@ -34,6 +37,7 @@ __host__ inline Rng make_rng(const RmabRng* r) {
   g.t = r->t;
   g.env0 = r->env0;
   g.arm0 = r->arm0;
+  g.t_base = r->t_base;
   return g;
 }
 
@@ -73,7 +77,7 @@ __device__ __forceinline__ float philox_uniform(uint32_t k0, uint32_t k1, uint32
 __device__ __forceinline__ float draw_uniform(const Rng& g, const float* __restrict__ u_inject, int64_t idx, int e,
                                               int n) {
   if (u_inject) return u_inject[idx];
-  return philox_uniform(g.k0, g.k1, g.stream, g.t, g.env0 + (uint32_t)e, g.arm0 + (uint32_t)n);
+  return philox_uniform(g.k0, g.k1, g.stream, rng_t(g), g.env0 + (uint32_t)e, g.arm0 + (uint32_t)n);
 }
 
 // Inverse-CDF categorical draw: k = #{j : cdf_j <= u}, cdf accumulated left to right in fp32 with

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) gaussian_sample_kernel(int E, int D, cons
     if (eps_inject) eps = eps_inject[(int64_t)e * D + d];
     else {
       float z0, z1;
-      philox_normal_pair(g.k0, g.k1, g.stream, g.t, g.env0 + (uint32_t)e, (uint32_t)(d >> 1), z0, z1);
+      philox_normal_pair(g.k0, g.k1, g.stream, rng_t(g), g.env0 + (uint32_t)e, (uint32_t)(d >> 1), z0, z1);
       eps = (d & 1) ? z1 : z0;
     }
     const float ls = log_std[d];
@@ -88,7 +88,7 @@ __global__ void cf_table_kernel(int domain, int E, int N, const uint8_t* __restr
     p = fminf(fmaxf(p, lo), hi);
     float acc = 0.f;
     for (int tr = 0; tr < n_trials; ++tr) {
-      const uint4 x = philox4x32_10(RMAB_STREAM_CF, g.t * (uint32_t)n_trials + (uint32_t)tr, g.env0 + (uint32_t)e,
+      const uint4 x = philox4x32_10(RMAB_STREAM_CF, rng_t(g) * (uint32_t)n_trials + (uint32_t)tr, g.env0 + (uint32_t)e,
                                     g.arm0 + (uint32_t)n, g.k0, g.k1);
       const int sn = cf_table_next(domain, si, ai, p, u24(x.x));
       acc += __ldg(R + (int64_t)n * S + sn);
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(128) cf_sis_kernel(int E, int N, int pop, cons
     }
     float acc = 0.f;
     for (int tr = 0; tr < n_trials; ++tr) {
-      const uint4 x = philox4x32_10(RMAB_STREAM_CF, g.t * (uint32_t)n_trials + (uint32_t)tr, g.env0 + (uint32_t)e,
+      const uint4 x = philox4x32_10(RMAB_STREAM_CF, rng_t(g) * (uint32_t)n_trials + (uint32_t)tr, g.env0 + (uint32_t)e,
                                     g.arm0 + (uint32_t)n, g.k0, g.k1);
       const float u = u24(x.x);
       int cnt = 0;
@@ -201,7 +201,7 @@ extern "C" int rmab_gaussian_sample(int E, int D, const float* mu, const float* 
                                     const float* eps_inject, float* a, float* logp, rmab_stream_t stream) {
   RMAB_REQUIRE(E > 0 && D > 0 && mu && log_std && a && logp && (rng || eps_inject), RMAB_E_BADARG,
                "rmab_gaussian_sample: bad argument");
-  RmabRng z = {0, RMAB_STREAM_NATURE, 0, 0, 0};
+  RmabRng z = {0, RMAB_STREAM_NATURE, 0, 0, 0, nullptr};
   gaussian_sample_kernel<<<E, 256, 0, (cudaStream_t)stream>>>(E, D, mu, log_std, make_rng(rng ? rng : &z), eps_inject, a,
                                                              logp);
   return check_launch("rmab_gaussian_sample");

@@ -516,8 +516,18 @@ using namespace rmab::nat;
 
 static const int kL1Chunks = 4, kMChunks = 8, kDChunks = 8;
 
+// arm chunks of the layer-1 forward: at least kL1Chunks, more when there are few sample tiles (the rollout's per-step
+// forward has M = E samples: 4 tiles at E = 256), so that the grid still covers the GPU
+static int l1_chunks(int M, int n_loc) {
+  const int mt = (M + TS - 1) / TS;
+  int want = (2 * kNumSMs + mt - 1) / mt;
+  if (want < kL1Chunks) want = kL1Chunks;
+  if (want > 32) want = 32;
+  return chunks_for(n_loc, TS, want);
+}
+
 extern "C" size_t rmab_nat_ws_bytes(int M, int H, int n_loc, int Dl) {
-  size_t a = (size_t)kL1Chunks * M * H;                              // l1 forward partials
+  size_t a = (size_t)l1_chunks(M, n_loc > 0 ? n_loc : 1) * M * H;   // l1 forward partials
   size_t b = (size_t)kMChunks * ((size_t)(Dl > 0 ? Dl : 1) * (H + 2));   // out backward (W): dW3, db3, dls partials
   size_t c = (size_t)kDChunks * M * H;                               // out backward (A): da2 partials
   size_t d = (size_t)kMChunks * ((size_t)2 * n_loc * H);             // l1 backward partials (state and action blocks)
@@ -549,7 +559,7 @@ extern "C" int rmab_nat_l1_fwd(int M, int E, int H, int n_loc, const uint8_t* x0
     cudaMemsetAsync(z1, 0, (size_t)M * H * 4, st);
     return RMAB_OK;
   }
-  const int ch = chunks_for(n_loc, TS, kL1Chunks);
+  const int ch = l1_chunks(M, n_loc);
   const int per = ((n_loc + ch - 1) / ch + TS - 1) / TS * TS;
   const int nch = (n_loc + per - 1) / per;
   l1_fwd_kernel<<<dim3((M + TS - 1) / TS, nch), NT, 0, st>>>(M, E, H, n_loc, per, x0, stride0, sc0, W0, x1, stride1, W1,

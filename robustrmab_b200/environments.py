@@ -103,6 +103,18 @@ class _RobustEnvBase:
         self._resets = 0
         return [seed1]
 
+    def counter_base(self, dev_word=None):
+        """Route the Philox time counter through a device word: with `dev_word` (int32 CUDA tensor of one element, holding the
+        current `_t`) the kernels get `t - _t` as argument and add the word when they run, so a captured CUDA graph of a
+        rollout can be replayed in later epochs after the caller refreshes the word.  None switches it off."""
+        self._t_word, self._t_origin = dev_word, (self._t if dev_word is not None else 0)
+
+    def _step_rng(self, stream=_lib.STREAM_ENV):
+        word = getattr(self, "_t_word", None)
+        if word is None:
+            return ops.rng(self._key, stream, self._t, arm0=self.arm0)
+        return ops.rng(self._key, stream, self._t - self._t_origin, arm0=self.arm0, t_base=word)
+
     def reset_device(self):
         """Uniform random start states (reference reset: random_stream.choice / randint)."""
         r = ops.rng(self._key, _lib.STREAM_RESET, self._resets, arm0=self.arm0)
@@ -201,7 +213,7 @@ class CounterExampleRobustEnv(_RobustEnvBase):
         """a_agent `[N,E]` u8, a_nature `[N]` (shared by the envs) or `[N,E]`; returns device (s', r)."""
         ranges = self._ranges()
         nature, per_env = self._nature_dev(a_nature, ())
-        r = ops.rng(self._key, _lib.STREAM_ENV, self._t, arm0=self.arm0)
+        r = self._step_rng()
         return ops.env_step_table(self.domain, self._state, a_agent, nature, ranges, self._R_dev, r=r,
                                   nature_per_env=per_env, want_reward=want_reward)
 
@@ -282,7 +294,7 @@ class ARMMANRobustEnv(_RobustEnvBase):
             if not has_env:
                 nature = nature[:, :, None].expand(self.N, 2, self.n_envs).contiguous()
             per_env = True
-        r = ops.rng(self._key, _lib.STREAM_ENV, self._t, arm0=self.arm0)
+        r = self._step_rng()
         return ops.env_step_table(self.domain, self._state, a_agent, nature, ranges, self._R_dev, r=r,
                                   nature_per_env=per_env, want_reward=want_reward)
 
@@ -390,7 +402,7 @@ class SISRobustEnv(_RobustEnvBase):
 
     def step_device(self, a_agent, a_nature, want_reward=True):
         nature, per_env = self._nature_dev(a_nature, (4,))
-        r = ops.rng(self._key, _lib.STREAM_ENV, self._t, arm0=self.arm0)
+        r = self._step_rng()
         return ops.env_step_sis(self.pop_size, self._state, a_agent, nature, self._R_dev, r=r, nature_per_env=per_env,
                                 want_reward=want_reward)
 

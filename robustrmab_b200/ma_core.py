@@ -91,6 +91,16 @@ class RMABLambdaNatureOracle(nn.Module):
     def seed(self, seed):
         self._seed, self._steps = int(seed), 0
 
+    def counter_base(self, dev_word=None):
+        """As environments.counter_base: route the step counter of the NATURE / ACT streams through a device word."""
+        self._t_word, self._t_origin = dev_word, (self._steps if dev_word is not None else 0)
+
+    def _step_rng(self, stream, arm0=0):
+        word = getattr(self, "_t_word", None)
+        if word is None:
+            return ops.rng(self._seed, stream, self._steps, arm0=arm0)
+        return ops.rng(self._seed, stream, self._steps - self._t_origin, arm0=arm0, t_base=word)
+
     def _net(self, E, extra):
         return ops.net_desc(self.n_local, E, self.n_states, self.act_dim_agent, self.hidden_sizes[0], self.one_hot_encode,
                             float(self.state_norm) if self.state_norm else 1.0, n_extra=self.act_dim_nature if extra else 0)
@@ -160,7 +170,7 @@ class RMABLambdaNatureOracle(nn.Module):
         sc_a, sc_c = self.nature_scales()
         with torch.no_grad():
             mu = nets.actor_mu(s_all.contiguous(), sc_a)
-            r_n = ops.rng(self._seed, _lib.STREAM_NATURE, self._steps)
+            r_n = self._step_rng(_lib.STREAM_NATURE)
             log_std = nets.actor.ls(nets.actor.p)
             a_nat, logp_nat = ops.gaussian_sample(mu, log_std, r=None if eps is not None else r_n, eps=eps)
             nat_b = self.bound_nature_device(a_nat, s_all)
@@ -171,7 +181,7 @@ class RMABLambdaNatureOracle(nn.Module):
             else:
                 w1 = w1n_split if w1n_split is not None else ops.split16_rows(self.W1n.reshape(-1, D))
                 extra = ops.gemm3h(w1, ops.split16_rows(nat_b), D, n_fast=True).reshape(self.n_local, -1, E)
-            r_a = ops.rng(self._seed, _lib.STREAM_ACT, self._steps, arm0=self.arm0)
+            r_a = self._step_rng(_lib.STREAM_ACT, arm0=self.arm0)
             a, v, logp, p1, _ = ops.ac_step(self._net(E, True), self.Wpi, self.Wv, s, lamb,
                                             r=None if u is not None else r_a, u=u, extra=extra)
             v_nat = None

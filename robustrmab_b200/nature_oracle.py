@@ -70,6 +70,9 @@ class MARolloutTrainer:
     profile = False
     # A/B switch: RMAB_MA_LIBRARY_GEMM=1 evaluates the nature-block products as three library TF32 GEMMs (round 1)
     library_gemm = os.environ.get("RMAB_MA_LIBRARY_GEMM", "0") == "1"
+    # RMAB_MA_GRAPHS=0: launch every rollout step eagerly (default: the per-step sequence is captured as CUDA graphs in the
+    # second rollout and replayed afterwards, one graph per time step)
+    use_graphs = os.environ.get("RMAB_MA_GRAPHS", "1") == "1"
 
     def __init__(self, env, ac, T, gamma, lam_other, clip_ratio, pi_lr_agent, pi_lr_nature, vf_lr_agent, vf_lr_nature,
                  lm_lr, pi_iters, v_iters, epochs, lamb_update_freq, final_train_lambdas, ent0, ent1, seed,
@@ -108,6 +111,13 @@ class MARolloutTrainer:
         self.steps_pi = self.steps_v = 0
         self.pi_lr_nature, self.vf_lr_nature = float(pi_lr_nature), float(vf_lr_nature)
         self._gpad = self._gout = None
+        # static inputs of the (graph-captured) rollout step
+        self.lamb_buf = torch.empty((E,), dtype=_F32, device=dev)
+        self.a_boot = torch.empty((N, E), dtype=torch.uint8, device=dev)
+        self.v_boot = torch.empty((N, E), dtype=_F32, device=dev)
+        self.t_words = torch.zeros((2, 1), dtype=torch.int32, device=dev)
+        self._w1n_split = None
+        self.graphs, self.graph_pol, self.graph_pool, self.graph_ok, self.rollouts_done = None, None, None, None, 0
         self.nets = ac.nature_nets()       # packed nature actor / critic + their Adam state (nature_nets.py)
         self.R = torch.as_tensor(np.asarray(env.R), dtype=_F32, device=dev).contiguous()
         self.C = torch.as_tensor(np.asarray(env.C), dtype=_F32, device=dev).contiguous()
@@ -161,54 +171,117 @@ class MARolloutTrainer:
                         self.lm_lr, n, allreduce=self._allreduce if self.world > 1 else None)
 
     # ---------------------------------------------------------------------------------------------
+    # One time step of the rollout (nature_oracle.py:673-735) on static buffers: everything it reads that changes between
+    # epochs (lambda, the W1n split, the Philox counters) lives in preallocated device memory, so that the step can be
+    # captured once as a CUDA graph and replayed (the host side of ~35 small launches per step is what bounds the sharded
+    # rollout).  Sharded: `s_full` is the static all-gather buffer, filled eagerly before the step.
+    def _step(self, t, agent_pol):
+        env, ac, T, N = self.env, self.ac, self.T, self.N
+        sharded = self.world > 1
+        sl = slice(self.arm0, self.arm0 + N)
+        s = self.s_traj[:, t].contiguous()
+        s_full = self._gout[:self.N_total] if sharded else None
+        d = ac.step_device(s, self.lamb_buf, w1n_split=self._w1n_split, s_full=s_full, nat_nets=self.nets, want_v_nature=False)
+        ac._steps -= 1                                                          # _advance() owns the host counters
+        if t == T:                                                              # the bootstrap ac.step (:754)
+            self.a_boot.copy_(d["a_agent"])
+            self.v_boot.copy_(d["v_agent"])
+            return
+        self.a[:, t] = d["a_agent"]
+        nat_env = nature_env_layout(d["a_nature_bounded"], self.N_total)
+        if sharded:
+            nat_env = nat_env[sl].contiguous()
+        env._state = s
+        s_next, r = env.step_device(d["a_agent"], nat_env)
+        a_test = agent_pol.act_test_device(s_full if sharded else s)
+        if sharded:
+            a_test = a_test[sl].contiguous()
+        word = getattr(env, "_t_word", None)
+        rng = ops.rng(self.seed, _lib.STREAM_CF, env._t - (env._t_origin if word is not None else 0), arm0=self.arm0, t_base=word)
+        r_test = ops.env_counterfactual(env.domain, s, a_test, nat_env, env._ranges() if env.domain != _lib.DOMAIN_SIS
+                                        else self.R, self.R, rng, NUM_TEST_POLICY_RUNS, nature_per_env=True)
+        torch.sum(r, dim=0, out=self.part[t, 0])
+        torch.sum(r_test, dim=0, out=self.part[t, 1])
+        torch.sum(self.C[d["a_agent"].long()], dim=0, out=self.part[t, 2])
+        self.logp[:, t], self.val[:, t], self.s_traj[:, t + 1] = d["logp_agent"], d["v_agent"], s_next
+        self.a_nat[t], self.nat_b[t] = d["a_nature"], d["a_nature_bounded"]
+        self.logp_nat[t] = d["logp_nature"]
+
+    def _advance(self, t):
+        """Host-side counters of one step (what the eager step would have advanced)."""
+        if t < self.T:
+            self.env._t += 1
+            self.ac._steps += 1
+
     def rollout(self, agent_pol):
         env, ac, T, N, E = self.env, self.ac, self.T, self.N, self.E
         sharded = self.world > 1
         s0 = self.s.contiguous()
         lamb, h1 = self._lambda(s0)
+        self.lamb_buf.copy_(lamb)
         self.s_traj[:, 0] = s0
         # W1n is constant over the rollout: split it once (fp16 hi/lo rows for gemm3h, or tf32 hi/lo for the library arm)
-        w1n_split = ops.split_tf32(ac.W1n.reshape(-1, self.D)) if self.library_gemm else ops.split16_rows(ac.W1n.reshape(-1, self.D))
-        sl = slice(self.arm0, self.arm0 + N)
-        ret_local = torch.zeros((E,), dtype=_F32, device=self.dev)
-        for t in range(T + 1):                                                  # step T = the bootstrap ac.step (:754)
-            s = self.s_traj[:, t].contiguous()
-            s_full = self._gather_arms(s) if sharded else None
-            d = ac.step_device(s, lamb, w1n_split=w1n_split, s_full=s_full, nat_nets=self.nets, want_v_nature=False)
-            if t == T:
-                ac._steps -= 1
-                break
-            self.a[:, t] = d["a_agent"]
-            nat_env = nature_env_layout(d["a_nature_bounded"], self.N_total)
-            if sharded:
-                nat_env = nat_env[sl].contiguous()
-            env._state = s
-            s_next, r = env.step_device(d["a_agent"], nat_env)
-            a_test = agent_pol.act_test_device(s_full if sharded else s)
-            if sharded:
-                a_test = a_test[sl].contiguous()
-            rng = ops.rng(self.seed, _lib.STREAM_CF, env._t, arm0=self.arm0)
-            r_test = ops.env_counterfactual(env.domain, s, a_test, nat_env, env._ranges() if env.domain != _lib.DOMAIN_SIS
-                                            else self.R, self.R, rng, NUM_TEST_POLICY_RUNS, nature_per_env=True)
-            env._t += 1
-            self.part[t, 0], self.part[t, 1] = r.sum(dim=0), r_test.sum(dim=0)
-            ret_local += self.part[t, 0]
-            self.part[t, 2] = self.C[d["a_agent"].long()].sum(dim=0)
-            self.logp[:, t], self.val[:, t], self.s_traj[:, t + 1] = d["logp_agent"], d["v_agent"], s_next
-            self.a_nat[t], self.nat_b[t] = d["a_nature"], d["a_nature_bounded"]
-            self.logp_nat[t] = d["logp_nature"]
+        if self.library_gemm:
+            self._w1n_split = ops.split_tf32(ac.W1n.reshape(-1, self.D))
+        else:
+            self._w1n_split = ops.split16_rows(ac.W1n.reshape(-1, self.D), out=self._w1n_split)
+        # Philox counters of this rollout through device words (see environments.counter_base)
+        self.t_words[0].fill_(env._t)
+        self.t_words[1].fill_(ac._steps)
+        env.counter_base(self.t_words[0])
+        ac.counter_base(self.t_words[1])
+        use_graphs = self.use_graphs and not self.library_gemm and self.graph_ok is not False
+        replay = use_graphs and self.graphs is not None and self.graph_pol is agent_pol
+        capture = use_graphs and not replay and self.rollouts_done >= 1
+        if capture:
+            self.graphs, self.graph_pol = [], agent_pol
+        t_env0, t_ac0 = env._t, ac._steps
+        try:
+            for t in range(T + 1):
+                if sharded:
+                    self._gather_arms(self.s_traj[:, t].contiguous())
+                if replay:
+                    self.graphs[t].replay()
+                elif capture:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=self.graph_pool):
+                        self._step(t, agent_pol)
+                    if self.graph_pool is None:
+                        self.graph_pool = g.pool()
+                    self.graphs.append(g)
+                    g.replay()                           # capture does not execute
+                else:
+                    self._step(t, agent_pol)
+                self._advance(t)
+        except Exception:
+            if not capture:
+                raise
+            # the agent strategy (or something else in the step) cannot be captured, e.g. it synchronises: run this and
+            # every later rollout eagerly
+            self.graph_ok, self.graphs = False, None
+            torch.cuda.synchronize()
+            env._t, ac._steps = t_env0, t_ac0
+            for t in range(T + 1):
+                if sharded:
+                    self._gather_arms(self.s_traj[:, t].contiguous())
+                self._step(t, agent_pol)
+                self._advance(t)
+        env.counter_base(None)
+        ac.counter_base(None)
+        self.rollouts_done += 1
+        ret_local = self.part[:, 0].sum(dim=0)
         if sharded:
             self._allreduce(self.part)
             self._allreduce(ret_local)
         # nature critic over [obs, a_agent] of ALL arms and all T + 1 steps (:318-325) in one batch: every rank's layer-1
         # partial over its own arms, one all-reduce of [(T+1) E, h]
-        a_ext = torch.cat([self.a, d["a_agent"][:, None]], dim=1).contiguous()
+        a_ext = torch.cat([self.a, self.a_boot[:, None]], dim=1).contiguous()
         vn = self.nets.critic_values(self.s_traj, a_ext, ac.nature_scales()[1], T + 1, E,
                                      allreduce=self._allreduce if sharded else None).view(T + 1, E)
         self.val_nat.copy_(vn[:T])
         last_v_nature = vn[T].contiguous()
         torch.sub(self.part[:, 0] - self.part[:, 1], lamb * self.part[:, 2], out=self.rew_nat)   # lamb_adjusted_r_nature (:707-719)
-        return lamb, h1, s0, d["v_agent"], last_v_nature, ret_local
+        return lamb, h1, s0, self.v_boot.clone(), last_v_nature, ret_local
 
     def update(self, lamb, h1, s0, last_v_agent, last_v_nature):
         ac, T, N, E, D = self.ac, self.T, self.N, self.E, self.D

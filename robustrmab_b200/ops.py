@@ -30,8 +30,13 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def rng(seed, stream, t, env0=0, arm0=0):
-    return RmabRng(int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream), int(t) & 0xFFFFFFFF, int(env0), int(arm0))
+def rng(seed, stream, t, env0=0, arm0=0, t_base=None):
+    """t_base: optional int32 CUDA tensor of one element that the kernel adds to t when it RUNS (a captured CUDA graph
+    replays with the counter the tensor holds at replay time)."""
+    r = RmabRng(int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream), int(t) & 0xFFFFFFFF, int(env0), int(arm0),
+                None if t_base is None else t_base.data_ptr())
+    r._keep = t_base   # the struct only holds the address
+    return r
 
 
 def net_desc(N, E, S, A, hidden, one_hot=True, state_norm=1.0, n_extra=0):
@@ -217,14 +222,19 @@ def _ldk(K):
     return (int(K) + 7) // 8 * 8
 
 
-def split16_rows(x):
-    """x `[R,K]` fp32 (row stride may exceed K) -> (hi, lo `[R,ldk]` fp16, rs `[R]`): the K-major operand form of gemm3h."""
+def split16_rows(x, out=None):
+    """x `[R,K]` fp32 (row stride may exceed K) -> (hi, lo `[R,ldk]` fp16, rs `[R]`): the K-major operand form of gemm3h.
+    `out` = a previous result to overwrite (static buffers for CUDA-graph replay)."""
     assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == f32 and x.is_cuda, "split16_rows: [R,K] fp32 CUDA rows"
     R, K = x.shape
     ldk = _ldk(K)
-    hi = torch.empty((R, ldk), dtype=f16, device=x.device)
-    lo = torch.empty((R, ldk), dtype=f16, device=x.device)
-    rs = torch.empty((R,), dtype=f32, device=x.device)
+    if out is None:
+        hi = torch.empty((R, ldk), dtype=f16, device=x.device)
+        lo = torch.empty((R, ldk), dtype=f16, device=x.device)
+        rs = torch.empty((R,), dtype=f32, device=x.device)
+    else:
+        hi, lo, rs = out
+        assert hi.shape == (R, ldk) and lo.shape == (R, ldk) and rs.shape == (R,)
     check(lib().rmab_split16_rows(R, K, C.c_void_p(x.data_ptr()), x.stride(0), ldk, _p(hi, f16), _p(lo, f16), _p(rs, f32),
                                   _stream()))
     return hi, lo, rs

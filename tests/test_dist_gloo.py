@@ -82,7 +82,7 @@ def _ma_worker(rank, world, port, out):
     from robustrmab_b200.nature_oracle import MARolloutTrainer
     N, E, T = 7, 3, 4                                   # ragged: 4 + 3 arms
     a0, n = mt.arm_shard(N, rank, world)
-    me = SimpleNamespace(world=world, pg=None, per=(N + world - 1) // world, N_total=N, N=n, arm0=a0)
+    me = SimpleNamespace(world=world, pg=None, per=(N + world - 1) // world, N_total=N, N=n, arm0=a0, _gpad=None, _gout=None)
     full = torch.arange(N * T * E, dtype=torch.int64).remainder(251).to(torch.uint8).reshape(N, T, E)
     got = MARolloutTrainer._gather_arms(me, full[a0:a0 + n].contiguous())
     res = {"gather_ok": bool(torch.equal(got, full))}
@@ -99,6 +99,33 @@ def _ma_worker(rank, world, port, out):
     MARolloutTrainer.export_lambda(me)
     res["w1"] = net[0].weight.detach().numpy().copy()
     res["b1"] = net[0].bias.detach().numpy().copy()
+    # sharded nature-net training: after the Adam steps every rank owns the rows of its arms (W1T, W3, b3, log_std of the
+    # actor; both W1T blocks of the critic); exchange_shards must give every rank the same, complete parameters
+    from robustrmab_b200.nature_nets import NatureNets
+    h, k = 8, 2
+    mk = lambda i, o: torch.nn.Sequential(torch.nn.Linear(i, h), torch.nn.Tanh(), torch.nn.Linear(h, h), torch.nn.Tanh(),
+                                          torch.nn.Linear(h, o))
+    torch.manual_seed(3)
+    acn = SimpleNamespace(N=N, act_dim_nature=k * N, hidden_sizes=[h, h], device_=torch.device("cpu"),
+                          pi_nature=SimpleNamespace(mu_net=mk(N, k * N), log_std=torch.nn.Parameter(torch.zeros(k * N))),
+                          v_nature=SimpleNamespace(v_net=mk(2 * N, 1)))
+    nets = NatureNets(acn, a0, n)
+    before = nets.actor.p.clone()
+    for net_ in (nets.actor, nets.critic):
+        net_.p[:net_.ob1].view(-1, h)[a0:a0 + n] += 10.0 * (rank + 1)          # W1T rows of own arms
+    nets.critic.p[:nets.critic.ob1].view(-1, h)[N + a0:N + a0 + n] += 10.0 * (rank + 1)
+    nets.actor.W3(nets.actor.p, a0 * k, n * k).add_(10.0 * (rank + 1))
+    nets.actor.b3(nets.actor.p, a0 * k, n * k).add_(10.0 * (rank + 1))
+    nets.actor.ls(nets.actor.p, a0 * k, n * k).add_(10.0 * (rank + 1))
+    nets.exchange_shards(lambda t: MARolloutTrainer._allreduce(me, t))
+    own = torch.zeros(N)
+    own[:4], own[4:] = 10.0, 20.0
+    d = nets.actor.p - before
+    res["nat_ok"] = bool(torch.equal(d[:nets.actor.ob1].view(N, h), own[:, None].expand(N, h)) and
+                         float(d[nets.actor.ob1:nets.actor.oW3].abs().max()) == 0.0 and
+                         torch.equal(d[nets.actor.oW3:nets.actor.ob3].view(N, k, h)[:, 0, 0], own) and
+                         torch.equal(d[nets.actor.ols:].view(N, k)[:, 1], own))
+    res["nat_p"] = nets.critic.p.numpy().copy()
     out[rank] = res
     dist.destroy_process_group()
 
@@ -115,3 +142,5 @@ def test_ma_sharding_host_logic_world2():
         w1 = out[r]["w1"]
         assert np.array_equal(w1[:, :4], np.full((8, 4), 1.0)) and np.array_equal(w1[:, 4:], np.full((8, 3), 2.0))
         assert np.array_equal(out[r]["b1"], np.full(8, 5.0))
+        assert out[r]["nat_ok"]
+    assert np.array_equal(out[0]["nat_p"], out[1]["nat_p"])
