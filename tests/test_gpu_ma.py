@@ -507,3 +507,148 @@ def test_gemm3h_matches_fp64_product(K, M, N, Kd):
     big = torch.zeros((M, N + 8), device="cuda")
     ops.gemm3h(ops.split16_rows(a), ops.split16_rows(b), Kd, out=big[:, :N])
     assert torch.equal(big[:, :N], ops.gemm3h(ops.split16_rows(a), ops.split16_rows(b), Kd)) and float(big[:, N:].abs().max()) == 0.0
+
+
+def _nature_problem(K, N, k, h, T, E, seed):
+    """A tiny actor-critic shell with torch nature modules + random trajectories for the nature-net kernel tests."""
+    import torch
+    from types import SimpleNamespace
+    torch.manual_seed(seed)
+    dev = K.dev
+    mk = lambda i, o: torch.nn.Sequential(torch.nn.Linear(i, h), torch.nn.Tanh(), torch.nn.Linear(h, h), torch.nn.Tanh(),
+                                          torch.nn.Linear(h, o)).to(dev)
+    D = k * N
+    ac = SimpleNamespace(N=N, act_dim_nature=D, hidden_sizes=[h, h], device_=dev,
+                         pi_nature=SimpleNamespace(mu_net=mk(N, D), log_std=torch.nn.Parameter(torch.full((D,), -0.5, device=dev))),
+                         v_nature=SimpleNamespace(v_net=mk(2 * N, 1)))
+    g = torch.Generator(device=dev).manual_seed(seed)
+    s_traj = torch.randint(0, 5, (N, T + 1, E), dtype=torch.uint8, device=dev, generator=g)
+    a = torch.randint(0, 3, (N, T, E), dtype=torch.uint8, device=dev, generator=g)
+    act = torch.randn((T * E, D), device=dev, generator=g)
+    logp_old = torch.randn((T * E,), device=dev, generator=g) * 0.3 - 0.9 * D
+    adv = torch.randn((T * E,), device=dev, generator=g)
+    ret = torch.randn((T * E,), device=dev, generator=g)
+    return ac, s_traj, a, act, logp_old, adv, ret
+
+
+@pytest.mark.parametrize("N,k,h,T,E", [(7, 1, 8, 3, 5), (13, 4, 16, 5, 9), (70, 2, 64, 4, 33)])
+def test_nature_net_kernels_vs_torch_autograd(K, N, k, h, T, E):
+    """rmab_nat_* (csrc/nature.cu) against the torch modules they replace: forward (mu, nature value), then three Adam steps
+    of compute_loss_pi_nature (nature_oracle.py:359-386, PPO clip on the summed Normal log-prob) and of compute_loss_v_nature
+    (:421-428) -- unsharded, and as two arm shards whose all-reduces are emulated by sums.  fp32 against fp32 with a different
+    summation order; Adam divides by sqrt(v), so an element whose gradient is near zero turns a 1e-7 gradient difference
+    into a visible fraction of a step: bound = 1e-4 absolute = 1 % of one step of lr 1e-2 (measured: 4e-5 on 7 of 17 944
+    elements at the largest shape, < 2e-5 elsewhere), on weights of magnitude 0.1-0.5."""
+    import copy
+    import torch
+    from robustrmab_b200.nature_nets import NatureNets
+    ac, s_traj, a, act, logp_old, adv, ret = _nature_problem(K, N, k, h, T, E, N + h)
+    M, D, sc, clip, lr = T * E, k * N, 0.25, 0.3, 1e-2
+    logp_old = logp_old * 0 + torch.distributions.Normal(ac.pi_nature.mu_net((s_traj[:, :T].permute(1, 2, 0).reshape(M, N).float() * sc)),
+                                                         torch.exp(ac.pi_nature.log_std)).log_prob(act).sum(-1).detach() + 0.2 * adv
+    # ---- torch reference: the modules, autograd, torch.optim.Adam ----
+    mu_ref, v_ref = copy.deepcopy(ac.pi_nature.mu_net), copy.deepcopy(ac.v_nature.v_net)
+    ls_ref = torch.nn.Parameter(ac.pi_nature.log_std.detach().clone())
+    opt_pi = torch.optim.Adam(list(mu_ref.parameters()) + [ls_ref], lr=lr)
+    opt_v = torch.optim.Adam(v_ref.parameters(), lr=lr)
+    obs = s_traj[:, :T].permute(1, 2, 0).reshape(M, N).float() * sc
+    xa = torch.cat([obs, a.permute(1, 2, 0).reshape(M, N).float()], dim=1)
+    nets = NatureNets(ac)
+    # forward parity first
+    s0 = s_traj[:, 0].contiguous()
+    np.testing.assert_allclose(K.n(nets.actor_mu(s0, sc)), K.n(mu_ref(s0.t().float() * sc)), rtol=1e-5, atol=2e-6)
+    vn = nets.critic_values(s_traj, torch.cat([a, a[:, :1]], dim=1).contiguous(), sc, T, E)
+    np.testing.assert_allclose(K.n(vn), K.n(v_ref(xa)[:, 0]), rtol=1e-5, atol=2e-6)
+    for _ in range(3):
+        opt_pi.zero_grad()
+        pi = torch.distributions.Normal(mu_ref(obs), torch.exp(ls_ref))
+        ratio = torch.exp(pi.log_prob(act).sum(-1) - logp_old)
+        (-(torch.min(ratio * adv, torch.clamp(ratio, 1 - clip, 1 + clip) * adv)).mean()).backward()
+        opt_pi.step()
+        opt_v.zero_grad()
+        ((v_ref(xa)[:, 0] - ret) ** 2).mean().backward()
+        opt_v.step()
+    # ---- kernels, one rank ----
+    for _ in range(3):
+        nets.actor_step(s_traj, T, E, sc, act, logp_old, adv, clip, lr)
+        nets.critic_step(s_traj, a, T, E, sc, ret, lr)
+    # ---- kernels, two arm shards on one GPU (all-reduce = sum of the two shards' buffers) ----
+    cut = N // 2 + 1
+    ac2 = _nature_problem(K, N, k, h, T, E, N + h)[0]
+    sh = [NatureNets(ac2, 0, cut), NatureNets(ac2, cut, N - cut)]
+    st = [s_traj[:cut].contiguous(), s_traj[cut:].contiguous()]
+    aa = [a[:cut].contiguous(), a[cut:].contiguous()]
+
+    # the two shards run in lockstep on two threads: an "all-reduce" parks its tensor, and when both have arrived the
+    # tensors are summed in place
+    import threading
+    bar = threading.Barrier(2)
+    slots = [None, None]
+
+    def make_ar(r):
+        def ar(t):
+            torch.cuda.synchronize()
+            slots[r] = t
+            bar.wait()
+            if r == 0:
+                tot = slots[0] + slots[1]
+                slots[0].copy_(tot)
+                slots[1].copy_(tot)
+                torch.cuda.synchronize()
+            bar.wait()
+            return t
+        return ar
+
+    def worker(r):
+        torch.cuda.set_device(K.dev)
+        for _ in range(3):
+            sh[r].actor_step(st[r], T, E, sc, act, logp_old, adv, clip, lr, allreduce=make_ar(r))
+            sh[r].critic_step(st[r], aa[r], T, E, sc, ret, lr, allreduce=make_ar(r))
+        sh[r].exchange_shards(make_ar(r))
+    th = [threading.Thread(target=worker, args=(r,)) for r in (0, 1)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for name, packed_list in (("one rank", [nets]), ("two shards", sh)):
+        for pk in packed_list:
+            ref_actor = torch.cat([mu_ref[0].weight.detach().t().reshape(-1), mu_ref[0].bias.detach(), mu_ref[2].weight.detach().reshape(-1),
+                                   mu_ref[2].bias.detach(), mu_ref[4].weight.detach().reshape(-1), mu_ref[4].bias.detach(), ls_ref.detach()])
+            ref_critic = torch.cat([v_ref[0].weight.detach().t().reshape(-1), v_ref[0].bias.detach(), v_ref[2].weight.detach().reshape(-1),
+                                    v_ref[2].bias.detach(), v_ref[4].weight.detach().reshape(-1), v_ref[4].bias.detach()])
+            np.testing.assert_allclose(K.n(pk.actor.p), K.n(ref_actor), atol=1e-4, rtol=0, err_msg=name + " actor")
+            np.testing.assert_allclose(K.n(pk.critic.p), K.n(ref_critic), atol=1e-4, rtol=0, err_msg=name + " critic")
+    assert torch.equal(sh[0].actor.p, sh[1].actor.p) and torch.equal(sh[0].critic.p, sh[1].critic.p)
+
+
+def test_ma_rollout_graphs_equal_eager(K):
+    """The CUDA-graph replay of the rollout step (Philox counters through device words) gives exactly the eager rollout:
+    two trainers on the same problem, one with graphs, five epochs with updates in between -- every trajectory byte and
+    every net bit-equal."""
+    import torch
+    from robustrmab_b200.environments import SISRobustEnv
+    from robustrmab_b200.evaluate import PessimisticAgentPolicy
+    from robustrmab_b200.ma_core import RMABLambdaNatureOracle
+    from robustrmab_b200.nature_oracle import MARolloutTrainer
+    N, E, T, h, pop = 9, 6, 5, 64, 10
+    out = []
+    for graphs in (False, True):
+        env = SISRobustEnv(N, 2.0, pop, 4, n_envs=E)
+        env.random_stream.seed(4)
+        env.sampled_parameter_ranges = env.sample_parameter_ranges()
+        torch.manual_seed(7)
+        ac = RMABLambdaNatureOracle(env.observation_space, env.action_space, env.sampled_parameter_ranges, env.action_dim_nature,
+                                    env, hidden_sizes=[h, h], C=env.C, N=N, B=env.B, one_hot_encode=False, non_ohe_obs_dim=1,
+                                    state_norm=pop, nature_state_norm=1, n_envs=E)
+        tr = MARolloutTrainer(env, ac, T, 0.9, 0.97, 2.0, 2e-3, 2e-3, 2e-3, 2e-3, 2e-3, 2, 2, 8, 2, 1, 0.5, 0.0, 4)
+        tr.use_graphs = graphs
+        pess = PessimisticAgentPolicy(N)
+        trace = []
+        for _ in range(5):
+            tr.epoch(pess)
+            trace.append((tr.s_traj.clone(), tr.a.clone(), tr.a_nat.clone(), tr.rew_nat.clone(), tr.val.clone()))
+        assert (tr.graphs is not None) == graphs
+        out.append((trace, ac.Wpi.clone(), ac.Wv.clone(), ac.W1n.clone(), tr.nets.actor.p.clone(), tr.nets.critic.p.clone()))
+    for (ta, tb) in zip(out[0][0], out[1][0]):
+        for x, y in zip(ta, tb):
+            assert torch.equal(x, y)
+    for x, y in zip(out[0][1:], out[1][1:]):
+        assert torch.equal(x, y)
