@@ -514,7 +514,9 @@ static int chunks_for(int total, int tile, int want) {
 using namespace rmab;
 using namespace rmab::nat;
 
-static const int kL1Chunks = 4, kMChunks = 8, kDChunks = 8;
+// chunk counts of the two-stage reductions: fine enough that a rank's shard of the work still fills the GPU (a CTA walks
+// at most a few 64-wide tiles; these kernels are latency-bound per CTA, not throughput-bound)
+static const int kL1Chunks = 4, kMChunks = 32, kDChunks = 32;
 
 // arm chunks of the layer-1 forward: at least kL1Chunks, more when there are few sample tiles (the rollout's per-step
 // forward has M = E samples: 4 tiles at E = 256), so that the grid still covers the GPU

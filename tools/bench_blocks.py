@@ -241,12 +241,12 @@ def whittle_block(dev, hbm_peak, peak_src, want_cpu=True, N=99_999, L=64):
     simulator.py:504-521) and the Whittle index by bisection on the indifference condition (lp_methods.py:181).
     Headline = counterexample domain at eps = 1e-8; eps = 1e-1 (simulator.py:595 default), ARMMAN (S = 3) and SIS pop = 50
     (S = 51, general kernel) tables beside it."""
-    from oracle import envs as oenv, vi as ovi
+    from robustrmab_b200.trainer import RMABPPOTrainer
     gamma, rounds = 0.9, 20
     out = {"metric": "Whittle-index arms/sec", "unit": "arms/s", "dtype": "f64", "variants": {}}
 
     def ce_tables(n):
-        p = oenv.ce_param_ranges(n).mean(-1)
+        p = RMABPPOTrainer.default_ranges(_lib.DOMAIN_CE, n, None).mean(-1)      # midpoints of PARAMETER_RANGES (:790-824)
         T = np.zeros((n, 2, 2, 2))
         T[:, 0] = 0.5
         T[:, 1, 0, 0] = 1.0
@@ -312,6 +312,7 @@ def whittle_block(dev, hbm_peak, peak_src, want_cpu=True, N=99_999, L=64):
                 "config": {"workload": head["workload"] + f"; Whittle index by {rounds}-round bisection per (arm, state)"},
                 "roofline": head["roofline"]})
     if want_cpu:
+        from oracle import vi as ovi        # the CPU leg: the oracle port of mdptoolbox ValueIteration (checker code, timed here)
         n_cpu = 200
         lam_lim = 10.0
         t0 = time.perf_counter()

@@ -54,9 +54,8 @@ for _ in range(reps):
     ops.gae(s_traj, at, val, last, lamb, Cc, R[:Ng].contiguous(), 0.9, 0.97, normalize=True)
 del s_traj, at, val
 # ---- batched VI, counterexample tables, 99 999 arms x 64 probes, eps 1e-8
-from oracle import envs as oenv  # noqa: E402  (table generator only)
 Nv, L = 99_999, 64
-p = oenv.ce_param_ranges(Nv).mean(-1)
+p = RMABPPOTrainer.default_ranges(_lib.DOMAIN_CE, Nv, None).mean(-1)
 Tt = np.zeros((Nv, 2, 2, 2))
 Tt[:, 0] = 0.5
 Tt[:, 1, 0, 0] = 1.0
