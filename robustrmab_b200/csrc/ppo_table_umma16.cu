@@ -135,15 +135,20 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args 
                               (float)sqrt(1.0 - pow(g.hp.beta2, (double)(step0 + k + 1))));
   uint32_t gt = 0;   // tiles issued so far: every barrier completes one phase per tile
 
+  // A row's 32-byte chunks sit at only four bank positions (128-byte pitch), so the 8 rows of a warp that share a position
+  // would serialise 8-fold on a 16-byte store; rows with bit 2 of the row index set write the upper half of every chunk first
+  // (4-fold = the minimum for 512 bytes).  The data swap is selects, the address swap one per-thread constant.
+  const bool up = (r >> 2) & 1;
+  const uint32_t h0 = up ? 16u : 0u, h1 = 16u - h0;
+  auto st_pair = [&](unsigned char* p, const uint32_t* v) {
+    *reinterpret_cast<uint4*>(p + h0) = make_uint4(up ? v[4] : v[0], up ? v[5] : v[1], up ? v[6] : v[2], up ? v[7] : v[3]);
+    *reinterpret_cast<uint4*>(p + h1) = make_uint4(up ? v[0] : v[4], up ? v[1] : v[5], up ? v[2] : v[6], up ? v[3] : v[7]);
+  };
   auto store_row = [&](uint32_t tile, const uint32_t (&hi)[FW], const uint32_t (&lo)[FW]) {
-    *reinterpret_cast<uint4*>(base + tile + off_c[0]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(base + tile + off_c[0] + 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-    *reinterpret_cast<uint4*>(base + tile + off_c[1]) = make_uint4(hi[8], hi[9], hi[10], hi[11]);
-    *reinterpret_cast<uint4*>(base + tile + off_c[1] + 16) = make_uint4(hi[12], hi[13], hi[14], hi[15]);
-    *reinterpret_cast<uint4*>(base + tile + off_c[2]) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    *reinterpret_cast<uint4*>(base + tile + off_c[2] + 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-    *reinterpret_cast<uint4*>(base + tile + off_c[3]) = make_uint4(lo[8], lo[9], lo[10], lo[11]);
-    *reinterpret_cast<uint4*>(base + tile + off_c[3] + 16) = make_uint4(lo[12], lo[13], lo[14], lo[15]);
+    st_pair(base + tile + off_c[0], &hi[0]);
+    st_pair(base + tile + off_c[1], &hi[8]);
+    st_pair(base + tile + off_c[2], &lo[0]);
+    st_pair(base + tile + off_c[3], &lo[8]);
   };
 
   for (int it = 0; it < iters; ++it) {
