@@ -68,7 +68,7 @@ struct EpochArgs {
 // re-reads (two backward passes).  The byte arrays are still written when the caller passes `a` (MA-RMABPPO, tests,
 // keep_buffers); with a == NULL nothing but the statistics leaves the SM.
 template <int H, int DOMAIN, bool ONCHIP>
-__global__ void __launch_bounds__(256, 2) epoch_table_kernel(EpochArgs g) {
+__global__ void __launch_bounds__(256, (H <= 16 ? 4 : 2)) epoch_table_kernel(EpochArgs g) {
   constexpr int S = DOMAIN == RMAB_DOMAIN_CE ? 2 : 3;
   constexpr int A = 2;
   constexpr int PL = S == 2 ? 2 : 3;   // bit planes per 32 steps: action, state bit 0 (, state bit 1)
