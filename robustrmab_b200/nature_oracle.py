@@ -105,6 +105,7 @@ class MARolloutTrainer:
         self.val_nat = torch.empty((T, E), dtype=_F32, device=dev)
         self.rew_nat = torch.empty((T, E), dtype=_F32, device=dev)
         self.part = torch.zeros((T, 3, E), dtype=_F32, device=dev)        # per step: sum r, sum counterfactual r, sum cost
+        self.cf = torch.empty((T, N, E), dtype=_F32, device=dev)          # counterfactual reward estimates per step
         self.adam_pi = torch.zeros((N, 2, ac.Wpi.shape[1]), dtype=_F32, device=dev)
         self.adam_v = torch.zeros((N, 2, ac.Wv.shape[1]), dtype=_F32, device=dev)
         self.m_w1n, self.v_w1n = torch.zeros_like(ac.W1n), torch.zeros_like(ac.W1n)
@@ -192,17 +193,14 @@ class MARolloutTrainer:
         if sharded:
             nat_env = nat_env[sl].contiguous()
         env._state = s
-        s_next, r = env.step_device(d["a_agent"], nat_env)
+        s_next, _ = env.step_device(d["a_agent"], nat_env, want_reward=False)   # rewards are R[arm, s'] (summed after the loop)
         a_test = agent_pol.act_test_device(s_full if sharded else s)
         if sharded:
             a_test = a_test[sl].contiguous()
         word = getattr(env, "_t_word", None)
         rng = ops.rng(self.seed, _lib.STREAM_CF, env._t - (env._t_origin if word is not None else 0), arm0=self.arm0, t_base=word)
-        r_test = ops.env_counterfactual(env.domain, s, a_test, nat_env, env._ranges() if env.domain != _lib.DOMAIN_SIS
-                                        else self.R, self.R, rng, NUM_TEST_POLICY_RUNS, nature_per_env=True)
-        torch.sum(r, dim=0, out=self.part[t, 0])
-        torch.sum(r_test, dim=0, out=self.part[t, 1])
-        torch.sum(self.C[d["a_agent"].long()], dim=0, out=self.part[t, 2])
+        ops.env_counterfactual(env.domain, s, a_test, nat_env, env._ranges() if env.domain != _lib.DOMAIN_SIS else self.R,
+                               self.R, rng, NUM_TEST_POLICY_RUNS, nature_per_env=True, out=self.cf[t])
         self.logp[:, t], self.val[:, t], self.s_traj[:, t + 1] = d["logp_agent"], d["v_agent"], s_next
         self.a_nat[t], self.nat_b[t] = d["a_nature"], d["a_nature_bounded"]
         self.logp_nat[t] = d["logp_nature"]
@@ -269,6 +267,12 @@ class MARolloutTrainer:
         env.counter_base(None)
         ac.counter_base(None)
         self.rollouts_done += 1
+        # per-step sums over this rank's arms, all T steps at once: rewards R[arm, s_{t+1}] (:521-527), the counterfactual
+        # estimates, the action costs
+        rew = torch.gather(self.R, 1, self.s_traj[:, 1:].reshape(N, -1).long()).view(N, T, E)
+        self.part[:, 0].copy_(rew.sum(dim=0))
+        self.part[:, 1].copy_(self.cf.sum(dim=1))
+        self.part[:, 2].copy_(self.C[self.a.long()].sum(dim=0))
         ret_local = self.part[:, 0].sum(dim=0)
         if sharded:
             self._allreduce(self.part)

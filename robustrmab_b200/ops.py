@@ -165,10 +165,10 @@ def gaussian_sample(mu, log_std, r=None, eps=None):
     return a, logp
 
 
-def env_counterfactual(domain, s, a, nature, ranges, R, r, n_trials, nature_per_env=False):
+def env_counterfactual(domain, s, a, nature, ranges, R, r, n_trials, nature_per_env=False, out=None):
     """Mean over n_trials independent env steps from the same state of the reward, per (arm, env)."""
     N, E = s.shape
-    out = torch.empty((N, E), dtype=f32, device=s.device)
+    out = torch.empty((N, E), dtype=f32, device=s.device) if out is None else out
     check(lib().rmab_env_counterfactual(int(domain), E, N, R.shape[1], _p(s, u8, "s"), _p(a, u8, "a"),
                                         _p(nature, f32, "nature"), int(bool(nature_per_env)), _p(ranges, f32, "ranges"),
                                         _p(R, f32, "R"), _rng_ptr(r), int(n_trials), _p(out, f32), _stream()))
