@@ -280,6 +280,12 @@ int rmab_split16_cols(int Rk, int Cn, const float* X, int64_t ldx, int ldk, void
                       rmab_stream_t stream);
 int rmab_gemm3h(int M, int N, int K, int ldk, const void* Ah, const void* Al, const float* rsA, const void* Bh, const void* Bl,
                 const float* rsB, float* C, int64_t ldc, int n_fast, rmab_stream_t stream);
+/* The same product as a GRADIENT consumed in the epilogue: P [M, N] (row stride ldc) is the parameter tensor, Mo / Vo its
+ * Adam moments; every element gets exactly rmab_adam_step's update with g = the product, under the next tile's main loop
+ * (dW1n = dz1^T . nat followed by the Adam step of nature_oracle.py:520-527, without materialising dW1n). */
+int rmab_gemm3h_adam(int M, int N, int K, int ldk, const void* Ah, const void* Al, const float* rsA, const void* Bh, const void* Bl,
+                     const float* rsB, float* P, float* Mo, float* Vo, int64_t ldc, double lr, double beta1, double beta2,
+                     double eps, int step, int n_fast, rmab_stream_t stream);
 
 /* ---- the dense nature nets of MA-RMABPPO ------------------------------------------------- */
 

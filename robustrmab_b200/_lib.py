@@ -87,6 +87,7 @@ SIGNATURES = {
     "rmab_split16_rows": [_I, _I, _P, C.c_int64, _I, _P, _P, _P, _P],
     "rmab_split16_cols": [_I, _I, _P, C.c_int64, _I, _P, _P, _P, _P, _P],
     "rmab_gemm3h": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, C.c_int64, _I, _P],
+    "rmab_gemm3h_adam": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, _D, _D, _D, _D, _I, _I, _P],
     "rmab_select_ws_bytes": [_I, _I, _I],
     "rmab_budget_select_binary": [_I, _I, _P, _F, _F, _I, _P, _P, C.c_size_t, _P],
     "rmab_select_hist": [_I, _I, _P, _I, _P, C.c_size_t, _P, _P],

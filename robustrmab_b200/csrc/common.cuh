@@ -95,6 +95,18 @@ __device__ __forceinline__ int categorical(const float (&p)[K], float u) {
   return k < last ? k : last;
 }
 
+// One Adam update (torch.optim.Adam defaults form) with every rounding spelled out, so that the stand-alone step and the
+// fused GEMM epilogue give the same bits: returns the new parameter, updates m and v.
+__device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, float lerp_w, float beta2, float omb2,
+                                             float step_size, float bc2s, float eps) {
+  const float mi = __fmaf_rn(lerp_w, __fsub_rn(g, m), m);
+  const float vi = __fmaf_rn(__fmul_rn(omb2, g), g, __fmul_rn(v, beta2));
+  m = mi;
+  v = vi;
+  const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2s), eps);
+  return __fsub_rn(p, __fmul_rn(step_size, __fdiv_rn(mi, denom)));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

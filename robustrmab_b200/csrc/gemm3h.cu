@@ -17,6 +17,7 @@
 // mbarrier ring, the leader CTA's MMA warp issues 4 k-steps x 3 products of tcgen05.mma M=256 N=256 K=16.
 // Warps: 0 = TMA producer, 1 = MMA issuer (leader CTA), 2..5 = epilogue (TMEM -> registers -> scale -> global).
 #include <cuda.h>
+#include <math.h>
 #include <cuda_fp16.h>
 #include "common.cuh"
 #include "umma.cuh"
@@ -35,7 +36,8 @@ constexpr int STAGES = 3;
 constexpr uint32_t TILE_BYTES = BM * BK * 2;            // 16 KB: one 128 x 64 fp16 operand tile
 constexpr uint32_t STAGE_BYTES = 4 * TILE_BYTES;        // A hi, A lo, B hi, B lo
 constexpr uint32_t SMEM_TILES = STAGES * STAGE_BYTES;   // 192 KB
-constexpr uint32_t SMEM_BYTES = SMEM_TILES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr uint32_t EPI_BYTES = 4 * 32 * 33 * 4;           // per-epilogue-warp transpose buffers
+constexpr uint32_t SMEM_BYTES = SMEM_TILES + 1024 /*alignment slack*/ + 256 /*barriers*/ + EPI_BYTES;
 constexpr int NTHREADS = 192;
 constexpr int ACC_COLS = BN;       // fp32 accumulator columns per stage
 
@@ -106,7 +108,17 @@ struct Shape {
   int vec_ok;     // C and rsB are 16-byte aligned and ldc % 4 == 0: float4 epilogue stores
   int n_fast;     // 1: consecutive tiles walk N (the A block stays), 0: they walk M (the B block stays)
   long long ldc;
+  // fused Adam epilogue (adam != 0): the product is a gradient; C is the parameter tensor, updated in place with its
+  // moments m, v (same layout) exactly as rmab_adam_step does -- the gradient never reaches HBM, and the 6 x |C| bytes of
+  // optimiser traffic run under the next tile's main loop
+  int adam;
+  float* m; float* v;
+  float lerp_w, beta2, omb2, step_size, bc2s, eps;
 };
+
+__device__ __forceinline__ float adam_elem(const Shape& sh, float g, float p, float& m, float& v) {
+  return adam_update(p, g, m, v, sh.lerp_w, sh.beta2, sh.omb2, sh.step_size, sh.bc2s, sh.eps);
+}
 
 __device__ __forceinline__ void tile_coords(const Shape& sh, int t, int& mb, int& nb) {
   if (sh.n_fast) { mb = t / sh.tiles_n; nb = t - mb * sh.tiles_n; }
@@ -213,6 +225,7 @@ gemm3h_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
   } else {
     // ===== epilogue: TMEM lane = output row; 16 columns per tcgen05.ld; scale and store fp32 =====
     const int q = warp & 3;                                     // TMEM lane quarter this warp may access
+    float* es = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + SMEM_TILES + 256) + (warp - 2) * 32 * 33;
     const uint32_t tempty0 = mapa_rank(bar_tempty, 0);
     int it = 0;
     for (int t = pair; t < n_tiles; t += n_pairs, ++it) {
@@ -221,37 +234,61 @@ gemm3h_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ C
       const int acc = it & 1;
       mbar_wait_cl(bar_tfull + 8 * acc, (it >> 1) & 1);
       umma::tc_fence_after();
-      const int m = mb * (2 * BM) + (int)rank * BM + q * 32 + lane;
+      const int m_base = mb * (2 * BM) + (int)rank * BM + q * 32;
       const int n0 = nb * BN;
-      const float sa = (m < sh.M) ? (rsA ? rsA[m] : 1.f) : 0.f;
-      float* crow = C + (long long)m * sh.ldc + n0;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+      // TMEM gives a thread 32 consecutive columns of ONE row; global rows are ldc floats apart, so the chunk goes through a
+      // per-warp shared-memory transpose and leaves as 4 rows x 128 contiguous bytes per warp instruction
+      const int col4 = (lane & 7) * 4, rsub = lane >> 3;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v0[16], v1[16];
         umma::tmem_ld16(taddr + c * 32, v0);
         umma::tmem_ld16(taddr + c * 32 + 16, v1);
         umma::tmem_wait_ld();
-        const int nn = n0 + c * 32;
-        if (m < sh.M) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const uint32_t* v = j < 16 ? &v0[j] : &v1[j - 16];
-            if (nn + j + 3 < sh.N && sh.vec_ok) {
-              float4 sb = rsB ? *reinterpret_cast<const float4*>(rsB + nn + j) : make_float4(1.f, 1.f, 1.f, 1.f);
-              float4 o;
-              o.x = __uint_as_float(v[0]) * (sa * sb.x);
-              o.y = __uint_as_float(v[1]) * (sa * sb.y);
-              o.z = __uint_as_float(v[2]) * (sa * sb.z);
-              o.w = __uint_as_float(v[3]) * (sa * sb.w);
-              *reinterpret_cast<float4*>(crow + c * 32 + j) = o;
-            } else {
+        for (int j = 0; j < 16; ++j) {
+          es[lane * 33 + j] = __uint_as_float(v0[j]);
+          es[lane * 33 + 16 + j] = __uint_as_float(v1[j]);
+        }
+        __syncwarp();
+        const int nn = n0 + c * 32 + col4;
+        const bool vec = sh.vec_ok && nn + 3 < sh.N;
+        float sb[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (nn + j + i < sh.N) crow[c * 32 + j + i] = __uint_as_float(v[i]) * (sa * (rsB ? rsB[nn + j + i] : 1.f));
+        for (int i = 0; i < 4; ++i) sb[i] = (rsB && nn + i < sh.N) ? rsB[nn + i] : 1.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int row = k * 4 + rsub, mm = m_base + row;
+          if (mm >= sh.M) continue;
+          const float sa = rsA ? rsA[mm] : 1.f;
+          float g[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) g[i] = es[row * 33 + col4 + i] * (sa * sb[i]);
+          const long long off = (long long)mm * sh.ldc + nn;
+          if (vec) {
+            if (sh.adam) {
+              float4 pm = *reinterpret_cast<const float4*>(sh.m + off), pv = *reinterpret_cast<const float4*>(sh.v + off);
+              const float4 pp = *reinterpret_cast<const float4*>(C + off);
+              g[0] = adam_elem(sh, g[0], pp.x, pm.x, pv.x);
+              g[1] = adam_elem(sh, g[1], pp.y, pm.y, pv.y);
+              g[2] = adam_elem(sh, g[2], pp.z, pm.z, pv.z);
+              g[3] = adam_elem(sh, g[3], pp.w, pm.w, pv.w);
+              *reinterpret_cast<float4*>(sh.m + off) = pm;
+              *reinterpret_cast<float4*>(sh.v + off) = pv;
             }
+            *reinterpret_cast<float4*>(C + off) = make_float4(g[0], g[1], g[2], g[3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (nn + i < sh.N) {
+                float x = g[i];
+                if (sh.adam) x = adam_elem(sh, x, C[off + i], sh.m[off + i], sh.v[off + i]);
+                C[off + i] = x;
+              }
           }
         }
+        __syncwarp();
       }
       umma::tc_fence_before();
       __syncwarp();
@@ -436,8 +473,9 @@ extern "C" int rmab_split16_cols(int Rk, int Cn, const float* X, int64_t ldx, in
   return check_launch("rmab_split16_cols");
 }
 
-extern "C" int rmab_gemm3h(int M, int N, int K, int ldk, const void* Ah, const void* Al, const float* rsA, const void* Bh,
-                           const void* Bl, const float* rsB, float* C, int64_t ldc, int n_fast, rmab_stream_t stream) {
+static int gemm3h_launch(int M, int N, int K, int ldk, const void* Ah, const void* Al, const float* rsA, const void* Bh,
+                         const void* Bl, const float* rsB, float* C, int64_t ldc, int n_fast, const g3::Shape* adam,
+                         rmab_stream_t stream) {
   RMAB_REQUIRE(M > 0 && N > 0 && K > 0 && Ah && Al && Bh && Bl && C && ldk >= K && (ldk % 8) == 0 && ldc >= N, RMAB_E_BADARG,
                "rmab_gemm3h: bad argument (ldk must be a multiple of 8 and >= K)");
   RMAB_REQUIRE(((uintptr_t)Ah % 16) == 0 && ((uintptr_t)Al % 16) == 0 && ((uintptr_t)Bh % 16) == 0 && ((uintptr_t)Bl % 16) == 0,
@@ -453,15 +491,34 @@ extern "C" int rmab_gemm3h(int M, int N, int K, int ldk, const void* Ah, const v
                  RMAB_E_LAUNCH, "rmab_gemm3h: cannot reserve %u B of shared memory", g3::SMEM_BYTES);
     attr_set = true;
   }
-  g3::Shape sh;
+  g3::Shape sh = {};
+  if (adam) sh = *adam;
   sh.M = M; sh.N = N; sh.K = K;
   sh.tiles_m = (M + 2 * g3::BM - 1) / (2 * g3::BM);
   sh.tiles_n = (N + g3::BN - 1) / g3::BN;
   sh.n_fast = n_fast ? 1 : 0;
   sh.ldc = (long long)ldc;
-  sh.vec_ok = ((ldc & 3) == 0 && ((uintptr_t)C % 16) == 0 && (!rsB || ((uintptr_t)rsB % 16) == 0)) ? 1 : 0;
+  sh.vec_ok = ((ldc & 3) == 0 && ((uintptr_t)C % 16) == 0 && (!rsB || ((uintptr_t)rsB % 16) == 0) &&
+               (!adam || (((uintptr_t)sh.m % 16) == 0 && ((uintptr_t)sh.v % 16) == 0))) ? 1 : 0;
   const int tiles = sh.tiles_m * sh.tiles_n;
   const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
   g3::gemm3h_kernel<<<2 * pairs, g3::NTHREADS, g3::SMEM_BYTES, (cudaStream_t)stream>>>(mAh, mAl, mBh, mBl, sh, rsA, rsB, C);
   return check_launch("rmab_gemm3h");
+}
+
+extern "C" int rmab_gemm3h(int M, int N, int K, int ldk, const void* Ah, const void* Al, const float* rsA, const void* Bh,
+                           const void* Bl, const float* rsB, float* C, int64_t ldc, int n_fast, rmab_stream_t stream) {
+  return gemm3h_launch(M, N, K, ldk, Ah, Al, rsA, Bh, Bl, rsB, C, ldc, n_fast, nullptr, stream);
+}
+
+extern "C" int rmab_gemm3h_adam(int M, int N, int K, int ldk, const void* Ah, const void* Al, const float* rsA, const void* Bh,
+                                const void* Bl, const float* rsB, float* P, float* Mo, float* Vo, int64_t ldc, double lr,
+                                double beta1, double beta2, double eps, int step, int n_fast, rmab_stream_t stream) {
+  RMAB_REQUIRE(P && Mo && Vo && step >= 1, RMAB_E_BADARG, "rmab_gemm3h_adam: bad argument");
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  g3::Shape a = {};
+  a.adam = 1; a.m = Mo; a.v = Vo;
+  a.lerp_w = (float)(1.0 - beta1); a.beta2 = (float)beta2; a.omb2 = (float)(1.0 - beta2);
+  a.step_size = (float)(lr / bc1); a.bc2s = (float)sqrt(bc2); a.eps = (float)eps;
+  return gemm3h_launch(M, N, K, ldk, Ah, Al, rsA, Bh, Bl, rsB, P, ldc, n_fast, &a, stream);
 }

@@ -171,12 +171,10 @@ __global__ void adam_step_kernel(int64_t n, float* __restrict__ p, const float* 
                                  float* __restrict__ v, float lerp_w, float beta2, float omb2, float step_size, float bc2s,
                                  float eps) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float gi = grad[i];
-    const float mi = m[i] + lerp_w * (gi - m[i]);
-    const float vi = v[i] * beta2 + (omb2 * gi) * gi;
+    float mi = m[i], vi = v[i];
+    p[i] = adam_update(p[i], grad[i], mi, vi, lerp_w, beta2, omb2, step_size, bc2s, eps);
     m[i] = mi;
     v[i] = vi;
-    p[i] = p[i] - step_size * (mi / (sqrtf(vi) / bc2s + eps));
   }
 }
 

@@ -337,13 +337,16 @@ class MARolloutTrainer:
                 dh, dl = ops.split_tf32(dz1.reshape(M, N * h))
                 gW1n = ops.matmul_3xtf32((dh.t(), dl.t()), natM).reshape(N, h, D)    # dW1_nature = dz1^T . nature, one GEMM
                 del dh, dl, dz1
+                st.mark("critics.adam")
+                self.steps_v += 1
+                ops.adam_step(ac.W1n, gW1n, self.m_w1n, self.v_w1n, self.vf_lr_agent, self.steps_v)
+                del gW1n
             else:
-                gW1n = ops.gemm3h(ops.split16_cols(dz1.reshape(M, N * h)), nat_cols, M, n_fast=True).reshape(N, h, D)
+                # dW1n = dz1^T . nature and its Adam step in one kernel: the gradient is consumed in the product's epilogue
+                self.steps_v += 1
+                ops.gemm3h_adam(ops.split16_cols(dz1.reshape(M, N * h)), nat_cols, M, ac.W1n.view(N * h, D),
+                                self.m_w1n.view(N * h, D), self.v_w1n.view(N * h, D), self.vf_lr_agent, self.steps_v, n_fast=True)
                 del dz1
-            st.mark("critics.adam")
-            self.steps_v += 1
-            ops.adam_step(ac.W1n, gW1n, self.m_w1n, self.v_w1n, self.vf_lr_agent, self.steps_v)
-            del gW1n
         # ---- lambda net and the nature nets, every lamb_update_freq epochs (:516-576) ----
         st.mark("lambda_and_nature_nets")
         if ep % self.freq == 0 and ep > 0:

@@ -268,6 +268,19 @@ def gemm3h(a, b, K, out=None, n_fast=True):
     return out
 
 
+def gemm3h_adam(a, b, K, p, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, n_fast=True):
+    """p `[M,N]` (with Adam moments m, v) <- Adam step with the gradient a . b^T, which is consumed in the product's epilogue."""
+    Ah, Al, rsA = a
+    Bh, Bl, rsB = b
+    M, ldk = Ah.shape
+    N = Bh.shape[0]
+    assert p.shape == (M, N) and p.stride(1) == 1 and m.shape == p.shape and v.shape == p.shape and m.is_contiguous() and \
+        v.is_contiguous() and p.stride(0) == N, "gemm3h_adam: parameter and moments must be contiguous [M,N]"
+    check(lib().rmab_gemm3h_adam(M, N, int(K), ldk, _p(Ah, f16), _p(Al, f16), _p(rsA, f32), _p(Bh, f16), _p(Bl, f16), _p(rsB, f32),
+                                 _p(p, f32), _p(m, f32), _p(v, f32), p.stride(0), float(lr), beta1, beta2, eps, int(step),
+                                 int(bool(n_fast)), _stream()))
+
+
 def adam_step(p, grad, m, v, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
     check(lib().rmab_adam_step(p.numel(), _p(p, f32, "p"), _p(grad, f32, "grad"), _p(m, f32, "m"), _p(v, f32, "v"),
                                float(lr), float(beta1), float(beta2), float(eps), int(step), _stream()))

@@ -652,3 +652,23 @@ def test_ma_rollout_graphs_equal_eager(K):
             assert torch.equal(x, y)
     for x, y in zip(out[0][1:], out[1][1:]):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("M,N,Kd", [(300, 520, 200), (1024, 768, 512)])
+def test_gemm3h_adam_epilogue_equals_separate_adam(K, M, N, Kd):
+    """rmab_gemm3h_adam (the gradient consumed in the product's epilogue) == rmab_gemm3h followed by rmab_adam_step, bit
+    for bit, over three steps (parameters and both moments)."""
+    import torch
+    ops = K.ops
+    g = torch.Generator(device="cuda").manual_seed(M + Kd)
+    p0 = torch.randn((M, N), device="cuda", generator=g) * 0.05
+    pa, ma, va = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    pb, mb, vb = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    for step in (1, 2, 3):
+        a = torch.randn((M, Kd), device="cuda", generator=g) * 1e-3
+        b = torch.randn((N, Kd), device="cuda", generator=g)
+        sa, sb = ops.split16_rows(a), ops.split16_rows(b)
+        grad = ops.gemm3h(sa, sb, Kd)
+        ops.adam_step(pa, grad, ma, va, 2e-3, step)
+        ops.gemm3h_adam(sa, sb, Kd, pb, mb, vb, 2e-3, step)
+        assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb), step
