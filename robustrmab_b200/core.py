@@ -236,6 +236,34 @@ class MLPActorCriticRMAB(nn.Module):
             return ops.budget_select_binary(p1, float(self.C[1]), float(self.B), positive_only=True)
         return ops.budget_select_multi(probs, Cc, float(self.B))
 
+    def shard(self, arm0, arm1):
+        """The same strategy restricted to arms [arm0, arm1): a shallow copy that holds only those arms' nets (the
+        lambda-net stays whole) and selects its share of the GLOBAL budget with `act_test_device_sharded`."""
+        import copy
+        sh = copy.copy(self)
+        sh.N, sh.arm0, sh.n_total = int(arm1) - int(arm0), self.arm0 + int(arm0), self.n_total
+        sh.Wpi, sh.Wv = self.Wpi[arm0:arm1].contiguous(), self.Wv[arm0:arm1].contiguous()
+        sh._views()
+        return sh
+
+    def act_test_device_sharded(self, s_local, rank, world, group=None):
+        """`act_test_device` when the arms are sharded over ranks: s_local `[N_local, E]` holds this rank's arms.
+        lambda = lambda-net of ALL states (first-layer partial sums, one all-reduce of [E,8]); the budgeted selection is the
+        global top-k by radix select with all-reduced digit histograms (ops.budget_select_binary_sharded).  Binary actions."""
+        import torch.distributed as dist
+        if not (self.act_dim == 2 and float(self.C[0]) == 0.0):
+            raise NotImplementedError("sharded act_test covers binary actions; gather the states and use act_test_device")
+        scale = 1.0 if self.one_hot_encode else 1.0 / float(self.state_norm)
+        params = self.lambda_net.packed().to(self.device_)
+        _, h1 = ops.lambda_forward(params, s_local, self.n_total, self.arm0, scale, want_h1=True, want_lamb=False)
+        if world > 1:
+            dist.all_reduce(h1, group=group)
+        lamb, _ = ops.lambda_forward(params, s_local, self.n_total, self.arm0, scale, h1_in=h1)
+        _, _, _, p1, _ = self.step_device(s_local, lamb)
+        self._steps -= 1
+        return ops.budget_select_binary_sharded(p1, float(self.C[1]), float(self.B), self.n_total, rank, world, group,
+                                                positive_only=True)
+
     def act_test(self, obs):
         E = self.n_envs
         a = self.act_test_device(self._obs_dev(np.asarray(obs).reshape(-1) if E == 1 else obs, E))

@@ -112,6 +112,7 @@ class MARolloutTrainer:
         self.steps_pi = self.steps_v = 0
         self.pi_lr_nature, self.vf_lr_nature = float(pi_lr_nature), float(vf_lr_nature)
         self._gpad = self._gout = None
+        self._pol_shard = (None, None)
         # static inputs of the (graph-captured) rollout step
         self.lamb_buf = torch.empty((E,), dtype=_F32, device=dev)
         self.a_boot = torch.empty((N, E), dtype=torch.uint8, device=dev)
@@ -194,9 +195,13 @@ class MARolloutTrainer:
             nat_env = nat_env[sl].contiguous()
         env._state = s
         s_next, _ = env.step_device(d["a_agent"], nat_env, want_reward=False)   # rewards are R[arm, s'] (summed after the loop)
-        a_test = agent_pol.act_test_device(s_full if sharded else s)
-        if sharded:
-            a_test = a_test[sl].contiguous()
+        if self._sharded_policy(agent_pol):
+            # a learned strategy evaluates only this rank's arms and takes its share of the global top-k
+            a_test = self._agent_shard(agent_pol).act_test_device_sharded(s, self.rank, self.world, self.pg)
+        else:
+            a_test = agent_pol.act_test_device(s_full if sharded else s)
+            if sharded:
+                a_test = a_test[sl].contiguous()
         word = getattr(env, "_t_word", None)
         rng = ops.rng(self.seed, _lib.STREAM_CF, env._t - (env._t_origin if word is not None else 0), arm0=self.arm0, t_base=word)
         ops.env_counterfactual(env.domain, s, a_test, nat_env, env._ranges() if env.domain != _lib.DOMAIN_SIS else self.R,
@@ -204,6 +209,18 @@ class MARolloutTrainer:
         self.logp[:, t], self.val[:, t], self.s_traj[:, t + 1] = d["logp_agent"], d["v_agent"], s_next
         self.a_nat[t], self.nat_b[t] = d["a_nature"], d["a_nature_bounded"]
         self.logp_nat[t] = d["logp_nature"]
+
+    def _sharded_policy(self, agent_pol):
+        """A learned binary-action strategy under arm sharding selects through the sharded radix select (collectives inside
+        the step, so such rollouts are launched eagerly)."""
+        return (self.world > 1 and hasattr(agent_pol, "act_test_device_sharded") and getattr(agent_pol, "act_dim", 0) == 2
+                and float(np.asarray(agent_pol.C)[0]) == 0.0)
+
+    def _agent_shard(self, agent_pol):
+        key = id(agent_pol)
+        if self._pol_shard[0] != key:
+            self._pol_shard = (key, agent_pol.shard(self.arm0, self.arm0 + self.N))
+        return self._pol_shard[1]
 
     def _advance(self, t):
         """Host-side counters of one step (what the eager step would have advanced)."""
@@ -228,7 +245,8 @@ class MARolloutTrainer:
         self.t_words[1].fill_(ac._steps)
         env.counter_base(self.t_words[0])
         ac.counter_base(self.t_words[1])
-        use_graphs = self.use_graphs and not self.library_gemm and self.graph_ok is not False
+        use_graphs = (self.use_graphs and not self.library_gemm and self.graph_ok is not False
+                      and not self._sharded_policy(agent_pol))
         replay = use_graphs and self.graphs is not None and self.graph_pol is agent_pol
         capture = use_graphs and not replay and self.rollouts_done >= 1
         if capture:

@@ -50,6 +50,14 @@ def main():
         _, ac_s, sh = make(domain, N, E, dev, (a0, a0 + n), rank, world)
         _, ac_f, full = make(domain, N, E, dev, None, rank, world)
         pess = PessimisticAgentPolicy(N)
+        if domain == "counterexample":
+            # a learned RMABPPO strategy as the agent: under sharding it evaluates its local arms only and takes its share of
+            # the GLOBAL budget through the sharded radix select (act_test_device_sharded); unsharded it sees all arms
+            from robustrmab_b200.core import MLPActorCriticRMAB
+            torch.manual_seed(5)
+            env_ = full.env
+            pess = MLPActorCriticRMAB(env_.observation_space, env_.action_space, hidden_sizes=[16, 16], C=env_.C, N=N, B=env_.B,
+                                      n_envs=E, device=dev)
         for ep in range(3):
             st_s, st_f = sh.epoch(pess), full.epoch(pess)
             same_s = torch.equal(sh.s_traj, full.s_traj[sl])
