@@ -111,6 +111,30 @@ def kernel_lines(dev, hbm_peak, peak_src, N=100_000, E=1024, T=10):
     out["gae"] = {"workload": f"finish_path + get: GAE-lambda, returns, per-arm advantage normalisation, {Ng} arms x T={T} x {E} envs",
                   "arm_steps_per_s": Ng * T * E / (ms * 1e-3), "bytes_per_arm_step": 14,
                   "roofline": _hbm(14 * Ng * T * E, ms, hbm_peak, peak_src)}
+    del s_traj, at, val
+    # ---- SIS env step (binomial next-state law evaluated on the fly, fp64) and the exact multiple-choice knapsack of the
+    # Hawkins baseline (lp_methods.py:221-271) at the configs[3] shape: latency / ALU bound, rates only
+    Ns, Es, pop = 2048, 256, 50
+    ss = torch.randint(0, pop + 1, (Ns, Es), dtype=torch.uint8, device=dev, generator=g)
+    sa = torch.randint(0, 3, (Ns, Es), dtype=torch.uint8, device=dev, generator=g)
+    lo = torch.tensor([0.5, 1.0, 1.0, 1.0], device=dev)
+    hi = torch.tensor([0.99, 10.0, 10.0, 10.0], device=dev)
+    prm = (lo + torch.rand((Ns, 4), device=dev, generator=g) * (hi - lo)).contiguous()
+    Rs = torch.linspace(0, 1, pop + 1, device=dev).repeat(Ns, 1).contiguous()
+
+    def sis():
+        k[0] += 1
+        ops.env_step_sis(pop, ss, sa, prm, Rs, r=ops.rng(0, _lib.STREAM_ENV, k[0]))
+    ms = _timed(sis)
+    out["env_step_sis"] = {"workload": f"SIS env.step, pop={pop}, {Ns} arms x {Es} envs (binomial pmf per transition, fp64)",
+                           "arm_steps_per_s": Ns * Es / (ms * 1e-3), "ms_per_launch": ms, "bound": "ALU (fp64 pmf recurrence)"}
+    vals = torch.rand((Ns, 3, Es), device=dev, dtype=torch.float64, generator=g)
+    Bk = int(0.2 * Ns)
+    ms = _timed(lambda: ops.knapsack_multichoice(vals, [0, 1, 2], Bk), reps=2, warm=1)
+    out["knapsack_multichoice"] = {"workload": f"exact multiple-choice knapsack, {Ns} arms x 3 actions (costs 0,1,2), budget {Bk} "
+                                               f"met with equality, {Es} envs (one CTA per env, DP over arms)",
+                                   "arms_per_s": Ns * Es / (ms * 1e-3), "ms_per_launch": ms,
+                                   "bound": "latency (N dependent DP layers of B+1 fp64 cells)"}
     return out
 
 
