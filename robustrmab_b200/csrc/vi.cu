@@ -206,6 +206,8 @@ __global__ void __launch_bounds__(128) whittle_small_kernel(int N, const double*
   }
 }
 
+constexpr int kViLp = 4;   // probes per work item of the generic sweep
+
 // ---- generic S: one CTA per arm, T in shared memory ----------------------------------------------
 // mode 0: L given probes.  mode 1 (Whittle): L = S probes, probe l bisects the index of state l.
 __global__ void __launch_bounds__(256) vi_generic_kernel(int S, int A, int L, const double* __restrict__ T,
@@ -286,21 +288,46 @@ __global__ void __launch_bounds__(256) vi_generic_kernel(int S, int A, int L, co
     for (int guard = 0; guard < kViCap; ++guard) {
       if (tid == 0) s_any = 0;
       __syncthreads();
-      for (int i = tid; i < L * S; i += blockDim.x) {
-        const int l = i / S, s = i - l * S;
-        if (!sAct[l]) { Vn[i] = Vc[i]; continue; }
-        const double* Vl = Vc + (size_t)l * S;
-        double best = 0.0;
-        int ba = 0;
-        for (int a = 0; a < A; ++a) {
-          const double* row = sT + ((size_t)s * A + a) * S;
-          double ev = 0.0;
-          for (int t = 0; t < S; ++t) ev += row[t] * Vl[t];
-          const double q = RMAB_REW(s, a, l) + p.gamma * ev;
-          if (a == 0 || q > best) { best = q; ba = a; }
+      // One work item = one state and a group of kViLp probes: a transition row element is read from shared memory once
+      // for the whole group (consecutive lanes = consecutive states, so the V reads are broadcasts).  The sweep is bound by
+      // shared-memory bandwidth, not by the fp64 pipe; per probe the sum over t keeps its order.
+      const int LG = (L + kViLp - 1) / kViLp;
+      for (int i = tid; i < LG * S; i += blockDim.x) {
+        const int lg = i / S, s = i - lg * S, l0 = lg * kViLp;
+        bool on[kViLp], any = false;
+        int lj[kViLp];
+#pragma unroll
+        for (int j = 0; j < kViLp; ++j) {
+          lj[j] = min(l0 + j, L - 1);
+          on[j] = (l0 + j < L) && sAct[lj[j]];
+          any |= on[j];
         }
-        Vn[i] = best;
-        sPol[i] = (uint8_t)ba;
+        if (any) {
+          double best[kViLp];
+          int ba[kViLp];
+          for (int a = 0; a < A; ++a) {
+            const double* row = sT + ((size_t)s * A + a) * S;
+            double ev[kViLp];
+#pragma unroll
+            for (int j = 0; j < kViLp; ++j) ev[j] = 0.0;
+            for (int t = 0; t < S; ++t) {
+              const double r = row[t];
+#pragma unroll
+              for (int j = 0; j < kViLp; ++j) ev[j] += r * Vc[(size_t)lj[j] * S + t];
+            }
+#pragma unroll
+            for (int j = 0; j < kViLp; ++j) {
+              const double q = RMAB_REW(s, a, lj[j]) + p.gamma * ev[j];
+              if (a == 0 || q > best[j]) { best[j] = q; ba[j] = a; }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < kViLp; ++j)
+            if (on[j]) { Vn[(size_t)lj[j] * S + s] = best[j]; sPol[(size_t)lj[j] * S + s] = (uint8_t)ba[j]; }
+        }
+#pragma unroll
+        for (int j = 0; j < kViLp; ++j)
+          if (l0 + j < L && !on[j]) Vn[(size_t)lj[j] * S + s] = Vc[(size_t)lj[j] * S + s];
       }
       __syncthreads();
       for (int l = tid; l < L; l += blockDim.x) {
