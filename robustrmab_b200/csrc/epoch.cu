@@ -60,6 +60,7 @@ struct EpochArgs {
   uint8_t* s_traj; uint8_t* a;
   float* stats; float* arm_stats; double* env_part;
   float* adv; float* ret; float* last_val;
+  int tables_ready;   // the p / log p / v rows of `stats` were filled by the tcgen05 pre-pass (table_fwd_umma64.cu)
 };
 
 // ONCHIP: the trajectory of every (arm, env) chain stays in shared memory as bit planes -- one 32-bit word per 32 time
@@ -89,8 +90,10 @@ __global__ void __launch_bounds__(256, (H <= 16 ? 4 : 2)) epoch_table_kernel(Epo
 
   for (int n = blockIdx.x; n < N; n += gridDim.x) {
     __syncthreads();  // previous arm's readers of the staged nets are done
-    stage_net(sp, Lp, g.Wpi + (int64_t)n * Gp.P);
-    stage_net(sv, Lv, g.Wv + (int64_t)n * Gv.P);
+    if (!g.tables_ready) {
+      stage_net(sp, Lp, g.Wpi + (int64_t)n * Gp.P);
+      stage_net(sv, Lv, g.Wv + (int64_t)n * Gv.P);
+    }
     __syncthreads();
     // clamped nature parameter per (state, action) of this arm (:867-874 / :583-592)
     float pn0[S], pn1[S], Rn[S];
@@ -116,6 +119,16 @@ __global__ void __launch_bounds__(256, (H <= 16 ? 4 : 2)) epoch_table_kernel(Epo
     for (int e = threadIdx.x; e < E; e += blockDim.x) {
       const float lam = g.lamb[e];
       float p0t[S], p1t[S], vt[S];
+      if (g.tables_ready) {
+        // hidden 64: the tcgen05 pre-pass parked p(a | s) in the (still unused) advantage rows and wrote log p and v
+        const float* st = g.stats + ((int64_t)n * SR::K) * E + e;
+#pragma unroll
+        for (int si = 0; si < S; ++si) {
+          p0t[si] = st[(int64_t)(SR::kAp + si * A + 0) * E];
+          p1t[si] = st[(int64_t)(SR::kAp + si * A + 1) * E];
+          vt[si] = st[(int64_t)(SR::kV + si) * E];
+        }
+      } else
 #pragma unroll
       for (int si = 0; si < S; ++si) {
         float a1[H], logit[kMaxA], vout[kMaxA], p[kMaxA], lp[kMaxA];
@@ -346,6 +359,9 @@ __global__ void part_sum_kernel(int nb, int64_t ke, const double* __restrict__ i
   if (lane == 0) out[i] = (float)acc;
 }
 
+int table_fwd_umma64_run(const RmabNetDesc* net, const float* Wpi, const float* Wv, const float* lamb, float* stats, int K,
+                         int row_p, int row_lp, int row_v, cudaStream_t st);   // table_fwd_umma64.cu
+
 template <typename K>
 static int set_smem_attr(K kernel, size_t bytes) {
   if (bytes <= 48 * 1024) return 0;
@@ -407,6 +423,17 @@ extern "C" int rmab_epoch_table(int domain, const RmabNetDesc* net, int T, const
   RMAB_REQUIRE(a || onchip, RMAB_E_BADARG, "rmab_epoch_table: a == NULL needs the on-chip trajectory (T = %d, E = %d is too "
                "large for shared memory)", T, net->n_envs);
   if (onchip) smem += bit_bytes;
+  cudaStream_t st0 = (cudaStream_t)stream;
+  static const bool ffma_tables = getenv("RMAB_EPOCH_FFMA_TABLES") != nullptr;   // A/B switch: thread-per-row pre-pass at h = 64
+  g.tables_ready = 0;
+  if (h == 64 && !ffma_tables) {
+    int rc = S == 2 ? table_fwd_umma64_run(net, Wpi, Wv, lamb, stats, StatRows<2, 2>::K, StatRows<2, 2>::kAp,
+                                           StatRows<2, 2>::kLp, StatRows<2, 2>::kV, st0)
+                    : table_fwd_umma64_run(net, Wpi, Wv, lamb, stats, StatRows<3, 2>::K, StatRows<3, 2>::kAp,
+                                           StatRows<3, 2>::kLp, StatRows<3, 2>::kV, st0);
+    if (rc) return rc;
+    g.tables_ready = 1;
+  }
   const int grid = epoch_grid(net->n_arms);
   int threads = ((net->n_envs + 31) / 32) * 32;
   threads = threads > 256 ? 256 : threads;
