@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librmab_b200.so")
-SOURCES = ["common.cu", "env.cu", "ac.cu", "gae.cu", "epoch.cu", "ppo.cu", "ppo_table.cu", "ppo_table_mma.cu", "ppo_table_mma64.cu", "ppo_table_umma64.cu", "ppo_table_umma16.cu", "ma.cu", "select.cu", "vi.cu", "gemm3h.cu", "nature.cu", "table_fwd_umma64.cu"]
+SOURCES = ["common.cu", "env.cu", "ac.cu", "gae.cu", "epoch.cu", "ppo.cu", "ppo_table.cu", "ppo_table_mma.cu", "ppo_table_mma64.cu", "ppo_table_umma64.cu", "ppo_table_umma16.cu", "ma.cu", "select.cu", "vi.cu", "gemm3h.cu", "nature.cu", "table_fwd_umma64.cu", "ac_umma64.cu"]
 HEADERS = ["common.cuh", "mlp.cuh", "umma.cuh", os.path.join("..", "..", "include", "rmab.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

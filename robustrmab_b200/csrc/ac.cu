@@ -5,6 +5,7 @@
 // mlp :24-29, MLPLambdaNet :108-115; agent_oracle.py compute_loss_lambda :360-376, rollout loop :506-570.
 // One CTA per arm: the arm's packed actor + critic weights are staged once in shared memory and every
 // thread (one env each) reads them as warp-uniform float4 broadcasts.
+#include <stdlib.h>
 #include "common.cuh"
 #include "mlp.cuh"
 
@@ -374,6 +375,12 @@ static int check_net(const RmabNetDesc* d, const char* who) {
   return RMAB_OK;
 }
 
+namespace rmab {
+int ac_step_umma64_run(const RmabNetDesc* net, const float* Wpi, const float* Wv, const uint8_t* s, const float* lamb,
+                       const float* extra, const Rng& rng, const float* u_inject, uint8_t* a, float* v, float* logp, float* p1,
+                       float* probs, cudaStream_t st);   // ac_umma64.cu
+}
+
 extern "C" int rmab_ac_step(const RmabNetDesc* net, const float* Wpi, const float* Wv, const uint8_t* s,
                             const float* lamb, const float* extra, const RmabRng* rng, const float* u_inject,
                             uint8_t* a, float* v, float* logp, float* p1, float* probs, rmab_stream_t stream) {
@@ -388,6 +395,9 @@ extern "C" int rmab_ac_step(const RmabNetDesc* net, const float* Wpi, const floa
   const int in_dim = (net->one_hot ? net->n_states : 1) + 1;
   const size_t smem = sizeof(float) * (SmemNet(in_dim, net->hidden, net->n_actions).size + SmemNet(in_dim, net->hidden, 1).size);
   cudaStream_t st = (cudaStream_t)stream;
+  // hidden 64 with at least half a 128-row tile of envs per arm: the tcgen05 forward (ac_umma64.cu); RMAB_AC_FFMA=1 = A/B arm
+  if (net->hidden == 64 && net->n_envs >= 64 && getenv("RMAB_AC_FFMA") == nullptr)
+    return ac_step_umma64_run(net, Wpi, Wv, s, lamb, extra, g, u_inject, a, v, logp, p1, probs, st);
 #define LAUNCH(H)                                                                                              \
   {                                                                                                            \
     RMAB_REQUIRE(set_smem(ac_step_kernel<H>, smem) == 0, RMAB_E_LAUNCH, "rmab_ac_step: cannot reserve %zu B smem", smem); \

@@ -676,3 +676,36 @@ def test_update_kernels_run_to_run_deterministic(K, kind, N, T, E, S, h):
         outs.append((K.n(Wp), K.n(Wv_), K.n(ap), K.n(av)))
     for o in outs[1:]:
         assert all(np.array_equal(x, y) for x, y in zip(o, outs[0]))
+
+
+@pytest.mark.parametrize("one_hot,S,A,extra", [(False, 21, 3, True), (False, 51, 3, False), (True, 3, 2, False), (True, 2, 2, True)])
+def test_ac_step_h64_tcgen05_vs_ffma(K, one_hot, S, A, extra, monkeypatch):
+    """rmab_ac_step at hidden 64: the tcgen05 forward (ac_umma64.cu, E >= 64) against the thread-per-env FFMA kernel of the
+    same entry point (RMAB_AC_FFMA=1, itself pinned to the reference goldens at E = 1): values, log-probs and probabilities
+    to 2e-6 (3xTF32 products vs sequential fp32 sums), actions equal wherever the injected uniform is not within 1e-5 of a
+    cdf edge; ragged tile (E = 300), arms with different nets, the MA critic addend."""
+    torch = K.torch
+    N, E, h = 5, 300, 64
+    rs = np.random.RandomState(S + A)
+    in_dim = (S if one_hot else 1) + 1
+    Wpi = K.t(onets.init_linear_default(rs, N, in_dim, h, A))
+    Wv = K.t(onets.init_linear_default(rs, N, in_dim, h, 1))
+    s = K.t(rs.randint(0, S, (N, E)).astype(np.uint8))
+    lamb = K.t(rs.rand(E).astype(F32) * 3)
+    u = K.t(rs.rand(N, E).astype(F32))
+    ex = K.t((rs.randn(N, h, E) * 0.3).astype(F32)) if extra else None
+    net = K.ops.net_desc(N, E, S, A, h, one_hot, float(S - 1) if not one_hot else 1.0, n_extra=7 if extra else 0)
+    got = K.ops.ac_step(net, Wpi, Wv, s, lamb, u=u, want_probs=True, extra=ex)
+    monkeypatch.setenv("RMAB_AC_FFMA", "1")
+    want = K.ops.ac_step(net, Wpi, Wv, s, lamb, u=u, want_probs=True, extra=ex)
+    monkeypatch.delenv("RMAB_AC_FFMA")
+    a_g, v_g, lp_g, p1_g, pr_g = [K.n(x) for x in got]
+    a_w, v_w, lp_w, p1_w, pr_w = [K.n(x) for x in want]
+    np.testing.assert_allclose(v_g, v_w, rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(pr_g, pr_w, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(p1_g, p1_w, rtol=0, atol=2e-6)
+    cdf = np.cumsum(pr_w, axis=1)                                    # [N, A, E]
+    near = (np.abs(cdf - K.n(u)[:, None, :]) < 1e-5).any(axis=1)
+    assert np.array_equal(a_g[~near], a_w[~near]) and near.mean() < 1e-3
+    same = a_g == a_w
+    np.testing.assert_allclose(lp_g[same], lp_w[same], rtol=0, atol=4e-6)
