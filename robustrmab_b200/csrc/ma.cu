@@ -156,8 +156,14 @@ __global__ void __launch_bounds__(128) cf_sis_kernel(int E, int N, int pop, cons
       const uint4 x = philox4x32_10(RMAB_STREAM_CF, rng_t(g) * (uint32_t)n_trials + (uint32_t)tr, g.env0 + (uint32_t)e,
                                     g.arm0 + (uint32_t)n, g.k0, g.k1);
       const float u = u24(x.x);
-      int cnt = 0;
-      for (int j = 0; j <= si; ++j) cnt += (cdf[j] <= u) ? 1 : 0;
+      // cnt = #{j <= si : cdf[j] <= u}; the cdf is non-decreasing (round-to-nearest sums of non-negative terms), so that is
+      // the first index with cdf > u: a binary search instead of si + 1 comparisons per trial
+      int lo = 0, hi = si + 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+      }
+      const int cnt = lo;
       const int sn = pop - si + (cnt < last ? cnt : last);
       acc += __ldg(R + (int64_t)n * S + sn);
     }
