@@ -49,6 +49,8 @@ def _problem(domain, N, E, h, seed):
 
 @pytest.mark.parametrize("domain,h,N,E,T", [(0, 16, 9, 40, 25), (1, 64, 5, 128, 10), (1, 8, 700, 3, 6),
                                             (0, 32, 4, 300, 12),
+                                            # hidden 64: the table pre-pass runs on tcgen05 (table_fwd_umma64.cu); ragged tiles
+                                            (0, 64, 4, 96, 12), (1, 64, 3, 171, 7), (0, 64, 2, 1, 9),
                                             # on-chip trajectory words: T = 32 / 33 / 64 / 100 cross 32-step word boundaries
                                             (0, 16, 3, 33, 32), (1, 16, 3, 33, 33), (1, 8, 2, 70, 64), (0, 16, 2, 256, 100),
                                             (1, 16, 2, 64, 131),
