@@ -256,6 +256,18 @@ int rmab_epoch_table(int domain, const RmabNetDesc* net, int T, const float* Wpi
                      uint32_t arm0, uint8_t* s_traj, uint8_t* a, float* stats, float* arm_stats, float* env_sums,
                      void* ws, size_t ws_bytes, float* adv, float* ret, float* last_val, rmab_stream_t stream);
 
+/* rmab_epoch_table for ENV-sharded ranks (the reference's MPI layout, mpi_tools.py: every rank all arms, a slice of the
+ * envs given by env0): get() normalises an arm's advantages with mean / std over the envs of ALL ranks
+ * (mpi_statistics_scalar, agent_oracle.py:152-155).  First launch: adv_moments_out [N,2] fp64 receives this rank's raw sums
+ * (sum adv, sum adv^2; the statistics written are to be ignored); the caller all-reduces them; second launch (same seeds =
+ * same trajectory): adv_moments_in [N,2] = global (mean, std) used for the statistics.  Exactly one of the two is given. */
+int rmab_epoch_table_envshard(int domain, const RmabNetDesc* net, int T, const float* Wpi, const float* Wv,
+                              const float* lamb, const float* nature, const float* ranges, const float* R, const float* C,
+                              double gamma, double lam, uint64_t seed, uint32_t t_act0, uint32_t t_env0, uint32_t env0,
+                              uint32_t arm0, uint8_t* s_traj, uint8_t* a, float* stats, float* arm_stats, float* env_sums,
+                              void* ws, size_t ws_bytes, float* last_val, double* adv_moments_out,
+                              const float* adv_moments_in, rmab_stream_t stream);
+
 /* update() (agent_oracle.py:399-436) on the statistics of rmab_epoch_table: the same pi_iters + v_iters
  * full-batch Adam steps as rmab_ppo_update, evaluated on S*E rows per arm instead of T*E samples (exact
  * regrouping of the loss sums; see csrc/epoch.cu).  T only enters as the 1/(T*E) mean. */

@@ -72,6 +72,8 @@ SIGNATURES = {
     "rmab_epoch_ws_bytes": [_I, _I],
     "rmab_epoch_table": [_I, C.POINTER(RmabNetDesc), _I, _P, _P, _P, _P, _P, _P, _P, _D, _D, C.c_uint64, C.c_uint32,
                          C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P, C.c_size_t, _P, _P, _P, _P],
+    "rmab_epoch_table_envshard": [_I, C.POINTER(RmabNetDesc), _I, _P, _P, _P, _P, _P, _P, _P, _D, _D, C.c_uint64, C.c_uint32,
+                                  C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P, C.c_size_t, _P, _P, _P, _P],
     "rmab_ppo_update_table": [C.POINTER(RmabNetDesc), C.POINTER(RmabHyper), _I, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                               _P],
     "rmab_nat_ws_bytes": [_I, _I, _I, _I],

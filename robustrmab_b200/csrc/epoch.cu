@@ -60,6 +60,11 @@ struct EpochArgs {
   uint8_t* s_traj; uint8_t* a;
   float* stats; float* arm_stats; double* env_part;
   float* adv; float* ret; float* last_val;
+  // env-sharded ranks (the reference's MPI layout: every rank all arms, a slice of the envs): the advantage moments are
+  // per arm over ALL envs, so a first launch exports the raw sums of this rank's envs and a second one is given the global
+  // (mean, std) -- mpi_statistics_scalar of get() (agent_oracle.py:152-155, mpi_tools.py:76-97)
+  double* mom_out;        // [N,2] sum adv, sum adv^2 over this launch's envs (may be NULL)
+  const float* mom_in;    // [N,2] (mean, std) to normalise with instead of the launch's own (may be NULL)
   int tables_ready;   // the p / log p / v rows of `stats` were filled by the tcgen05 pre-pass (table_fwd_umma64.cu)
 };
 
@@ -228,6 +233,8 @@ __global__ void __launch_bounds__(256, (H <= 16 ? 4 : 2)) epoch_table_kernel(Epo
       var = var > 0.0 ? var : 0.0;
       s_ms[0] = (float)mean;
       s_ms[1] = (float)sqrt(var);
+      if (g.mom_out) { g.mom_out[2 * (int64_t)n] = s1; g.mom_out[2 * (int64_t)n + 1] = s2; }
+      if (g.mom_in) { s_ms[0] = g.mom_in[2 * (int64_t)n]; s_ms[1] = g.mom_in[2 * (int64_t)n + 1]; }
       if (g.arm_stats) { g.arm_stats[4 * (int64_t)n] = s_ms[0]; g.arm_stats[4 * (int64_t)n + 1] = s_ms[1]; }
     }
     __syncthreads();
@@ -385,12 +392,12 @@ extern "C" int rmab_stat_rows(int domain) {
 
 extern "C" size_t rmab_epoch_ws_bytes(int N, int E) { return (size_t)epoch_grid(N) * 2 * (size_t)E * sizeof(double); }
 
-extern "C" int rmab_epoch_table(int domain, const RmabNetDesc* net, int T, const float* Wpi, const float* Wv,
-                                const float* lamb, const float* nature, const float* ranges, const float* R,
-                                const float* C, double gamma, double lam, uint64_t seed, uint32_t t_act0,
-                                uint32_t t_env0, uint32_t env0, uint32_t arm0, uint8_t* s_traj, uint8_t* a,
-                                float* stats, float* arm_stats, float* env_sums, void* ws, size_t ws_bytes, float* adv,
-                                float* ret, float* last_val, rmab_stream_t stream) {
+static int epoch_table_impl(int domain, const RmabNetDesc* net, int T, const float* Wpi, const float* Wv,
+                            const float* lamb, const float* nature, const float* ranges, const float* R,
+                            const float* C, double gamma, double lam, uint64_t seed, uint32_t t_act0,
+                            uint32_t t_env0, uint32_t env0, uint32_t arm0, uint8_t* s_traj, uint8_t* a,
+                            float* stats, float* arm_stats, float* env_sums, void* ws, size_t ws_bytes, float* adv,
+                            float* ret, float* last_val, double* mom_out, const float* mom_in, rmab_stream_t stream) {
   RMAB_REQUIRE(net, RMAB_E_BADARG, "rmab_epoch_table: null net descriptor");
   RMAB_REQUIRE(domain == RMAB_DOMAIN_CE || domain == RMAB_DOMAIN_ARMMAN, RMAB_E_BADARG,
                "rmab_epoch_table: domain %d is not a table domain", domain);
@@ -415,6 +422,7 @@ extern "C" int rmab_epoch_table(int domain, const RmabNetDesc* net, int T, const
   g.t_act0 = t_act0; g.t_env0 = t_env0; g.env0 = env0; g.arm0 = arm0;
   g.s_traj = s_traj; g.a = a; g.stats = stats; g.arm_stats = arm_stats; g.env_part = env_sums ? (double*)ws : nullptr;
   g.adv = adv; g.ret = ret; g.last_val = last_val;
+  g.mom_out = mom_out; g.mom_in = mom_in;
   size_t smem = sizeof(float) * (SmemNet(S + 1, h, 2).size + SmemNet(S + 1, h, 1).size);
   // on-chip trajectory: (T / 32 + 1) words x (1 action + 1 or 2 state) planes x E envs; two CTAs per SM must still fit
   const size_t bit_bytes = (size_t)(T / 32 + 1) * (S == 2 ? 2 : 3) * (size_t)net->n_envs * sizeof(uint32_t);
@@ -461,4 +469,28 @@ extern "C" int rmab_epoch_table(int domain, const RmabNetDesc* net, int T, const
   const int64_t ke = 2 * (int64_t)net->n_envs;
   part_sum_kernel<<<(int)((ke + 7) / 8), 256, 0, st>>>(grid, ke, (const double*)ws, env_sums);
   return check_launch("rmab_epoch_table(sum)");
+}
+
+extern "C" int rmab_epoch_table(int domain, const RmabNetDesc* net, int T, const float* Wpi, const float* Wv,
+                                const float* lamb, const float* nature, const float* ranges, const float* R,
+                                const float* C, double gamma, double lam, uint64_t seed, uint32_t t_act0,
+                                uint32_t t_env0, uint32_t env0, uint32_t arm0, uint8_t* s_traj, uint8_t* a,
+                                float* stats, float* arm_stats, float* env_sums, void* ws, size_t ws_bytes, float* adv,
+                                float* ret, float* last_val, rmab_stream_t stream) {
+  return epoch_table_impl(domain, net, T, Wpi, Wv, lamb, nature, ranges, R, C, gamma, lam, seed, t_act0, t_env0, env0, arm0,
+                          s_traj, a, stats, arm_stats, env_sums, ws, ws_bytes, adv, ret, last_val, nullptr, nullptr, stream);
+}
+
+extern "C" int rmab_epoch_table_envshard(int domain, const RmabNetDesc* net, int T, const float* Wpi, const float* Wv,
+                                         const float* lamb, const float* nature, const float* ranges, const float* R,
+                                         const float* C, double gamma, double lam, uint64_t seed, uint32_t t_act0,
+                                         uint32_t t_env0, uint32_t env0, uint32_t arm0, uint8_t* s_traj, uint8_t* a,
+                                         float* stats, float* arm_stats, float* env_sums, void* ws, size_t ws_bytes,
+                                         float* last_val, double* adv_moments_out, const float* adv_moments_in,
+                                         rmab_stream_t stream) {
+  RMAB_REQUIRE((adv_moments_out != nullptr) != (adv_moments_in != nullptr), RMAB_E_BADARG,
+               "rmab_epoch_table_envshard: give exactly one of adv_moments_out (first launch) / adv_moments_in (second)");
+  return epoch_table_impl(domain, net, T, Wpi, Wv, lamb, nature, ranges, R, C, gamma, lam, seed, t_act0, t_env0, env0, arm0,
+                          s_traj, a, stats, arm_stats, env_sums, ws, ws_bytes, nullptr, nullptr, last_val, adv_moments_out,
+                          adv_moments_in, stream);
 }

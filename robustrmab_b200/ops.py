@@ -374,6 +374,18 @@ def epoch_table(domain, net, T, Wpi, Wv, lamb, nature, ranges, R, Cc, gamma, lam
     return stats, arm_stats, env_sums
 
 
+def epoch_table_envshard(domain, net, T, Wpi, Wv, lamb, nature, ranges, R, Cc, gamma, lam, seed, t0, s_traj, stats, arm_stats,
+                         env_sums, ws, last_val, env0, mom_out=None, mom_in=None):
+    """rmab_epoch_table for env-sharded ranks: launch once with mom_out `[N,2]` fp64 (raw advantage sums of this rank's envs),
+    all-reduce, launch again with mom_in `[N,2]` fp32 (global mean, std)."""
+    check(lib().rmab_epoch_table_envshard(int(domain), C.byref(net), int(T), _p(Wpi, f32), _p(Wv, f32), _p(lamb, f32),
+                                          _p(nature, f32), _p(ranges, f32), _p(R, f32), _p(Cc, f32), float(gamma), float(lam),
+                                          int(seed) & 0xFFFFFFFFFFFFFFFF, int(t0), int(t0), int(env0), 0, _p(s_traj, u8), None,
+                                          _p(stats, f32), _p(arm_stats, f32), _p(env_sums, f32), _p(ws, f64),
+                                          ws.numel() * ws.element_size(), _p(last_val, f32), _p(mom_out, f64), _p(mom_in, f32),
+                                          _stream()))
+
+
 def ppo_update_table(net, hp, T, Wpi, Wv, adam_pi, adam_v, stats, arm_stats, lamb, want_loss=False):
     N = net.n_arms
     dev = stats.device

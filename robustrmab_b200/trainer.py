@@ -318,3 +318,123 @@ class RMABPPOTrainer:
                                                                    arm0=self.arm0))
         self.last_stats = stats
         return stats
+
+
+class EnvShardedRMABPPOTrainer(RMABPPOTrainer):
+    """The reference's own MPI layout (SpinningUp `mpi_fork`: every process all N arms, its own environments; gradients
+    averaged with `mpi_avg_grads`, advantage statistics with `mpi_statistics_scalar` -- utils/mpi_pytorch.py:19-30,
+    mpi_tools.py:76-97) on k GPUs: rank r simulates envs [r E/k, (r+1) E/k) of ALL arms.  What crosses NVLink per epoch:
+
+      * the raw advantage moments `[N,2]` fp64 (all-reduce) -- get()'s per-arm normalisation is over the envs of all ranks;
+        the fused rollout kernel runs twice (export moments, then normalise with the global ones: same Philox counters, same
+        trajectory) instead of writing the trajectory to HBM;
+      * the loss statistics, re-sharded from envs to ARMS (all-to-all of `[N/k, K, E/k]` blocks): averaging per-sample
+        gradients over all ranks' envs IS the full-batch gradient, and the statistics are the batch -- so a
+        rank then runs the fused update kernels for its N/k arms over all E envs; no `[N,P]` gradient all-reduce per Adam
+        iteration (3.7 GB each at BASELINE configs[2]);
+      * the updated nets of every rank's arms (all-gather `[N,P]`), lambda `[E]` (all-gather), the lambda-net gradient
+        (all-reduce) and the logging sums.
+
+    The small-N / large-E fallback of SURVEY.md 8(e); the arm-sharded RMABPPOTrainer is the fast path."""
+
+    def __init__(self, domain, n_arms, n_envs, steps_per_epoch, rank=0, world_size=1, process_group=None, **kw):
+        kw.pop("keep_trajectory", None)
+        E_total = int(n_envs)
+        if E_total % int(world_size):
+            raise ValueError("env sharding needs n_envs divisible by the number of ranks")
+        self.E_total, self.erank, self.eworld, self.epg = E_total, int(rank), int(world_size), process_group
+        self.env0 = self.erank * (E_total // self.eworld)
+        super().__init__(domain, n_arms, E_total // self.eworld, steps_per_epoch, rank=0, world_size=1, **kw)
+        N, dev = self.N, self.dev
+        per = (N + self.eworld - 1) // self.eworld
+        self.per = per
+        self.a0 = min(self.erank * per, N)
+        self.a1 = min(self.a0 + per, N)
+        self.mom = torch.zeros((N, 2), dtype=torch.float64, device=dev)
+        self.mom_in = torch.zeros((N, 2), dtype=torch.float32, device=dev)
+        K = self.stats.shape[1]
+        self.stats_send = torch.zeros((self.eworld * per, K, self.E), dtype=torch.float32, device=dev)
+        self.stats_recv = torch.empty_like(self.stats_send)
+        self.net_upd = ops.net_desc(self.a1 - self.a0, E_total, self.S, self.A, self.h, True, 1.0)
+        self.s_traj[:, 0] = ops.reset_states(N, self.E, self.S, ops.rng(self.seed, _lib.STREAM_RESET, 0, env0=self.env0))
+
+    def _ar(self, t):
+        if self.eworld > 1:
+            torch.distributed.all_reduce(t, group=self.epg)
+        return t
+
+    def _gather_rows(self, x_local):
+        """Rows [a0, a1) of every rank -> the full [N, ...] tensor (ragged last shard padded)."""
+        if self.eworld == 1:
+            return x_local
+        pad = torch.zeros((self.per,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=self.dev)
+        pad[:x_local.shape[0]] = x_local
+        out = torch.empty((self.eworld * self.per,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=self.dev)
+        torch.distributed.all_gather_into_tensor(out, pad, group=self.epg)
+        return out[:self.N]
+
+    @staticmethod
+    def reshard_env_to_arm(send, recv, k, per, group=None):
+        """send `[k * per, K, E_loc]` = this rank's env slice of ALL arms (rows padded to k * per) -> `[per, K, k * E_loc]` = ALL
+        envs (rank order = env order) of this rank's `per` arms: one all-to-all of `[per, K, E_loc]` blocks."""
+        torch.distributed.all_to_all_single(recv, send, group=group)
+        E_loc = send.shape[2]
+        # recv block j = this rank's arm rows as simulated by rank j: [k, per, K, E_loc] -> [per, K, k, E_loc]
+        return recv.view(k, per, -1, E_loc).permute(1, 2, 0, 3).reshape(per, -1, k * E_loc)
+
+    def epoch(self, want_stats=True, keep_buffers=False):
+        if keep_buffers:
+            raise ValueError("the env-sharded trainer keeps the trajectory on chip")
+        ep, N, E, T, k = self.epoch_idx, self.N, self.E, self.T, self.eworld
+        s0 = self._s0()
+        lamb, h1 = ops.lambda_forward(self.lam_params, s0, N, 0, 1.0, want_h1=True)      # all arms are local
+        args = (self.domain, self.net, T, self.Wpi, self.Wv, lamb, self.nature, self.ranges, self.R, self.C, self.gamma,
+                self.lam_other, self.seed, self.t_global, self.s_traj[:, 0], self.stats, self.arm_stats, self.env_sums, self.ws,
+                self.last_val, self.env0)
+        ops.epoch_table_envshard(*args, mom_out=self.mom)
+        self._ar(self.mom)
+        cnt = float(T) * float(self.E_total)
+        mean = self.mom[:, 0] / cnt
+        var = (self.mom[:, 1] / cnt - mean * mean).clamp_min(0.0)
+        self.mom_in[:, 0], self.mom_in[:, 1] = mean.float(), var.sqrt().float()
+        ops.epoch_table_envshard(*args, mom_in=self.mom_in)
+        as2 = self.arm_stats[:, 2].contiguous()
+        self._ar(as2)
+        self.arm_stats[:, 2] = as2
+        # ---- statistics: env-sharded -> arm-sharded ----
+        if k > 1:
+            self.stats_send[:N] = self.stats
+            st_arm = self.reshard_env_to_arm(self.stats_send, self.stats_recv, k, self.per, self.epg)[:self.a1 - self.a0].contiguous()
+            lam_all = torch.empty((self.E_total,), dtype=torch.float32, device=self.dev)
+            torch.distributed.all_gather_into_tensor(lam_all, lamb.contiguous(), group=self.epg)
+        else:
+            st_arm, lam_all = self.stats, lamb
+        hp = ops.hyper(self.clip_ratio, self.entropy_coeff(ep), self.pi_lr, self.vf_lr, self.pi_iters, self.v_iters,
+                       self.steps_pi, self.steps_v)
+        sl = slice(self.a0, self.a1)
+        if self.a1 > self.a0:
+            wpi, wv = self.Wpi[sl].contiguous(), self.Wv[sl].contiguous()
+            ops.ppo_update_table(self.net_upd, hp, T, wpi, wv, self.adam_pi[sl], self.adam_v[sl], st_arm,
+                                 self.arm_stats[sl].contiguous(), lam_all)
+        else:
+            wpi, wv = self.Wpi[sl], self.Wv[sl]
+        self.steps_pi += self.pi_iters
+        self.steps_v += self.v_iters
+        self.Wpi.copy_(self._gather_rows(wpi))
+        self.Wv.copy_(self._gather_rows(wv))
+        # ---- lambda-net SGD step (compute_loss_lambda, agent_oracle.py:360-376): mean over ALL envs = average of the ranks' ----
+        if self.lambda_update_due(ep):
+            coef = self.B / (1.0 - self.gamma) - self.env_sums[1]
+            grad = ops.lambda_sgd(self.lam_params, s0, N, 0, 1.0, h1, coef.contiguous(), 0.0, want_grad=True)
+            self._ar(grad)
+            self.lam_params.add_(grad, alpha=-self.lm_lr / k)
+        stats = None
+        if want_stats:
+            ret_all = torch.empty((self.E_total,), dtype=torch.float32, device=self.dev) if k > 1 else None
+            if k > 1:
+                torch.distributed.all_gather_into_tensor(ret_all, self.env_sums[0].contiguous(), group=self.epg)
+            stats = {"EpActualRet": ret_all if k > 1 else self.env_sums[0].clone(), "Lamb": lam_all}
+        self.epoch_idx += 1
+        self.t_global += T
+        self.s_traj[:, 0] = ops.reset_states(N, E, self.S, ops.rng(self.seed, _lib.STREAM_RESET, self.epoch_idx, env0=self.env0))
+        return stats

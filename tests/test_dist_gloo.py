@@ -126,6 +126,16 @@ def _ma_worker(rank, world, port, out):
                          torch.equal(d[nets.actor.oW3:nets.actor.ob3].view(N, k, h)[:, 0, 0], own) and
                          torch.equal(d[nets.actor.ols:].view(N, k)[:, 1], own))
     res["nat_p"] = nets.critic.p.numpy().copy()
+    # env-sharded -> arm-sharded statistics (EnvShardedRMABPPOTrainer): rank r holds envs [r E_loc, (r+1) E_loc) of all arms
+    from robustrmab_b200.trainer import EnvShardedRMABPPOTrainer
+    Nn, Kk, El = 5, 3, 4                                 # ragged: per = 3 arms per rank
+    per = (Nn + world - 1) // world
+    full_st = torch.arange(Nn * Kk * El * world, dtype=torch.float32).reshape(Nn, Kk, El * world)
+    send = torch.zeros((world * per, Kk, El))
+    send[:Nn] = full_st[:, :, rank * El:(rank + 1) * El]
+    got_st = EnvShardedRMABPPOTrainer.reshard_env_to_arm(send, torch.empty_like(send), world, per)
+    lo_, hi_ = rank * per, min((rank + 1) * per, Nn)
+    res["reshard_ok"] = bool(torch.equal(got_st[:hi_ - lo_], full_st[lo_:hi_]))
     out[rank] = res
     dist.destroy_process_group()
 
@@ -143,4 +153,5 @@ def test_ma_sharding_host_logic_world2():
         assert np.array_equal(w1[:, :4], np.full((8, 4), 1.0)) and np.array_equal(w1[:, 4:], np.full((8, 3), 2.0))
         assert np.array_equal(out[r]["b1"], np.full(8, 5.0))
         assert out[r]["nat_ok"]
+        assert out[r]["reshard_ok"]
     assert np.array_equal(out[0]["nat_p"], out[1]["nat_p"])
