@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librmab_b200.so")
+LIB_PATH = os.environ.get("RMAB_LIB_PATH") or os.path.join(HERE, "librmab_b200.so")   # override: A/B against another build
 
 OK, E_BADARG, E_SHAPE, E_ARCH, E_LAUNCH = 0, -1, -2, -3, -4
 DOMAIN_CE, DOMAIN_ARMMAN, DOMAIN_SIS = 0, 1, 2

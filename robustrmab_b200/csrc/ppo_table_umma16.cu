@@ -26,9 +26,13 @@ constexpr int H16 = 16, HH16 = 256, TM16 = 128, NT16 = 128;
 constexpr int CTAS16 = 4;   // measured: 3 CTAs with the E3 row sums in registers (170 regs) is 5 % slower, occupancy wins
 // shared memory (bytes from a 1024-byte aligned base): swizzled [128 x (hi16 | lo16)] tiles, K-major 16 x 16 tiles
 constexpr uint32_t S_D2 = 0, S_A1 = 16384, S_W2H = 32768, S_W2L = 33792, S_WTH = 34816, S_WTL = 35840, S_END = 36864;
+// the former static shared objects live in the dynamic block as well, so that every shared address is a compile-time
+// constant (+ a per-thread offset): mbarriers, the TMEM base word, the reduction scratch, the Adam table, then the floats
+constexpr uint32_t S_BARS = S_END, S_TMEM = S_END + 24, S_RED = S_END + 32, S_ADAM = S_RED + 256;
 // TMEM columns (128 allocated per CTA)
-constexpr uint32_t Q_D = 0, Q_OM1 = 16, Q_A1H = 32, Q_A1L = 48, Q_D2H = 64, Q_D2L = 80, Q_DW2 = 96;
 constexpr int kAdamTab = 128;
+constexpr uint32_t S_FLOATS = S_ADAM + 8 * kAdamTab;
+constexpr uint32_t Q_D = 0, Q_OM1 = 16, Q_A1H = 32, Q_A1L = 48, Q_D2H = 64, Q_D2L = 80, Q_DW2 = 96;
 constexpr int SCRA = 36, SCRB = 20;   // row pitches (floats) of the dW2 readback scratch: 16-byte stores at 144 B / 80 B pitch
 constexpr uint32_t DESC16_HI_K = (512u >> 4) | (1u << 14);                 // SBO = 512 (next 8 rows of a 16-column tile)
 constexpr uint32_t DESC16_HI_MN = (512u >> 4) | (1u << 14) | (1u << 29);   // SBO = 512 (next 4 rows), layout type 1
@@ -45,39 +49,46 @@ struct U16Args {
   const float* lamb; const float* stats; const float* arm_stats;
   float* loss_out;
   int stage_lamb;
+  // float images of the hyper-parameters, rounded once on the host: inside the tile loop the compiler would otherwise
+  // re-derive them from the doubles (DADD + F2F per tile at the 128-register cap)
+  float clip_lo, clip_hi, beta_ent, lerp_w, beta2f, omb2, epsf, invM;
 };
 
 }  // namespace
 
 template <int S, bool IS_PI>
-__global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args g) {
+__global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(const __grid_constant__ U16Args g) {
   constexpr int H = H16, HH = HH16, A = 2, OUT = IS_PI ? A : 1, IN = S + 1, SA = S * A, FW = 16;
   constexpr int ROW0 = IS_PI ? 0 : 3 * SA, KST = 4 * SA + 3 * S;
-  constexpr int NQ = 2 + S + OUT;   // per-feature row sums: db2, dW1[:, lambda], dW1[:, s] x S, dW3 x OUT
-  extern __shared__ unsigned char smraw16[];
-  __shared__ __align__(8) uint64_t bars[3];
-  __shared__ uint32_t tmem_s;
-  __shared__ float red[64];
-  __shared__ float2 adam_tab[kAdamTab];   // (lr / (1 - beta1^t), sqrt(1 - beta2^t)) of every Adam step of this launch
-  unsigned char* base = smraw16 + ((1024u - (u::smem_u32(smraw16) & 1023u)) & 1023u);
-  const uint32_t sbase = u::smem_u32(base);
-  const int E = g.d.n_envs, T = g.T;
-  const MlpLayout L(IN, H, OUT);
-  const int P = L.P, Ps = L.padded() - HH;   // w / G hold the packed layout WITHOUT the W2 block
-  float* w = reinterpret_cast<float*>(base + S_END);
-  float* wb = w + Ps;                 // [S][H]  (W1[:, s] + b1) * kTanhScale
-  float* wl = wb + S * H;             // [H]     W1[:, lambda] * kTanhScale
-  float* b2s = wl + H;                // [H]     b2 * kTanhScale
-  float* redw = b2s + H;              // [4 warps][NQ][16]
-  float* scrA = redw + 4 * NQ * FW;   // [16][SCRA]  dW2 readback: hi rows (cols 0..15 = a1 hi, 16..31 = a1 lo)
-  float* scrB = scrA + H * SCRA;      // [16][SCRB]  lo rows x hi cols
-  float* mom = scrB + H * SCRB;       // [2][P]  Adam m, v of this arm: resident in shared memory for the whole launch
-  float* slam_s = mom + 2 * ((P + 3) & ~3);   // [E] when it fits
-  const float* slam = g.stage_lamb ? slam_s : g.lamb;
-  float* W2H = reinterpret_cast<float*>(base + S_W2H);
-  float* W2L = reinterpret_cast<float*>(base + S_W2L);
-  float* WTH = reinterpret_cast<float*>(base + S_WTH);
-  float* WTL = reinterpret_cast<float*>(base + S_WTL);
+  constexpr int NQ = 3 + S;         // per-feature row sums: db2, dW1[:, lambda], dW1[:, s] x S, dW3 (policy: of action 0)
+  // packed net layout (MlpLayout) as compile-time constants
+  constexpr int oW1 = 0, ob1 = H * IN, oW2 = ob1 + H, ob2 = oW2 + HH, oW3 = ob2 + H, ob3 = oW3 + OUT * H, P = ob3 + OUT;
+  constexpr int Ps = ((P + 3) & ~3) - HH;   // w holds the packed layout WITHOUT the W2 block
+  // The whole block is dynamic and declared 1024-byte aligned (no static shared objects in this kernel), so the tiles sit
+  // at the constants S_* of the CTA's shared window and no address is derived from a run-time alignment fix-up.
+  extern __shared__ __align__(1024) unsigned char smraw16[];
+  // The window address is pinned in one register (an opaque asm): left alone, the compiler re-derives it from
+  // SR_CgaCtaId in every phase of the tile loop (S2R + MOV + LEA, eight times per tile) to save that register.
+  uint32_t sbase = u::smem_u32(smraw16);
+  asm volatile("" : "+r"(sbase));
+  unsigned char* const base = reinterpret_cast<unsigned char*>(__cvta_shared_to_generic(sbase));
+  float* const red = reinterpret_cast<float*>(base + S_RED);                // [64]
+  float2* const adam_tab = reinterpret_cast<float2*>(base + S_ADAM);        // (lr / (1 - beta1^t), sqrt(1 - beta2^t)) per step
+  const int E = g.d.n_envs;
+  float* const w = reinterpret_cast<float*>(base + S_FLOATS);
+  float* const wb = w + Ps;                 // [S][H]  (W1[:, s] + b1) * kTanhScale
+  float* const wl = wb + S * H;             // [H]     W1[:, lambda] * kTanhScale
+  float* const b2s = wl + H;                // [H]     b2 * kTanhScale
+  float* const w3d = b2s + H;               // [H + 4] policy: W3[0] - W3[1] then b3[0] - b3[1]; value: W3[0], b3[0]
+  float* const redw = w3d + H + 4;          // [4 warps][NQ][16]
+  float* const scrA = redw + 4 * NQ * FW;   // [16][SCRA]  dW2 readback: hi rows (cols 0..15 = a1 hi, 16..31 = a1 lo)
+  float* const scrB = scrA + H * SCRA;      // [16][SCRB]  lo rows x hi cols
+  float* const mom = scrB + H * SCRB;       // [2][P]  Adam m, v of this arm: resident in shared memory for the whole launch
+  float* const slam_s = mom + 2 * ((P + 3) & ~3);   // [E] when it fits
+  float* const W2H = reinterpret_cast<float*>(base + S_W2H);
+  float* const W2L = reinterpret_cast<float*>(base + S_W2L);
+  float* const WTH = reinterpret_cast<float*>(base + S_WTH);
+  float* const WTL = reinterpret_cast<float*>(base + S_WTL);
 
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, r = tid;
   float* Wn = g.W + (int64_t)n * P;
@@ -86,10 +97,10 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args 
     const float x = Wn[i];
     mom[i] = An[i];
     mom[P + i] = An[P + i];
-    if (i < L.oW2) w[i] = x;
-    else if (i >= L.ob2) w[i - HH] = x;
+    if (i < oW2) w[i] = x;
+    else if (i >= ob2) w[i - HH] = x;
     else {
-      const int j = (i - L.oW2) >> 4, c = (i - L.oW2) & 15;
+      const int j = (i - oW2) >> 4, c = (i - oW2) & 15;
       uint32_t hi, lo;
       u::split_u(x, hi, lo);
       W2H[kmaj16(j, c)] = __uint_as_float(hi); W2L[kmaj16(j, c)] = __uint_as_float(lo);
@@ -99,36 +110,29 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args 
   if (g.stage_lamb)
     for (int i = tid; i < E; i += NT16) slam_s[i] = g.lamb[i];
   if (tid == 0) {
-    for (int b = 0; b < 3; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(u::smem_u32(&bars[b])));
+    for (int b = 0; b < 3; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(sbase + S_BARS + 8 * b));
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;\n" ::"r"(u::smem_u32(&tmem_s)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;\n" ::"r"(sbase + S_TMEM) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   u::tc_fence_before();
   __syncthreads();
   u::tc_fence_after();
-  const uint32_t tmem = tmem_s;
+  const uint32_t tmem = *reinterpret_cast<const uint32_t*>(base + S_TMEM);
   const uint32_t tl = tmem + ((uint32_t)(32 * warp) << 16);   // this warp's lane quarter
-  const uint32_t bar1 = u::smem_u32(&bars[0]), bar2 = u::smem_u32(&bars[1]), bar3 = u::smem_u32(&bars[2]);
-  // this thread's row of the swizzled tiles: four 32-byte chunks (hi 0..7, hi 8..15, lo 0..7, lo 8..15)
-  const uint32_t rowb = (uint32_t)(r >> 2) * 512 + (uint32_t)(r & 3) * 128;
-  uint32_t off_c[4];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) off_c[c] = rowb + (uint32_t)((c ^ (r & 3)) * 32);
-
+  const uint32_t bar1 = sbase + S_BARS, bar2 = sbase + S_BARS + 8, bar3 = sbase + S_BARS + 16;
   const float* st = g.stats + ((int64_t)n * KST + ROW0) * E;
+  asm volatile("" : "+l"(st));   // opaque: one 64-bit base + 32-bit offsets per load instead of a 64-bit re-derivation each
   const int M = S * E;
   const int n_tiles = (M + TM16 - 1) / TM16;
-  const float invM = 1.f / (float)((int64_t)T * E);
+  const float invM = g.invM;
   const int iters = IS_PI ? g.hp.pi_iters : g.hp.v_iters;
   const double lr = IS_PI ? g.hp.pi_lr : g.hp.vf_lr;
   const int step0 = IS_PI ? g.hp.adam_step0_pi : g.hp.adam_step0_v;
-  const float clip_lo = (float)(1.0 - g.hp.clip_ratio), clip_hi = (float)(1.0 + g.hp.clip_ratio);
-  const float beta_ent = (float)g.hp.entropy_coeff;
-  const float lerp_w = (float)(1.0 - g.hp.beta1), beta2f = (float)g.hp.beta2, omb2 = (float)(1.0 - g.hp.beta2);
-  const float epsf = (float)g.hp.adam_eps;
+  const float clip_lo = g.clip_lo, clip_hi = g.clip_hi, beta_ent = g.beta_ent;
+  const float lerp_w = g.lerp_w, beta2f = g.beta2f, omb2 = g.omb2, epsf = g.epsf;
   double b1p = pow(g.hp.beta1, (double)step0), b2p = pow(g.hp.beta2, (double)step0);
   for (int k = tid; k < min(iters, kAdamTab); k += NT16)   // the double-precision bias corrections once, in parallel
     adam_tab[k] = make_float2((float)(lr / (1.0 - pow(g.hp.beta1, (double)(step0 + k + 1)))),
@@ -138,27 +142,35 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args 
   // A row's 32-byte chunks sit at only four bank positions (128-byte pitch), so the 8 rows of a warp that share a position
   // would serialise 8-fold on a 16-byte store; rows with bit 2 of the row index set write the upper half of every chunk first
   // (4-fold = the minimum for 512 bytes).  The data swap is selects, the address swap one per-thread constant.
+  // This thread's row of the swizzled tiles is four 32-byte chunks (hi 0..7, hi 8..15, lo 0..7, lo 8..15), chunk c at
+  // position c ^ (r & 3).  One address register serves all eight stores: position and half are XORs of its bits 4..6.
   const bool up = (r >> 2) & 1;
-  const uint32_t h0 = up ? 16u : 0u, h1 = 16u - h0;
-  auto st_pair = [&](unsigned char* p, const uint32_t* v) {
-    *reinterpret_cast<uint4*>(p + h0) = make_uint4(up ? v[4] : v[0], up ? v[5] : v[1], up ? v[6] : v[2], up ? v[7] : v[3]);
-    *reinterpret_cast<uint4*>(p + h1) = make_uint4(up ? v[0] : v[4], up ? v[1] : v[5], up ? v[2] : v[6], up ? v[3] : v[7]);
+  const uint32_t arow = sbase + (uint32_t)(r >> 2) * 512 + (uint32_t)(r & 3) * 160 + (up ? 16u : 0u);   // (r&3) * (128 + 32)
+  auto st_pair = [&](uint32_t addr, const uint32_t* v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(up ? v[4] : v[0]), "r"(up ? v[5] : v[1]),
+                 "r"(up ? v[6] : v[2]), "r"(up ? v[7] : v[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr ^ 16u), "r"(up ? v[0] : v[4]), "r"(up ? v[1] : v[5]),
+                 "r"(up ? v[2] : v[6]), "r"(up ? v[3] : v[7]) : "memory");
   };
   auto store_row = [&](uint32_t tile, const uint32_t (&hi)[FW], const uint32_t (&lo)[FW]) {
-    st_pair(base + tile + off_c[0], &hi[0]);
-    st_pair(base + tile + off_c[1], &hi[8]);
-    st_pair(base + tile + off_c[2], &lo[0]);
-    st_pair(base + tile + off_c[3], &lo[8]);
+    st_pair(arow + tile, &hi[0]);
+    st_pair((arow ^ 32u) + tile, &hi[8]);
+    st_pair((arow ^ 64u) + tile, &lo[0]);
+    st_pair((arow ^ 96u) + tile, &lo[8]);
   };
 
   for (int it = 0; it < iters; ++it) {
     for (int i = tid; i < S * H; i += NT16) {
       const int s = i >> 4, k = i & 15;
-      wb[i] = u::kTanhScale * (w[L.oW1 + k * IN + s] + w[L.ob1 + k]);
+      wb[i] = u::kTanhScale * (w[oW1 + k * IN + s] + w[ob1 + k]);
     }
     if (tid < H) {
-      wl[tid] = u::kTanhScale * w[L.oW1 + tid * IN + IN - 1];
-      b2s[tid] = u::kTanhScale * w[L.ob2 - HH + tid];
+      wl[tid] = u::kTanhScale * w[oW1 + tid * IN + IN - 1];
+      b2s[tid] = u::kTanhScale * w[ob2 - HH + tid];
+      // Two actions: softmax, entropy and their gradients depend on the logit DIFFERENCE only, and the two logit
+      // gradients of a row sum to zero (gl[1] = -gl[0]); so the output layer runs on W3[0] - W3[1] with one gradient.
+      w3d[tid] = IS_PI ? w[oW3 - HH + tid] - w[oW3 - HH + H + tid] : w[oW3 - HH + tid];
+      if (tid == 0) w3d[H] = IS_PI ? w[ob3 - HH] - w[ob3 - HH + 1] : w[ob3 - HH];
     }
     {
       const uint32_t z[FW] = {};
@@ -167,17 +179,11 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args 
     }
     __syncthreads();
 
-    float s_b2[FW], s_w3[OUT][FW], s_w1r[S], s_b3[OUT], s_wlr = 0.f;
+    float s_b2[FW], s_w3[FW], s_w1r[S], s_b3 = 0.f, s_wlr = 0.f;
 #pragma unroll
-    for (int k = 0; k < FW; ++k) {
-      s_b2[k] = 0.f;
-#pragma unroll
-      for (int a = 0; a < OUT; ++a) s_w3[a][k] = 0.f;
-    }
+    for (int k = 0; k < FW; ++k) s_b2[k] = s_w3[k] = 0.f;
 #pragma unroll
     for (int c = 0; c < S; ++c) s_w1r[c] = 0.f;
-#pragma unroll
-    for (int a = 0; a < OUT; ++a) s_b3[a] = 0.f;
     float loss_acc = 0.f;
 
     for (int t = 0; t < n_tiles; ++t, ++gt) {
@@ -185,19 +191,21 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args 
       const bool valid = m < M;
       const int mm = valid ? m : M - 1;
       const int srow = (mm >= E) + (mm >= 2 * E), erow = mm - srow * E;   // S <= 3: no integer division
-      const float lam = slam[erow];
-      // statistics of this row (L2 resident), in flight during E1 and G1
-      const float* sp = st + erow;
-      const float wrow = sp[(3 * SA - ROW0 + srow) * E];   // CntS
+      const float lam = g.stage_lamb ? slam_s[erow] : g.lamb[erow];
+      // statistics of this row (L2 resident), in flight during E1 and G1; one uniform base + 32-bit element offsets
+      const uint32_t o_s = (uint32_t)erow + (uint32_t)srow * (uint32_t)E;   // row `srow` of a per-state block
+      const float wrow = __ldg(st + (o_s + (uint32_t)((3 * SA - ROW0) * E)));   // CntS
       float stA[IS_PI ? 6 : 1];
       if (IS_PI) {
+        const uint32_t o_sa = o_s + (uint32_t)srow * (uint32_t)((A - 1) * E);    // row `srow * A` of a per-(state, action) block
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
-          const int c = srow * A + a;
-          stA[a] = sp[c * E]; stA[2 + a] = sp[(SA + c) * E]; stA[4 + a] = sp[(2 * SA + c) * E];
+          stA[a] = __ldg(st + (o_sa + (uint32_t)(a * E)));
+          stA[2 + a] = __ldg(st + (o_sa + (uint32_t)((SA + a) * E)));
+          stA[4 + a] = __ldg(st + (o_sa + (uint32_t)((2 * SA + a) * E)));
         }
       } else {
-        stA[0] = sp[(3 * SA + S - ROW0 + srow) * E];
+        stA[0] = __ldg(st + (o_s + (uint32_t)((3 * SA + S - ROW0) * E)));
       }
 
       // ---- E1: a1 = tanh(W1 x + b1); hi/lo -> TMEM (A of G1) and the smem tile (B of G3); 1 - a1^2 parked in TMEM ----
@@ -261,28 +269,21 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args 
           a2[4 * k4 + 3] = u::tanh_scaled_u(fmaf(__uint_as_float(v[4 * k4 + 3]), u::kTanhScale, b.w));
         }
       }
-      float gl[OUT];
+      float gl = 0.f;   // dLoss / d(logit 0) (policy; logit 1 gets -gl) or dLoss / dv (value)
       {
-        float logit[OUT];
+        float pl = w3d[H];
 #pragma unroll
-        for (int a = 0; a < OUT; ++a) {
-          const float4* w34 = reinterpret_cast<const float4*>(w + L.oW3 - HH + a * H);
-          float pl = w[L.ob3 - HH + a];
-#pragma unroll
-          for (int k4 = 0; k4 < FW / 4; ++k4) {
-            const float4 w3 = w34[k4];
-            pl = fmaf(w3.x, a2[4 * k4], pl); pl = fmaf(w3.y, a2[4 * k4 + 1], pl);
-            pl = fmaf(w3.z, a2[4 * k4 + 2], pl); pl = fmaf(w3.w, a2[4 * k4 + 3], pl);
-          }
-          logit[a] = pl;
-          gl[a] = 0.f;
+        for (int k4 = 0; k4 < FW / 4; ++k4) {
+          const float4 w3 = *reinterpret_cast<const float4*>(w3d + 4 * k4);
+          pl = fmaf(w3.x, a2[4 * k4], pl); pl = fmaf(w3.y, a2[4 * k4 + 1], pl);
+          pl = fmaf(w3.z, a2[4 * k4 + 2], pl); pl = fmaf(w3.w, a2[4 * k4 + 3], pl);
         }
-        if (IS_PI) {
-          const float mx = fmaxf(logit[0], logit[OUT - 1]);
-          const float e0 = __expf(logit[0] - mx), e1 = __expf(logit[OUT - 1] - mx);
-          const float sum = e0 + e1, lse = __logf(sum), inv = __fdividef(1.f, sum);
-          const float p[2] = {e0 * inv, e1 * inv};
-          const float lp[2] = {(logit[0] - mx) - lse, (logit[OUT - 1] - mx) - lse};
+        if (IS_PI) {   // pl = logit 0 - logit 1
+          const float e = __expf(-fabsf(pl));   // exp(smaller logit - larger logit); the larger one contributes exp(0) = 1
+          const float sum = 1.f + e, lse = __logf(sum), inv = __fdividef(1.f, sum);
+          const bool z = pl >= 0.f;             // logit 0 is the larger one
+          const float p[2] = {z ? inv : e * inv, z ? e * inv : inv};
+          const float lp[2] = {(z ? 0.f : pl) - lse, (z ? -pl : 0.f) - lse};
           const float ent = -(p[0] * lp[0] + p[1] * lp[1]);
           float ga[2], sumg = 0.f, lrow = 0.f;
 #pragma unroll
@@ -295,37 +296,29 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args 
           }
           if (valid) {
             loss_acc += lrow - beta_ent * wrow * ent;
-#pragma unroll
-            for (int a = 0; a < 2; ++a) gl[a < OUT ? a : 0] = invM * (ga[a] - p[a] * sumg + beta_ent * wrow * p[a] * (lp[a] + ent));
+            gl = invM * (ga[0] - p[0] * sumg + beta_ent * wrow * p[0] * (lp[0] + ent));
           }
         } else {
-          const float diff = logit[0] - stA[0];
+          const float diff = pl - stA[0];
           if (valid) {
             loss_acc = fmaf(wrow * diff, diff, loss_acc);
-            gl[0] = invM * 2.f * wrow * diff;
+            gl = invM * 2.f * wrow * diff;
           }
         }
-#pragma unroll
-        for (int a = 0; a < OUT; ++a) s_b3[a] += gl[a];
+        s_b3 += gl;
       }
       {
         uint32_t hi[FW], lo[FW];
 #pragma unroll
         for (int k4 = 0; k4 < FW / 4; ++k4) {
-          float up[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int a = 0; a < OUT; ++a) {
-            const float4 w3 = *reinterpret_cast<const float4*>(w + L.oW3 - HH + a * H + 4 * k4);
-            up[0] = fmaf(gl[a], w3.x, up[0]); up[1] = fmaf(gl[a], w3.y, up[1]);
-            up[2] = fmaf(gl[a], w3.z, up[2]); up[3] = fmaf(gl[a], w3.w, up[3]);
-          }
+          const float4 w3 = *reinterpret_cast<const float4*>(w3d + 4 * k4);
+          const float up[4] = {gl * w3.x, gl * w3.y, gl * w3.z, gl * w3.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int k = 4 * k4 + j;
             const float x = a2[k], d2 = up[j] * fmaf(-x, x, 1.f);
             s_b2[k] += d2;
-#pragma unroll
-            for (int a = 0; a < OUT; ++a) s_w3[a][k] = fmaf(gl[a], x, s_w3[a][k]);
+            s_w3[k] = fmaf(gl, x, s_w3[k]);
             u::split_u(d2, hi[k], lo[k]);
           }
         }
@@ -403,19 +396,14 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args 
       vals[1] = s_wlr;
 #pragma unroll
       for (int c = 0; c < S; ++c) vals[2 + c] = s_w1r[c];
-#pragma unroll
-      for (int a = 0; a < OUT; ++a) vals[2 + S + a] = u::colsum16(s_w3[a], lane);
+      vals[2 + S] = u::colsum16(s_w3, lane);
       if ((lane & 1) == 0)
 #pragma unroll
         for (int v = 0; v < NQ; ++v) redw[(warp * NQ + v) * FW + (lane >> 1)] = vals[v];
     }
-    float b3tot[OUT];
-#pragma unroll
-    for (int a = 0; a < OUT; ++a) b3tot[a] = warp_sum(s_b3[a]);
+    const float b3tot = warp_sum(s_b3);
     const float loss_tot = g.loss_out ? block_sum(loss_acc, red) : 0.f;
-    if (lane == 0)
-#pragma unroll
-      for (int a = 0; a < OUT; ++a) red[40 + warp * OUT + a] = b3tot[a];
+    if (lane == 0) red[40 + warp] = b3tot;
     u::mbar_wait(bar3, (gt - 1) & 1);   // every G3 of this pass has landed in TMEM
     u::tc_fence_after();
     if (warp < 2) {   // M = 64 accumulator: row m sits on lane (m % 16) + 32 (m / 16): warp 0 = d2 hi rows, warp 1 = d2 lo rows
@@ -473,7 +461,7 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args 
       const int p = tid + k * NT16;
       const int j = ((p >> 7) << 3) | ((p >> 2) & 7), c = (((p >> 5) & 3) << 2) | (p & 3);
       const float gi = (scrA[j * SCRA + c] + scrA[j * SCRA + 16 + c]) + scrB[j * SCRB + c];   // hi.hi + hi.lo + lo.hi
-      const float xn = adam(W2H[p] + W2L[p], gi, L.oW2 + j * H + c);                    // hi + lo = exact fp32 weight
+      const float xn = adam(W2H[p] + W2L[p], gi, oW2 + j * H + c);                    // hi + lo = exact fp32 weight
       uint32_t hi, lo;
       u::split_u(xn, hi, lo);
       W2H[p] = __uint_as_float(hi); W2L[p] = __uint_as_float(lo);
@@ -485,23 +473,25 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args 
       return ((redw[(0 * NQ + v) * FW + f] + redw[(1 * NQ + v) * FW + f]) + redw[(2 * NQ + v) * FW + f]) + redw[(3 * NQ + v) * FW + f];
     };
     for (int k = tid; k < P - HH; k += NT16) {
-      const int i = k < L.oW2 ? k : k + HH;
+      const int i = k < oW2 ? k : k + HH;
       float gi;
-      if (k < L.ob1) {                       // W1[f][c]: c < S state columns, c == S the lambda column
+      if (k < ob1) {                       // W1[f][c]: c < S state columns, c == S the lambda column
         const int f = k / IN, c = k - f * IN;
         gi = sum4(f, c == IN - 1 ? 1 : 2 + c);
-      } else if (k < L.oW2) {                // b1 = sum over states of dW1[:, s]
+      } else if (k < oW2) {                // b1 = sum over states of dW1[:, s]
         gi = 0.f;
 #pragma unroll
-        for (int c = 0; c < S; ++c) gi += sum4(k - L.ob1, 2 + c);
-      } else if (k < L.oW3 - HH) {           // b2
-        gi = sum4(k - (L.ob2 - HH), 0);
-      } else if (k < L.ob3 - HH) {           // W3[a][f]
-        const int a = (k - (L.oW3 - HH)) >> 4, f = (k - (L.oW3 - HH)) & 15;
-        gi = sum4(f, 2 + S + a);
+        for (int c = 0; c < S; ++c) gi += sum4(k - ob1, 2 + c);
+      } else if (k < oW3 - HH) {           // b2
+        gi = sum4(k - (ob2 - HH), 0);
+      } else if (k < ob3 - HH) {           // W3[a][f]
+        const int a = (k - (oW3 - HH)) >> 4, f = (k - (oW3 - HH)) & 15;
+        gi = sum4(f, 2 + S);
+        if (a == 1) gi = -gi;
       } else {                               // b3[a]
-        const int a = k - (L.ob3 - HH);
-        gi = ((red[40 + a] + red[40 + OUT + a]) + red[40 + 2 * OUT + a]) + red[40 + 3 * OUT + a];
+        const int a = k - (ob3 - HH);
+        gi = ((red[40] + red[41]) + red[42]) + red[43];
+        if (a == 1) gi = -gi;
       }
       w[k] = adam(w[k], gi, i);
     }
@@ -511,10 +501,10 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args 
   for (int i = tid; i < P; i += NT16) {
     An[i] = mom[i];
     An[P + i] = mom[P + i];
-    if (i < L.oW2) Wn[i] = w[i];
-    else if (i >= L.ob2) Wn[i] = w[i - HH];
+    if (i < oW2) Wn[i] = w[i];
+    else if (i >= ob2) Wn[i] = w[i - HH];
     else {
-      const int j = (i - L.oW2) >> 4, c = (i - L.oW2) & 15;
+      const int j = (i - oW2) >> 4, c = (i - oW2) & 15;
       Wn[i] = W2H[kmaj16(j, c)] + W2L[kmaj16(j, c)];
     }
   }
@@ -525,10 +515,10 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(U16Args 
 
 static size_t umma16_smem_bytes(int S, int OUT, int E) {
   const MlpLayout L(S + 1, H16, OUT);
-  const int NQ = 2 + S + OUT;
-  const size_t fl = (size_t)(L.padded() - HH16) + S * H16 + 2 * H16 + 4 * NQ * 16 + H16 * SCRA + H16 * SCRB +
+  const int NQ = 3 + S;
+  const size_t fl = (size_t)(L.padded() - HH16) + S * H16 + 3 * H16 + 4 + 4 * NQ * 16 + H16 * SCRA + H16 * SCRB +
                     2 * (size_t)((L.P + 3) & ~3) + (((size_t)E + 3) & ~(size_t)3);
-  return 1024 + S_END + fl * sizeof(float);
+  return S_FLOATS + fl * sizeof(float);
 }
 
 template <int S, bool IS_PI>
@@ -551,6 +541,11 @@ int ppo_table_umma16_run(const RmabNetDesc* net, const RmabHyper* hp, int T, flo
                          float* loss_v, cudaStream_t st) {
   U16Args g = {};
   g.d = *net; g.hp = *hp; g.T = T; g.lamb = lamb; g.stats = stats; g.arm_stats = arm_stats;
+  g.clip_lo = (float)(1.0 - hp->clip_ratio); g.clip_hi = (float)(1.0 + hp->clip_ratio);
+  g.beta_ent = (float)hp->entropy_coeff;
+  g.lerp_w = (float)(1.0 - hp->beta1); g.beta2f = (float)hp->beta2; g.omb2 = (float)(1.0 - hp->beta2);
+  g.epsf = (float)hp->adam_eps;
+  g.invM = 1.f / (float)((int64_t)T * net->n_envs);
   U16Args gp = g, gv = g;
   gp.W = Wpi; gp.adam = adam_pi; gp.loss_out = loss_pi;
   gv.W = Wv; gv.adam = adam_v; gv.loss_out = loss_v;
