@@ -23,6 +23,9 @@ namespace {
 namespace u = umma;
 
 constexpr int H16 = 16, HH16 = 256, TM16 = 128, NT16 = 128;
+#ifndef U16_SWAP
+#define U16_SWAP 1      // half-swapped 16-byte tile stores (0: natural order, 2-way bank conflicts, 32 selects fewer per store_row)
+#endif
 constexpr int CTAS16 = 4;   // measured: 3 CTAs with the E3 row sums in registers (170 regs) is 5 % slower, occupancy wins
 // shared memory (bytes from a 1024-byte aligned base): swizzled [128 x (hi16 | lo16)] tiles, K-major 16 x 16 tiles
 constexpr uint32_t S_D2 = 0, S_A1 = 16384, S_W2H = 32768, S_W2L = 33792, S_WTH = 34816, S_WTL = 35840, S_END = 36864;
@@ -90,6 +93,7 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(const __
   float* const WTH = reinterpret_cast<float*>(base + S_WTH);
   float* const WTL = reinterpret_cast<float*>(base + S_WTL);
 
+  // (tid is NOT pinned like the window base: measured 4.03 vs 3.99 ms -- the register is worth more than the S2R re-reads)
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, r = tid;
   float* Wn = g.W + (int64_t)n * P;
   float* An = g.adam + (int64_t)n * 2 * P;
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(const __
   // (4-fold = the minimum for 512 bytes).  The data swap is selects, the address swap one per-thread constant.
   // This thread's row of the swizzled tiles is four 32-byte chunks (hi 0..7, hi 8..15, lo 0..7, lo 8..15), chunk c at
   // position c ^ (r & 3).  One address register serves all eight stores: position and half are XORs of its bits 4..6.
-  const bool up = (r >> 2) & 1;
+  const bool up = U16_SWAP ? (r >> 2) & 1 : false;
   const uint32_t arow = sbase + (uint32_t)(r >> 2) * 512 + (uint32_t)(r & 3) * 160 + (up ? 16u : 0u);   // (r&3) * (128 + 32)
   auto st_pair = [&](uint32_t addr, const uint32_t* v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(up ? v[4] : v[0]), "r"(up ? v[5] : v[1]),
@@ -363,16 +367,16 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(const __
         u::tmem_ld16(tl + Q_D, v);
         u::tmem_ld16(tl + Q_OM1, om);
         u::tmem_wait_ld();
-        float d1[FW], d1l[FW];
+        float d1[FW];
 #pragma unroll
-        for (int k = 0; k < FW; ++k) {
-          d1[k] = __uint_as_float(v[k]) * __uint_as_float(om[k]);
-          d1l[k] = d1[k] * lam;
-        }
-        s_wlr += u::colsum16(d1l, lane);
-        // db1 / dW1[:, s]: the tile's column sums go straight to one register per state (lane l holds feature l / 2)
+        for (int k = 0; k < FW; ++k) d1[k] = __uint_as_float(v[k]) * __uint_as_float(om[k]);
+        // db1 / dW1[:, s] / dW1[:, lambda]: the tile's column sums go straight to one register each (lane l holds feature l / 2)
         const int m_lo = min(t * TM16 + 32 * warp, M - 1), m_hi = min(t * TM16 + 32 * warp + 31, M - 1);
         const int s_lo = (m_lo >= E) + (m_lo >= 2 * E), s_hi = (m_hi >= E) + (m_hi >= 2 * E);
+        float d1l[FW];
+#pragma unroll
+        for (int k = 0; k < FW; ++k) d1l[k] = d1[k] * lam;
+        s_wlr += u::colsum16(d1l, lane);
         if (s_lo == s_hi) {   // warp-uniform: all 32 rows are in one state
           const float x = u::colsum16(d1, lane);
 #pragma unroll

@@ -42,6 +42,8 @@ struct UmmaArgs {
   const float* adv; const float* logp_old; const float* ret;
   const float* z1_extra; float* dz1_out;   // MODE 2, sample-major [T*E, N, h]
   int stage_lamb;                          // lambda [E] staged in shared memory (else read through L1 / L2)
+  // float images of the hyper-parameters, rounded once on the host (the tile loop otherwise re-derives them from the doubles)
+  float clip_lo, clip_hi, beta_ent, lerp_w, beta2f, omb2, epsf, invM;
 };
 
 // Row sources.  MODE 0: one row per (state, env) carrying the loss statistics of rmab_epoch_table (one-hot inputs, S <= 3).
@@ -53,21 +55,27 @@ constexpr int kAdamTab64 = 128;
 }  // namespace
 
 template <int S, int A, bool IS_PI, int MODE>
-__global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
+__global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(const __grid_constant__ UmmaArgs g) {
   constexpr bool TABLE = MODE == kRowsTable, EXTRA = MODE == kRowsSampleExtra;
   static_assert(TABLE ? (A == 2 && (S == 2 || S == 3)) : (S == 1 && A >= 2 && A <= 3), "row mode / shape");
   constexpr int OUT = IS_PI ? A : 1, IN = S + 1, SA = S * A;   // sample rows: IN = 2 = (s / state_norm, lambda)
   constexpr int ROW0 = IS_PI ? 0 : 3 * SA, KST = 4 * SA + 3 * S;
   // per-feature row sums: db2, dW1[:, lambda], then table: dW1[:, s] x S (db1 is their sum) | sample: dW1[:, 0], db1; dW3 x OUT
   constexpr int NW1 = TABLE ? S : 2;
-  constexpr int NQ = 2 + NW1 + OUT;
+  // Two-action table policy: softmax, entropy and their gradients depend on the logit DIFFERENCE only and the two logit
+  // gradients of a row sum to zero, so the output layer runs on W3[0] - W3[1] with ONE gradient per row (OUTL = 1).
+  constexpr bool DIFF = TABLE && IS_PI;
+  constexpr int OUTL = DIFF ? 1 : OUT;
+  constexpr int NQ = 2 + NW1 + OUTL;
   extern __shared__ unsigned char smraw[];
   __shared__ __align__(8) uint64_t bars[3];
   __shared__ uint32_t tmem_s;
   __shared__ float red[64];
   __shared__ float2 adam_tab[kAdamTab64];   // (lr / (1 - beta1^t), sqrt(1 - beta2^t)) of every Adam step of this launch
-  unsigned char* base = smraw + ((1024u - (smem_u32(smraw) & 1023u)) & 1023u);
-  const uint32_t sbase = smem_u32(base);
+  // 1024-aligned window address, pinned in one register (left alone the compiler re-derives it from SR_CgaCtaId per phase)
+  uint32_t sbase = (smem_u32(smraw) + 1023u) & ~1023u;
+  asm volatile("" : "+r"(sbase));
+  unsigned char* const base = reinterpret_cast<unsigned char*>(__cvta_shared_to_generic(sbase));
   const int E = g.d.n_envs, T = g.T;
   const MlpLayout L(IN, H, OUT);
   const int P = L.P, Ps = L.padded() - HH;   // w / G hold the packed layout WITHOUT the W2 block
@@ -77,8 +85,9 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
   float* wl = wb + S * H;             // [H]     W1[:, lambda] * kTanhScale
   float* b2s = wl + H;                // [H]     b2 * kTanhScale
   float* wa = b2s + H;                // [H]     W1[:, 0] * kTanhScale (sample rows)
-  float* plog = wa + H;              // [4 cq][128 rows][OUT] partial logits
-  float* redw = plog + 4 * TM * OUT;  // [NW][NQ][16]
+  float* w3d = wa + H;                // [H] table policy: W3[0] - W3[1]
+  float* plog = w3d + H;              // [4 cq][128 rows][OUTL] partial logits
+  float* redw = plog + 4 * TM * OUTL;  // [NW][NQ][16]
   float* slam_s = redw + NW * NQ * FW;  // [E] when it fits
   const float* slam = g.stage_lamb ? slam_s : g.lamb;
   float* W2H = reinterpret_cast<float*>(base + T_W2H);
@@ -87,7 +96,11 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
   float* WTL = reinterpret_cast<float*>(base + T_WTL);
   float* scratch = reinterpret_cast<float*>(base + T_A1H);   // dW2 [64][64] between the last GEMM of an iteration and Adam
 
-  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int tid = threadIdx.x;
+#ifndef U64_NO_PIN_TID
+  asm volatile("" : "+r"(tid));   // pinned (no SR_TID.X re-reads inside the tile loop)
+#endif
+  const int n = blockIdx.x, lane = tid & 31, warp = tid >> 5;
   const int q = warp & 3, cq = warp >> 2, r = 32 * q + lane, f0 = FW * cq;
   float* Wn = g.W + (int64_t)n * P;
   float* An = g.adam + (int64_t)n * 2 * P;
@@ -124,6 +137,7 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
   const uint32_t off_c0 = rowb + (uint32_t)(((2 * (cq & 1)) ^ (r & 3)) * 32), off_c1 = rowb + (uint32_t)(((2 * (cq & 1) + 1) ^ (r & 3)) * 32);
 
   const float* st = TABLE ? g.stats + ((int64_t)n * KST + ROW0) * E : nullptr;
+  asm volatile("" : "+l"(st));   // opaque base: 32-bit offsets per load instead of a 64-bit re-derivation each
   const int M = TABLE ? S * E : T * E;
   // floor(2^32 / E): m / E with one correction step.  E = 1 (the reference's own shape) would overflow the 32-bit magic to
   // 0 and leave env indices >= 1 -- lambda was then read past its single entry; 2^32 - 1 gives m - 1 there, corrected to m.
@@ -133,14 +147,12 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
   const int s_max = g.d.n_states - 1;
   const float state_norm = g.d.state_norm;
   const int n_tiles = (M + TM - 1) / TM;
-  const float invM = 1.f / (float)((int64_t)T * E);
+  const float invM = g.invM;
   const int iters = IS_PI ? g.hp.pi_iters : g.hp.v_iters;
   const double lr = IS_PI ? g.hp.pi_lr : g.hp.vf_lr;
   const int step0 = IS_PI ? g.hp.adam_step0_pi : g.hp.adam_step0_v;
-  const float clip_lo = (float)(1.0 - g.hp.clip_ratio), clip_hi = (float)(1.0 + g.hp.clip_ratio);
-  const float beta_ent = (float)g.hp.entropy_coeff;
-  const float lerp_w = (float)(1.0 - g.hp.beta1), beta2f = (float)g.hp.beta2, omb2 = (float)(1.0 - g.hp.beta2);
-  const float epsf = (float)g.hp.adam_eps;
+  const float clip_lo = g.clip_lo, clip_hi = g.clip_hi, beta_ent = g.beta_ent;
+  const float lerp_w = g.lerp_w, beta2f = g.beta2f, omb2 = g.omb2, epsf = g.epsf;
   double b1p = pow(g.hp.beta1, (double)step0), b2p = pow(g.hp.beta2, (double)step0);
   for (int k = tid; k < min(iters, kAdamTab64); k += NTHR)   // the double-precision bias corrections once, in parallel
     adam_tab[k] = make_float2((float)(lr / (1.0 - pow(g.hp.beta1, (double)(step0 + k + 1)))),
@@ -156,20 +168,21 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
       wl[i] = kTanhScale * w[L.oW1 + i * IN + IN - 1];
       b2s[i] = kTanhScale * w[L.ob2 - HH + i];
       wa[i] = kTanhScale * w[L.oW1 + i * IN];
+      if (DIFF) w3d[i] = w[L.oW3 - HH + i] - w[L.oW3 - HH + H + i];
     }
     __syncthreads();
 
-    float s_b2[FW], s_w3[OUT][FW], s_w1r[NW1], s_b3[OUT], s_wlr = 0.f;
+    float s_b2[FW], s_w3[OUTL][FW], s_w1r[NW1], s_b3[OUTL], s_wlr = 0.f;
 #pragma unroll
     for (int k = 0; k < FW; ++k) {
       s_b2[k] = 0.f;
 #pragma unroll
-      for (int a = 0; a < OUT; ++a) s_w3[a][k] = 0.f;
+      for (int a = 0; a < OUTL; ++a) s_w3[a][k] = 0.f;
     }
 #pragma unroll
     for (int c = 0; c < NW1; ++c) s_w1r[c] = 0.f;
 #pragma unroll
-    for (int a = 0; a < OUT; ++a) s_b3[a] = 0.f;
+    for (int a = 0; a < OUTL; ++a) s_b3[a] = 0.f;
     float loss_acc = 0.f;
     struct Row { int srow; int mm; float x0, lam, keep; };   // table: state of the row | sample: index and scalar input
 
@@ -340,16 +353,18 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
       int act = 0;
       if (TABLE) {
         const int srow = (mm >= E) + (mm >= 2 * E), erow = mm - srow * E;
-        const float* sp = st + erow;
-        wrow = sp[(3 * SA - ROW0 + srow) * E];   // CntS
+        const uint32_t o_s = (uint32_t)erow + (uint32_t)srow * (uint32_t)E;   // row `srow` of a per-state block
+        wrow = __ldg(st + (o_s + (uint32_t)((3 * SA - ROW0) * E)));   // CntS
         if (IS_PI) {
+          const uint32_t o_sa = o_s + (uint32_t)srow * (uint32_t)((A - 1) * E);   // row `srow * A` of a per-(state, action) block
 #pragma unroll
           for (int a = 0; a < 2; ++a) {
-            const int c = srow * A + a;
-            stA[a] = sp[c * E]; stA[2 + a] = sp[(SA + c) * E]; stA[4 + a] = sp[(2 * SA + c) * E];
+            stA[a] = __ldg(st + (o_sa + (uint32_t)(a * E)));
+            stA[2 + a] = __ldg(st + (o_sa + (uint32_t)((SA + a) * E)));
+            stA[4 + a] = __ldg(st + (o_sa + (uint32_t)((2 * SA + a) * E)));
           }
         } else {
-          stA[0] = sp[(3 * SA + S - ROW0 + srow) * E];
+          stA[0] = __ldg(st + (o_s + (uint32_t)((3 * SA + S - ROW0) * E)));
         }
       } else if (IS_PI) {
         act = g.a_buf[smp_base + mm];
@@ -381,8 +396,8 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
         }
       }
 #pragma unroll
-      for (int a = 0; a < OUT; ++a) {
-        const float4* w34 = reinterpret_cast<const float4*>(w + L.oW3 - HH + a * H + f0);
+      for (int a = 0; a < OUTL; ++a) {
+        const float4* w34 = reinterpret_cast<const float4*>(DIFF ? w3d + f0 : w + L.oW3 - HH + a * H + f0);
         float pl = 0.f;
 #pragma unroll
         for (int k4 = 0; k4 < FW / 4; ++k4) {
@@ -390,18 +405,40 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
           pl = fmaf(w3.x, a2[4 * k4], pl); pl = fmaf(w3.y, a2[4 * k4 + 1], pl);
           pl = fmaf(w3.z, a2[4 * k4 + 2], pl); pl = fmaf(w3.w, a2[4 * k4 + 3], pl);
         }
-        plog[(cq * TM + r) * OUT + a] = pl;
+        plog[(cq * TM + r) * OUTL + a] = pl;
       }
       asm volatile("bar.sync %0, 128;\n" ::"r"(1 + q) : "memory");   // the four warps that share these 32 rows
-      float gl[OUT];
+      float gl[OUTL];
       {
-        float logit[OUT];
+        float logit[OUTL];
 #pragma unroll
-        for (int a = 0; a < OUT; ++a) {
-          logit[a] = ((plog[(0 * TM + r) * OUT + a] + plog[(1 * TM + r) * OUT + a]) + plog[(2 * TM + r) * OUT + a]) +
-                     plog[(3 * TM + r) * OUT + a] + w[L.ob3 - HH + a];
+        for (int a = 0; a < OUTL; ++a) {
+          logit[a] = ((plog[(0 * TM + r) * OUTL + a] + plog[(1 * TM + r) * OUTL + a]) + plog[(2 * TM + r) * OUTL + a]) +
+                     plog[(3 * TM + r) * OUTL + a] + (DIFF ? w[L.ob3 - HH] - w[L.ob3 - HH + 1] : w[L.ob3 - HH + a]);
           gl[a] = 0.f;
         }
+        if (DIFF) {   // logit[0] = logit of action 0 - logit of action 1
+          const float pl = logit[0];
+          const float e = __expf(-fabsf(pl));   // exp(smaller logit - larger logit); the larger one contributes exp(0) = 1
+          const float sum = 1.f + e, lse = __logf(sum), inv = __fdividef(1.f, sum);
+          const bool z = pl >= 0.f;
+          const float p[2] = {z ? inv : e * inv, z ? e * inv : inv};
+          const float lp[2] = {(z ? 0.f : pl) - lse, (z ? -pl : 0.f) - lse};
+          const float ent = -(p[0] * lp[0] + p[1] * lp[1]);
+          float ga[2], sumg = 0.f, lrow = 0.f;
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            const float Ap = stA[a], Am = stA[IS_PI ? 2 + a : 0];
+            const float ratio = __expf(lp[a] - stA[IS_PI ? 4 + a : 0]);
+            lrow -= fminf(ratio, clip_hi) * Ap + fmaxf(ratio, clip_lo) * Am;
+            ga[a] = -((ratio <= clip_hi ? ratio * Ap : 0.f) + (ratio >= clip_lo ? ratio * Am : 0.f));
+            sumg += ga[a];
+          }
+          if (valid) {
+            if (cq == 0) loss_acc += lrow - beta_ent * wrow * ent;
+            gl[0] = invM * (ga[0] - p[0] * sumg + beta_ent * wrow * p[0] * (lp[0] + ent));
+          }
+        } else
         if (IS_PI) {
           float mx = logit[0];
 #pragma unroll
@@ -458,7 +495,7 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
         }
         if (cq == 0)
 #pragma unroll
-          for (int a = 0; a < OUT; ++a) s_b3[a] += gl[a];
+          for (int a = 0; a < OUTL; ++a) s_b3[a] += gl[a];
       }
       // d2 (FMA pipe) interleaved with the NEXT tile's layer 1 (MUFU pipe); z2's a1 operand in TMEM is free once G1 is done
       {
@@ -486,8 +523,8 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
           }
           float up[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int a = 0; a < OUT; ++a) {
-            const float4 w3 = *reinterpret_cast<const float4*>(w + L.oW3 - HH + a * H + f0 + 4 * k4);
+          for (int a = 0; a < OUTL; ++a) {
+            const float4 w3 = *reinterpret_cast<const float4*>((DIFF ? w3d : w + L.oW3 - HH + a * H) + f0 + 4 * k4);
             up[0] = fmaf(gl[a], w3.x, up[0]); up[1] = fmaf(gl[a], w3.y, up[1]);
             up[2] = fmaf(gl[a], w3.z, up[2]); up[3] = fmaf(gl[a], w3.w, up[3]);
           }
@@ -498,7 +535,7 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
             const float x = a2[k], d2 = up[j] * fmaf(-x, x, 1.f);
             s_b2[k] += d2;
 #pragma unroll
-            for (int a = 0; a < OUT; ++a) s_w3[a][k] = fmaf(gl[a], x, s_w3[a][k]);
+            for (int a = 0; a < OUTL; ++a) s_w3[a][k] = fmaf(gl[a], x, s_w3[a][k]);
             split_u(d2, h[j], l[j]);
           }
           tmem_st4(tl + C_D2H + f0 + 4 * k4, h[0], h[1], h[2], h[3]);
@@ -542,18 +579,18 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
 #pragma unroll
       for (int c = 0; c < NW1; ++c) vals[2 + c] = s_w1r[c];
 #pragma unroll
-      for (int a = 0; a < OUT; ++a) vals[2 + NW1 + a] = colsum16(s_w3[a], lane);
+      for (int a = 0; a < OUTL; ++a) vals[2 + NW1 + a] = colsum16(s_w3[a], lane);
       if ((lane & 1) == 0)
 #pragma unroll
         for (int v = 0; v < NQ; ++v) redw[(warp * NQ + v) * FW + (lane >> 1)] = vals[v];
     }
-    float b3tot[OUT];
+    float b3tot[OUTL];
 #pragma unroll
-    for (int a = 0; a < OUT; ++a) b3tot[a] = warp_sum(s_b3[a]);
+    for (int a = 0; a < OUTL; ++a) b3tot[a] = warp_sum(s_b3[a]);
     const float loss_tot = g.loss_out ? block_sum(loss_acc, red) : 0.f;
     if (lane == 0 && cq == 0)
 #pragma unroll
-      for (int a = 0; a < OUT; ++a) red[40 + q * OUT + a] = b3tot[a];
+      for (int a = 0; a < OUTL; ++a) red[40 + q * OUTL + a] = b3tot[a];
     mbar_wait(bar3, (gt - 1) & 1);   // every G3 of this pass has landed in TMEM
     tc_fence_after();
     __syncthreads();                 // all E3 reads of the a1 tile are done: its space becomes the dW2 scratch
@@ -581,12 +618,16 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
       else if (v < 2 + NW1) {
         if (TABLE || v == 2) G[L.oW1 + k * IN + (v - 2)] = x;   // table: dW1[:, state]; sample: dW1[:, 0]
         else G[L.ob1 + k] = x;                                   // sample: db1
-      } else G[L.oW3 - HH + (v - 2 - NW1) * H + k] = x;
+      } else {
+        G[L.oW3 - HH + (v - 2 - NW1) * H + k] = x;
+        if (DIFF) G[L.oW3 - HH + H + k] = -x;   // dW3[1] = -dW3[0]
+      }
     }
-    if (tid < OUT) {
+    if (tid < OUTL) {
       float x = 0.f;
-      for (int qq = 0; qq < 4; ++qq) x += red[40 + qq * OUT + tid];
+      for (int qq = 0; qq < 4; ++qq) x += red[40 + qq * OUTL + tid];
       G[L.ob3 - HH + tid] = x;
+      if (DIFF) G[L.ob3 - HH + 1] = -x;
     }
     if (g.loss_out && tid == 0) {
       float extra = 0.f;
@@ -668,7 +709,7 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(UmmaArgs g) {
 static size_t umma64_smem_bytes(int S, int OUT, bool table, int E) {
   const MlpLayout L(S + 1, H, OUT);
   const int NQ = 2 + (table ? S : 2) + OUT;
-  const size_t fl = 2 * (size_t)(L.padded() - HH) + S * H + 3 * H + 4 * TM * OUT + NW * NQ * FW + (((size_t)E + 3) & ~(size_t)3);
+  const size_t fl = 2 * (size_t)(L.padded() - HH) + S * H + 4 * H + 4 * TM * OUT + NW * NQ * FW + (((size_t)E + 3) & ~(size_t)3);
   return 1024 + T_END + fl * sizeof(float);
 }
 
@@ -678,6 +719,11 @@ template <int S, int A, bool IS_PI, int MODE>
 static int launch_umma64(const UmmaArgs& g0, cudaStream_t st, const char* what) {
   constexpr int OUT = IS_PI ? A : 1;
   UmmaArgs g = g0;
+  g.clip_lo = (float)(1.0 - g.hp.clip_ratio); g.clip_hi = (float)(1.0 + g.hp.clip_ratio);
+  g.beta_ent = (float)g.hp.entropy_coeff;
+  g.lerp_w = (float)(1.0 - g.hp.beta1); g.beta2f = (float)g.hp.beta2; g.omb2 = (float)(1.0 - g.hp.beta2);
+  g.epsf = (float)g.hp.adam_eps;
+  g.invM = 1.f / (float)((int64_t)g.T * g.d.n_envs);
   size_t smem = umma64_smem_bytes(S, OUT, MODE == kRowsTable, g.d.n_envs);
   g.stage_lamb = smem <= kUmmaSmemLimit;
   if (!g.stage_lamb) smem = umma64_smem_bytes(S, OUT, MODE == kRowsTable, 0);   // large E: lambda stays in global memory
