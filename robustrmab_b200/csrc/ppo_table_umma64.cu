@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(const __grid_
   float* plog = w3d + H;              // [4 cq][128 rows][OUTL] partial logits
   float* redw = plog + 4 * TM * OUTL;  // [NW][NQ][16]
   float* slam_s = redw + NW * NQ * FW;  // [E] when it fits
-  const float* slam = g.stage_lamb ? slam_s : g.lamb;
+  const float* slam = g.stage_lamb ? slam_s : g.lamb;   // one generic pointer (typed LDS / LDG selects measured slower: 44.2 vs 43.9 ms)
   float* W2H = reinterpret_cast<float*>(base + T_W2H);
   float* W2L = reinterpret_cast<float*>(base + T_W2L);
   float* WTH = reinterpret_cast<float*>(base + T_WTH);
