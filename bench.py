@@ -316,6 +316,7 @@ def run_ours(a):
     if not a.no_ma:        # first: its rollout is launch-latency sensitive and measured slower right after the seconds-long ARMMAN epochs
         blocks["ma_sis"] = bb.guarded(bb.ma_sis_block, dev, peaks, rank, world)
     if not a.no_armman and a.hidden != 64:
+        blocks["ce_h64"] = bb.guarded(bb.ce_h64_block, dev, peaks, rank, world)
         blocks["armman_full"] = bb.guarded(bb.armman_block, dev, peaks, rank, world)
     if rank != 0:
         if world > 1:

@@ -181,6 +181,47 @@ def armman_block(dev, peaks, rank=0, world=1, n_total=100_000, E=1024, T=10, h=6
                          "peak_source": "measured bf16 sustained / 2 (tf32)" if "bf16_tflops_sustained" in peaks else "fallback"}}
 
 
+def ce_h64_block(dev, peaks, rank=0, world=1, n_per_gpu=4098, E=256, T=100, h=64, iters=20, steps=5, warm=2):
+    """SURVEY 8(d) config 2, second width: the headline problem (CE, 4098 arms per GPU x 256 envs, T = 100, 20+20 Adam steps)
+    with hidden [64,64] -- the hidden-64 tcgen05 kernels (table pre-pass of the rollout kernel, update) on S*E = 512 rows per
+    arm.  Weak-scaled like the headline under torchrun."""
+    from robustrmab_b200.trainer import RMABPPOTrainer
+    n_total = n_per_gpu * world
+    tr = RMABPPOTrainer("counterexample", n_total, E, T, hidden=h, train_pi_iters=iters, train_v_iters=iters, epochs=20, seed=0,
+                        device=dev, rank=rank, world_size=world)
+    tr.prewarm()
+    for _ in range(warm):
+        tr.epoch()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    tr.timers = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        tr.epoch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = _max_over_ranks(e0.elapsed_time(e1) / steps, dev, world)
+    stage_ms = tr.stage_times()
+    upd = stage_ms.get("ppo_update", 0.0)
+    rows = ((2 * E + 127) // 128) * 128
+    flops = float(tr.N) * 2 * iters * rows * 3 * 3 * 2 * h * h     # 3 GEMMs x 3 tf32 products per row and Adam step
+    tf32_peak = peaks.get("bf16_tflops_sustained", 2250.0 * 0.6) / 2
+    ach = flops / (upd * 1e-3) / 1e12 if upd else 0.0
+    del tr
+    torch.cuda.empty_cache()
+    return {"metric": METRIC, "unit": UNIT, "value": float(n_total) * E * T / (ms * 1e-3), "ms_per_step": ms, "steps": steps,
+            "n_gpus": world, "scaling": "weak" if world > 1 else "single GPU", "stage_ms_per_step": stage_ms,
+            "dtype": "f32 (3xTF32 tcgen05 GEMMs, fp32 accumulation in TMEM)",
+            "config": {"workload": f"RMABPPO counterexample domain, N={n_per_gpu} arms/GPU x {E} envs, T={T}, hidden [{h},{h}], "
+                                   f"{iters}+{iters} iters, binary action"},
+            "roofline": {"bound": "tensor", "kernel": "ppo_table_umma64_kernel (pi + v), rank 0", "achieved": ach,
+                         "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak if tf32_peak else None, "traffic": None,
+                         "executed_tf32_flops_per_launch": flops, "ms_per_launch": upd, "fp32_equivalent_TFLOPs": ach / 3,
+                         "peak_source": "measured bf16 sustained / 2 (tf32)" if "bf16_tflops_sustained" in peaks else "fallback"}}
+
+
 # ------------------------------------------------------------------------------------------ configs[3]
 def ma_sis_block(dev, peaks, rank=0, world=1, N=2048, E=256, T=20, pop=50, h=64, pi_iters=4, v_iters=4, steps=3, warm=2):
     """BASELINE configs[3]: SIS epidemic domain (S = 51, A = 3, C = [0,1,2]) with the MA-RMABPPO nature oracle against
