@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(const __
   // SR_CgaCtaId in every phase of the tile loop (S2R + MOV + LEA, eight times per tile) to save that register.
   uint32_t sbase = u::smem_u32(smraw16);
   asm volatile("" : "+r"(sbase));
+  if (sbase & 1023u) __trap();   // the swizzled tiles and the UMMA descriptors rely on the declared alignment
   unsigned char* const base = reinterpret_cast<unsigned char*>(__cvta_shared_to_generic(sbase));
   float* const red = reinterpret_cast<float*>(base + S_RED);                // [64]
   float2* const adam_tab = reinterpret_cast<float2*>(base + S_ADAM);        // (lr / (1 - beta1^t), sqrt(1 - beta2^t)) per step
