@@ -318,13 +318,21 @@ __global__ void __launch_bounds__(256) lambda_sgd_small_kernel(int E, float* __r
       acc[k] += d;  // b1
     }
   }
-  // deterministic reduction: threads add into smem one after another in warp-sized rounds
-  for (int t = 0; t < (int)blockDim.x; ++t) {
-    if ((int)threadIdx.x == t && t < E)
+  // deterministic reduction: a fixed butterfly inside every warp, then the warps in order (threads without an env hold
+  // zeros).  Round 1 added the threads into smem one after another: blockDim.x block barriers, 125 us.
+  __shared__ float gw[8][NS];
 #pragma unroll
-      for (int i = 0; i < NS; ++i) g[i] += acc[i];
-    __syncthreads();
+  for (int i = 0; i < NS; ++i) {
+    const float x = warp_sum(acc[i]);
+    if ((threadIdx.x & 31) == 0) gw[threadIdx.x >> 5][i] = x;
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NS; i += blockDim.x) {
+    float x = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) x += gw[w][i];
+    g[i] = x;
+  }
+  __syncthreads();
   for (int i = threadIdx.x; i < NS; i += blockDim.x) {
     small[i] = wl[i] - lr * g[i];
     if (grad_out) grad_out[(int64_t)kLamH * n_total + i] = g[i];
