@@ -59,7 +59,11 @@ struct U16Args {
 
 }  // namespace
 
-template <int S, bool IS_PI>
+// RAGGED = the env count is not a multiple of the tile height: tiles may straddle two states and the last one may hold rows
+// past the end (their a1 is forced to 0 and they are excluded from the sums).  The other instantiation (E % 128 == 0, the
+// BASELINE shapes) knows every tile lies in ONE state -- the state index is uniform arithmetic on the tile number -- and drops
+// the row predication (16 predicated FMULs in E1 alone) and the straddling branch of E3.
+template <int S, bool IS_PI, bool RAGGED>
 __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(const __grid_constant__ U16Args g) {
   constexpr int H = H16, HH = HH16, A = 2, OUT = IS_PI ? A : 1, IN = S + 1, SA = S * A, FW = 16;
   constexpr int ROW0 = IS_PI ? 0 : 3 * SA, KST = 4 * SA + 3 * S;
@@ -193,9 +197,10 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(const __
 
     for (int t = 0; t < n_tiles; ++t, ++gt) {
       const int m = t * TM16 + r;
-      const bool valid = m < M;
+      const bool valid = RAGGED ? m < M : true;
       const int mm = valid ? m : M - 1;
-      const int srow = (mm >= E) + (mm >= 2 * E), erow = mm - srow * E;   // S <= 3: no integer division
+      const int mrow = RAGGED ? mm : t * TM16;                             // aligned: the tile's first row decides the state
+      const int srow = (mrow >= E) + (mrow >= 2 * E), erow = mm - srow * E;   // S <= 3: no integer division
       const float lam = g.stage_lamb ? slam_s[erow] : g.lamb[erow];
       // statistics of this row (L2 resident), in flight during E1 and G1; one uniform base + 32-bit element offsets
       const uint32_t o_s = (uint32_t)erow + (uint32_t)srow * (uint32_t)E;   // row `srow` of a per-state block
@@ -224,7 +229,7 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(const __
           const float4 l = *reinterpret_cast<const float4*>(wl + 4 * k4);
           float x[4] = {u::tanh_scaled_u(fmaf(l.x, lam, b.x)), u::tanh_scaled_u(fmaf(l.y, lam, b.y)),
                         u::tanh_scaled_u(fmaf(l.z, lam, b.z)), u::tanh_scaled_u(fmaf(l.w, lam, b.w))};
-          if (last) { x[0] *= keep; x[1] *= keep; x[2] *= keep; x[3] *= keep; }
+          if (RAGGED && last) { x[0] *= keep; x[1] *= keep; x[2] *= keep; x[3] *= keep; }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             u::split_u(x[j], hi[4 * k4 + j], lo[4 * k4 + j]);
@@ -378,10 +383,10 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(const __
 #pragma unroll
         for (int k = 0; k < FW; ++k) d1l[k] = d1[k] * lam;
         s_wlr += u::colsum16(d1l, lane);
-        if (s_lo == s_hi) {   // warp-uniform: all 32 rows are in one state
+        if (!RAGGED || s_lo == s_hi) {   // warp-uniform: all 32 rows are in one state
           const float x = u::colsum16(d1, lane);
 #pragma unroll
-          for (int c = 0; c < S; ++c) s_w1r[c] += (c == s_lo) ? x : 0.f;
+          for (int c = 0; c < S; ++c) s_w1r[c] += (c == (RAGGED ? s_lo : srow)) ? x : 0.f;
         } else {              // the warp's rows straddle a state boundary: masked sums for this tile
 #pragma unroll
           for (int c = 0; c < S; ++c) {
@@ -526,18 +531,23 @@ static size_t umma16_smem_bytes(int S, int OUT, int E) {
   return S_FLOATS + fl * sizeof(float);
 }
 
-template <int S, bool IS_PI>
-static int launch_umma16(const U16Args& g0, cudaStream_t st) {
+template <int S, bool IS_PI, bool RAGGED>
+static int launch_umma16_r(const U16Args& g0, cudaStream_t st) {
   constexpr int OUT = IS_PI ? 2 : 1;
   U16Args g = g0;
   size_t smem = umma16_smem_bytes(S, OUT, g.d.n_envs);
   g.stage_lamb = smem <= (size_t)(226 / CTAS16) * 1024;   // CTAS16 CTAs per SM
   if (!g.stage_lamb) smem = umma16_smem_bytes(S, OUT, 0);
-  auto kern = ppo_table_umma16_kernel<S, IS_PI>;
+  auto kern = ppo_table_umma16_kernel<S, IS_PI, RAGGED>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return fail(RMAB_E_LAUNCH, "rmab_ppo_update_table: cannot reserve %zu B of shared memory", smem);
   kern<<<g.d.n_arms, NT16, smem, st>>>(g);
   return check_launch(IS_PI ? "rmab_ppo_update_table(pi, tcgen05 h16)" : "rmab_ppo_update_table(v, tcgen05 h16)");
+}
+
+template <int S, bool IS_PI>
+static int launch_umma16(const U16Args& g, cudaStream_t st) {
+  return g.d.n_envs % TM16 ? launch_umma16_r<S, IS_PI, true>(g, st) : launch_umma16_r<S, IS_PI, false>(g, st);
 }
 
 // Entry used by rmab_ppo_update_table (ppo_table.cu) for H = 16.
