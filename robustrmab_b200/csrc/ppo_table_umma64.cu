@@ -54,7 +54,10 @@ constexpr int kAdamTab64 = 128;
 
 }  // namespace
 
-template <int S, int A, bool IS_PI, int MODE>
+// RAGGED = tiles may hold rows past the end (their a1 is forced to 0, they are excluded from the sums) and, for table rows,
+// straddle two states.  The other instantiation (table rows: E % 128 == 0; sample rows: T * E % 128 == 0 -- every BASELINE
+// shape) drops the row predication and takes the state of a tile from its first row.
+template <int S, int A, bool IS_PI, int MODE, bool RAGGED>
 __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(const __grid_constant__ UmmaArgs g) {
   constexpr bool TABLE = MODE == kRowsTable, EXTRA = MODE == kRowsSampleExtra;
   static_assert(TABLE ? (A == 2 && (S == 2 || S == 3)) : (S == 1 && A >= 2 && A <= 3), "row mode / shape");
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(const __grid_
         z0 = fmaf(kTanhScale, x.x, z0); z1 = fmaf(kTanhScale, x.y, z1); z2 = fmaf(kTanhScale, x.z, z2); z3 = fmaf(kTanhScale, x.w, z3);
       }
       float x0 = tanh_scaled_u(z0), x1 = tanh_scaled_u(z1), x2 = tanh_scaled_u(z2), x3 = tanh_scaled_u(z3);
-      if (last1) { x0 *= rw.keep; x1 *= rw.keep; x2 *= rw.keep; x3 *= rw.keep; }   // rows past the end: a1 = 0 (so d2 = d1 = 0)
+      if (RAGGED && last1) { x0 *= rw.keep; x1 *= rw.keep; x2 *= rw.keep; x3 *= rw.keep; }   // rows past the end: a1 = 0 (so d2 = d1 = 0)
       uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
       split_u(x0, h0, l0); split_u(x1, h1, l1); split_u(x2, h2, l2); split_u(x3, h3, l3);
       tmem_st4(tl + C_A1H + f0 + 4 * k4, h0, h1, h2, h3);
@@ -209,11 +212,12 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(const __grid_
     // row of this thread in tile tt
     auto row_of = [&](int tt, Row& rw) {
       const int m = tt * TM + r;
-      const int mm = m < M ? m : M - 1;
+      const int mm = !RAGGED || m < M ? m : M - 1;
       rw.mm = mm;
-      rw.keep = m < M ? 1.f : 0.f;
+      rw.keep = !RAGGED || m < M ? 1.f : 0.f;
       if (TABLE) {
-        rw.srow = (mm >= E) + (mm >= 2 * E);   // S <= 3: no integer division
+        const int mrow = RAGGED ? mm : tt * TM;   // aligned: the tile's first row decides the state
+        rw.srow = (mrow >= E) + (mrow >= 2 * E);   // S <= 3: no integer division
         rw.lam = slam[mm - rw.srow * E];
         rw.x0 = 0.f;
       } else {
@@ -297,10 +301,10 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(const __grid_
         // db1 / dW1[:, s]: the tile's column sums go straight to one register per state (lane l holds feature f0 + l / 2)
         const int m_lo = min(tt * TM + 32 * q, M - 1), m_hi = min(tt * TM + 32 * q + 31, M - 1);
         const int s_lo = (m_lo >= E) + (m_lo >= 2 * E), s_hi = (m_hi >= E) + (m_hi >= 2 * E);
-        if (s_lo == s_hi) {   // warp-uniform: all 32 rows are in one state
+        if (!RAGGED || s_lo == s_hi) {   // warp-uniform: all 32 rows are in one state
           const float x = colsum16(d1, lane);
 #pragma unroll
-          for (int c = 0; c < NW1; ++c) s_w1r[c] += (c == s_lo) ? x : 0.f;
+          for (int c = 0; c < NW1; ++c) s_w1r[c] += (c == (RAGGED ? s_lo : rw.srow)) ? x : 0.f;
         } else {              // the warp's rows straddle a state boundary: masked sums for this tile
 #pragma unroll
           for (int c = 0; c < NW1; ++c) {
@@ -344,7 +348,7 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(const __grid_
 
     for (int t = 0; t < n_tiles; ++t, ++gt) {
       const int m = t * TM + r;
-      const bool valid = m < M;
+      const bool valid = RAGGED ? m < M : true;
       const int mm = valid ? m : M - 1;
       // loss inputs of this row (L2 resident), in flight while G1 runs.  Table rows: statistics Ap Am Lp per action, CntS
       // (policy) / RetMean, CntS (value).  Sample rows: action, advantage, old log-prob (policy) / return (value).
@@ -352,7 +356,8 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(const __grid_
       float stA[IS_PI ? 6 : 1];
       int act = 0;
       if (TABLE) {
-        const int srow = (mm >= E) + (mm >= 2 * E), erow = mm - srow * E;
+        const int mrow = RAGGED ? mm : t * TM;
+        const int srow = (mrow >= E) + (mrow >= 2 * E), erow = mm - srow * E;
         const uint32_t o_s = (uint32_t)erow + (uint32_t)srow * (uint32_t)E;   // row `srow` of a per-state block
         wrow = __ldg(st + (o_s + (uint32_t)((3 * SA - ROW0) * E)));   // CntS
         if (IS_PI) {
@@ -715,8 +720,8 @@ static size_t umma64_smem_bytes(int S, int OUT, bool table, int E) {
 
 constexpr size_t kUmmaSmemLimit = 227 * 1024 - 512;   // 512 B of static __shared__
 
-template <int S, int A, bool IS_PI, int MODE>
-static int launch_umma64(const UmmaArgs& g0, cudaStream_t st, const char* what) {
+template <int S, int A, bool IS_PI, int MODE, bool RAGGED>
+static int launch_umma64_r(const UmmaArgs& g0, cudaStream_t st, const char* what) {
   constexpr int OUT = IS_PI ? A : 1;
   UmmaArgs g = g0;
   g.clip_lo = (float)(1.0 - g.hp.clip_ratio); g.clip_hi = (float)(1.0 + g.hp.clip_ratio);
@@ -727,11 +732,17 @@ static int launch_umma64(const UmmaArgs& g0, cudaStream_t st, const char* what) 
   size_t smem = umma64_smem_bytes(S, OUT, MODE == kRowsTable, g.d.n_envs);
   g.stage_lamb = smem <= kUmmaSmemLimit;
   if (!g.stage_lamb) smem = umma64_smem_bytes(S, OUT, MODE == kRowsTable, 0);   // large E: lambda stays in global memory
-  auto kern = ppo_table_umma64_kernel<S, A, IS_PI, MODE>;
+  auto kern = ppo_table_umma64_kernel<S, A, IS_PI, MODE, RAGGED>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return fail(RMAB_E_LAUNCH, "%s: cannot reserve %zu B of shared memory", what, smem);
   kern<<<g.d.n_arms, NTHR, smem, st>>>(g);
   return check_launch(what);
+}
+
+template <int S, int A, bool IS_PI, int MODE>
+static int launch_umma64(const UmmaArgs& g, cudaStream_t st, const char* what) {
+  const int64_t rows = MODE == kRowsTable ? (int64_t)g.d.n_envs : (int64_t)g.T * g.d.n_envs;   // table rows: per state
+  return rows % TM ? launch_umma64_r<S, A, IS_PI, MODE, true>(g, st, what) : launch_umma64_r<S, A, IS_PI, MODE, false>(g, st, what);
 }
 
 // Does the tcgen05 kernel's shared-memory plan fit this shape?  (Always: lambda is staged only when there is room.)
