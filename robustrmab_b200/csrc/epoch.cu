@@ -73,8 +73,12 @@ struct EpochArgs {
 // that a warp's accesses are consecutive -- instead of the [N,T+1,E] / [N,T,E] byte arrays in HBM that only this kernel
 // re-reads (two backward passes).  The byte arrays are still written when the caller passes `a` (MA-RMABPPO, tests,
 // keep_buffers); with a == NULL nothing but the statistics leaves the SM.
-template <int H, int DOMAIN, bool ONCHIP>
+// TRAJ: 0 = trajectory through HBM (s_traj [N,T+1,E], a [N,T,E]); 1 = on chip as bit planes, per-sample outputs (a, adv, ret)
+// written when the caller passes them; 2 = on chip and no per-sample output requested (the trainers' epoch): the per-step
+// pointer tests are compiled out.
+template <int H, int DOMAIN, int TRAJ>
 __global__ void __launch_bounds__(256, (H <= 16 ? 4 : 2)) epoch_table_kernel(EpochArgs g) {
+  constexpr bool ONCHIP = TRAJ != 0, LEAN = TRAJ == 2;
   constexpr int S = DOMAIN == RMAB_DOMAIN_CE ? 2 : 3;
   constexpr int A = 2;
   constexpr int PL = S == 2 ? 2 : 3;   // bit planes per 32 steps: action, state bit 0 (, state bit 1)
@@ -149,7 +153,7 @@ __global__ void __launch_bounds__(256, (H <= 16 ? 4 : 2)) epoch_table_kernel(Epo
         st[(int64_t)(SR::kV + si) * E] = vout[0];
       }
       uint8_t* tr = g.s_traj + traj0 + e;
-      uint8_t* ac = g.a ? g.a + step0 + e : nullptr;
+      uint8_t* ac = !LEAN && g.a ? g.a + step0 + e : nullptr;
       int si = tr[0];
       si = si < S ? si : S - 1;
       const uint32_t ge = g.env0 + (uint32_t)e;
@@ -162,10 +166,10 @@ __global__ void __launch_bounds__(256, (H <= 16 ? 4 : 2)) epoch_table_kernel(Epo
         if (t == 0 || (tt & 1u) == 0u) blk = philox_step_block(g.k0, g.k1, tt, ge, gn);  // one Philox block per two steps
         float pr[2] = {pick_f<S>(p0t, si), pick_f<S>(p1t, si)};
         const int act = categorical<2>(pr, u24(step_word(blk, tt, true)));
-        if (!ONCHIP || ac) ac[(int64_t)t * E] = (uint8_t)act;
+        if (!ONCHIP || (!LEAN && ac)) ac[(int64_t)t * E] = (uint8_t)act;
         const float p = act ? pick_f<S>(pn1, si) : pick_f<S>(pn0, si);
         si = table_next<DOMAIN>(si, act, p, u24(step_word(blk, tt, false)));
-        if (!ONCHIP || ac) tr[(int64_t)(t + 1) * E] = (uint8_t)si;
+        if (!ONCHIP || (!LEAN && ac)) tr[(int64_t)(t + 1) * E] = (uint8_t)si;
         if (ONCHIP) {
           aw |= (uint32_t)act << (t & 31);
           const int b = (t + 1) & 31;
@@ -295,8 +299,8 @@ __global__ void __launch_bounds__(256, (H <= 16 ? 4 : 2)) epoch_table_kernel(Epo
         rsum += r;
         const float x = __fmul_rn(__fsub_rn((float)adv_acc, mean), inv_std);  // (adv - mean) / std in fp32 (:155)
         const float rf = (float)ret_acc;
-        if (g.adv) g.adv[step0 + (int64_t)t * E + e] = x;
-        if (g.ret) g.ret[step0 + (int64_t)t * E + e] = rf;
+        if (!LEAN && g.adv) g.adv[step0 + (int64_t)t * E + e] = x;
+        if (!LEAN && g.ret) g.ret[step0 + (int64_t)t * E + e] = rf;
         const int cell = s_t * A + a_t;
         const float xp = fmaxf(x, 0.f), xm = fminf(x, 0.f);
 #pragma unroll
@@ -452,7 +456,7 @@ static int epoch_table_impl(int domain, const RmabNetDesc* net, int T, const flo
     epoch_table_kernel<H, D, O><<<grid, threads, smem, st>>>(g);                                               \
   }
 #define LAUNCH(H, D) \
-  if (onchip) LAUNCH2(H, D, true) else LAUNCH2(H, D, false)
+  if (onchip && !a && !adv && !ret) LAUNCH2(H, D, 2) else if (onchip) LAUNCH2(H, D, 1) else LAUNCH2(H, D, 0)
 #define LAUNCH_H(D)               \
   switch (h) {                    \
     case 8: LAUNCH(8, D) break;   \
