@@ -161,14 +161,13 @@ __global__ void __launch_bounds__(256, (H <= 16 ? 4 : 2)) epoch_table_kernel(Epo
       // bit t of the state planes = s_t (t = 0..T), bit t of the action plane = a_t (t = 0..T-1)
       uint32_t aw = 0u, sw0 = (uint32_t)(si & 1), sw1 = (uint32_t)(si >> 1);
       uint32_t* bw = bits + e;
-      for (int t = 0; t < T; ++t) {
-        const uint32_t tt = g.t_act0 + (uint32_t)t;
-        if (t == 0 || (tt & 1u) == 0u) blk = philox_step_block(g.k0, g.k1, tt, ge, gn);  // one Philox block per two steps
+      // one step of the chain given its two Philox words (action draw, transition draw)
+      auto chain_step = [&](int t, uint32_t w_act, uint32_t w_env) {
         float pr[2] = {pick_f<S>(p0t, si), pick_f<S>(p1t, si)};
-        const int act = categorical<2>(pr, u24(step_word(blk, tt, true)));
+        const int act = categorical<2>(pr, u24(w_act));
         if (!ONCHIP || (!LEAN && ac)) ac[(int64_t)t * E] = (uint8_t)act;
         const float p = act ? pick_f<S>(pn1, si) : pick_f<S>(pn0, si);
-        si = table_next<DOMAIN>(si, act, p, u24(step_word(blk, tt, false)));
+        si = table_next<DOMAIN>(si, act, p, u24(w_env));
         if (!ONCHIP || (!LEAN && ac)) tr[(int64_t)(t + 1) * E] = (uint8_t)si;
         if (ONCHIP) {
           aw |= (uint32_t)act << (t & 31);
@@ -182,6 +181,23 @@ __global__ void __launch_bounds__(256, (H <= 16 ? 4 : 2)) epoch_table_kernel(Epo
           sw0 |= (uint32_t)(si & 1) << b;
           sw1 |= (uint32_t)(si >> 1) << b;
         }
+      };
+      // One Philox block serves the two steps 2k, 2k + 1 of the GLOBAL step counter (x, y = transition / action draw of the
+      // even step, z, w of the odd one).  Even t_act0 (every epoch when T is even): steps walked in pairs, no parity tests.
+      int t = 0;
+      if (g.t_act0 & 1u) {   // odd start: the first step uses the upper half of its block
+        blk = philox_step_block(g.k0, g.k1, g.t_act0, ge, gn);
+        chain_step(0, blk.w, blk.z);
+        t = 1;
+      }
+      for (; t + 1 < T; t += 2) {
+        blk = philox_step_block(g.k0, g.k1, g.t_act0 + (uint32_t)t, ge, gn);
+        chain_step(t, blk.y, blk.x);
+        chain_step(t + 1, blk.w, blk.z);
+      }
+      if (t < T) {           // a last even step without its partner
+        blk = philox_step_block(g.k0, g.k1, g.t_act0 + (uint32_t)t, ge, gn);
+        chain_step(t, blk.y, blk.x);
       }
       if (ONCHIP) {       // the last (partial) word: s_T sits at bit T & 31
         uint32_t* wp = bw + (int64_t)(T >> 5) * wstride;
