@@ -95,6 +95,14 @@ __device__ __forceinline__ int categorical(const float (&p)[K], float u) {
   return k < last ? k : last;
 }
 
+// Two categories: the general rule above reduces to one conjunction -- with p[1] > 0 the clamp is min(k, 1) and
+// p[0] + p[1] <= u implies p[0] <= u (round-to-nearest addition of a non-negative term is monotone), so k >= 1 exactly when
+// p[0] <= u; with p[1] <= 0 (or NaN) the last admissible category is 0.  Same result for every input, NaNs included.
+template <>
+__device__ __forceinline__ int categorical<2>(const float (&p)[2], float u) {
+  return (p[1] > 0.f && p[0] <= u) ? 1 : 0;
+}
+
 // One Adam update (torch.optim.Adam defaults form) with every rounding spelled out, so that the stand-alone step and the
 // fused GEMM epilogue give the same bits: returns the new parameter, updates m and v.
 __device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, float lerp_w, float beta2, float omb2,

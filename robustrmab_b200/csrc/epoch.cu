@@ -319,18 +319,22 @@ __global__ void __launch_bounds__(256, (H <= 16 ? 4 : 2)) epoch_table_kernel(Epo
         if (!LEAN && g.ret) g.ret[step0 + (int64_t)t * E + e] = rf;
         const int cell = s_t * A + a_t;
         const float xp = fmaxf(x, 0.f), xm = fminf(x, 0.f);
+        // predicated accumulates (one @P FADD / DADD / DFMA each) rather than select-then-add pairs
+        const double rd = (double)rf;
 #pragma unroll
         for (int cc = 0; cc < S * A; ++cc) {
-          const bool hit = cell == cc;
-          Ap[cc] += hit ? xp : 0.f;
-          Am[cc] += hit ? xm : 0.f;
-          cnt[cc] += hit ? 1 : 0;
+          if (cell == cc) {
+            Ap[cc] += xp;
+            Am[cc] += xm;
+            cnt[cc] += 1;
+          }
         }
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-          const bool hit = s_t == s;
-          Sr[s] += hit ? (double)rf : 0.0;
-          Sr2[s] = hit ? fma((double)rf, (double)rf, Sr2[s]) : Sr2[s];
+          if (s_t == s) {
+            Sr[s] += rd;
+            Sr2[s] = fma(rd, rd, Sr2[s]);
+          }
         }
         next_v = v;
         sn = s_t;
