@@ -30,6 +30,13 @@ __device__ __forceinline__ float pick_f(const float (&t)[S], int s) {
   return v;
 }
 
+// Integer threshold of the two-category draw: (p1 > 0 && c0 <= m 2^-24)  <=>  m >= thr_draw(c0, p1) for every 24-bit m.
+// c0 2^24 and its ceiling are exact in fp32; c0 > 1, p1 <= 0 and NaNs give 2^24 (never), a negative c0 gives 0 (always).
+__device__ __forceinline__ uint32_t thr_draw(float c0, float p1) {
+  if (!(p1 > 0.f) || !(c0 <= 1.f)) return 0x1000000u;
+  return (uint32_t)ceilf(fmaxf(c0, 0.f) * 16777216.f);
+}
+
 template <int DOMAIN>
 __device__ __forceinline__ int table_next(int s, int a, float p, float u) {
   if (DOMAIN == RMAB_DOMAIN_CE) {
@@ -119,6 +126,8 @@ __global__ void __launch_bounds__(256, (H <= 16 ? 4 : 2)) epoch_table_kernel(Epo
         pn1[si] = fminf(fmaxf(__ldg(g.nature + c0 + 1), __ldg(g.ranges + 2 * c0 + 2)), __ldg(g.ranges + 2 * c0 + 3));
       }
     }
+    // CE transition out of (s = 1, a = 1): next = 1 iff p > 0 and fsub_rn(1, p) <= u (table_next, categorical<2>)
+    const uint32_t thr_e11 = thr_draw(__fsub_rn(1.f, pn1[S - 1]), pn1[S - 1]);
     const int64_t traj0 = (int64_t)n * (g.a ? (int64_t)(T + 1) * E : (int64_t)E);   // a == NULL: s_traj is the [N,E] start states
     const int64_t step0 = (int64_t)n * T * E;
     const uint32_t gn = g.arm0 + (uint32_t)n;
@@ -161,13 +170,27 @@ __global__ void __launch_bounds__(256, (H <= 16 ? 4 : 2)) epoch_table_kernel(Epo
       // bit t of the state planes = s_t (t = 0..T), bit t of the action plane = a_t (t = 0..T-1)
       uint32_t aw = 0u, sw0 = (uint32_t)(si & 1), sw1 = (uint32_t)(si >> 1);
       uint32_t* bw = bits + e;
+      // Draws in the integer domain: u = m 2^-24 with m = word >> 8, so `c <= u` is `m >= ceil(c 2^24)` exactly (c 2^24 and
+      // the ceiling are exact in fp32).  The action rule categorical<2>({p0, p1}, u) = (p1 > 0 && p0 <= u) becomes one
+      // threshold per state, computed once per (arm, env); thr_draw() maps "never" (p1 <= 0, NaN) to 2^24.
+      uint32_t thr_a[S];
+#pragma unroll
+      for (int k = 0; k < S; ++k) thr_a[k] = thr_draw(p0t[k], p1t[k]);
       // one step of the chain given its two Philox words (action draw, transition draw)
       auto chain_step = [&](int t, uint32_t w_act, uint32_t w_env) {
-        float pr[2] = {pick_f<S>(p0t, si), pick_f<S>(p1t, si)};
-        const int act = categorical<2>(pr, u24(w_act));
+        uint32_t ta = thr_a[0];
+#pragma unroll
+        for (int k = 1; k < S; ++k) ta = (si == k) ? thr_a[k] : ta;
+        const int act = (w_act >> 8) >= ta ? 1 : 0;
         if (!ONCHIP || (!LEAN && ac)) ac[(int64_t)t * E] = (uint8_t)act;
-        const float p = act ? pick_f<S>(pn1, si) : pick_f<S>(pn0, si);
-        si = table_next<DOMAIN>(si, act, p, u24(w_env));
+        if (DOMAIN == RMAB_DOMAIN_CE) {
+          // table_next<CE>: s = 0 -> (0.5 <= u); s = 1, a = 0 -> 0; s = 1, a = 1 -> (p > 0 && 1 - p <= u)
+          const uint32_t te = si == 0 ? 0x800000u : (act ? thr_e11 : 0x1000000u);
+          si = (w_env >> 8) >= te ? 1 : 0;
+        } else {
+          const float p = act ? pick_f<S>(pn1, si) : pick_f<S>(pn0, si);
+          si = table_next<DOMAIN>(si, act, p, u24(w_env));
+        }
         if (!ONCHIP || (!LEAN && ac)) tr[(int64_t)(t + 1) * E] = (uint8_t)si;
         if (ONCHIP) {
           aw |= (uint32_t)act << (t & 31);
