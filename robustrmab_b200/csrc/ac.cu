@@ -182,7 +182,20 @@ __global__ void __launch_bounds__(1024) lambda_forward_kernel(int E, int N, cons
 #pragma unroll
   for (int j = 0; j < kLamH; ++j) h[j] = 0.f;
   if (h1_in) {
-    if (w == 0 && e < E)
+    if (blockDim.x >= 256) {
+      // split sums spread over the block: thread t adds (env t >> 3 of this block, feature t & 7) over the splits in split
+      // order (deterministic, and the same order as the one-warp form below); consecutive threads read consecutive words
+      const int le = threadIdx.x >> 3, j = threadIdx.x & 7, ee = blockIdx.x * 32 + le;
+      float acc = 0.f;
+      if (threadIdx.x < 256 && ee < E)
+#pragma unroll 8
+        for (int k = 0; k < n_split; ++k) acc += __ldg(h1_in + ((int64_t)k * E + ee) * kLamH + j);
+      if (threadIdx.x < 256) red[0][j][le] = acc;
+      __syncthreads();
+      if (w == 0 && e < E)
+#pragma unroll
+        for (int jj = 0; jj < kLamH; ++jj) h[jj] = red[0][jj][lane];
+    } else if (w == 0 && e < E)
 #pragma unroll 4
       for (int k = 0; k < n_split; ++k) {  // partial sums of the arm splits, added in split order (deterministic)
         static_assert(kLamH == 8, "two float4 per (split, env)");
@@ -482,7 +495,7 @@ extern "C" int rmab_lambda_forward(int E, int N, const float* params, int n_tota
                                                                    (float*)ws);
     int rc = check_launch("rmab_lambda_forward(partial)");
     if (rc) return rc;
-    lambda_forward_kernel<<<(E + 31) / 32, 32, 0, st>>>(E, N, params, n_total, arm0, s, obs_scale, (const float*)ws, nsp,
+    lambda_forward_kernel<<<(E + 31) / 32, 256, 0, st>>>(E, N, params, n_total, arm0, s, obs_scale, (const float*)ws, nsp,
                                                        h1_partial, lamb);
     return check_launch("rmab_lambda_forward(tail)");
   }
