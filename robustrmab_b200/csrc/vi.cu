@@ -99,40 +99,87 @@ struct SmallMdp {
       pol[s] = ba;
     }
   }
-  // ValueIteration(...).run(); returns iterations (or -1) and fills V, pol, max_iter
+  // one Bellman backup with the rewards of this lambda tabulated by the caller (same arithmetic as bellman())
+  __device__ __forceinline__ void backup(const double (&V)[S], const double (&rw)[S][A], const ViParams& p, double (&Vn)[S],
+                                         int (&pol)[S]) const {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      double best = 0.0;
+      int ba = 0;
+#pragma unroll
+      for (int a = 0; a < A; ++a) {
+        double ev = 0.0;
+#pragma unroll
+        for (int t = 0; t < S; ++t) ev += P[a][s][t] * V[t];
+        const double q = rw[s][a] + p.gamma * ev;
+        if (a == 0 || q > best) { best = q; ba = a; }
+      }
+      Vn[s] = best;
+      pol[s] = ba;
+    }
+  }
+  // the stopping rule of one sweep (mdp.py:1375-1396); true = stop.  MODE is the stop mode as a compile-time constant: only
+  // its own variation is evaluated (the run-time form computed all three per sweep, half of the loop's instructions).
+  template <int MODE>
+  __device__ __forceinline__ bool sweep_done(const double (&Vn)[S], const double (&V)[S], int it, int max_iter,
+                                             const ViParams& p) const {
+    double dmx = Vn[0] - V[0], dmn = dmx;
+#pragma unroll
+    for (int s = 1; s < S; ++s) {
+      const double dd = Vn[s] - V[s];
+      dmx = fmax(dmx, dd);
+      if (MODE != RMAB_STOP_FULL) dmn = fmin(dmn, dd);
+    }
+    double variation = MODE == RMAB_STOP_FAST ? dmx - dmn : dmx;
+    if (MODE == RMAB_STOP_ABS) variation = fmax(fabs(dmx), fabs(dmn));  // sup-norm change: true convergence
+    return variation < p.thresh || (it == max_iter && MODE != RMAB_STOP_ABS) || it >= kViCap;
+  }
+  // ValueIteration(...).run(); returns iterations (or -1) and fills V, pol, max_iter.  The sweeps ping-pong between two
+  // register sets (no copy per sweep) over rewards tabulated once per lambda; the arithmetic of a sweep is bellman()'s.
   __device__ int solve(double lam, const ViParams& p, double (&V)[S], int (&pol)[S], int& max_iter) const {
-    double Vz[S], V1[S];
+    if (p.stop_mode == RMAB_STOP_FULL) return solve_mode<RMAB_STOP_FULL>(lam, p, V, pol, max_iter);
+    if (p.stop_mode == RMAB_STOP_FAST) return solve_mode<RMAB_STOP_FAST>(lam, p, V, pol, max_iter);
+    return solve_mode<RMAB_STOP_ABS>(lam, p, V, pol, max_iter);
+  }
+  template <int MODE>
+  __device__ int solve_mode(double lam, const ViParams& p, double (&V)[S], int (&pol)[S], int& max_iter) const {
+    double rw[S][A];
 #pragma unroll
-    for (int s = 0; s < S; ++s) { Vz[s] = 0.0; pol[s] = 0; }
-    bellman(Vz, lam, p, V1, pol);
-    double mx = V1[0], mn = V1[0];
+    for (int s = 0; s < S; ++s)
 #pragma unroll
-    for (int s = 1; s < S; ++s) { mx = fmax(mx, V1[s]); mn = fmin(mn, V1[s]); }
+      for (int a = 0; a < A; ++a) rw[s][a] = use_ra ? Ra[s][a] : (R[s] - lam * C[a]);
+    double Va[S], Vb[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) { Va[s] = 0.0; pol[s] = 0; }
+    backup(Va, rw, p, Vb, pol);
+    double mx = Vb[0], mn = Vb[0];
+#pragma unroll
+    for (int s = 1; s < S; ++s) { mx = fmax(mx, Vb[s]); mn = fmin(mn, Vb[s]); }
     max_iter = bound_iter(k, mx - mn, p);
-    if (p.stop_mode == RMAB_STOP_ABS && max_iter == -1) max_iter = kViCap;
+    if (MODE == RMAB_STOP_ABS && max_iter == -1) max_iter = kViCap;
     if (max_iter == -1) {
 #pragma unroll
       for (int s = 0; s < S; ++s) V[s] = __longlong_as_double(0x7ff8000000000000ll);
       return -1;
     }
+    // sweep 1 from V = 0 is the backup above (Vb, pol)
+    int it = 1;
+    if (!sweep_done<MODE>(Vb, Va, it, max_iter, p)) {
+      while (true) {
+        ++it;
+        backup(Vb, rw, p, Va, pol);
+        if (sweep_done<MODE>(Va, Vb, it, max_iter, p)) {
 #pragma unroll
-    for (int s = 0; s < S; ++s) V[s] = 0.0;
-    int it = 0;
-    while (true) {
-      ++it;
-      double Vn[S];
-      bellman(V, lam, p, Vn, pol);
-      double dmx = Vn[0] - V[0], dmn = dmx;
-#pragma unroll
-      for (int s = 1; s < S; ++s) { const double dd = Vn[s] - V[s]; dmx = fmax(dmx, dd); dmn = fmin(dmn, dd); }
-#pragma unroll
-      for (int s = 0; s < S; ++s) V[s] = Vn[s];
-      double variation = p.stop_mode == RMAB_STOP_FAST ? dmx - dmn : dmx;
-      if (p.stop_mode == RMAB_STOP_ABS) variation = fmax(fabs(dmx), fabs(dmn));  // sup-norm change: true convergence
-      if (variation < p.thresh) break;
-      if (it == max_iter && p.stop_mode != RMAB_STOP_ABS) break;
-      if (it >= kViCap) break;
+          for (int s = 0; s < S; ++s) V[s] = Va[s];
+          return it;
+        }
+        ++it;
+        backup(Va, rw, p, Vb, pol);
+        if (sweep_done<MODE>(Vb, Va, it, max_iter, p)) break;
+      }
     }
+#pragma unroll
+    for (int s = 0; s < S; ++s) V[s] = Vb[s];
     return it;
   }
   __device__ __forceinline__ double q(int s, int a, double lam, const ViParams& p, const double (&V)[S]) const {
