@@ -30,6 +30,15 @@ __device__ __forceinline__ int bound_iter(double k, double span, const ViParams&
   const double v = log(p.thresh / span) / den;
   return (int)ceil(v);
 }
+// The same with log(gamma * k) supplied by the caller: it depends on the arm only, and the Whittle bisection solves the
+// same arm at 20 values of lambda (one fp64 log per solve less; the value is the one bound_iter computes).
+__device__ __forceinline__ int bound_iter_den(double k, double den, double span, const ViParams& p) {
+  const double gk = p.gamma * k;
+  if (!(span > 0.0) || !(gk > 0.0) || gk == 1.0) return -1;
+  if (den == 0.0) return -1;
+  const double v = log(p.thresh / span) / den;
+  return (int)ceil(v);
+}
 
 // ---- small MDPs: everything in registers ---------------------------------------------------------
 template <int S, int A>
@@ -137,12 +146,16 @@ struct SmallMdp {
   // ValueIteration(...).run(); returns iterations (or -1) and fills V, pol, max_iter.  The sweeps ping-pong between two
   // register sets (no copy per sweep) over rewards tabulated once per lambda; the arithmetic of a sweep is bellman()'s.
   __device__ int solve(double lam, const ViParams& p, double (&V)[S], int (&pol)[S], int& max_iter) const {
-    if (p.stop_mode == RMAB_STOP_FULL) return solve_mode<RMAB_STOP_FULL>(lam, p, V, pol, max_iter);
-    if (p.stop_mode == RMAB_STOP_FAST) return solve_mode<RMAB_STOP_FAST>(lam, p, V, pol, max_iter);
-    return solve_mode<RMAB_STOP_ABS>(lam, p, V, pol, max_iter);
+    return solve(lam, p, V, pol, max_iter, log(p.gamma * k));
+  }
+  // log_gk = log(gamma * k) of this arm (bound_iter_den)
+  __device__ int solve(double lam, const ViParams& p, double (&V)[S], int (&pol)[S], int& max_iter, double log_gk) const {
+    if (p.stop_mode == RMAB_STOP_FULL) return solve_mode<RMAB_STOP_FULL>(lam, p, V, pol, max_iter, log_gk);
+    if (p.stop_mode == RMAB_STOP_FAST) return solve_mode<RMAB_STOP_FAST>(lam, p, V, pol, max_iter, log_gk);
+    return solve_mode<RMAB_STOP_ABS>(lam, p, V, pol, max_iter, log_gk);
   }
   template <int MODE>
-  __device__ int solve_mode(double lam, const ViParams& p, double (&V)[S], int (&pol)[S], int& max_iter) const {
+  __device__ int solve_mode(double lam, const ViParams& p, double (&V)[S], int (&pol)[S], int& max_iter, double log_gk) const {
     double rw[S][A];
 #pragma unroll
     for (int s = 0; s < S; ++s)
@@ -155,7 +168,7 @@ struct SmallMdp {
     double mx = Vb[0], mn = Vb[0];
 #pragma unroll
     for (int s = 1; s < S; ++s) { mx = fmax(mx, Vb[s]); mn = fmin(mn, Vb[s]); }
-    max_iter = bound_iter(k, mx - mn, p);
+    max_iter = bound_iter_den(k, log_gk, mx - mn, p);
     if (MODE == RMAB_STOP_ABS && max_iter == -1) max_iter = kViCap;
     if (max_iter == -1) {
 #pragma unroll
@@ -240,11 +253,12 @@ __global__ void __launch_bounds__(128) whittle_small_kernel(int N, const double*
     SmallMdp<S, A> m;
     m.load(T + (int64_t)n * S * A * S, R + (int64_t)n * S, C);
     double lo = lam_lo, hi = lam_hi;
+    const double log_gk = log(p.gamma * m.k);
     for (int r = 0; r < n_rounds; ++r) {
       const double mid = 0.5 * (lo + hi);
       double V[S];
       int pol[S], mi;
-      const int it = m.solve(mid, p, V, pol, mi);
+      const int it = m.solve(mid, p, V, pol, mi, log_gk);
       bool act = false;
       if (it != -1) act = (m.q(st, 1, mid, p, V) - m.q(st, 0, mid, p, V)) > 0.0;
       if (act) lo = mid; else hi = mid;
