@@ -10,6 +10,11 @@
 //     followed by the a1 tile in memory, which is what the M = 64 operand's second 32-feature block reads (ignored rows);
 //   * G1 / G2 are six MMAs each (M = 128, N = 16): A = hi / lo in TMEM, B = W2 / W2^T K-major 16 x 16 tiles in smem.
 // tools/umma_probe.cu modes 6 and 7 pin these two patterns against a CPU product on the device.
+// The kernel is bound by instruction issue (4 warps per scheduler, ~ 900 instructions per warp and tile), so what is left is
+// what the instructions are spent on: all of shared memory at compile-time offsets of ONE pinned window
+// register, float hyper-parameters from the host, the two-action policy head on the logit difference with one logit gradient
+// per row, and two instantiations -- `RAGGED` for env counts that are not a multiple of the tile height, the aligned one with
+// one state per tile and no row predication for the BASELINE shapes.
 //
 // Reference behaviour: agent_oracle.py compute_loss_pi :285-322, compute_loss_v :325-339, update :399-436.
 #include "common.cuh"
