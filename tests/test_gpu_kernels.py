@@ -344,7 +344,9 @@ def test_gae_oracle(K, domain, N, T, E):
                                                  (11, 3, 16, False, 3, 12, 8),
                                                  # hidden 64 + scalar state input: the tcgen05 per-sample kernel
                                                  (11, 3, 64, False, 3, 12, 8), (51, 3, 64, False, 2, 20, 40),
-                                                 (6, 2, 64, False, 2, 5, 3)])
+                                                 (6, 2, 64, False, 2, 5, 3),
+                                                 # T * E a multiple of 128: the instantiation without row predication
+                                                 (51, 3, 64, False, 2, 8, 32), (7, 2, 64, False, 2, 4, 64)])
 def test_ppo_update(K, S, A, h, one_hot, N, T, E):
     rs = np.random.RandomState(S + h + T)
     in_dim = (S if one_hot else 1) + 1

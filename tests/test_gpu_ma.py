@@ -105,7 +105,7 @@ def test_agent_critic_extra_batched(K):
         K.ops.ac_step(net, K.t(Wpi), K.t(Wv), K.t(s), K.t(lamb), u=K.t(u))      # n_extra > 0 without the addend
 
 
-@pytest.mark.parametrize("N,T,E,S", [(3, 6, 8, 11), (2, 20, 40, 51), (4, 3, 50, 7)])
+@pytest.mark.parametrize("N,T,E,S", [(3, 6, 8, 11), (2, 20, 40, 51), (4, 3, 50, 7), (2, 8, 32, 11)])   # last: T * E = 256, aligned tiles
 def test_critic_extra_iter_tcgen05_vs_per_sample_kernel(K, N, T, E, S):
     """rmab_critic_extra_iter at hidden 64 with the scalar state input: the sample-major call runs the tcgen05 kernel,
     the arm-major call the per-sample FFMA kernel (itself pinned to the oracle by the MA loop tests); same loss, dLoss/dz1
