@@ -104,7 +104,9 @@ __global__ void __launch_bounds__(NT16, CTAS16) ppo_table_umma16_kernel(const __
   float* const WTL = reinterpret_cast<float*>(base + S_WTL);
 
   // (tid is NOT pinned like the window base: measured 4.03 vs 3.99 ms -- the register is worth more than the S2R re-reads)
-  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, r = tid;
+  // the warp index through a shuffle broadcast: the compiler then knows it is warp-uniform, keeps the TMEM addresses derived
+  // from it in uniform registers (no R2UR in front of every tcgen05.ld / st) and turns `warp == 0` into uniform branches
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), r = tid;
   float* Wn = g.W + (int64_t)n * P;
   float* An = g.adam + (int64_t)n * 2 * P;
   for (int i = tid; i < P; i += NT16) {

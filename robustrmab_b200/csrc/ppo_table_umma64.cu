@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(NTHR, 1) ppo_table_umma64_kernel(const __grid_
 #ifndef U64_NO_PIN_TID
   asm volatile("" : "+r"(tid));   // pinned (no SR_TID.X re-reads inside the tile loop)
 #endif
-  const int n = blockIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = blockIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform (see the h16 kernel)
   const int q = warp & 3, cq = warp >> 2, r = 32 * q + lane, f0 = FW * cq;
   float* Wn = g.W + (int64_t)n * P;
   float* An = g.adam + (int64_t)n * 2 * P;
