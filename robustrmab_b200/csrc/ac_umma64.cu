@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(NTHR, 2) ac_step_umma64_kernel(AcArgs g) {
   float* w3 = b2s + H;                                   // [kMaxA][H]
   float* b3 = w3 + kMaxA * H;                            // [kMaxA]
   float* plog = b3 + kMaxA;                              // [4 cq][128 rows][kMaxA]
-  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
   const int q = warp & 3, cq = warp >> 2, r = 32 * q + lane, f0 = FW * cq;
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar)));

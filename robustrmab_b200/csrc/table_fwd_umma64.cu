@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(NTHR, 2) table_fwd_umma64_kernel(FwdArgs g) {
   float* w3 = b2s + H;                                   // [OUT][H]
   float* b3 = w3 + OUT * H;                              // [OUT] (padded to 4)
   float* plog = b3 + 4;                                  // [4 cq][128 rows][OUT] partial output dots
-  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
   const int q = warp & 3, cq = warp >> 2, r = 32 * q + lane, f0 = FW * cq;
   const float* Wn = g.W + (int64_t)n * L.P;
   for (int i = tid; i < HH; i += NTHR) {
