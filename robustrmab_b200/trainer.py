@@ -264,11 +264,28 @@ class RMABPPOTrainer:
     def epoch_host(self, s0_host, nature_host):
         """End-to-end epoch through host buffers: H2D of the start states and the nature policy's parameter
         table (pinned), the epoch, D2H of the per-env results."""
-        self.s_traj[:, 0].copy_(s0_host.to(self.dev, non_blocking=True))
+        if self.s_traj.shape[1] == 1:                       # [N,1,E]: row 0 is a contiguous [N,E] view, one H2D copy
+            self.s_traj[:, 0].copy_(s0_host, non_blocking=True)
+        else:
+            self.s_traj[:, 0].copy_(s0_host.to(self.dev, non_blocking=True))
         self.nature.copy_(nature_host, non_blocking=True)
         st = self.epoch(want_stats=True)
-        out = {k: v.to("cpu", non_blocking=True) for k, v in st.items()}
+        # the per-env results packed into ONE device buffer and read back by ONE copy into pinned memory (three copies into
+        # pageable memory before: each of those is synchronous); the returned arrays are views of that pinned buffer, valid
+        # until the next call
+        keys = list(st.keys())
+        sizes = [int(st[k].numel()) for k in keys]
+        total = sum(sizes)
+        if getattr(self, "_host_out", None) is None or self._host_out.numel() != total:
+            self._dev_out = torch.empty(total, dtype=torch.float32, device=self.dev)
+            self._host_out = torch.empty(total, dtype=torch.float32).pin_memory()
+        torch.cat([st[k].reshape(-1).to(torch.float32) for k in keys], out=self._dev_out)
+        self._host_out.copy_(self._dev_out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        out, o = {}, 0
+        for k, n_ in zip(keys, sizes):
+            out[k] = self._host_out[o:o + n_].view(st[k].shape)
+            o += n_
         return out
 
     def epoch(self, want_stats=True, keep_buffers=False):
